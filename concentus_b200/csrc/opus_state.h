@@ -1,0 +1,48 @@
+// opus_state.h — the per-stream persistent codec state as it lives in HBM (and, serialised, inside the
+// caller-visible OpusDecoder / OpusEncoder blocks).  Plain C layout, no pointers: the block can be
+// memcpy'd, relocated and snapshotted exactly like the reference's states
+// (opus-fix/tests/test_opus_decode.c:84-95, src/opus_decoder.c:55-79, celt/celt_decoder.c:67-100).
+#pragma once
+#include <stdint.h>
+
+#define CB_NB_EBANDS 21
+#define CB_OVERLAP 120
+#define CB_DEC_BUF 2048
+#define CB_DEC_MEM (CB_DEC_BUF + CB_OVERLAP)   /* per channel */
+#define CB_LPC_ORDER 24
+
+#define CB_MODE_SILK_ONLY 1000
+#define CB_MODE_HYBRID 1001
+#define CB_MODE_CELT_ONLY 1002
+
+typedef struct CbDecState {
+    /* ---- configuration: survives OPUS_RESET_STATE (src/opus_decoder.c:55-63) ---- */
+    int32_t channels;       /* output channels CC */
+    int32_t Fs;             /* API sampling rate */
+    int32_t downsample;     /* resampling_factor(Fs), celt/celt.c:62-91 */
+    int32_t decode_gain;    /* Q8 dB */
+    /* ---- OPUS_DECODER_RESET_START (src/opus_decoder.c:66-78) ---- */
+    int32_t stream_channels;
+    int32_t bandwidth;
+    int32_t mode;
+    int32_t prev_mode;
+    int32_t frame_size;
+    int32_t prev_redundancy;
+    int32_t last_packet_duration;
+    uint32_t rangeFinal;
+    /* ---- CELT DECODER_RESET_START (celt/celt_decoder.c:80-99) ---- */
+    uint32_t rng;
+    int32_t error;
+    int32_t last_pitch_index;
+    int32_t loss_count;
+    int32_t postfilter_period, postfilter_period_old;
+    int32_t postfilter_gain, postfilter_gain_old;   /* Q15, value range of opus_val16 */
+    int32_t postfilter_tapset, postfilter_tapset_old;
+    int32_t preemph_memD[2];
+    int16_t oldEBands[2 * CB_NB_EBANDS];
+    int16_t oldLogE[2 * CB_NB_EBANDS];
+    int16_t oldLogE2[2 * CB_NB_EBANDS];
+    int16_t backgroundLogE[2 * CB_NB_EBANDS];
+    int16_t lpc[2 * CB_LPC_ORDER];
+    int32_t decode_mem[2 * CB_DEC_MEM];
+} CbDecState;
