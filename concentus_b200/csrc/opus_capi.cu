@@ -1,0 +1,690 @@
+// opus_capi.cu — kernels and the C ABI of libconcentus_b200.so (declared in include/opus_b200.h).
+//
+// Boundary: libopus's public decoder API (opus-fix/include/opus.h:406-512) plus our batch / span calls.
+// Host side = argument checks, ctl, state residency and copies; everything from ec_dec_init down runs in
+// decode_span_kernel, one warp per stream, F packets per launch, per-stream state resident in HBM.
+// There is NO CPU path: if CUDA is unusable every codec call returns OPUS_INTERNAL_ERROR.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/opus_b200.h"
+#include "opus_decoder_dev.cuh"
+
+using namespace cb;
+
+// ------------------------------------------------------------------------------------------------
+// Caller-visible state block.  Pointer-free and memcpy-able like the reference's (tests/test_opus_decode.c:84-95):
+// `st` is the authoritative serialised state whenever host_current != 0; after a batch/span call the
+// authoritative copy is the HBM slot (slot, gen) and host_current == 0 until the next sync.
+// ------------------------------------------------------------------------------------------------
+struct OpusDecoder {
+    uint32_t magic;
+    int32_t slot;          // device pool slot or -1
+    uint64_t gen;          // generation of the slot contents this block refers to
+    int32_t host_current;  // 1: `st` below is up to date
+    int32_t reserved;
+    CbDecState st;
+};
+static const uint32_t kDecMagic = 0x0B200DECu;
+
+// ------------------------------------------------------------------------------------------------
+// Kernels
+// ------------------------------------------------------------------------------------------------
+#define CB_WPB 4   // warps (= streams) per block
+
+// One warp per stream; packets f0..f1 of every stream.  PCM row of packet (s,f) starts at
+// pcm[(s*pcm_F + (f-pcm_f0)) * cap * channels].
+__global__ void __launch_bounds__(CB_WPB * 32)
+decode_span_kernel(CbDecState *pool, const int *slots, const uint8_t *data, const int64_t *offs, const int32_t *lens,
+                   int16_t *pcm, int n, int F, int f0, int f1, int pcm_F, int pcm_f0, int cap, int decode_fec, int *rets) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_WPB + warp;
+    if (s >= n) return;
+    DecScratch &S = *(reinterpret_cast<DecScratch *>(smem) + warp);
+    CbDecState *st = pool + slots[s];
+    const int channels = st->channels;
+    Team tm{lane};
+    for (int f = f0; f < f1; f++) {
+        const size_t idx = (size_t)s * F + f;
+        const int len = lens[idx];
+        const uint8_t *p = len > 0 ? data + offs[idx] : nullptr;
+        int16_t *out = pcm + ((size_t)s * pcm_F + (f - pcm_f0)) * cap * channels;
+        int r = opus_decode_packet(tm, st, S, p, len, out, cap, decode_fec);
+        if (lane == 0) rets[idx] = r;
+        __syncwarp();
+    }
+}
+
+// state staging <-> pool
+__global__ void scatter_states_kernel(CbDecState *pool, const int *slots, const CbDecState *stage, int n) {
+    const int words = sizeof(CbDecState) / 4;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int *src = reinterpret_cast<const int *>(stage + k);
+        int *dst = reinterpret_cast<int *>(pool + slots[k]);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+}
+__global__ void gather_states_kernel(const CbDecState *pool, const int *slots, CbDecState *stage, int n) {
+    const int words = sizeof(CbDecState) / 4;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int *src = reinterpret_cast<const int *>(pool + slots[k]);
+        int *dst = reinterpret_cast<int *>(stage + k);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Runtime context
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct SlotInfo {
+    const void *owner;
+    uint64_t gen;
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+};
+
+struct Ctx {
+    std::mutex mu;
+    bool tried = false, ok = false;
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    CbDecState *pool = nullptr;
+    int pool_cap = 0;
+    std::vector<SlotInfo> reg;
+    std::vector<int> free_slots;
+    DevBuf d_slots, d_data, d_offs, d_lens, d_pcm[2], d_rets, d_stage;
+    PinBuf h_stage, h_slots, h_misc;
+    long long launches = 0;
+    float last_ms = 0.f;
+    int smem_per_block = 0;
+};
+Ctx g;
+
+enum { kStageStates = 256 };
+
+bool ctx_init_locked() {
+    if (g.tried) return g.ok;
+    g.tried = true;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        fprintf(stderr, "concentus_b200: no CUDA device available — this library has no CPU path\n");
+        return false;
+    }
+    if (g.device >= ndev) g.device = 0;
+    if (cudaSetDevice(g.device) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    cudaEventCreate(&g.ev0);
+    cudaEventCreate(&g.ev1);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&g.ev_chunk[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g.ev_copy[i], cudaEventDisableTiming);
+    }
+    g.smem_per_block = (int)(CB_WPB * sizeof(DecScratch));
+    cudaFuncSetAttribute(decode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_per_block);
+    cudaFuncSetAttribute(decode_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (!g.h_stage.reserve(sizeof(CbDecState) * kStageStates)) return false;
+    if (!g.d_stage.reserve(sizeof(CbDecState) * kStageStates)) return false;
+    g.ok = (cudaGetLastError() == cudaSuccess);
+    return g.ok;
+}
+
+bool pool_reserve_locked(int need_total) {
+    if (need_total <= g.pool_cap) return true;
+    int ncap = g.pool_cap ? g.pool_cap : 64;
+    while (ncap < need_total) ncap *= 2;
+    CbDecState *np = nullptr;
+    if (cudaMalloc(&np, sizeof(CbDecState) * (size_t)ncap) != cudaSuccess) return false;
+    if (g.pool) {
+        cudaMemcpyAsync(np, g.pool, sizeof(CbDecState) * (size_t)g.pool_cap, cudaMemcpyDeviceToDevice, g.stream);
+        cudaStreamSynchronize(g.stream);
+        cudaFree(g.pool);
+    }
+    for (int i = ncap - 1; i >= g.pool_cap; i--) g.free_slots.push_back(i);
+    g.reg.resize(ncap, SlotInfo{nullptr, 0});
+    g.pool = np;
+    g.pool_cap = ncap;
+    return true;
+}
+
+inline bool resident(const OpusDecoder *d) {
+    return d->slot >= 0 && d->slot < g.pool_cap && g.reg[d->slot].owner == d && g.reg[d->slot].gen == d->gen;
+}
+
+// Bring the host copy of `d` up to date (download from its slot when the slot holds the newer state).
+int make_host_current_locked(OpusDecoder *d) {
+    if (d->host_current) return OPUS_OK;
+    // stale host block: the state it refers to must still be in its slot with the same generation
+    // (this also covers a block that was memcpy'd while its original was device-resident)
+    if (d->slot < 0 || d->slot >= g.pool_cap || g.reg[d->slot].gen != d->gen) return OPUS_INVALID_STATE;
+    if (cudaMemcpyAsync(&d->st, g.pool + d->slot, sizeof(CbDecState), cudaMemcpyDeviceToHost, g.stream) != cudaSuccess)
+        return OPUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    d->host_current = 1;
+    return OPUS_OK;
+}
+
+void release_slot_locked(OpusDecoder *d) {
+    if (d->slot >= 0 && d->slot < g.pool_cap && g.reg[d->slot].owner == d) {
+        g.reg[d->slot].owner = nullptr;
+        g.reg[d->slot].gen++;
+        g.free_slots.push_back(d->slot);
+    }
+    d->slot = -1;
+}
+
+// Make every state resident in the pool; fills h_slots[0..n).  Uploads go through a pinned staging buffer.
+int make_resident_locked(OpusDecoder **st, int n, int *h_slots) {
+    int need_new = 0;
+    for (int i = 0; i < n; i++) {
+        OpusDecoder *d = st[i];
+        if (!d || d->magic != kDecMagic) return OPUS_BAD_ARG;
+        if (!resident(d)) need_new++;
+    }
+    int in_use = g.pool_cap - (int)g.free_slots.size();
+    if (!pool_reserve_locked(in_use + need_new)) return OPUS_ALLOC_FAIL;
+    std::vector<int> up_idx;
+    for (int i = 0; i < n; i++) {
+        OpusDecoder *d = st[i];
+        if (resident(d)) {
+            if (d->host_current) up_idx.push_back(i);   // host block is authoritative (e.g. after a ctl): refresh slot
+        } else {
+            if (!d->host_current) {
+                int rc = make_host_current_locked(d);
+                if (rc != OPUS_OK) return rc;
+            }
+            d->slot = g.free_slots.back();
+            g.free_slots.pop_back();
+            g.reg[d->slot].owner = d;
+            d->gen = ++g.reg[d->slot].gen;
+            up_idx.push_back(i);
+        }
+        h_slots[i] = d->slot;
+    }
+    // duplicates in one batch would race on one state
+    // (cheap check only for small n; large batches are the caller's responsibility)
+    if (n <= 64)
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++)
+                if (st[i] == st[j]) return OPUS_BAD_ARG;
+    CbDecState *hs = (CbDecState *)g.h_stage.p;
+    int *hsl = (int *)g.h_slots.p;   // caller reserved >= n ints... use a separate region at the tail
+    (void)hsl;
+    for (size_t base = 0; base < up_idx.size(); base += kStageStates) {
+        int cnt = (int)((up_idx.size() - base) < (size_t)kStageStates ? (up_idx.size() - base) : kStageStates);
+        std::vector<int> sl(cnt);
+        for (int k = 0; k < cnt; k++) {
+            OpusDecoder *d = st[up_idx[base + k]];
+            memcpy(&hs[k], &d->st, sizeof(CbDecState));
+            sl[k] = d->slot;
+        }
+        if (!g.d_slots.reserve(sizeof(int) * (size_t)(n > kStageStates ? n : kStageStates))) return OPUS_ALLOC_FAIL;
+        cudaMemcpyAsync(g.d_stage.p, hs, sizeof(CbDecState) * (size_t)cnt, cudaMemcpyHostToDevice, g.stream);
+        cudaMemcpyAsync(g.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, g.stream);
+        scatter_states_kernel<<<cnt, 256, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (const CbDecState *)g.d_stage.p, cnt);
+        if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    }
+    return OPUS_OK;
+}
+
+// After a launch: the slot now holds a newer state than the host block.
+void mark_device_newer_locked(OpusDecoder **st, int n) {
+    for (int i = 0; i < n; i++) {
+        OpusDecoder *d = st[i];
+        d->gen = ++g.reg[d->slot].gen;
+        d->host_current = 0;
+    }
+}
+
+int sync_states_locked(OpusDecoder **st, int n, bool release) {
+    std::vector<int> idx;
+    for (int i = 0; i < n; i++) {
+        OpusDecoder *d = st[i];
+        if (!d || d->magic != kDecMagic) return OPUS_BAD_ARG;
+        if (!d->host_current) {
+            if (!resident(d)) {
+                int rc = make_host_current_locked(d);
+                if (rc != OPUS_OK) return rc;
+            } else {
+                idx.push_back(i);
+            }
+        }
+    }
+    CbDecState *hs = (CbDecState *)g.h_stage.p;
+    for (size_t base = 0; base < idx.size(); base += kStageStates) {
+        int cnt = (int)((idx.size() - base) < (size_t)kStageStates ? (idx.size() - base) : kStageStates);
+        std::vector<int> sl(cnt);
+        for (int k = 0; k < cnt; k++) sl[k] = st[idx[base + k]]->slot;
+        if (!g.d_slots.reserve(sizeof(int) * (size_t)kStageStates)) return OPUS_ALLOC_FAIL;
+        cudaMemcpyAsync(g.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, g.stream);
+        gather_states_kernel<<<cnt, 256, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (CbDecState *)g.d_stage.p, cnt);
+        cudaMemcpyAsync(hs, g.d_stage.p, sizeof(CbDecState) * (size_t)cnt, cudaMemcpyDeviceToHost, g.stream);
+        if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+        for (int k = 0; k < cnt; k++) {
+            OpusDecoder *d = st[idx[base + k]];
+            memcpy(&d->st, &hs[k], sizeof(CbDecState));
+            d->host_current = 1;
+        }
+    }
+    if (release)
+        for (int i = 0; i < n; i++) release_slot_locked(st[i]);
+    return OPUS_OK;
+}
+
+void launch_decode(const int *d_slots, const uint8_t *d_data, const int64_t *d_offs, const int32_t *d_lens, int16_t *d_pcm,
+                   int n, int F, int f0, int f1, int pcm_F, int pcm_f0, int cap, int fec, int *d_rets, cudaStream_t s) {
+    int blocks = (n + CB_WPB - 1) / CB_WPB;
+    decode_span_kernel<<<blocks, CB_WPB * 32, g.smem_per_block, s>>>(g.pool, d_slots, d_data, d_offs, d_lens, d_pcm, n, F, f0, f1,
+                                                                     pcm_F, pcm_f0, cap, fec, d_rets);
+    g.launches++;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI — runtime
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int opus_b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.tried) g.device = device;
+    return ctx_init_locked() ? OPUS_OK : OPUS_INTERNAL_ERROR;
+}
+int opus_b200_synchronize(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(g.copy_stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    return OPUS_OK;
+}
+void *opus_b200_stream(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ctx_init_locked()) return nullptr;
+    return (void *)g.stream;
+}
+long long opus_b200_kernel_launches(void) { return g.launches; }
+float opus_b200_last_kernel_ms(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return g.last_ms;
+}
+
+const char *opus_strerror(int error) {
+    static const char *const s[8] = {"success", "invalid argument", "buffer too small", "internal error", "corrupted stream",
+                                     "request not implemented", "invalid state", "memory allocation failed"};
+    if (error > 0 || error < -7) return "unknown error";
+    return s[-error];
+}
+const char *opus_get_version_string(void) { return "libopus 1.1.2-fixed (concentus_b200, sm_100a CELT engine)"; }
+
+// ---- packet helpers (host) ----
+int opus_packet_parse(const unsigned char *data, opus_int32 len, unsigned char *out_toc, const unsigned char *frames[48],
+                      opus_int16 size[48], int *payload_offset) {
+    if (size == nullptr || len < 0) return OPUS_BAD_ARG;
+    int off = 0;
+    int count = pkt_parse(data, len, 0, out_toc, size, &off, nullptr);
+    if (count < 0) return count;
+    if (payload_offset) *payload_offset = off;
+    if (frames) {
+        const unsigned char *p = data + off;
+        for (int i = 0; i < count; i++) {
+            frames[i] = p;
+            p += size[i];
+        }
+    }
+    return count;
+}
+int opus_packet_get_bandwidth(const unsigned char *data) { return pkt_bandwidth(data); }
+int opus_packet_get_samples_per_frame(const unsigned char *data, opus_int32 Fs) { return pkt_samples_per_frame(data, Fs); }
+int opus_packet_get_nb_channels(const unsigned char *data) { return pkt_nb_channels(data); }
+int opus_packet_get_nb_frames(const unsigned char packet[], opus_int32 len) {
+    if (len < 1) return OPUS_BAD_ARG;
+    int count = packet[0] & 0x3;
+    if (count == 0) return 1;
+    if (count != 3) return 2;
+    if (len < 2) return OPUS_INVALID_PACKET;
+    return packet[1] & 0x3F;
+}
+int opus_packet_get_nb_samples(const unsigned char packet[], opus_int32 len, opus_int32 Fs) {
+    int count = opus_packet_get_nb_frames(packet, len);
+    if (count < 0) return count;
+    int samples = count * pkt_samples_per_frame(packet, Fs);
+    if (samples * 25 > Fs * 3) return OPUS_INVALID_PACKET;
+    return samples;
+}
+int opus_decoder_get_nb_samples(const OpusDecoder *dec, const unsigned char packet[], opus_int32 len) {
+    return opus_packet_get_nb_samples(packet, len, dec->st.Fs);
+}
+
+// ---- decoder lifecycle ----
+int opus_decoder_get_size(int channels) {
+    if (channels < 1 || channels > 2) return 0;
+    return (int)sizeof(OpusDecoder);
+}
+int opus_decoder_init(OpusDecoder *st, opus_int32 Fs, int channels) {
+    if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2))
+        return OPUS_BAD_ARG;
+    memset(st, 0, sizeof(OpusDecoder));
+    st->magic = kDecMagic;
+    st->slot = -1;
+    st->gen = 0;
+    st->host_current = 1;
+    if (dec_state_init(&st->st, Fs, channels) != 0) return OPUS_BAD_ARG;
+    return OPUS_OK;
+}
+OpusDecoder *opus_decoder_create(opus_int32 Fs, int channels, int *error) {
+    if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2)) {
+        if (error) *error = OPUS_BAD_ARG;
+        return nullptr;
+    }
+    OpusDecoder *st = (OpusDecoder *)malloc(sizeof(OpusDecoder));
+    if (!st) {
+        if (error) *error = OPUS_ALLOC_FAIL;
+        return nullptr;
+    }
+    int ret = opus_decoder_init(st, Fs, channels);
+    if (error) *error = ret;
+    if (ret != OPUS_OK) {
+        free(st);
+        st = nullptr;
+    }
+    return st;
+}
+void opus_decoder_destroy(OpusDecoder *st) {
+    if (!st) return;
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        if (g.ok && st->magic == kDecMagic) release_slot_locked(st);
+    }
+    free(st);
+}
+
+int opus_decoder_ctl(OpusDecoder *st, int request, ...) {
+    int ret = OPUS_OK;
+    va_list ap;
+    va_start(ap, request);
+    // any ctl that reads or writes codec state needs the host block current
+    {
+        std::lock_guard<std::mutex> lk(g.mu);
+        if (!st->host_current) {
+            if (!ctx_init_locked()) { va_end(ap); return OPUS_INTERNAL_ERROR; }
+            int rc = make_host_current_locked(st);
+            if (rc != OPUS_OK) { va_end(ap); return rc; }
+        }
+    }
+    CbDecState *s = &st->st;
+    switch (request) {
+    case OPUS_GET_BANDWIDTH_REQUEST: {
+        opus_int32 *v = va_arg(ap, opus_int32 *);
+        if (!v) { ret = OPUS_BAD_ARG; break; }
+        *v = s->bandwidth;
+    } break;
+    case OPUS_GET_FINAL_RANGE_REQUEST: {
+        opus_uint32 *v = va_arg(ap, opus_uint32 *);
+        if (!v) { ret = OPUS_BAD_ARG; break; }
+        *v = s->rangeFinal;
+    } break;
+    case OPUS_RESET_STATE: {
+        std::lock_guard<std::mutex> lk(g.mu);
+        dec_state_reset(s);
+        // host block is now authoritative; a resident slot is refreshed on the next batch call
+    } break;
+    case OPUS_GET_SAMPLE_RATE_REQUEST: {
+        opus_int32 *v = va_arg(ap, opus_int32 *);
+        if (!v) { ret = OPUS_BAD_ARG; break; }
+        *v = s->Fs;
+    } break;
+    case OPUS_GET_PITCH_REQUEST: {
+        opus_int32 *v = va_arg(ap, opus_int32 *);
+        if (!v) { ret = OPUS_BAD_ARG; break; }
+        *v = s->prev_mode == CB_MODE_CELT_ONLY ? s->postfilter_period : 0;
+    } break;
+    case OPUS_GET_GAIN_REQUEST: {
+        opus_int32 *v = va_arg(ap, opus_int32 *);
+        if (!v) { ret = OPUS_BAD_ARG; break; }
+        *v = s->decode_gain;
+    } break;
+    case OPUS_SET_GAIN_REQUEST: {
+        opus_int32 v = va_arg(ap, opus_int32);
+        if (v < -32768 || v > 32767) { ret = OPUS_BAD_ARG; break; }
+        s->decode_gain = v;
+    } break;
+    case OPUS_GET_LAST_PACKET_DURATION_REQUEST: {
+        opus_uint32 *v = va_arg(ap, opus_uint32 *);
+        if (!v) { ret = OPUS_BAD_ARG; break; }
+        *v = (opus_uint32)s->last_packet_duration;
+    } break;
+    default:
+        ret = OPUS_UNIMPLEMENTED;
+        break;
+    }
+    va_end(ap);
+    return ret;
+}
+
+// ---- decode ----
+int opus_decode_span_device(OpusDecoder **st, int n, int F, const unsigned char *d_data, const int64_t *d_offs,
+                            const opus_int32 *d_len, opus_int16 *d_pcm, int frame_size, int *d_ret) {
+    if (!st || n <= 0 || F <= 0 || frame_size <= 0) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    if (!g.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    int *hsl = (int *)g.h_slots.p;
+    int rc = make_resident_locked(st, n, hsl);
+    if (rc != OPUS_OK) return rc;
+    if (!g.d_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    cudaMemcpyAsync(g.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, g.stream);
+    cudaEventRecord(g.ev0, g.stream);
+    launch_decode((const int *)g.d_slots.p, d_data, d_offs, d_len, d_pcm, n, F, 0, F, F, 0, frame_size, 0, d_ret, g.stream);
+    cudaEventRecord(g.ev1, g.stream);
+    mark_device_newer_locked(st, n);
+    if (cudaGetLastError() != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    return OPUS_OK;
+}
+
+// Host-buffer span decode.  The packet bytes go up in one copy; the kernel then runs in time chunks whose
+// PCM is copied back on a second stream while the next chunk decodes (double-buffered).
+static int decode_span_host_locked(OpusDecoder **st, int n, int F, const unsigned char *data, int64_t data_bytes,
+                                   const int64_t *offs, const opus_int32 *len, opus_int16 *pcm, int frame_size,
+                                   int decode_fec, int *ret, bool keep_resident) {
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    const int channels = st[0]->st.channels;
+    for (int i = 0; i < n; i++) {
+        if (!st[i] || st[i]->magic != kDecMagic) return OPUS_BAD_ARG;
+        if (st[i]->st.channels != channels) return OPUS_BAD_ARG;
+    }
+    if (!g.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    int *hsl = (int *)g.h_slots.p;
+    int rc = make_resident_locked(st, n, hsl);
+    if (rc != OPUS_OK) return rc;
+    const size_t NF = (size_t)n * F;
+    if (!g.d_slots.reserve(sizeof(int) * (size_t)n) || !g.d_data.reserve((size_t)data_bytes + 16) ||
+        !g.d_offs.reserve(sizeof(int64_t) * NF) || !g.d_lens.reserve(sizeof(int32_t) * NF) || !g.d_rets.reserve(sizeof(int) * NF))
+        return OPUS_ALLOC_FAIL;
+    // time chunking: about 64 MiB of PCM per chunk
+    const size_t row = (size_t)frame_size * channels * sizeof(int16_t);
+    int Fc = (int)((64u << 20) / (row * (size_t)n));
+    if (Fc < 1) Fc = 1;
+    if (Fc > F) Fc = F;
+    const size_t chunk_bytes = (size_t)n * Fc * row;
+    const int nchunks = (F + Fc - 1) / Fc;
+    if (!g.d_pcm[0].reserve(chunk_bytes) || (nchunks > 1 && !g.d_pcm[1].reserve(chunk_bytes))) return OPUS_ALLOC_FAIL;
+    cudaMemcpyAsync(g.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, g.stream);
+    if (data_bytes > 0) cudaMemcpyAsync(g.d_data.p, data, (size_t)data_bytes, cudaMemcpyHostToDevice, g.stream);
+    cudaMemcpyAsync(g.d_offs.p, offs, sizeof(int64_t) * NF, cudaMemcpyHostToDevice, g.stream);
+    cudaMemcpyAsync(g.d_lens.p, len, sizeof(int32_t) * NF, cudaMemcpyHostToDevice, g.stream);
+    cudaEventRecord(g.ev0, g.stream);
+    for (int c = 0; c < nchunks; c++) {
+        const int b = c & 1;
+        const int f0 = c * Fc, f1 = (f0 + Fc < F) ? f0 + Fc : F;
+        if (c >= 2) cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0);   // buffer b drained?
+        launch_decode((const int *)g.d_slots.p, (const uint8_t *)g.d_data.p, (const int64_t *)g.d_offs.p, (const int32_t *)g.d_lens.p,
+                      (int16_t *)g.d_pcm[b].p, n, F, f0, f1, Fc, f0, frame_size, decode_fec, (int *)g.d_rets.p, g.stream);
+        cudaEventRecord(g.ev_chunk[b], g.stream);
+        cudaStreamWaitEvent(g.copy_stream, g.ev_chunk[b], 0);
+        // rows of (f1-f0) packets per stream: device pitch Fc*row, host pitch F*row
+        cudaMemcpy2DAsync((char *)pcm + (size_t)f0 * row, (size_t)F * row, g.d_pcm[b].p, (size_t)Fc * row, (size_t)(f1 - f0) * row,
+                          (size_t)n, cudaMemcpyDeviceToHost, g.copy_stream);
+        cudaEventRecord(g.ev_copy[b], g.copy_stream);
+    }
+    cudaEventRecord(g.ev1, g.stream);
+    cudaMemcpyAsync(ret, g.d_rets.p, sizeof(int) * NF, cudaMemcpyDeviceToHost, g.stream);
+    mark_device_newer_locked(st, n);
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess || cudaStreamSynchronize(g.copy_stream) != cudaSuccess) {
+        fprintf(stderr, "concentus_b200: CUDA failure in decode span: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return OPUS_INTERNAL_ERROR;
+    }
+    cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+    if (!keep_resident) return sync_states_locked(st, n, true);
+    return OPUS_OK;
+}
+
+int opus_decode_span(OpusDecoder **st, int n, int F, const unsigned char *data, const int64_t *offs, const opus_int32 *len,
+                     opus_int16 *pcm, int frame_size, int *ret) {
+    if (!st || n <= 0 || F <= 0 || frame_size <= 0 || !offs || !len || !pcm || !ret) return OPUS_BAD_ARG;
+    int64_t bytes = 0;
+    const size_t NF = (size_t)n * F;
+    for (size_t i = 0; i < NF; i++) {
+        if (len[i] < 0) return OPUS_BAD_ARG;
+        int64_t e = offs[i] + len[i];
+        if (len[i] > 0 && e > bytes) bytes = e;
+    }
+    std::lock_guard<std::mutex> lk(g.mu);
+    return decode_span_host_locked(st, n, F, data, bytes, offs, len, pcm, frame_size, 0, ret, true);
+}
+
+int opus_decode_batch(OpusDecoder **st, const unsigned char *const *data, const opus_int32 *len, opus_int16 *const *pcm,
+                      int frame_size, int decode_fec, int *ret, int n) {
+    if (!st || !len || !pcm || !ret || n <= 0) return OPUS_BAD_ARG;
+    if (frame_size <= 0) {
+        for (int i = 0; i < n; i++) ret[i] = OPUS_BAD_ARG;
+        return OPUS_OK;
+    }
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    // group by channel count (the span kernel wants a uniform PCM row size)
+    for (int pass = 1; pass <= 2; pass++) {
+        std::vector<int> idx;
+        for (int i = 0; i < n; i++)
+            if (st[i] && st[i]->magic == kDecMagic && st[i]->st.channels == pass) idx.push_back(i);
+        if (idx.empty()) continue;
+        const int m = (int)idx.size();
+        std::vector<OpusDecoder *> sts(m);
+        std::vector<int64_t> offs(m);
+        std::vector<int32_t> lens(m);
+        std::vector<int> rets(m);
+        int64_t total = 0;
+        for (int k = 0; k < m; k++) {
+            int i = idx[k];
+            sts[k] = st[i];
+            int l = (data && data[i]) ? len[i] : 0;
+            if (len[i] < 0) l = -1;
+            lens[k] = l;
+            offs[k] = total;
+            if (l > 0) total += l;
+        }
+        std::vector<unsigned char> blob((size_t)total + 1);
+        for (int k = 0; k < m; k++)
+            if (lens[k] > 0) memcpy(blob.data() + offs[k], data[idx[k]], (size_t)lens[k]);
+        std::vector<int16_t> out((size_t)m * frame_size * pass);
+        // negative len is a scalar-API argument error: report per stream, do not launch for it
+        bool any_neg = false;
+        for (int k = 0; k < m; k++) any_neg |= lens[k] < 0;
+        if (any_neg) {
+            for (int k = 0; k < m; k++) if (lens[k] < 0) { ret[idx[k]] = OPUS_BAD_ARG; lens[k] = 0; sts[k] = nullptr; }
+            std::vector<OpusDecoder *> s2; std::vector<int> map2;
+            std::vector<int64_t> o2; std::vector<int32_t> l2;
+            for (int k = 0; k < m; k++) if (sts[k]) { s2.push_back(sts[k]); map2.push_back(idx[k]); o2.push_back(offs[k]); l2.push_back(lens[k]); }
+            if (s2.empty()) continue;
+            std::vector<int> r2(s2.size());
+            int rc = decode_span_host_locked(s2.data(), (int)s2.size(), 1, blob.data(), total, o2.data(), l2.data(), out.data(),
+                                             frame_size, decode_fec, r2.data(), true);
+            if (rc != OPUS_OK) return rc;
+            for (size_t k = 0; k < s2.size(); k++) {
+                ret[map2[k]] = r2[k];
+                if (r2[k] > 0) memcpy(pcm[map2[k]], out.data() + k * (size_t)frame_size * pass, (size_t)r2[k] * pass * sizeof(int16_t));
+            }
+            continue;
+        }
+        int rc = decode_span_host_locked(sts.data(), m, 1, blob.data(), total, offs.data(), lens.data(), out.data(), frame_size,
+                                         decode_fec, rets.data(), true);
+        if (rc != OPUS_OK) return rc;
+        for (int k = 0; k < m; k++) {
+            ret[idx[k]] = rets[k];
+            if (rets[k] > 0) memcpy(pcm[idx[k]], out.data() + (size_t)k * frame_size * pass, (size_t)rets[k] * pass * sizeof(int16_t));
+        }
+    }
+    for (int i = 0; i < n; i++)
+        if (!st[i] || st[i]->magic != kDecMagic) ret[i] = OPUS_BAD_ARG;
+    return OPUS_OK;
+}
+
+int opus_decoder_sync(OpusDecoder **st, int n) {
+    if (!st || n <= 0) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    return sync_states_locked(st, n, true);
+}
+
+// Scalar call = batch of one; the host block is left current (write-back) so it stays memcpy-able.
+int opus_decode(OpusDecoder *st, const unsigned char *data, opus_int32 len, opus_int16 *pcm, int frame_size, int decode_fec) {
+    if (frame_size <= 0) return OPUS_BAD_ARG;
+    if (!st || st->magic != kDecMagic || !pcm) return OPUS_BAD_ARG;
+    if (len < 0) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    const int channels = st->st.channels;
+    // clamp the capacity handed to the kernel: a packet never carries more than 120 ms
+    int cap = frame_size;
+    const int max_cap = st->st.Fs / 25 * 3;
+    if (cap > max_cap && !(decode_fec || len == 0 || data == nullptr)) cap = max_cap;
+    if (cap > 4 * max_cap) return OPUS_BAD_ARG;
+    int64_t off = 0;
+    int32_t l = (data == nullptr) ? 0 : len;
+    int r = 0;
+    std::vector<int16_t> out((size_t)cap * channels);
+    OpusDecoder *one = st;
+    int rc = decode_span_host_locked(&one, 1, 1, data, l, &off, &l, out.data(), cap, decode_fec, &r, false);
+    if (rc != OPUS_OK) return rc;
+    if (r > 0) memcpy(pcm, out.data(), (size_t)r * channels * sizeof(int16_t));
+    return r;
+}
+
+}  // extern "C"

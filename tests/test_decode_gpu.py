@@ -1,0 +1,128 @@
+"""GPU parity: CUDA decode (through the C ABI of libconcentus_b200.so) vs the oracle (unmodified opus-fix build),
+PCM sample-for-sample, final range per packet and return code per packet."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cb():
+    import concentus_b200 as cb
+    assert cb.lib().opus_b200_init(0) == 0, "CUDA device required: no CPU fallback exists"
+    return cb
+
+
+def _make_streams(cfgs, nsec):
+    """cfgs: list of (kind, channels_in, frame_size, bitrate, vbr, cvbr, seed); all decoded by `channels`-ch decoders."""
+    datas, lens_all, offs_all = [], [], []
+    base = 0
+    for (kind, ch, fs, br, vbr, cvbr, seed) in cfgs:
+        pcm = O.test_signal(48000 * nsec, ch, seed, kind)
+        d, o, l, _ = O.encode_stream(pcm, fs, br, vbr=vbr, cvbr=cvbr)
+        d, o = O.pack(d, o, l)
+        datas.append(d)
+        offs_all.append(o + base)
+        lens_all.append(l)
+        base += len(d)
+    return np.concatenate(datas), np.concatenate(offs_all), np.concatenate(lens_all)
+
+
+def _check(cfgs, dec_channels, frame_size, nsec=1):
+    cb = _cb()
+    data, offs, lens = _make_streams(cfgs, nsec)
+    n = len(cfgs)
+    F = len(lens) // n
+    dec = cb.DecoderBatch(n, 48000, dec_channels)
+    # decode in two spans to exercise state residency across launches
+    F1 = F // 2
+    idx = np.arange(n * F).reshape(n, F)
+    pcm = np.zeros((n, F, frame_size * dec_channels), dtype=np.int16)
+    rets = np.zeros((n, F), dtype=np.int32)
+    for (a, b) in ((0, F1), (F1, F)):
+        sel = idx[:, a:b].reshape(-1)
+        p, r = dec.decode_span(data, offs[sel], lens[sel], b - a, frame_size)
+        pcm[:, a:b] = p.reshape(n, b - a, -1)
+        rets[:, a:b] = r.reshape(n, b - a)
+    fr = dec.final_ranges()
+    dec.close()
+    for s in range(n):
+        sel = idx[s]
+        rp, rr, rret = O.decode_stream(data, offs[sel], lens[sel], frame_size, dec_channels)
+        assert np.array_equal(rret, rets[s]), ("ret", cfgs[s])
+        bad = np.nonzero((rp.reshape(F, -1) != pcm[s]).any(axis=1))[0]
+        assert bad.size == 0, ("pcm mismatch", cfgs[s], "first bad frame", int(bad[0]))
+        assert int(rr[-1]) == int(fr[s]), ("final range", cfgs[s])
+
+
+@pytest.mark.parametrize("fs", [120, 240, 480, 960])
+@pytest.mark.parametrize("ch", [1, 2])
+def test_sweep_framesize_channels(fs, ch):
+    cfgs = []
+    seed = 100 * ch + fs
+    for kind in ("music", "tone", "clicks", "noise"):
+        for br in (32000, 64000, 128000, 510000):
+            for (vbr, cvbr) in ((1, 0), (0, 0), (1, 1)):
+                cfgs.append((kind, ch, fs, br, vbr, cvbr, seed))
+                seed += 1
+    _check(cfgs, ch, fs, nsec=1)
+
+
+def test_mono_stream_into_stereo_decoder_and_back():
+    cfgs = [("music", 1, 960, 48000, 1, 0, 5), ("tone", 1, 480, 64000, 0, 0, 6)]
+    _check([cfgs[0]], 2, 960)
+    _check([cfgs[1]], 2, 480)
+    cfgs2 = [("music", 2, 960, 96000, 1, 0, 7)]
+    _check(cfgs2, 1, 960)
+
+
+def test_scalar_api_matches_oracle_and_state_is_memcpyable():
+    cb = _cb()
+    L = cb.lib()
+    pcm_in = O.test_signal(48000, 2, 11, "music")
+    d, o, l, _ = O.encode_stream(pcm_in, 960, 64000)
+    rp, rr, _ = O.decode_stream(d, o, l, 960, 2)
+    err = C.c_int(0)
+    h = L.opus_decoder_create(48000, 2, C.byref(err))
+    assert h and err.value == 0
+    size = L.opus_decoder_get_size(2)
+    out = np.zeros((960, 2), dtype=np.int16)
+    v = C.c_uint32(0)
+    for f in range(len(l)):
+        if f == 20:
+            # clone the state block with memcpy and continue on the clone (tests/test_opus_decode.c:84-95)
+            buf = C.create_string_buffer(size)
+            C.memmove(buf, h, size)
+            L.opus_decoder_destroy(C.c_void_p(h))
+            h = C.cast(buf, C.c_void_p).value
+        pkt = d[o[f]:o[f] + l[f]].copy()
+        r = L.opus_decode(C.c_void_p(h), O.ptr(pkt), int(l[f]), O.ptr(out), 960, 0)
+        assert r == 960
+        assert np.array_equal(out, rp[f * 960:(f + 1) * 960]), f
+        L.opus_decoder_ctl(C.c_void_p(h), cb.OPUS_GET_FINAL_RANGE_REQUEST, C.byref(v))
+        assert v.value == int(rr[f])
+
+
+def test_error_codes_and_scope_edge():
+    cb = _cb()
+    L = cb.lib()
+    err = C.c_int(0)
+    assert not L.opus_decoder_create(44100, 2, C.byref(err)) and err.value == cb.OPUS_BAD_ARG
+    assert L.opus_decoder_get_size(3) == 0
+    h = L.opus_decoder_create(48000, 2, C.byref(err))
+    out = np.zeros((5760, 2), dtype=np.int16)
+    silk = np.array([0x08, 1, 2, 3], dtype=np.uint8)       # SILK-only TOC: outside this engine
+    assert L.opus_decode(C.c_void_p(h), O.ptr(silk), 4, O.ptr(out), 960, 0) == cb.OPUS_UNIMPLEMENTED
+    celt = np.array([0xFC, 1, 2, 3], dtype=np.uint8)
+    assert L.opus_decode(C.c_void_p(h), O.ptr(celt), 4, O.ptr(out), 120, 0) == cb.OPUS_BUFFER_TOO_SMALL
+    assert L.opus_decode(C.c_void_p(h), O.ptr(celt), 4, O.ptr(out), 0, 0) == cb.OPUS_BAD_ARG
+    bad = np.array([0xFD, 1, 2, 3], dtype=np.uint8)        # code 1 with odd payload
+    assert L.opus_decode(C.c_void_p(h), O.ptr(bad), 4, O.ptr(out), 5760, 0) == cb.OPUS_INVALID_PACKET
+    # before any packet, concealment returns zeros (opus_decoder.c:265-272)
+    out[:] = 7
+    assert L.opus_decode(C.c_void_p(h), None, 0, O.ptr(out), 960, 0) == 960
+    assert not out[:960].any()
+    L.opus_decoder_destroy(C.c_void_p(h))
