@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — CELT decode throughput (audio-seconds per wall-second, x realtime) on N B200s.
+
+Workload (BASELINE.json configs[1]): 4,096 independent 48 kHz stereo 64 kbps (CBR) 20 ms CELT streams, 60 s each,
+per GPU.  One "step" = one pass over that whole batch (245,760 audio-seconds per GPU).  Streams are sharded
+across GPUs by host-side partitioning, no collective on the data path ("scaling": "weak": per-GPU work fixed).
+
+Arms
+  default            our CUDA engine through the C ABI of libconcentus_b200.so
+                       value : packets and PCM resident in HBM, one kernel launch per step (opus_decode_span_device)
+                       e2e   : host (pinned) packets in, host PCM out through opus_decode_span (H2D + D2H inside the timing)
+  --impl reference   the UNMODIFIED opus-fix C build (oracle/_ref), one stream per thread on all host cores, on a bounded
+                     sample of the same workload.
+
+Input packets are synthetic: produced by the reference encoder (restricted-lowdelay, 64 kbps CBR, complexity 10) from the
+generate_music / tone / clicks test signals — `--base` distinct 60 s programmes, replicated across the streams with
+per-stream packet rotation so no two neighbouring warps are in lock step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FS = 48000
+CH = 2
+FRAME = 960
+BITRATE = 64000
+METRIC = "CELT decode audio-sec per sec (x realtime), 48k stereo"
+
+
+def make_base_streams(nbase, seconds, threads):
+    """nbase distinct programmes encoded by the oracle -> (packets uint8 [nbase, F, plen], plen)."""
+    import oracle_lib as O
+    F = seconds * FS // FRAME
+    kinds = ["music", "tone", "clicks", "music"]
+    pcm = np.zeros((nbase, F * FRAME, CH), dtype=np.int16)
+    # 10 s of signal per programme, tiled (keeps generation cheap); programmes differ by seed / kind
+    seg = 10 * FS
+    for b in range(nbase):
+        x = O.test_signal(min(seg, F * FRAME), CH, 13371337 + b, kinds[b % len(kinds)])
+        reps = (F * FRAME + len(x) - 1) // len(x)
+        pcm[b] = np.tile(x, (reps, 1))[:F * FRAME]
+    stride = 256
+    out = np.zeros((nbase, F, stride), dtype=np.uint8)
+    lens = np.zeros((nbase, F), dtype=np.int32)
+    cfg = O.RefEncCfg(O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, BITRATE, 0, 0, 10, stride, 0, 0)
+    O.ref().ref_encode_streams_mt(nbase, F, threads, O.ptr(pcm), FRAME, CH, FS, C.byref(cfg), O.ptr(out), stride, O.ptr(lens), None)
+    assert (lens == lens[0, 0]).all() and lens[0, 0] > 2, "CBR packets expected"
+    plen = int(lens[0, 0])
+    return np.ascontiguousarray(out[:, :, :plen]), plen
+
+
+def build_workload(streams, seconds, nbase, chunk_frames, threads):
+    """Packed packet blob laid out [chunk][stream][frame-in-chunk] plus offs/lens in [stream][frame] order."""
+    F = seconds * FS // FRAME
+    base, plen = make_base_streams(nbase, seconds, threads)
+    nchunks = (F + chunk_frames - 1) // chunk_frames
+    assert F % chunk_frames == 0
+    # stream s plays programme s % nbase starting (s // nbase) * 37 packets in (rotation)
+    prog = np.arange(streams) % nbase
+    rot = ((np.arange(streams) // nbase) * 37) % F
+    fidx = (np.arange(F)[None, :] + rot[:, None]) % F                     # [S, F]
+    pk = base[prog[:, None], fidx]                                        # [S, F, plen]
+    pk = pk.reshape(streams, nchunks, chunk_frames, plen).transpose(1, 0, 2, 3)   # [chunk, S, fc, plen]
+    blob = np.ascontiguousarray(pk).reshape(-1)
+    # offs[s, f]
+    c = np.arange(F) // chunk_frames
+    fi = np.arange(F) % chunk_frames
+    offs = ((c[None, :] * streams + np.arange(streams)[:, None]) * chunk_frames + fi[None, :]).astype(np.int64) * plen
+    lens = np.full((streams, F), plen, dtype=np.int32)
+    return blob, offs, lens, F, plen, nchunks
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md 'clocks' line)."""
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.rows = []
+        self.idx = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the unmodified opus-fix decoder, one stream per thread on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    seconds = args.seconds
+    n = min(args.streams, max(cores * 4, 16))
+    blob, offs, lens, F, plen, _ = build_workload(n, seconds, min(args.base, n), F_chunk(seconds), cores)
+    offs = np.ascontiguousarray(offs.reshape(-1)); lens = np.ascontiguousarray(lens.reshape(-1))
+    def step():
+        return O.ref().ref_decode_streams_mt(n, F, cores, O.ptr(blob), O.ptr(offs), O.ptr(lens), FRAME, CH, FS, None, None, None)
+    for _ in range(args.warmup):
+        step()
+    t = 0.0
+    for _ in range(args.steps):
+        t += step()
+    val = n * seconds * args.steps / t
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": val, "unit": "x realtime", "cores": cores, "kind": "reference",
+                             "sample": "%d streams x %d s (of %d streams per GPU), opus-fix -O2, one stream per thread" % (n, seconds, args.streams)},
+            "e2e": {"value": val, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def F_chunk(seconds):
+    F = seconds * FS // FRAME
+    for c in (250, 200, 100, 50, 25, 10, 5, 1):
+        if F % c == 0:
+            return c
+    return 1
+
+
+def workload_config(args, world):
+    return {"workload": "batched CELT decode: %d independent 48 kHz stereo 64 kbps CBR 20 ms streams per GPU, %d s each "
+                        "(BASELINE.json configs[1])" % (args.streams, args.seconds),
+            "streams_per_gpu": args.streams, "seconds_per_stream": args.seconds, "frame_ms": 20, "bitrate": BITRATE,
+            "parallelism": "streams sharded over %d GPU(s), host partitioning, no collective" % world,
+            "l2": "inputs+outputs per step (%.1f GB) >> 126 MB L2, no flush needed" % (args.streams * args.seconds * 50 * 4000 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--seconds", type=int, default=60, help="audio seconds per stream per step")
+    ap.add_argument("--base", type=int, default=64, help="distinct programmes encoded by the oracle")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import concentus_b200 as cb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CELT engine has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = cb.lib()
+    assert L.opus_b200_init(local) == 0
+    stream = torch.cuda.ExternalStream(L.opus_b200_stream(), device=torch.device("cuda", local))
+    cores = os.cpu_count() or 1
+
+    S, seconds = args.streams, args.seconds
+    fc = F_chunk(seconds)
+    blob, offs, lens, F, plen, nchunks = build_workload(S, seconds, min(args.base, S), fc, max(1, cores // max(world, 1)))
+    audio_s_per_step = S * seconds
+
+    # ---------------- value: everything resident in HBM, one launch per step ----------------
+    dev = torch.device("cuda", local)
+    d_blob = torch.from_numpy(blob).to(dev)
+    d_offs = torch.from_numpy(offs.reshape(-1)).to(dev)
+    d_lens = torch.from_numpy(lens.reshape(-1)).to(dev)
+    d_pcm = torch.empty((S * F * FRAME * CH,), dtype=torch.int16, device=dev)
+    d_ret = torch.zeros((S * F,), dtype=torch.int32, device=dev)
+    dec = cb.DecoderBatch(S, FS, CH)
+
+    def step_value():
+        rc = L.opus_decode_span_device(dec.handles, S, F, C.c_void_p(d_blob.data_ptr()), C.c_void_p(d_offs.data_ptr()),
+                                       C.c_void_p(d_lens.data_ptr()), C.c_void_p(d_pcm.data_ptr()), FRAME, C.c_void_p(d_ret.data_ptr()))
+        assert rc == 0, rc
+
+    def barrier():
+        torch.cuda.synchronize()
+        L.opus_b200_synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step_value()
+    barrier()
+    assert bool((d_ret == FRAME).all().item()), "decode returned errors"
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.opus_b200_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_value()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = L.opus_b200_kernel_launches() - launches0
+    kernel_ms = ms / max(launches, 1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * audio_s_per_step * args.steps / (ms / 1e3)
+    algo_bytes = float(lens.sum()) + float(S) * F * FRAME * CH * 2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = algo_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "decode_traffic.json"))).get("dram_bytes_per_launch_at_bench_size")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "decode_span_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "note": "integer-issue/latency bound path (SURVEY.md 8d): HBM fraction is reported as required, not the limiter"}
+
+    # ---------------- e2e: host buffers through opus_decode_span (H2D + kernel + D2H per chunk call) ----------------
+    e2e = None
+    if not args.no_e2e:
+        del d_pcm
+        torch.cuda.empty_cache()
+        h_blob = torch.from_numpy(blob).pin_memory()
+        chunk_bytes = S * fc * plen
+        h_pcm = torch.empty((S * fc * FRAME * CH,), dtype=torch.int16).pin_memory()
+        h_ret = torch.empty((S * fc,), dtype=torch.int32).pin_memory()
+        offs_c = np.ascontiguousarray((np.arange(S)[:, None] * fc + np.arange(fc)[None, :]).astype(np.int64) * plen).reshape(-1)
+        lens_c = np.full(S * fc, plen, dtype=np.int32)
+        dec2 = cb.DecoderBatch(S, FS, CH)
+
+        def step_e2e():
+            for c in range(nchunks):
+                rc = L.opus_decode_span(dec2.handles, S, fc, C.c_void_p(h_blob.data_ptr() + c * chunk_bytes), cb._p(offs_c), cb._p(lens_c),
+                                        C.c_void_p(h_pcm.data_ptr()), FRAME, C.c_void_p(h_ret.data_ptr()))
+                assert rc == 0, rc
+        for _ in range(args.warmup):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3)
+        if dist is not None:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        assert bool((h_ret == FRAME).all().item())
+        e2e = {"value": world * audio_s_per_step * args.steps / (ems / 1e3), "unit": "x realtime",
+               "h2d_bytes_per_step": int(blob.nbytes + nchunks * (offs_c.nbytes + lens_c.nbytes)),
+               "d2h_bytes_per_step": int(nchunks * (h_pcm.numel() * 2 + h_ret.numel() * 4)),
+               "ms_per_step": ems / args.steps,
+               "api": "opus_decode_span, %d calls of %d packets x %d streams per step, pinned host buffers" % (nchunks, fc, S)}
+        dec2.close()
+
+    # ---------------- cpu baseline (rank 0, N=1 only): the unmodified reference on all host cores, bounded sample ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib as O
+        n = min(S, max(cores * 8, 32))
+        sel = np.arange(n)
+        o2 = np.ascontiguousarray(offs[sel].reshape(-1)); l2 = np.ascontiguousarray(lens[sel].reshape(-1))
+        t = O.ref().ref_decode_streams_mt(n, F, cores, O.ptr(blob), O.ptr(o2), O.ptr(l2), FRAME, CH, FS, None, None, None)
+        cpu = {"value": n * seconds / t, "unit": "x realtime", "cores": cores, "kind": "reference",
+               "sample": "first %d of the %d streams x %d s, opus-fix -O2 build, one stream per thread, %.1f s wall" % (n, S, seconds, t)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    dec.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

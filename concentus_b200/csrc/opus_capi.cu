@@ -333,6 +333,7 @@ int opus_b200_synchronize(void) {
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.copy_stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    if (g.launches > 0) cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);   // last span kernel (events on g.stream)
     return OPUS_OK;
 }
 void *opus_b200_stream(void) {
