@@ -1,17 +1,18 @@
 // celt_bands.cuh — the band loop: theta/split coding, recursive partitioning, folding, stereo
-// recombination, anti-collapse and denormalisation (decoder side).
+// recombination (decoder side, stage A) and anti-collapse (stage B).
 //
-// Restates opus-fix/celt/bands.c:169-238 (denormalise_bands), :241-335 (anti_collapse), :375-424
-// (stereo_merge), :532-592 (hadamard (de)interleave, haar1), :596-616 (compute_qn), :645-817
-// (compute_theta), :819-859 (quant_band_n1), :864-1040 (quant_partition), :1044-1170 (quant_band),
-// :1176-1335 (quant_band_stereo) and :1337-1502 (quant_all_bands), all with encode=0 / resynth=1.
+// Restates opus-fix/celt/bands.c:241-335 (anti_collapse), :375-424 (stereo_merge), :532-592 (hadamard
+// (de)interleave, haar1), :596-616 (compute_qn), :645-817 (compute_theta), :819-859 (quant_band_n1),
+// :864-1040 (quant_partition), :1044-1170 (quant_band), :1176-1335 (quant_band_stereo) and :1337-1502
+// (quant_all_bands), all with encode=0 / resynth=1.
 //
-// Execution model: the whole band loop is executed by every lane of the team with identical scalar
-// state (range decoder, bit budgets, fill masks), so there is no divergence and no broadcast; the
-// normalised spectrum X, the folding source `norm` and a 176-entry scratch live in team-shared
-// memory and every vector operation is strided over the lanes.  The reference's recursion
-// (quant_partition, depth <= maxLM+1 = 4 splits) is unrolled into five non-inlined template
-// instances so the device needs no dynamic call stack.
+// Stage A is scalar: one thread walks the whole band loop of its frame with the range decoder in
+// registers.  Two structural changes keep the instruction footprint small (the first CUDA version was
+// instruction-cache bound, profiles/r1_v1_decode_ncu_summary.md):
+//   * quant_partition's recursion (depth <= maxLM+1 splits) is an explicit walker over a 5-entry frame
+//     stack, so the leaf code (PVQ decode / fold / noise) exists exactly once;
+//   * a band issues its (up to two) quant_band calls from one loop, so quant_band is instantiated once
+//     instead of at the reference's six call sites.
 #pragma once
 #include "celt_pvq.cuh"
 #include "celt_rate.cuh"
@@ -19,9 +20,8 @@
 namespace cb {
 
 struct BandCtx {
-    Team tm;
-    EcDec *ec;
-    int16_t *tmp;        // >= 176 int16 of team scratch (pulse vector / hadamard staging)
+    EcDec ec;            // by value: lives in registers for the whole band loop
+    int16_t *tmp;        // >= 176 int16 of thread scratch (pulse vector / hadamard staging)
     int i;               // band
     int intensity, spread, tf_change;
     int remaining_bits;
@@ -32,64 +32,54 @@ struct SplitCtx {
     int inv, imid, iside, delta, itheta, qalloc;
 };
 
-// ---- small vector kernels -------------------------------------------------------------------------
+// ---- small vector kernels (scalar) ------------------------------------------------------------------
 
-// haar1 (bands.c:581-594): independent 2-point butterflies.
-CB_DEV void haar1(Team tm, int16_t *X, int N0, int stride) {
+// haar1 (bands.c:581-594)
+CB_DEV_NOINLINE void haar1(int16_t *X, int N0, int stride) {
     N0 >>= 1;
-    CB_TEAM_FOR(p, N0 * stride, tm) {
-        int i = p % stride, j = p / stride;
-        int a = stride * 2 * j + i, b = stride * (2 * j + 1) + i;
-        int t1 = mul16_16(23170, X[a]);
-        int t2 = mul16_16(23170, X[b]);
-        X[a] = (int16_t)pshr32(wadd(t1, t2), 15);
-        X[b] = (int16_t)pshr32(wsub(t1, t2), 15);
-    }
-    CB_SYNC();
+    for (int i = 0; i < stride; i++)
+        for (int j = 0; j < N0; j++) {
+            int a = stride * 2 * j + i, b = stride * (2 * j + 1) + i;
+            int t1 = mul16_16(23170, X[a]);
+            int t2 = mul16_16(23170, X[b]);
+            X[a] = (int16_t)pshr32(wadd(t1, t2), 15);
+            X[b] = (int16_t)pshr32(wsub(t1, t2), 15);
+        }
 }
 
-// deinterleave_hadamard / interleave_hadamard (bands.c:532-579) through the team scratch.
-CB_DEV void deinterleave_hadamard(Team tm, int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
-    int N = N0 * stride;
+// deinterleave_hadamard / interleave_hadamard (bands.c:532-579) through the thread scratch.
+CB_DEV_NOINLINE void deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+    const int N = N0 * stride;
     const uint8_t *ordery = kOrdery + stride - 2;
-    CB_TEAM_FOR(p, N, tm) {
-        int i = p % stride, j = p / stride;   // source index p = j*stride+i
-        int row = hadamard ? ordery[i] : i;
-        tmp[row * N0 + j] = X[p];
+    for (int i = 0; i < stride; i++) {
+        const int row = hadamard ? ordery[i] : i;
+        for (int j = 0; j < N0; j++) tmp[row * N0 + j] = X[j * stride + i];
     }
-    CB_SYNC();
-    CB_TEAM_FOR(p, N, tm) X[p] = tmp[p];
-    CB_SYNC();
+    for (int p = 0; p < N; p++) X[p] = tmp[p];
 }
-CB_DEV void interleave_hadamard(Team tm, int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
-    int N = N0 * stride;
+CB_DEV_NOINLINE void interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+    const int N = N0 * stride;
     const uint8_t *ordery = kOrdery + stride - 2;
-    CB_TEAM_FOR(p, N, tm) {
-        int i = p % stride, j = p / stride;   // destination index p = j*stride+i
-        int row = hadamard ? ordery[i] : i;
-        tmp[p] = X[row * N0 + j];
+    for (int i = 0; i < stride; i++) {
+        const int row = hadamard ? ordery[i] : i;
+        for (int j = 0; j < N0; j++) tmp[j * stride + i] = X[row * N0 + j];
     }
-    CB_SYNC();
-    CB_TEAM_FOR(p, N, tm) X[p] = tmp[p];
-    CB_SYNC();
+    for (int p = 0; p < N; p++) X[p] = tmp[p];
 }
 
 // stereo_merge (bands.c:375-424)
-CB_DEV void stereo_merge(Team tm, int16_t *X, int16_t *Y, int mid, int N) {
+CB_DEV_NOINLINE void stereo_merge(int16_t *X, int16_t *Y, int mid, int N) {
     int xp = 0, side = 0;
-    CB_TEAM_FOR(j, N, tm) {
+    for (int j = 0; j < N; j++) {
         xp = mac16_16(xp, Y[j], X[j]);
         side = mac16_16(side, Y[j], Y[j]);
     }
-    xp = team_sum(xp);
-    side = team_sum(side);
     xp = mul16_32_q15(mid, xp);
     int mid2 = s16(mid >> 1);
     int El = wsub(wadd(mul16_16(mid2, mid2), side), wmul(2, xp));
     int Er = wadd(wadd(mul16_16(mid2, mid2), side), wmul(2, xp));
     if (Er < 161061 || El < 161061) {   // QCONST32(6e-4f, 28)
-        CB_TEAM_FOR(j, N, tm) Y[j] = X[j];
-        CB_SYNC();
+        for (int j = 0; j < N; j++) Y[j] = X[j];
         return;
     }
     int kl = celt_ilog2(El) >> 1;
@@ -100,13 +90,12 @@ CB_DEV void stereo_merge(Team tm, int16_t *X, int16_t *Y, int mid, int N) {
     int rgain = celt_rsqrt_norm(t);
     if (kl < 7) kl = 7;
     if (kr < 7) kr = 7;
-    CB_TEAM_FOR(j, N, tm) {
+    for (int j = 0; j < N; j++) {
         int l = s16(mul16_16_p15(mid, X[j]));
         int r = Y[j];
         X[j] = (int16_t)pshr32(mul16_16(lgain, s16(l - r)), kl + 1);
         Y[j] = (int16_t)pshr32(mul16_16(rgain, s16(l + r)), kr + 1);
     }
-    CB_SYNC();
 }
 
 // compute_qn (bands.c:596-620)
@@ -128,7 +117,7 @@ CB_DEV int compute_qn(int N, int b, int offset, int pulse_cap, int stereo) {
 
 // compute_theta, decoder half (bands.c:645-817): reads itheta with the pdf the split type calls for.
 CB_DEV void compute_theta(BandCtx &ctx, SplitCtx &sctx, int N, int *b, int B, int B0, int LM, int stereo, int *fill) {
-    EcDec &ec = *ctx.ec;
+    EcDec &ec = ctx.ec;
     int itheta = 0, inv = 0;
     int pulse_cap = kLogN[ctx.i] + LM * (1 << kBitRes);
     int offset = (pulse_cap >> 1) - (stereo && N == 2 ? kQThetaOffsetTwoPhase : kQThetaOffset);
@@ -193,141 +182,170 @@ CB_DEV void compute_theta(BandCtx &ctx, SplitCtx &sctx, int N, int *b, int B, in
 
 // quant_band_n1 (bands.c:819-859)
 CB_DEV unsigned quant_band_n1(BandCtx &ctx, int16_t *X, int16_t *Y, int16_t *lowband_out) {
-    EcDec &ec = *ctx.ec;
     int16_t *x = X;
-    int nch = Y != nullptr ? 2 : 1;
+    const int nch = Y != nullptr ? 2 : 1;
     for (int c = 0; c < nch; c++) {
         int sign = 0;
         if (ctx.remaining_bits >= 1 << kBitRes) {
-            sign = (int)ec.bits(1);
+            sign = (int)ctx.ec.bits(1);
             ctx.remaining_bits -= 1 << kBitRes;
         }
-        if (ctx.tm.lane == 0) x[0] = sign ? -16384 : 16384;
+        x[0] = sign ? -16384 : 16384;
         x = Y;
     }
-    CB_SYNC();
-    if (lowband_out && ctx.tm.lane == 0) lowband_out[0] = (int16_t)(X[0] >> 4);
-    CB_SYNC();
+    if (lowband_out) lowband_out[0] = (int16_t)(X[0] >> 4);
     return 1;
 }
 
-// quant_partition (bands.c:864-1040).  D = remaining split depth.
-template <int D>
-CB_DEV_NOINLINE unsigned quant_partition(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int gain, int fill) {
-    const Team tm = ctx.tm;
-    const uint8_t *cache = pulse_cache(ctx.i, LM);
+// One leaf of the partition tree (bands.c:989-1036): PVQ decode, or fill when no pulse was affordable.
+CB_DEV unsigned partition_leaf(BandCtx &ctx, int16_t *X, int N, int b, int B, const int16_t *lowband, int LM, int gain, int fill) {
     unsigned cm = 0;
-    bool split = false;
-    if constexpr (D > 0) split = (LM != -1 && b > cache[cache[0]] + 12 && N > 2);
-    if (split) {
-        if constexpr (D > 0) {
-            int B0 = B;
-            SplitCtx s;
-            N >>= 1;
-            int16_t *Y = X + N;
-            LM -= 1;
-            if (B == 1) fill = (fill & 1) | (fill << 1);
-            B = (B + 1) >> 1;
-            compute_theta(ctx, s, N, &b, B, B0, LM, 0, &fill);
-            int mid = s.imid, side = s.iside, delta = s.delta, itheta = s.itheta;
-            if (B0 > 1 && (itheta & 0x3fff)) {
-                if (itheta > 8192) delta -= delta >> (4 - LM);
-                else delta = imin(0, delta + (N << kBitRes >> (5 - LM)));
-            }
-            int mbits = imax(0, imin(b, (b - delta) / 2));
-            int sbits = b - mbits;
-            ctx.remaining_bits -= s.qalloc;
-            int16_t *next_lowband2 = lowband ? lowband + N : nullptr;
-            int rebalance = ctx.remaining_bits;
-            const int gmid = s16(mul16_16_p15(gain, mid));
-            const int gside = s16(mul16_16_p15(gain, side));
-            if (mbits >= sbits) {
-                cm = quant_partition<D - 1>(ctx, X, N, mbits, B, lowband, LM, gmid, fill);
-                rebalance = mbits - (rebalance - ctx.remaining_bits);
-                if (rebalance > 3 << kBitRes && itheta != 0) sbits += rebalance - (3 << kBitRes);
-                cm |= quant_partition<D - 1>(ctx, Y, N, sbits, B, next_lowband2, LM, gside, fill >> B) << (B0 >> 1);
-            } else {
-                cm = quant_partition<D - 1>(ctx, Y, N, sbits, B, next_lowband2, LM, gside, fill >> B) << (B0 >> 1);
-                rebalance = sbits - (rebalance - ctx.remaining_bits);
-                if (rebalance > 3 << kBitRes && itheta != 16384) mbits += rebalance - (3 << kBitRes);
-                cm |= quant_partition<D - 1>(ctx, X, N, mbits, B, lowband, LM, gmid, fill);
-            }
-        }
-    } else {
-        int q = bits2pulses(ctx.i, LM, b);
-        int curr_bits = pulses2bits(ctx.i, LM, q);
+    int q = bits2pulses(ctx.i, LM, b);
+    int curr_bits = pulses2bits(ctx.i, LM, q);
+    ctx.remaining_bits -= curr_bits;
+    while (ctx.remaining_bits < 0 && q > 0) {
+        ctx.remaining_bits += curr_bits;
+        q--;
+        curr_bits = pulses2bits(ctx.i, LM, q);
         ctx.remaining_bits -= curr_bits;
-        while (ctx.remaining_bits < 0 && q > 0) {
-            ctx.remaining_bits += curr_bits;
-            q--;
-            curr_bits = pulses2bits(ctx.i, LM, q);
-            ctx.remaining_bits -= curr_bits;
-        }
-        if (q != 0) {
-            int K = get_pulses(q);
-            cm = alg_unquant(tm, X, N, K, ctx.spread, B, *ctx.ec, gain, ctx.tmp);
+    }
+    if (q != 0) {
+        cm = alg_unquant(X, N, get_pulses(q), ctx.spread, B, ctx.ec, gain, ctx.tmp);
+    } else {
+        const unsigned cm_mask = (1u << B) - 1;
+        fill &= (int)cm_mask;
+        if (!fill) {
+            for (int j = 0; j < N; j++) X[j] = 0;
         } else {
-            unsigned cm_mask = (1u << B) - 1;
-            fill &= (int)cm_mask;
-            if (!fill) {
-                CB_TEAM_FOR(j, N, tm) X[j] = 0;
-                CB_SYNC();
-            } else {
-                // The LCG advances once per coefficient: every lane steps the (cheap) generator through
-                // the whole band so the seed stays identical team-wide, and stores only its own slots.
-                if (lowband == nullptr) {
-                    unsigned sd = ctx.seed;
-                    for (int j = 0; j < N; j++) {
-                        sd = lcg_rand(sd);
-                        if ((j % CB_LANES) == tm.lane) X[j] = (int16_t)((int)sd >> 20);
-                    }
-                    ctx.seed = sd;
-                    cm = cm_mask;
-                } else {
-                    unsigned sd = ctx.seed;
-                    for (int j = 0; j < N; j++) {
-                        sd = lcg_rand(sd);
-                        if ((j % CB_LANES) == tm.lane) {
-                            int t = (sd & 0x8000) ? 4 : -4;   // QCONST16(1.0f/256, 10)
-                            X[j] = (int16_t)(lowband[j] + t);
-                        }
-                    }
-                    ctx.seed = sd;
-                    cm = (unsigned)fill;
+            unsigned sd = ctx.seed;
+            if (lowband == nullptr) {
+                for (int j = 0; j < N; j++) {
+                    sd = lcg_rand(sd);
+                    X[j] = (int16_t)((int)sd >> 20);
                 }
-                CB_SYNC();
-                renormalise_vector(tm, X, N, gain);
+                cm = cm_mask;
+            } else {
+                for (int j = 0; j < N; j++) {
+                    sd = lcg_rand(sd);
+                    int t = (sd & 0x8000) ? 4 : -4;   // QCONST16(1.0f/256, 10)
+                    X[j] = (int16_t)(lowband[j] + t);
+                }
+                cm = (unsigned)fill;
             }
+            ctx.seed = sd;
+            renormalise_vector(SoloTeam{}, X, N, gain);
         }
     }
     return cm;
 }
 
+// quant_partition (bands.c:864-1040) as an explicit walker.  A frame holds the arguments of one call and,
+// once it has split, what the reference keeps in locals across its two recursive calls.
+struct PartFrame {
+    int16_t *X, *lowband;
+    int N, b, B, LM, gain, fill;
+    // after a split:
+    int16_t *Y, *lowband2;
+    int B0, mbits, sbits, itheta, rebalance0, gmid, gside, cm, mid_first;
+    int stage;   // 0 = entered, 1 = first child returned, 2 = second child returned
+};
+
+CB_DEV unsigned quant_partition(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int gain, int fill) {
+    PartFrame st[5];
+    int sp = 0;
+    st[0].X = X; st[0].lowband = lowband; st[0].N = N; st[0].b = b; st[0].B = B; st[0].LM = LM; st[0].gain = gain;
+    st[0].fill = fill; st[0].stage = 0;
+    unsigned ret = 0;
+    while (sp >= 0) {
+        PartFrame &f = st[sp];
+        if (f.stage == 0) {
+            const uint8_t *cache = pulse_cache(ctx.i, f.LM);
+            if (f.LM != -1 && f.b > cache[cache[0]] + 12 && f.N > 2) {
+                SplitCtx s;
+                const int n = f.N >> 1;
+                const int lm = f.LM - 1;
+                int fl = f.fill;
+                int bb = f.b;
+                const int B0 = f.B;
+                if (B0 == 1) fl = (fl & 1) | (fl << 1);
+                const int Bn = (B0 + 1) >> 1;
+                compute_theta(ctx, s, n, &bb, Bn, B0, lm, 0, &fl);
+                int delta = s.delta;
+                const int itheta = s.itheta;
+                if (B0 > 1 && (itheta & 0x3fff)) {
+                    if (itheta > 8192) delta -= delta >> (4 - lm);
+                    else delta = imin(0, delta + (n << kBitRes >> (5 - lm)));
+                }
+                const int mbits = imax(0, imin(bb, (bb - delta) / 2));
+                const int sbits = bb - mbits;
+                ctx.remaining_bits -= s.qalloc;
+                f.Y = f.X + n;
+                f.lowband2 = f.lowband ? f.lowband + n : nullptr;
+                f.B0 = B0; f.mbits = mbits; f.sbits = sbits; f.itheta = itheta;
+                f.rebalance0 = ctx.remaining_bits;
+                f.gmid = s16(mul16_16_p15(f.gain, s.imid));
+                f.gside = s16(mul16_16_p15(f.gain, s.iside));
+                // the frame now describes the halves
+                f.N = n; f.LM = lm; f.B = Bn; f.fill = fl;
+                f.stage = 1;
+                f.mid_first = mbits >= sbits;
+                PartFrame &c = st[sp + 1];
+                c.N = n; c.B = Bn; c.LM = lm; c.stage = 0;
+                if (f.mid_first) { c.X = f.X; c.lowband = f.lowband; c.b = mbits; c.gain = f.gmid; c.fill = fl; }
+                else { c.X = f.Y; c.lowband = f.lowband2; c.b = sbits; c.gain = f.gside; c.fill = fl >> Bn; }
+                sp++;
+            } else {
+                ret = partition_leaf(ctx, f.X, f.N, f.b, f.B, f.lowband, f.LM, f.gain, f.fill);
+                sp--;
+            }
+        } else if (f.stage == 1) {
+            PartFrame &c = st[sp + 1];
+            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
+            if (f.mid_first) {
+                f.cm = (int)ret;
+                int rebalance = f.mbits - (f.rebalance0 - ctx.remaining_bits);
+                if (rebalance > 3 << kBitRes && f.itheta != 0) f.sbits += rebalance - (3 << kBitRes);
+                c.X = f.Y; c.lowband = f.lowband2; c.b = f.sbits; c.gain = f.gside; c.fill = f.fill >> f.B;
+            } else {
+                f.cm = (int)(ret << (f.B0 >> 1));
+                int rebalance = f.sbits - (f.rebalance0 - ctx.remaining_bits);
+                if (rebalance > 3 << kBitRes && f.itheta != 16384) f.mbits += rebalance - (3 << kBitRes);
+                c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gmid; c.fill = f.fill;
+            }
+            f.stage = 2;
+            sp++;
+        } else {
+            if (f.mid_first) ret = (unsigned)f.cm | (ret << (f.B0 >> 1));
+            else ret = (unsigned)f.cm | ret;
+            sp--;
+        }
+    }
+    return ret;
+}
+
 // quant_band (bands.c:1044-1170)
-CB_DEV_NOINLINE unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM,
-                                    int16_t *lowband_out, int gain, int16_t *lowband_scratch, int fill) {
-    const Team tm = ctx.tm;
+CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int16_t *lowband_out, int gain,
+                           int16_t *lowband_scratch, int fill) {
     int N0 = N, N_B = N, N_B0, B0 = B;
     int time_divide = 0, recombine = 0;
     int tf_change = ctx.tf_change;
-    int longBlocks = B0 == 1;
+    const int longBlocks = B0 == 1;
     unsigned cm = 0;
     N_B = (int)udiv((unsigned)N_B, (unsigned)B);
     if (N == 1) return quant_band_n1(ctx, X, nullptr, lowband_out);
     if (tf_change > 0) recombine = tf_change;
     if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
-        CB_TEAM_FOR(j, N, tm) lowband_scratch[j] = lowband[j];
-        CB_SYNC();
+        for (int j = 0; j < N; j++) lowband_scratch[j] = lowband[j];
         lowband = lowband_scratch;
     }
     for (int k = 0; k < recombine; k++) {
-        if (lowband) haar1(tm, lowband, N >> k, 1 << k);
+        if (lowband) haar1(lowband, N >> k, 1 << k);
         fill = kBitInterleave[fill & 0xF] | kBitInterleave[fill >> 4] << 2;
     }
     B >>= recombine;
     N_B <<= recombine;
     while ((N_B & 1) == 0 && tf_change < 0) {
-        if (lowband) haar1(tm, lowband, N_B, B);
+        if (lowband) haar1(lowband, N_B, B);
         fill |= fill << B;
         B <<= 1;
         N_B >>= 1;
@@ -336,102 +354,38 @@ CB_DEV_NOINLINE unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int 
     }
     B0 = B;
     N_B0 = N_B;
-    if (B0 > 1 && lowband) deinterleave_hadamard(tm, lowband, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
+    if (B0 > 1 && lowband) deinterleave_hadamard(lowband, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
 
-    cm = quant_partition<4>(ctx, X, N, b, B, lowband, LM, gain, fill);
+    cm = quant_partition(ctx, X, N, b, B, lowband, LM, gain, fill);
 
     // resynthesis (decoder): undo the reorganisation
-    if (B0 > 1) interleave_hadamard(tm, X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
+    if (B0 > 1) interleave_hadamard(X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
     N_B = N_B0;
     B = B0;
     for (int k = 0; k < time_divide; k++) {
         B >>= 1;
         N_B <<= 1;
         cm |= cm >> B;
-        haar1(tm, X, N_B, B);
+        haar1(X, N_B, B);
     }
     for (int k = 0; k < recombine; k++) {
         cm = kBitDeinterleave[cm];
-        haar1(tm, X, N0 >> k, 1 << k);
+        haar1(X, N0 >> k, 1 << k);
     }
     B <<= recombine;
     if (lowband_out) {
-        int n = s16(celt_sqrt(shl32(N0, 22)));
-        CB_TEAM_FOR(j, N0, tm) lowband_out[j] = (int16_t)mul16_16_q15(n, X[j]);
-        CB_SYNC();
+        const int n = s16(celt_sqrt(shl32(N0, 22)));
+        for (int j = 0; j < N0; j++) lowband_out[j] = (int16_t)mul16_16_q15(n, X[j]);
     }
     cm &= (1u << B) - 1;
     return cm;
 }
 
-// quant_band_stereo (bands.c:1176-1335)
-CB_DEV_NOINLINE unsigned quant_band_stereo(BandCtx &ctx, int16_t *X, int16_t *Y, int N, int b, int B, int16_t *lowband, int LM,
-                                           int16_t *lowband_out, int16_t *lowband_scratch, int fill) {
-    const Team tm = ctx.tm;
-    EcDec &ec = *ctx.ec;
-    unsigned cm = 0;
-    if (N == 1) return quant_band_n1(ctx, X, Y, lowband_out);
-    int orig_fill = fill;
-    SplitCtx s;
-    compute_theta(ctx, s, N, &b, B, B, LM, 1, &fill);
-    int inv = s.inv, mid = s.imid, side = s.iside, delta = s.delta, itheta = s.itheta, qalloc = s.qalloc;
-    if (N == 2) {
-        int mbits = b, sbits = 0;
-        if (itheta != 0 && itheta != 16384) sbits = 1 << kBitRes;
-        mbits -= sbits;
-        int c = itheta > 8192;
-        ctx.remaining_bits -= qalloc + sbits;
-        int16_t *x2 = c ? Y : X;
-        int16_t *y2 = c ? X : Y;
-        int sign = 0;
-        if (sbits) sign = (int)ec.bits(1);
-        sign = 1 - 2 * sign;
-        cm = quant_band(ctx, x2, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, orig_fill);
-        if (tm.lane == 0) {
-            y2[0] = (int16_t)(-sign * x2[1]);
-            y2[1] = (int16_t)(sign * x2[0]);
-            X[0] = (int16_t)mul16_16_q15(mid, X[0]);
-            X[1] = (int16_t)mul16_16_q15(mid, X[1]);
-            Y[0] = (int16_t)mul16_16_q15(side, Y[0]);
-            Y[1] = (int16_t)mul16_16_q15(side, Y[1]);
-            int t = X[0];
-            X[0] = (int16_t)(t - Y[0]);
-            Y[0] = (int16_t)(t + Y[0]);
-            t = X[1];
-            X[1] = (int16_t)(t - Y[1]);
-            Y[1] = (int16_t)(t + Y[1]);
-        }
-        CB_SYNC();
-    } else {
-        int mbits = imax(0, imin(b, (b - delta) / 2));
-        int sbits = b - mbits;
-        ctx.remaining_bits -= qalloc;
-        int rebalance = ctx.remaining_bits;
-        if (mbits >= sbits) {
-            cm = quant_band(ctx, X, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, fill);
-            rebalance = mbits - (rebalance - ctx.remaining_bits);
-            if (rebalance > 3 << kBitRes && itheta != 0) sbits += rebalance - (3 << kBitRes);
-            cm |= quant_band(ctx, Y, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
-        } else {
-            cm = quant_band(ctx, Y, N, sbits, B, nullptr, LM, nullptr, side, nullptr, fill >> B);
-            rebalance = sbits - (rebalance - ctx.remaining_bits);
-            if (rebalance > 3 << kBitRes && itheta != 16384) mbits += rebalance - (3 << kBitRes);
-            cm |= quant_band(ctx, X, N, mbits, B, lowband, LM, lowband_out, 32767, lowband_scratch, fill);
-        }
-    }
-    if (N != 2) stereo_merge(tm, X, Y, mid, N);
-    if (inv) {
-        CB_TEAM_FOR(j, N, tm) Y[j] = (int16_t)(-Y[j]);
-        CB_SYNC();
-    }
-    return cm;
-}
-
-// quant_all_bands, decoder (bands.c:1337-1502).  X_: C*N int16 (channel-major), norm: C*(M*eBands[20]) int16.
-CB_DEV void quant_all_bands_dec(Team tm, int start, int end, int16_t *X_, int16_t *Y_, uint8_t *collapse_masks,
-                                const int *pulses, int shortBlocks, int spread, int dual_stereo, int intensity,
-                                const int *tf_res, int total_bits, int balance, EcDec &ec, int LM, int codedBands,
-                                unsigned *seed, int16_t *norm, int16_t *tmp) {
+// quant_all_bands, decoder (bands.c:1337-1502) with quant_band_stereo (bands.c:1176-1335) folded into the
+// per-band pass loop.  X_: C*N int16 (channel-major), norm: C*(M*eBands[20]) int16.
+CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, uint8_t *collapse_masks, const int *pulses,
+                                int shortBlocks, int spread, int dual_stereo, int intensity, const int *tf_res, int total_bits,
+                                int balance, EcDec &ec_io, int LM, int codedBands, unsigned *seed, int16_t *norm, int16_t *tmp) {
     const int M = 1 << LM;
     const int B = shortBlocks ? M : 1;
     const int C = Y_ != nullptr ? 2 : 1;
@@ -441,17 +395,18 @@ CB_DEV void quant_all_bands_dec(Team tm, int start, int end, int16_t *X_, int16_
     int lowband_offset = 0;
     int update_lowband = 1;
     BandCtx ctx;
-    ctx.tm = tm; ctx.ec = &ec; ctx.tmp = tmp;
+    ctx.ec = ec_io;
+    ctx.tmp = tmp;
     ctx.intensity = intensity; ctx.spread = spread; ctx.seed = *seed;
     for (int i = start; i < end; i++) {
         ctx.i = i;
-        int last = (i == end - 1);
+        const int last = (i == end - 1);
         int16_t *X = X_ + M * kEBands[i];
         int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;
-        int N = M * kEBands[i + 1] - M * kEBands[i];
-        int tell = (int)ec.tell_frac();
+        const int N = M * kEBands[i + 1] - M * kEBands[i];
+        const int tell = (int)ctx.ec.tell_frac();
         if (i != start) balance -= tell;
-        int remaining_bits = total_bits - tell - 1;
+        const int remaining_bits = total_bits - tell - 1;
         ctx.remaining_bits = remaining_bits;
         int b;
         if (i <= codedBands - 1) {
@@ -461,7 +416,7 @@ CB_DEV void quant_all_bands_dec(Team tm, int start, int end, int16_t *X_, int16_
             b = 0;
         }
         if (M * kEBands[i] - N >= M * kEBands[start] && (update_lowband || lowband_offset == 0)) lowband_offset = i;
-        int tf_change = tf_res[i];
+        const int tf_change = tf_res[i];
         ctx.tf_change = tf_change;
         if (i == end - 1) lowband_scratch = nullptr;
 
@@ -484,35 +439,122 @@ CB_DEV void quant_all_bands_dec(Team tm, int start, int end, int16_t *X_, int16_
         }
         if (dual_stereo && i == intensity) {
             dual_stereo = 0;
-            CB_TEAM_FOR(j, M * kEBands[i] - norm_offset, tm) norm[j] = (int16_t)((norm[j] + norm2[j]) >> 1);
-            CB_SYNC();
+            const int n = M * kEBands[i] - norm_offset;
+            for (int j = 0; j < n; j++) norm[j] = (int16_t)((norm[j] + norm2[j]) >> 1);
         }
         int16_t *lb = effective_lowband != -1 ? norm + effective_lowband : nullptr;
         int16_t *lb_out = last ? nullptr : norm + M * kEBands[i] - norm_offset;
-        if (dual_stereo) {
-            int16_t *lb2 = effective_lowband != -1 ? norm2 + effective_lowband : nullptr;
-            int16_t *lb2_out = last ? nullptr : norm2 + M * kEBands[i] - norm_offset;
-            x_cm = quant_band(ctx, X, N, b / 2, B, lb, LM, lb_out, 32767, lowband_scratch, (int)x_cm);
-            y_cm = quant_band(ctx, Y, N, b / 2, B, lb2, LM, lb2_out, 32767, lowband_scratch, (int)y_cm);
-        } else {
-            if (Y != nullptr) x_cm = quant_band_stereo(ctx, X, Y, N, b, B, lb, LM, lb_out, lowband_scratch, (int)(x_cm | y_cm));
-            else x_cm = quant_band(ctx, X, N, b, B, lb, LM, lb_out, 32767, lowband_scratch, (int)(x_cm | y_cm));
+
+        // ---- plan the quant_band passes of this band ----
+        enum { kMono, kDual, kStereo, kStereoN2 };
+        int mode, npass;
+        SplitCtx s;
+        int mbits = 0, sbits = 0, rebalance0 = 0, sfill = 0, orig_fill = 0, sign = 1;
+        int16_t *x2 = nullptr, *y2 = nullptr;
+        if (Y != nullptr && !dual_stereo && N == 1) {
+            x_cm = quant_band_n1(ctx, X, Y, lb_out);
             y_cm = x_cm;
+            npass = 0;
+            mode = kMono;
+        } else if (dual_stereo) {
+            mode = kDual; npass = 2;
+        } else if (Y != nullptr) {
+            // quant_band_stereo, first half (bands.c:1208-1246 / 1278-1284)
+            orig_fill = sfill = (int)(x_cm | y_cm);
+            int bs = b;   // quant_band_stereo works on its own copy of b (update_lowband below needs the original)
+            compute_theta(ctx, s, N, &bs, B, B, LM, 1, &sfill);
+            if (N == 2) {
+                mode = kStereoN2; npass = 1;
+                mbits = bs; sbits = 0;
+                if (s.itheta != 0 && s.itheta != 16384) sbits = 1 << kBitRes;
+                mbits -= sbits;
+                const int c = s.itheta > 8192;
+                ctx.remaining_bits -= s.qalloc + sbits;
+                x2 = c ? Y : X;
+                y2 = c ? X : Y;
+                int sg = 0;
+                if (sbits) sg = (int)ctx.ec.bits(1);
+                sign = 1 - 2 * sg;
+            } else {
+                mode = kStereo; npass = 2;
+                mbits = imax(0, imin(bs, (bs - s.delta) / 2));
+                sbits = bs - mbits;
+                ctx.remaining_bits -= s.qalloc;
+                rebalance0 = ctx.remaining_bits;
+            }
+        } else {
+            mode = kMono; npass = 1;
         }
-        if (tm.lane == 0) {
-            collapse_masks[i * C + 0] = (uint8_t)x_cm;
-            collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
+        unsigned cm_acc = 0;
+        for (int pass = 0; pass < npass; pass++) {
+            int16_t *px, *plb, *plb_out, *pscratch;
+            int pb, pgain, pfill;
+            if (mode == kMono) {
+                px = X; pb = b; plb = lb; plb_out = lb_out; pgain = 32767; pscratch = lowband_scratch; pfill = (int)(x_cm | y_cm);
+            } else if (mode == kDual) {
+                if (pass == 0) { px = X; plb = lb; plb_out = lb_out; pfill = (int)x_cm; }
+                else {
+                    px = Y;
+                    plb = effective_lowband != -1 ? norm2 + effective_lowband : nullptr;
+                    plb_out = last ? nullptr : norm2 + M * kEBands[i] - norm_offset;
+                    pfill = (int)y_cm;
+                }
+                pb = b / 2; pgain = 32767; pscratch = lowband_scratch;
+            } else if (mode == kStereoN2) {
+                px = x2; pb = mbits; plb = lb; plb_out = lb_out; pgain = 32767; pscratch = lowband_scratch; pfill = orig_fill;
+            } else {
+                // mid first when mbits >= sbits, else side first (bands.c:1286-1317); rebalance before the second
+                const bool mid_first = mbits >= sbits;
+                if (pass == 1) {
+                    if (mid_first) {
+                        int rebalance = mbits - (rebalance0 - ctx.remaining_bits);
+                        if (rebalance > 3 << kBitRes && s.itheta != 0) sbits += rebalance - (3 << kBitRes);
+                    } else {
+                        int rebalance = sbits - (rebalance0 - ctx.remaining_bits);
+                        if (rebalance > 3 << kBitRes && s.itheta != 16384) mbits += rebalance - (3 << kBitRes);
+                    }
+                }
+                const bool do_mid = (pass == 0) == mid_first;
+                if (do_mid) { px = X; pb = mbits; plb = lb; plb_out = lb_out; pgain = 32767; pscratch = lowband_scratch; pfill = sfill; }
+                else { px = Y; pb = sbits; plb = nullptr; plb_out = nullptr; pgain = s.iside; pscratch = nullptr; pfill = sfill >> B; }
+            }
+            unsigned cm = quant_band(ctx, px, N, pb, B, plb, LM, plb_out, pgain, pscratch, pfill);
+            if (mode == kDual) { if (pass == 0) x_cm = cm; else y_cm = cm; }
+            else cm_acc |= cm;
         }
-        CB_SYNC();
+        if (mode == kStereoN2) {
+            // bands.c:1250-1268
+            y2[0] = (int16_t)(-sign * x2[1]);
+            y2[1] = (int16_t)(sign * x2[0]);
+            X[0] = (int16_t)mul16_16_q15(s.imid, X[0]);
+            X[1] = (int16_t)mul16_16_q15(s.imid, X[1]);
+            Y[0] = (int16_t)mul16_16_q15(s.iside, Y[0]);
+            Y[1] = (int16_t)mul16_16_q15(s.iside, Y[1]);
+            int t = X[0];
+            X[0] = (int16_t)(t - Y[0]);
+            Y[0] = (int16_t)(t + Y[0]);
+            t = X[1];
+            X[1] = (int16_t)(t - Y[1]);
+            Y[1] = (int16_t)(t + Y[1]);
+        } else if (mode == kStereo) {
+            stereo_merge(X, Y, s.imid, N);
+        }
+        if ((mode == kStereo || mode == kStereoN2) && s.inv)
+            for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
+        if (npass > 0 && mode != kDual) x_cm = y_cm = cm_acc;
+        collapse_masks[i * C + 0] = (uint8_t)x_cm;
+        collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
         balance += pulses[i] + tell;
         update_lowband = b > (N << kBitRes);
     }
     *seed = ctx.seed;
+    ec_io = ctx.ec;
 }
 
-// anti_collapse (bands.c:241-335)
-CB_DEV void anti_collapse(Team tm, int16_t *X_, const uint8_t *collapse_masks, int LM, int C, int size, int start, int end,
-                          const int16_t *logE, const int16_t *prev1logE, const int16_t *prev2logE, const int *pulses, unsigned seed) {
+// anti_collapse (bands.c:241-335), stage B: X_ is the frame's spectrum in the IR (global memory).
+template <class TM>
+CB_DEV void anti_collapse(TM tm, int16_t *X_, const uint8_t *collapse_masks, int LM, int C, int size, int start, int end,
+                          const int16_t *logE, const int16_t *prev1logE, const int16_t *prev2logE, const int16_t *pulses, unsigned seed) {
     for (int i = start; i < end; i++) {
         int N0 = band_width(i);
         int depth = (int)udiv((unsigned)(1 + pulses[i]), (unsigned)N0) >> LM;
@@ -543,17 +585,18 @@ CB_DEV void anti_collapse(Team tm, int16_t *X_, const uint8_t *collapse_masks, i
             r = s16(mul16_16_q15(sqrt_1, r) >> shift);
             int16_t *X = X_ + c * size + (kEBands[i] << LM);
             int renormalize = 0;
-            unsigned mask = collapse_masks[i * C + c];
+            const unsigned mask = collapse_masks[i * C + c];
             for (int k = 0; k < 1 << LM; k++) {
                 if (!(mask & (1u << k))) {
+                    // every lane steps the generator so the seed stays team-uniform; lane j%W stores slot j
                     for (int j = 0; j < N0; j++) {
                         seed = lcg_rand(seed);
-                        if ((j % CB_LANES) == tm.lane) X[(j << LM) + k] = (int16_t)((seed & 0x8000) ? r : -r);
+                        if ((j % TM::W) == tm.lane()) X[(j << LM) + k] = (int16_t)((seed & 0x8000) ? r : -r);
                     }
                     renormalize = 1;
                 }
             }
-            CB_SYNC();
+            tm.sync();
             if (renormalize) renormalise_vector(tm, X, N0 << LM, 32767);
         }
     }

@@ -16,6 +16,9 @@ enum {
 #define CB_EC_CODE_TOP 0x80000000u
 #define CB_EC_CODE_BOT 0x00800000u
 
+// Heavy symbol readers are called from ~50 sites: they are kept out of line (CB_MEM_NOINLINE) so that stage A fits the
+// instruction cache; the short ones (bit_logp, tell, tell_frac) stay inline.
+
 struct EcDec {
     const uint8_t *buf;
     unsigned storage;      // bytes available to the coder (may shrink: redundancy / raw-bit reservations)
@@ -68,7 +71,7 @@ struct EcDec {
         return nbits - (unsigned)l;
     }
     // entdec.c:155-172
-    CB_MEM unsigned decode(unsigned ft) {
+    CB_MEM_NOINLINE unsigned decode(unsigned ft) {
         ext = rng / ft;
         unsigned s = val / ext;
         return ft - imin_u(s + 1, ft);
@@ -79,7 +82,7 @@ struct EcDec {
         return (1u << bits) - imin_u(s + 1u, 1u << bits);
     }
     // entdec.c:181-200
-    CB_MEM void update(unsigned fl, unsigned fh, unsigned ft) {
+    CB_MEM_NOINLINE void update(unsigned fl, unsigned fh, unsigned ft) {
         unsigned s = ext * (ft - fh);
         val -= s;
         rng = fl > 0 ? ext * (fh - fl) : rng - s;
@@ -95,7 +98,7 @@ struct EcDec {
         return ret;
     }
     // entdec.c:218-236
-    CB_MEM int icdf(const uint8_t *tab, unsigned ftb) {
+    CB_MEM_NOINLINE int icdf(const uint8_t *tab, unsigned ftb) {
         unsigned s = rng, d = val, r = s >> ftb, t;
         int ret = -1;
         do {
@@ -108,7 +111,7 @@ struct EcDec {
         return ret;
     }
     // entdec.c:284-316
-    CB_MEM unsigned bits(unsigned nb) {
+    CB_MEM_NOINLINE unsigned bits(unsigned nb) {
         unsigned window = end_window;
         int available = nend_bits;
         if ((unsigned)available < nb) {
@@ -126,7 +129,7 @@ struct EcDec {
         return ret;
     }
     // entdec.c:238-282
-    CB_MEM unsigned uint_(unsigned ft_in) {
+    CB_MEM_NOINLINE unsigned uint_(unsigned ft_in) {
         unsigned ft = ft_in - 1;
         int ftb = ec_ilog(ft);
         if (ftb > kEcUintBits) {
@@ -147,7 +150,7 @@ struct EcDec {
     }
 
     // laplace.c:44-49, :94-134.  fs = P(0) in Q15, decay in Q14.
-    CB_MEM int laplace(unsigned fs, int decay) {
+    CB_MEM_NOINLINE int laplace(unsigned fs, int decay) {
         int v = 0;
         unsigned fm = decode_bin(15);
         unsigned fl = 0;

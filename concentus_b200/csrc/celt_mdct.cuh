@@ -34,7 +34,8 @@ CB_DEV void tw_load(int idx, int &r, int &i) {
 }
 
 // opus_fft_impl over `nblocks` contiguous transforms of plan `s`.
-CB_DEV void fft_inplace(Team tm, Cpx *buf, int s, int nblocks) {
+template <class TM>
+CB_DEV void fft_inplace(TM tm, Cpx *buf, int s, int nblocks) {
     const FftPlan &pl = kFftPlan[s];
     const int nfft = pl.nfft;
     for (int st = 0; st < pl.nstages; st++) {
@@ -171,7 +172,7 @@ CB_DEV void fft_inplace(Team tm, Cpx *buf, int s, int nblocks) {
                 F[3 * m] = csub(s11, s12);
             }
         }
-        CB_SYNC();
+        tm.sync();
     }
 }
 
@@ -180,8 +181,8 @@ CB_DEV void fft_inplace(Team tm, Cpx *buf, int s, int nblocks) {
 // previous frame left).  shift = maxLM-LM for a long block, maxLM for short blocks.
 // Follows mdct.c:263-363 per block; the B blocks' pre-rotation/FFT/post-rotation are batched, then the
 // output is assembled in one pass: mirrored (windowed) regions [b*NB, b*NB+overlap) and straight copies.
-template <class FreqFn>
-CB_DEV void imdct_compute(Team tm, FreqFn freq, int B, int shift, int *fftbuf) {
+template <class TM, class FreqFn>
+CB_DEV void imdct_compute(TM tm, FreqFn freq, int B, int shift, int *fftbuf) {
     const int N2 = (kMaxFrame * 2 >> shift) >> 1;   // coefficients per block (= NB)
     const int N4 = N2 >> 1;
     int trig_off = 0;
@@ -200,7 +201,7 @@ CB_DEV void imdct_compute(Team tm, FreqFn freq, int B, int shift, int *fftbuf) {
         fftbuf[b * N2 + 2 * rev + 1] = yr;
         fftbuf[b * N2 + 2 * rev] = yi;
     }
-    CB_SYNC();
+    tm.sync();
     fft_inplace(tm, (Cpx *)fftbuf, shift, B);
     // post-rotate from both ends (mdct.c:309-343)
     CB_TEAM_FOR(w, B * ((N4 + 1) >> 1), tm) {
@@ -223,14 +224,15 @@ CB_DEV void imdct_compute(Team tm, FreqFn freq, int B, int shift, int *fftbuf) {
         yp1[0] = yr;
         yp0[1] = yi;
     }
-    CB_SYNC();
+    tm.sync();
 }
 
 // Second half of the inverse MDCT: block b produced P_b[k] = fftbuf[b*N2+k], destined for
 // out[b*N2 + overlap/2 + k]; positions [b*N2, b*N2+overlap) get the TDAC mirror (mdct.c:346-362).
 // The blocks' mirror regions are disjoint and each reads only un-mirrored P values (or, for block 0,
 // the tail the previous frame left in out[0..overlap/2)), so the whole output is written in one pass.
-CB_DEV void imdct_assemble(Team tm, int *out, int B, int shift, const int *fftbuf) {
+template <class TM>
+CB_DEV void imdct_assemble(TM tm, int *out, int B, int shift, const int *fftbuf) {
     const int N2 = (kMaxFrame * 2 >> shift) >> 1;
     const int N = B * N2;
     const int half = kOverlap >> 1;
@@ -255,7 +257,7 @@ CB_DEV void imdct_assemble(Team tm, int *out, int B, int shift, const int *fftbu
             out[j] = fftbuf[bb * N2 + k];
         }
     }
-    CB_SYNC();
+    tm.sync();
 }
 
 }  // namespace cb

@@ -7,7 +7,8 @@
 
 namespace cb {
 
-CB_DEV int celt_decode_lost_frame(Team, CbDecState *, DecScratch &, int16_t *, int, int, int, int) {
+template <class TM>
+CB_DEV int celt_decode_lost_frame(TM, CbDecState *, SynthScratch &, int16_t *, int) {
     return OPUS_UNIMPLEMENTED_;
 }
 

@@ -1,8 +1,10 @@
 // opus_capi.cu — kernels and the C ABI of libconcentus_b200.so (declared in include/opus_b200.h).
 //
 // Boundary: libopus's public decoder API (opus-fix/include/opus.h:406-512) plus our batch / span calls.
-// Host side = argument checks, ctl, state residency and copies; everything from ec_dec_init down runs in
-// decode_span_kernel, one warp per stream, F packets per launch, per-stream state resident in HBM.
+// Host side = argument checks, ctl, state residency and copies; everything from TOC parsing and ec_dec_init down runs on
+// the device as a two-stage pipeline: parse_kernel (one thread per run of packets: range decoder, allocation, PVQ band
+// loop -> IR in HBM) and synth_kernel (one warp per stream: energies, anti-collapse, IMDCT, post-filter, de-emphasis,
+// all persistent state).  Time chunks are double-buffered so stage A of chunk c+1 overlaps stage B of chunk c.
 // There is NO CPU path: if CUDA is unusable every codec call returns OPUS_INTERNAL_ERROR.
 #include <cuda_runtime.h>
 
@@ -34,30 +36,93 @@ struct OpusDecoder {
 static const uint32_t kDecMagic = 0x0B200DECu;
 
 // ------------------------------------------------------------------------------------------------
-// Kernels
+// Kernels (DESIGN.md §3)
 // ------------------------------------------------------------------------------------------------
-#define CB_WPB 4   // warps (= streams) per block
+#define CB_PARSE_THREADS 128   // stage A block
+#define CB_WPB 4               // stage B: warps (= streams) per block
 
-// One warp per stream; packets f0..f1 of every stream.  PCM row of packet (s,f) starts at
+struct IrView {
+    CbPacketIR *pk;      // [n * Fc]
+    CbFrameIR *fr;       // [n * Fc * kmax]
+    int16_t *X;          // [n * Fc * xstride]
+    int kmax;
+    int xstride;         // int16 per packet
+    int Fc;              // packets per stream in this chunk buffer
+};
+
+// Stage A — parse + PVQ, one THREAD per run of R consecutive packets of one stream.  Frames are independent given the
+// fold seed (= final range of the previous frame), which each thread recovers for the start of its run by re-parsing the
+// packet before it; inside the run the seed chains naturally.  No decoder state is written here (st->rng is read once per
+// launch for the very first packet of a stream).
+__global__ void __launch_bounds__(CB_PARSE_THREADS)
+parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, const int64_t *offs, const int32_t *lens, int n, int F,
+             int f0, int f1, int call_f0, int R, int cap, int decode_fec, IrView ir, ParseScratch *scratch) {
+    const int runs = (f1 - f0 + R - 1) / R;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * runs) return;
+    const int s = t / runs, r = t - s * runs;
+    const CbDecState *st = pool + slots[s];
+    const int Fs = st->Fs;
+    ParseScratch &ps = scratch[t];
+    const int first = f0 + r * R;
+    const int last = first + R < f1 ? first + R : f1;
+    const size_t slot0 = (size_t)s * ir.Fc + (first - f0);
+    // One loop, one call site of the (large) packet parser.  While `seeking`, f walks BACK from first-1 looking for the
+    // nearest packet that sets the fold seed (errors and losses do not), parsing into the run's first IR slot as scratch;
+    // then f walks forward over the run proper.
+    unsigned seed = 0;
+    bool seeking = first > call_f0;
+    if (!seeking) seed = st->rng;
+    int f = seeking ? first - 1 : first;
+    while (seeking || f < last) {
+        if (seeking && f < call_f0) {
+            seed = st->rng;
+            seeking = false;
+            f = first;
+            continue;
+        }
+        const size_t idx = (size_t)s * F + f;
+        const size_t slot = seeking ? slot0 : (size_t)s * ir.Fc + (f - f0);
+        const int len = lens[idx];
+        const uint8_t *p = len > 0 ? data + offs[idx] : nullptr;
+        CbPacketIR pk;   // built in registers, stored once
+        opus_parse_packet(p, len, cap, Fs, seeking ? 0 : decode_fec, ir.kmax, &seed, pk, ir.fr + slot * ir.kmax,
+                          ir.X + slot * ir.xstride, ps);
+        if (!seeking) ir.pk[slot] = pk;
+        if (seeking) {
+            bool parsed = false;   // did any frame of this packet run the range decoder (and so set `seed`)?
+            if (pk.ret >= 0 && !pk.lost)
+                for (int i = 0; i < pk.count; i++) parsed |= !(ir.fr[slot * ir.kmax + i].flags & CB_IR_LOST);
+            if (parsed) {
+                seeking = false;
+                f = first;
+            } else {
+                f--;
+            }
+        } else {
+            f++;
+        }
+    }
+}
+
+// Stage B — synthesis, one warp per stream, packets f0..f1 in order.  PCM row of packet (s,f) starts at
 // pcm[(s*pcm_F + (f-pcm_f0)) * cap * channels].
 __global__ void __launch_bounds__(CB_WPB * 32)
-decode_span_kernel(CbDecState *pool, const int *slots, const uint8_t *data, const int64_t *offs, const int32_t *lens,
-                   int16_t *pcm, int n, int F, int f0, int f1, int pcm_F, int pcm_f0, int cap, int decode_fec, int *rets) {
+synth_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n, int F, int f0, int f1, int pcm_F, int pcm_f0,
+             int cap, int *rets) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_WPB + warp;
     if (s >= n) return;
-    DecScratch &S = *(reinterpret_cast<DecScratch *>(smem) + warp);
+    SynthScratch &S = *(reinterpret_cast<SynthScratch *>(smem) + warp);
     CbDecState *st = pool + slots[s];
     const int channels = st->channels;
-    Team tm{lane};
+    WarpTeam tm{lane};
     for (int f = f0; f < f1; f++) {
-        const size_t idx = (size_t)s * F + f;
-        const int len = lens[idx];
-        const uint8_t *p = len > 0 ? data + offs[idx] : nullptr;
+        const size_t slot = (size_t)s * ir.Fc + (f - f0);
         int16_t *out = pcm + ((size_t)s * pcm_F + (f - pcm_f0)) * cap * channels;
-        int r = opus_decode_packet(tm, st, S, p, len, out, cap, decode_fec);
-        if (lane == 0) rets[idx] = r;
+        int r = opus_synth_packet(tm, st, S, ir.pk[slot], ir.fr + slot * ir.kmax, ir.X + slot * ir.xstride, out, cap);
+        if (lane == 0) rets[(size_t)s * F + f] = r;
         __syncwarp();
     }
 }
@@ -123,13 +188,17 @@ struct Ctx {
     std::mutex mu;
     bool tried = false, ok = false;
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, parse_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_parse[2] = {nullptr, nullptr}, ev_synth[2] = {nullptr, nullptr}, ev_call = nullptr;
     CbDecState *pool = nullptr;
     int pool_cap = 0;
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
     DevBuf d_slots, d_data, d_offs, d_lens, d_pcm[2], d_rets, d_stage;
+    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_scratch;
+    size_t ir_budget = (size_t)6 << 30;   // bytes of IR per chunk buffer (env CB200_IR_MB)
+    int run_len = 5;                      // packets per stage-A thread (env CB200_RUN)
     PinBuf h_stage, h_slots, h_misc;
     long long launches = 0;
     float last_ms = 0.f;
@@ -151,15 +220,25 @@ bool ctx_init_locked() {
     if (cudaSetDevice(g.device) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&g.parse_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     cudaEventCreate(&g.ev0);
     cudaEventCreate(&g.ev1);
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&g.ev_chunk[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g.ev_copy[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g.ev_parse[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g.ev_synth[i], cudaEventDisableTiming);
     }
-    g.smem_per_block = (int)(CB_WPB * sizeof(DecScratch));
-    cudaFuncSetAttribute(decode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_per_block);
-    cudaFuncSetAttribute(decode_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaEventCreateWithFlags(&g.ev_call, cudaEventDisableTiming);
+    if (const char *e = getenv("CB200_IR_MB")) g.ir_budget = (size_t)atol(e) << 20;
+    if (const char *e = getenv("CB200_RUN")) g.run_len = atoi(e) > 0 ? atoi(e) : 5;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && g.ir_budget > free_b / 8) g.ir_budget = free_b / 8;
+    }
+    g.smem_per_block = (int)(CB_WPB * sizeof(SynthScratch));
+    cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_per_block);
+    cudaFuncSetAttribute(parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // stage A wants L1, not shared
     if (!g.h_stage.reserve(sizeof(CbDecState) * kStageStates)) return false;
     if (!g.d_stage.reserve(sizeof(CbDecState) * kStageStates)) return false;
     g.ok = (cudaGetLastError() == cudaSuccess);
@@ -308,12 +387,62 @@ int sync_states_locked(OpusDecoder **st, int n, bool release) {
     return OPUS_OK;
 }
 
-void launch_decode(const int *d_slots, const uint8_t *d_data, const int64_t *d_offs, const int32_t *d_lens, int16_t *d_pcm,
-                   int n, int F, int f0, int f1, int pcm_F, int pcm_f0, int cap, int fec, int *d_rets, cudaStream_t s) {
-    int blocks = (n + CB_WPB - 1) / CB_WPB;
-    decode_span_kernel<<<blocks, CB_WPB * 32, g.smem_per_block, s>>>(g.pool, d_slots, d_data, d_offs, d_lens, d_pcm, n, F, f0, f1,
-                                                                     pcm_F, pcm_f0, cap, fec, d_rets);
-    g.launches++;
+// Geometry of one call: chunking of the time axis and the IR buffers behind it.
+struct Plan {
+    int n, F, cap, fec, kmax, xstride, Fc, nchunks, R;
+};
+
+bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
+    pl.n = n; pl.F = F; pl.cap = cap; pl.fec = fec;
+    int k = cap / (Fs / 400);
+    pl.kmax = k < 1 ? 1 : (k > 48 ? 48 : k);
+    pl.xstride = cap * (48000 / Fs) * 2;
+    pl.R = g.run_len;
+    const size_t per_packet = sizeof(CbPacketIR) + (size_t)pl.kmax * sizeof(CbFrameIR) + (size_t)pl.xstride * sizeof(int16_t);
+    size_t fc = g.ir_budget / (per_packet * (size_t)n);
+    if (fc < 1) fc = 1;
+    if (fc > (size_t)F) fc = (size_t)F;
+    if (fc > (size_t)pl.R) fc -= fc % pl.R;
+    pl.Fc = (int)fc;
+    pl.nchunks = (F + pl.Fc - 1) / pl.Fc;
+    const int nb = pl.nchunks > 1 ? 2 : 1;
+    const size_t slots = (size_t)n * pl.Fc;
+    for (int b = 0; b < nb; b++) {
+        if (!g.d_irpk[b].reserve(slots * sizeof(CbPacketIR)) || !g.d_irfr[b].reserve(slots * pl.kmax * sizeof(CbFrameIR)) ||
+            !g.d_irx[b].reserve(slots * pl.xstride * sizeof(int16_t)))
+            return false;
+    }
+    const size_t threads = (size_t)n * ((pl.Fc + pl.R - 1) / pl.R);
+    return g.d_scratch.reserve(threads * sizeof(ParseScratch));
+}
+
+IrView ir_view(const Plan &pl, int b) {
+    IrView v;
+    v.pk = (CbPacketIR *)g.d_irpk[b].p; v.fr = (CbFrameIR *)g.d_irfr[b].p; v.X = (int16_t *)g.d_irx[b].p;
+    v.kmax = pl.kmax; v.xstride = pl.xstride; v.Fc = pl.Fc;
+    return v;
+}
+
+// Enqueue stage A for chunk c on the parse stream and stage B on the main stream.  PCM goes to pcm_dst laid out with
+// pcm_F packets per stream starting at packet pcm_f0 (the caller decides: whole-call buffer or a chunk buffer).
+void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_data, const int64_t *d_offs, const int32_t *d_lens,
+                   int16_t *pcm_dst, int pcm_F, int pcm_f0, int *d_rets) {
+    const int b = c & 1;
+    const int f0 = c * pl.Fc, f1 = (f0 + pl.Fc < pl.F) ? f0 + pl.Fc : pl.F;
+    const int runs = (f1 - f0 + pl.R - 1) / pl.R;
+    const long long threads = (long long)pl.n * runs;
+    IrView v = ir_view(pl, b);
+    // stage A(c) may start once stage B(c-2) has drained IR buffer b, and (first chunk) once earlier calls are done
+    if (c == 0) cudaStreamWaitEvent(g.parse_stream, g.ev_call, 0);
+    if (c >= 2) cudaStreamWaitEvent(g.parse_stream, g.ev_synth[b], 0);
+    parse_kernel<<<(unsigned)((threads + CB_PARSE_THREADS - 1) / CB_PARSE_THREADS), CB_PARSE_THREADS, 0, g.parse_stream>>>(
+        g.pool, d_slots, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v, (ParseScratch *)g.d_scratch.p);
+    cudaEventRecord(g.ev_parse[b], g.parse_stream);
+    cudaStreamWaitEvent(g.stream, g.ev_parse[b], 0);
+    synth_kernel<<<(pl.n + CB_WPB - 1) / CB_WPB, CB_WPB * 32, g.smem_per_block, g.stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, pl.F, f0, f1,
+                                                                                            pcm_F, pcm_f0, pl.cap, d_rets);
+    cudaEventRecord(g.ev_synth[b], g.stream);
+    g.launches += 2;
 }
 
 }  // namespace
@@ -511,9 +640,13 @@ int opus_decode_span_device(OpusDecoder **st, int n, int F, const unsigned char 
     int rc = make_resident_locked(st, n, hsl);
     if (rc != OPUS_OK) return rc;
     if (!g.d_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    Plan pl;
+    if (!plan_call(pl, n, F, frame_size, 0, st[0]->st.Fs)) return OPUS_ALLOC_FAIL;
     cudaMemcpyAsync(g.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, g.stream);
     cudaEventRecord(g.ev0, g.stream);
-    launch_decode((const int *)g.d_slots.p, d_data, d_offs, d_len, d_pcm, n, F, 0, F, F, 0, frame_size, 0, d_ret, g.stream);
+    cudaEventRecord(g.ev_call, g.stream);
+    for (int c = 0; c < pl.nchunks; c++)
+        enqueue_chunk(pl, c, (const int *)g.d_slots.p, d_data, d_offs, d_len, d_pcm, F, 0, d_ret);
     cudaEventRecord(g.ev1, g.stream);
     mark_device_newer_locked(st, n);
     if (cudaGetLastError() != cudaSuccess) return OPUS_INTERNAL_ERROR;
@@ -539,25 +672,25 @@ static int decode_span_host_locked(OpusDecoder **st, int n, int F, const unsigne
     if (!g.d_slots.reserve(sizeof(int) * (size_t)n) || !g.d_data.reserve((size_t)data_bytes + 16) ||
         !g.d_offs.reserve(sizeof(int64_t) * NF) || !g.d_lens.reserve(sizeof(int32_t) * NF) || !g.d_rets.reserve(sizeof(int) * NF))
         return OPUS_ALLOC_FAIL;
-    // time chunking: about 64 MiB of PCM per chunk
+    // time chunking follows the IR plan; PCM of a chunk is copied back while the next chunk is decoded
+    Plan pl;
+    if (!plan_call(pl, n, F, frame_size, decode_fec, st[0]->st.Fs)) return OPUS_ALLOC_FAIL;
     const size_t row = (size_t)frame_size * channels * sizeof(int16_t);
-    int Fc = (int)((64u << 20) / (row * (size_t)n));
-    if (Fc < 1) Fc = 1;
-    if (Fc > F) Fc = F;
+    const int Fc = pl.Fc, nchunks = pl.nchunks;
     const size_t chunk_bytes = (size_t)n * Fc * row;
-    const int nchunks = (F + Fc - 1) / Fc;
     if (!g.d_pcm[0].reserve(chunk_bytes) || (nchunks > 1 && !g.d_pcm[1].reserve(chunk_bytes))) return OPUS_ALLOC_FAIL;
     cudaMemcpyAsync(g.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, g.stream);
     if (data_bytes > 0) cudaMemcpyAsync(g.d_data.p, data, (size_t)data_bytes, cudaMemcpyHostToDevice, g.stream);
     cudaMemcpyAsync(g.d_offs.p, offs, sizeof(int64_t) * NF, cudaMemcpyHostToDevice, g.stream);
     cudaMemcpyAsync(g.d_lens.p, len, sizeof(int32_t) * NF, cudaMemcpyHostToDevice, g.stream);
     cudaEventRecord(g.ev0, g.stream);
+    cudaEventRecord(g.ev_call, g.stream);
     for (int c = 0; c < nchunks; c++) {
         const int b = c & 1;
         const int f0 = c * Fc, f1 = (f0 + Fc < F) ? f0 + Fc : F;
-        if (c >= 2) cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0);   // buffer b drained?
-        launch_decode((const int *)g.d_slots.p, (const uint8_t *)g.d_data.p, (const int64_t *)g.d_offs.p, (const int32_t *)g.d_lens.p,
-                      (int16_t *)g.d_pcm[b].p, n, F, f0, f1, Fc, f0, frame_size, decode_fec, (int *)g.d_rets.p, g.stream);
+        if (c >= 2) cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0);   // PCM buffer b drained?
+        enqueue_chunk(pl, c, (const int *)g.d_slots.p, (const uint8_t *)g.d_data.p, (const int64_t *)g.d_offs.p,
+                      (const int32_t *)g.d_lens.p, (int16_t *)g.d_pcm[b].p, Fc, f0, (int *)g.d_rets.p);
         cudaEventRecord(g.ev_chunk[b], g.stream);
         cudaStreamWaitEvent(g.copy_stream, g.ev_chunk[b], 0);
         // rows of (f1-f0) packets per stream: device pitch Fc*row, host pitch F*row

@@ -1,8 +1,9 @@
-// opus_decoder_dev.cuh — the Opus decoder layer that sits between the C API and the CELT frame decoder,
-// executed by the team that owns the stream (so a whole span of packets is decoded without touching the host).
+// opus_decoder_dev.cuh — the Opus decoder layer between the C API and the CELT frame stages.
 //
 // Restates the MODE_CELT_ONLY subset of opus-fix/src/opus_decoder.c:200-596 (opus_decode_frame) and
-// :598-709 (opus_decode_native), plus state init / reset (:96-133, celt/celt_decoder.c:134-172,1188-1202).
+// :598-709 (opus_decode_native), plus state init / reset (:96-133, celt/celt_decoder.c:134-172,1188-1202),
+// split along the pipeline: opus_parse_packet (stage A: TOC, framing, per-frame CELT parse -> IR) and
+// opus_synth_packet (stage B: state latching, per-frame synthesis, gain, final range).
 // SILK-only and hybrid packets are outside this engine (SURVEY.md §8b "scope edge"): they return
 // OPUS_UNIMPLEMENTED and leave the state untouched — there is deliberately no CPU fallback.
 #pragma once
@@ -45,129 +46,155 @@ CB_HD int dec_state_init(CbDecState *st, int Fs, int channels) {
     return 0;
 }
 
-// opus_decode_frame, CELT-only (opus_decoder.c:200-596).  data == nullptr / len <= 1 => concealment.
-CB_DEV int opus_decode_frame(Team tm, CbDecState *st, DecScratch &S, const uint8_t *data, int len, int16_t *pcm,
-                             int frame_size, int decode_fec) {
-    const int F20 = st->Fs / 50, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
-    if (frame_size < F2_5) return OPUS_BUFFER_TOO_SMALL_;
-    frame_size = imin(frame_size, st->Fs / 25 * 3);
-    if (len <= 1) {
-        data = nullptr;
-        frame_size = imin(frame_size, st->frame_size);
+CB_DEV int bandwidth_to_endband(int bw) {   // opus_decoder.c:431-450
+    switch (bw) {
+    case kBwNarrow: return 13;
+    case kBwMedium:
+    case kBwWide: return 17;
+    case kBwSuperWide: return 19;
+    default: return 21;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage A: one packet -> IR.  `cap` = PCM capacity for this packet (samples per channel at Fs), kmax = frame IR
+// slots per packet.  *seed: fold/noise seed chained from frame to frame (previous frame's final rng).
+// Nothing here reads or writes decoder state.
+// ---------------------------------------------------------------------------------------------------
+CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int decode_fec, int kmax, unsigned *seed,
+                              CbPacketIR &pk, CbFrameIR *fr, int16_t *Xarea, ParseScratch &ps) {
+    pk.count = 0; pk.lost = 0; pk.frame_size = 0; pk.mode = 0; pk.bandwidth = 0; pk.stream_channels = 0; pk.reserved = 0;
+    if (decode_fec < 0 || decode_fec > 1) { pk.ret = OPUS_BAD_ARG_; return; }
+    if ((decode_fec || len == 0 || data == nullptr) && cap % (Fs / 400) != 0) { pk.ret = OPUS_BAD_ARG_; return; }
+    if (len == 0 || data == nullptr) { pk.ret = 0; pk.lost = 1; return; }
+    if (len < 0) { pk.ret = OPUS_BAD_ARG_; return; }
+    const int packet_mode = pkt_mode(data);
+    const int packet_frame_size = pkt_samples_per_frame(data, Fs);
+    int16_t size[48];
+    int offset;
+    uint8_t toc;
+    const int count = pkt_parse(data, len, 0, &toc, size, &offset, nullptr);
+    if (count < 0) { pk.ret = count; return; }
+    if (packet_mode != CB_MODE_CELT_ONLY) { pk.ret = OPUS_UNIMPLEMENTED_; return; }   // scope edge: no SILK / hybrid
+    if (decode_fec) { pk.ret = 0; pk.lost = 1; return; }   // CELT carries no in-band FEC (opus_decoder.c:655-657)
+    if (count * packet_frame_size > cap) { pk.ret = OPUS_BUFFER_TOO_SMALL_; return; }
+    if (count > kmax) { pk.ret = OPUS_BUFFER_TOO_SMALL_; return; }   // cannot happen when kmax = cap / (Fs/400)
+    pk.ret = 0;
+    pk.count = (int16_t)count;
+    pk.frame_size = packet_frame_size;
+    pk.mode = (int16_t)packet_mode;
+    pk.bandwidth = (int16_t)pkt_bandwidth(data);
+    pk.stream_channels = (int16_t)pkt_nb_channels(data);
+    const int C = pk.stream_channels;
+    const int end = bandwidth_to_endband(pk.bandwidth);
+    const int N = packet_frame_size * (48000 / Fs);   // CELT frame length at 48 kHz
+    int LM = 0;
+    while ((kShortMdct << LM) != N && LM < kMaxLM) LM++;
+    const uint8_t *p = data + offset;
+    int xoff = 0;
+    for (int i = 0; i < count; i++) {
+        CbFrameIR &ir = fr[i];
+        ir.x_off = xoff;
+        if (size[i] <= 1) {
+            // concealment frame: no symbols; the seed passes through (pitch PLC leaves st->rng alone)
+            ir.flags = CB_IR_LOST;
+            ir.len = size[i];
+            ir.LM = (uint8_t)LM; ir.C = (uint8_t)C; ir.end = (uint8_t)end;
+            ir.rng_final = 0; ir.seed_bands = *seed;
+        } else {
+            celt_parse_frame(p, size[i], LM, C, end, seed, ir, Xarea + xoff, ps);
+        }
+        xoff += N * C;
+        p += size[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stage B: consume one packet's IR in stream order.
+// ---------------------------------------------------------------------------------------------------
+
+// opus_decode_frame remainder for one frame (opus_decoder.c:246-252,265-272,452-596)
+template <class TM>
+CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int16_t *pcm, int room) {
+    const int F20 = st->Fs / 50, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
+    if (room < F2_5) return OPUS_BUFFER_TOO_SMALL_;
+    int frame_size = imin(room, st->Fs / 25 * 3);
+    const bool lost = (ir.flags & CB_IR_LOST) != 0;
     int audiosize, mode;
-    EcDec dec;
-    if (data != nullptr) {
+    if (!lost) {
         audiosize = st->frame_size;
         mode = st->mode;
-        dec.init(data, (unsigned)len);
     } else {
+        frame_size = imin(frame_size, st->frame_size);
         audiosize = frame_size;
         mode = st->prev_mode;
         if (mode == 0) {
             CB_TEAM_FOR(i, audiosize * st->channels, tm) pcm[i] = 0;
-            CB_SYNC();
+            tm.sync();
             return audiosize;
         }
-        // audiosize > 20 ms cannot happen here: it is clamped to st->frame_size, and CELT frames are <= 20 ms
-        // (the reference's chunking loop at opus_decoder.c:275-288 is only reachable after SILK packets).
+        // audiosize > 20 ms cannot happen: it is clamped to st->frame_size and CELT frames are <= 20 ms
         if (audiosize < F20) {
             if (audiosize > F10) audiosize = F10;
             else if (mode != CB_MODE_SILK_ONLY && audiosize > F5 && audiosize < F10) audiosize = F5;
         }
     }
-    // transitions to/from SILK cannot occur: this engine only ever latches MODE_CELT_ONLY.
     if (audiosize > frame_size) return OPUS_BAD_ARG_;
     frame_size = audiosize;
-    int endband = 21;
-    switch (st->bandwidth) {
-    case kBwNarrow: endband = 13; break;
-    case kBwMedium:
-    case kBwWide: endband = 17; break;
-    case kBwSuperWide: endband = 19; break;
-    case kBwFull: endband = 21; break;
-    }
-    const int C = st->stream_channels;
-    const int celt_frame_size = imin(F20, frame_size);
     int celt_ret;
-    if (data == nullptr || decode_fec) {
-        celt_ret = celt_decode_lost_frame(tm, st, S, pcm, celt_frame_size, C, 0, endband);
-    } else {
-        celt_ret = celt_decode_frame(tm, st, S, data, len, pcm, celt_frame_size, C, 0, endband, dec);
-    }
+    if (lost) celt_ret = celt_decode_lost_frame(tm, st, S, pcm, imin(F20, frame_size));
+    else celt_ret = celt_synth_frame(tm, st, S, ir, X, pcm);
     if (st->decode_gain) {
         int gain = celt_exp2(s16(mul16_16_p15(21771, st->decode_gain)));   // QCONST16(6.48814081e-4f, 25)
         CB_TEAM_FOR(i, frame_size * st->channels, tm) {
             int x = mul16_32_p16(pcm[i], gain);
             pcm[i] = (int16_t)(x > 32767 ? 32767 : (x < -32767 ? -32767 : x));
         }
-        CB_SYNC();
+        tm.sync();
     }
-    if (tm.lane == 0) {
-        st->rangeFinal = len <= 1 ? 0 : dec.rng;
+    if (tm.lane() == 0) {
+        st->rangeFinal = (lost || ir.len <= 1) ? 0 : ir.rng_final;
         st->prev_mode = mode;
         st->prev_redundancy = 0;
     }
-    CB_SYNC();
+    tm.sync();
     return celt_ret < 0 ? celt_ret : audiosize;
 }
 
-// Lost-packet branch of opus_decode_native (opus_decoder.c:613-627): conceal frame_size samples.
-CB_DEV int opus_conceal(Team tm, CbDecState *st, DecScratch &S, int16_t *pcm, int frame_size) {
-    int pcm_count = 0;
-    do {
-        int ret = opus_decode_frame(tm, st, S, nullptr, 0, pcm + pcm_count * st->channels, frame_size - pcm_count, 0);
-        if (ret < 0) return ret;
-        pcm_count += ret;
-    } while (pcm_count < frame_size);
-    if (tm.lane == 0) st->last_packet_duration = pcm_count;
-    CB_SYNC();
-    return pcm_count;
-}
-
-// opus_decode_native (opus_decoder.c:598-709).  frame_size = capacity of pcm in samples per channel.
-CB_DEV int opus_decode_packet(Team tm, CbDecState *st, DecScratch &S, const uint8_t *data, int len, int16_t *pcm,
-                              int frame_size, int decode_fec) {
-    if (decode_fec < 0 || decode_fec > 1) return OPUS_BAD_ARG_;
-    if ((decode_fec || len == 0 || data == nullptr) && frame_size % (st->Fs / 400) != 0) return OPUS_BAD_ARG_;
-    if (len == 0 || data == nullptr) {
-        return opus_conceal(tm, st, S, pcm, frame_size);
-    } else if (len < 0) {
-        return OPUS_BAD_ARG_;
+// opus_decode_native remainder for one packet (opus_decoder.c:613-627,682-708).  Returns what opus_decode returns.
+template <class TM>
+CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, const CbPacketIR &pk, const CbFrameIR *fr, int16_t *Xarea,
+                             int16_t *pcm, int cap) {
+    if (pk.ret < 0) return pk.ret;
+    if (pk.lost) {
+        // conceal `cap` samples, frame by frame
+        CbFrameIR lostir;
+        lostir.flags = CB_IR_LOST; lostir.len = 0; lostir.rng_final = 0;
+        int pcm_count = 0;
+        do {
+            int ret = opus_synth_frame(tm, st, S, lostir, nullptr, pcm + pcm_count * st->channels, cap - pcm_count);
+            if (ret < 0) return ret;
+            pcm_count += ret;
+        } while (pcm_count < cap);
+        if (tm.lane() == 0) st->last_packet_duration = pcm_count;
+        tm.sync();
+        return pcm_count;
     }
-    const int packet_mode = pkt_mode(data);
-    const int packet_bandwidth = pkt_bandwidth(data);
-    const int packet_frame_size = pkt_samples_per_frame(data, st->Fs);
-    const int packet_stream_channels = pkt_nb_channels(data);
-    int16_t size[48];
-    int offset;
-    uint8_t toc;
-    const int count = pkt_parse(data, len, 0, &toc, size, &offset, nullptr);
-    if (count < 0) return count;
-    if (packet_mode != CB_MODE_CELT_ONLY) return OPUS_UNIMPLEMENTED_;   // scope edge: no SILK / hybrid
-    data += offset;
-    if (decode_fec) {
-        // CELT carries no in-band FEC: run concealment (opus_decoder.c:655-657)
-        if (frame_size % (st->Fs / 400) != 0) return OPUS_BAD_ARG_;
-        return opus_conceal(tm, st, S, pcm, frame_size);
+    if (tm.lane() == 0) {
+        st->mode = pk.mode;
+        st->bandwidth = pk.bandwidth;
+        st->frame_size = pk.frame_size;
+        st->stream_channels = pk.stream_channels;
     }
-    if (count * packet_frame_size > frame_size) return OPUS_BUFFER_TOO_SMALL_;
-    if (tm.lane == 0) {
-        st->mode = packet_mode;
-        st->bandwidth = packet_bandwidth;
-        st->frame_size = packet_frame_size;
-        st->stream_channels = packet_stream_channels;
-    }
-    CB_SYNC();
+    tm.sync();
     int nb_samples = 0;
-    for (int i = 0; i < count; i++) {
-        int ret = opus_decode_frame(tm, st, S, data, size[i], pcm + nb_samples * st->channels, frame_size - nb_samples, 0);
+    for (int i = 0; i < pk.count; i++) {
+        int ret = opus_synth_frame(tm, st, S, fr[i], Xarea + fr[i].x_off, pcm + nb_samples * st->channels, cap - nb_samples);
         if (ret < 0) return ret;
-        data += size[i];
         nb_samples += ret;
     }
-    if (tm.lane == 0) st->last_packet_duration = nb_samples;
-    CB_SYNC();
+    if (tm.lane() == 0) st->last_packet_duration = nb_samples;
+    tm.sync();
     return nb_samples;
 }
 

@@ -1,11 +1,12 @@
 // tests/hostsim/hostsim.cpp — TEST TOOL, never part of the product library.
 //
-// Compiles the codec headers of concentus_b200/csrc with a plain C++ compiler (team width 1, see
-// celt_simt.cuh) so the integer semantics of the kernels can be diffed against the oracle on a
+// Compiles the codec headers of concentus_b200/csrc with a plain C++ compiler (1-lane teams, see
+// celt_simt.cuh) so the integer semantics of both pipeline stages can be diffed against the oracle on a
 // machine with no GPU.  The CUDA build of the very same headers is what ships; this file exists
 // only so `pytest -m "not gpu"` can localise a bit mismatch before GPU time is spent.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 #include "../../concentus_b200/csrc/opus_decoder_dev.cuh"
 
 extern "C" {
@@ -13,18 +14,27 @@ extern "C" {
 int hostsim_dec_state_size(void) { return (int)sizeof(CbDecState); }
 
 // Decode F packets of one stream (packed layout).  cap = pcm capacity per packet (samples per channel).
+// Stage A (parse -> IR) then stage B (synth) per packet, exactly the hand-off the two kernels use.
 int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F, int cap, int channels,
                           int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets) {
     CbDecState *st = (CbDecState *)calloc(1, sizeof(CbDecState));
-    cb::DecScratch *S = (cb::DecScratch *)calloc(1, sizeof(cb::DecScratch));
+    cb::SynthScratch *S = (cb::SynthScratch *)calloc(1, sizeof(cb::SynthScratch));
+    cb::ParseScratch *ps = (cb::ParseScratch *)calloc(1, sizeof(cb::ParseScratch));
     if (cb::dec_state_init(st, Fs, channels) != 0) return -1;
-    cb::Team tm{0};
+    const int kmax = cap / (Fs / 400) < 48 ? cap / (Fs / 400) : 48;
+    std::vector<CbFrameIR> fr(kmax > 0 ? kmax : 1);
+    std::vector<int16_t> X((size_t)cap * (48000 / Fs) * 2 + 16);
+    cb::SoloTeam tm;
     for (int f = 0; f < F; f++) {
         const uint8_t *p = lens[f] > 0 ? data + offs[f] : nullptr;
-        int r = cb::opus_decode_packet(tm, st, *S, p, lens[f], pcm + (size_t)f * cap * channels, cap, 0);
+        CbPacketIR pk;
+        unsigned seed = st->rng;   // chained by stage A in the kernels; equal to st->rng here because B(f-1) has run
+        cb::opus_parse_packet(p, lens[f], cap, Fs, 0, kmax, &seed, pk, fr.data(), X.data(), *ps);
+        int r = cb::opus_synth_packet(tm, st, *S, pk, fr.data(), X.data(), pcm + (size_t)f * cap * channels, cap);
         if (rets) rets[f] = r;
         if (ranges) ranges[f] = st->rangeFinal;
     }
+    free(ps);
     free(S);
     free(st);
     return 0;
