@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libconcentus_b200.so")
+LIB_PATH = os.environ.get("CB200_LIB", os.path.join(HERE, "libconcentus_b200.so"))   # override: A/B builds only
 
 OPUS_OK = 0
 OPUS_BAD_ARG = -1

@@ -26,6 +26,7 @@ struct BandCtx {
     int intensity, spread, tf_change;
     int remaining_bits;
     unsigned seed;
+    bool dry;            // seed-recovery pass: read every symbol (identical range-coder walk), skip all vector work
 };
 
 struct SplitCtx {
@@ -190,10 +191,10 @@ CB_DEV unsigned quant_band_n1(BandCtx &ctx, int16_t *X, int16_t *Y, int16_t *low
             sign = (int)ctx.ec.bits(1);
             ctx.remaining_bits -= 1 << kBitRes;
         }
-        x[0] = sign ? -16384 : 16384;
+        if (!ctx.dry) x[0] = sign ? -16384 : 16384;
         x = Y;
     }
-    if (lowband_out) lowband_out[0] = (int16_t)(X[0] >> 4);
+    if (lowband_out && !ctx.dry) lowband_out[0] = (int16_t)(X[0] >> 4);
     return 1;
 }
 
@@ -210,8 +211,9 @@ CB_DEV unsigned partition_leaf(BandCtx &ctx, int16_t *X, int N, int b, int B, co
         ctx.remaining_bits -= curr_bits;
     }
     if (q != 0) {
+        if (ctx.dry) { const int K = get_pulses(q); (void)ctx.ec.uint_(pvq_v(N, K)); return 0; }
         cm = alg_unquant(X, N, get_pulses(q), ctx.spread, B, ctx.ec, gain, ctx.tmp);
-    } else {
+    } else if (!ctx.dry) {
         const unsigned cm_mask = (1u << B) - 1;
         fill &= (int)cm_mask;
         if (!fill) {
@@ -334,6 +336,7 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     N_B = (int)udiv((unsigned)N_B, (unsigned)B);
     if (N == 1) return quant_band_n1(ctx, X, nullptr, lowband_out);
     if (tf_change > 0) recombine = tf_change;
+    if (ctx.dry) lowband = nullptr;
     if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
         for (int j = 0; j < N; j++) lowband_scratch[j] = lowband[j];
         lowband = lowband_scratch;
@@ -357,6 +360,7 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     if (B0 > 1 && lowband) deinterleave_hadamard(lowband, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
 
     cm = quant_partition(ctx, X, N, b, B, lowband, LM, gain, fill);
+    if (ctx.dry) return 0;
 
     // resynthesis (decoder): undo the reorganisation
     if (B0 > 1) interleave_hadamard(X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
@@ -385,7 +389,8 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
 // per-band pass loop.  X_: C*N int16 (channel-major), norm: C*(M*eBands[20]) int16.
 CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, uint8_t *collapse_masks, const int *pulses,
                                 int shortBlocks, int spread, int dual_stereo, int intensity, const int *tf_res, int total_bits,
-                                int balance, EcDec &ec_io, int LM, int codedBands, unsigned *seed, int16_t *norm, int16_t *tmp) {
+                                int balance, EcDec &ec_io, int LM, int codedBands, unsigned *seed, int16_t *norm, int16_t *tmp,
+                                bool dry) {
     const int M = 1 << LM;
     const int B = shortBlocks ? M : 1;
     const int C = Y_ != nullptr ? 2 : 1;
@@ -398,6 +403,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
     ctx.ec = ec_io;
     ctx.tmp = tmp;
     ctx.intensity = intensity; ctx.spread = spread; ctx.seed = *seed;
+    ctx.dry = dry;
     for (int i = start; i < end; i++) {
         ctx.i = i;
         const int last = (i == end - 1);
@@ -439,7 +445,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
         }
         if (dual_stereo && i == intensity) {
             dual_stereo = 0;
-            const int n = M * kEBands[i] - norm_offset;
+            const int n = dry ? 0 : M * kEBands[i] - norm_offset;
             for (int j = 0; j < n; j++) norm[j] = (int16_t)((norm[j] + norm2[j]) >> 1);
         }
         int16_t *lb = effective_lowband != -1 ? norm + effective_lowband : nullptr;
@@ -522,7 +528,9 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
             if (mode == kDual) { if (pass == 0) x_cm = cm; else y_cm = cm; }
             else cm_acc |= cm;
         }
-        if (mode == kStereoN2) {
+        if (dry) {
+            // nothing to recombine
+        } else if (mode == kStereoN2) {
             // bands.c:1250-1268
             y2[0] = (int16_t)(-sign * x2[1]);
             y2[1] = (int16_t)(sign * x2[0]);
@@ -539,7 +547,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
         } else if (mode == kStereo) {
             stereo_merge(X, Y, s.imid, N);
         }
-        if ((mode == kStereo || mode == kStereoN2) && s.inv)
+        if (!dry && (mode == kStereo || mode == kStereoN2) && s.inv)
             for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
         if (npass > 0 && mode != kDual) x_cm = y_cm = cm_acc;
         collapse_masks[i * C + 0] = (uint8_t)x_cm;

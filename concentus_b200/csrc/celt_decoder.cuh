@@ -6,13 +6,19 @@
 //   celt_synth_frame  (stage B, per team) :842-846,962-964,986-1066  energy prediction, anti_collapse, celt_synthesis
 //                                                    (:280-350) with denormalise_bands (bands.c:169-238) fused into the
 //                                                    IMDCT pre-rotation, comb_filter (celt.c:156-244), state update,
-//                                                    deemphasis (:185-275)
+//                                                    staging for stage C
+//   deemphasis_channel (stage C, scalar)  :185-275  de-emphasis + decode gain, one thread per (stream, channel)
 #pragma once
 #include "celt_bands.cuh"
 #include "celt_energy.cuh"
 #include "celt_ir.h"
 #include "celt_mdct.cuh"
 #include "opus_state.h"
+
+#if !defined(__CUDACC__)
+struct int4 { int x, y, z, w; };   // host simulation stand-in for the CUDA vector type
+#include <cstdint>
+#endif
 
 namespace cb {
 
@@ -42,8 +48,9 @@ struct ParseScratch {
 
 // Parse one received CELT frame (payload of `len` >= 2 bytes).  X: C*N int16 for this frame.  *seed is the
 // LCG seed on entry (previous frame's final rng) and the frame's final rng on exit.
+// dry = true: seed-recovery pass — the identical symbol walk, no spectrum is produced (X, ps untouched).
 CB_DEV void celt_parse_frame(const uint8_t *data, int len, int LM, int C, int end, unsigned *seed, CbFrameIR &ir, int16_t *X,
-                             ParseScratch &ps) {
+                             ParseScratch &ps, bool dry) {
     const int start = 0;
     const int M = 1 << LM;
     const int N = M * kShortMdct;
@@ -119,7 +126,7 @@ CB_DEV void celt_parse_frame(const uint8_t *data, int len, int LM, int C, int en
     unsigned sd = *seed;
     quant_all_bands_dec(start, end, X, C == 2 ? X + N : nullptr, ir.collapse, pulses, shortBlocks, spread_decision, dual_stereo,
                         intensity, tf_res, len * (8 << kBitRes) - anti_collapse_rsv, balance, dec, LM, codedBands, &sd, ps.norm,
-                        ps.tmp);
+                        ps.tmp, dry);
     int anti_collapse_on = 0;
     if (anti_collapse_rsv > 0) anti_collapse_on = (int)dec.bits(1);
     decode_energy_finalise(start, end, fine_quant, fine_priority, len * 8 - dec.tell(), dec, C, ir.eoff);
@@ -200,33 +207,53 @@ CB_DEV void comb_filter_inplace(TM tm, int *x, int T0, int T1, int N, int g0, in
     }
 }
 
-// deemphasis (celt_decoder.c:185-275, accum = 0): a 1-pole IIR per channel — order dependent.  Lane c filters
-// channel c (a 1-lane team does the channels one after the other).
-template <class TM>
-CB_DEV void deemphasis(TM tm, int *const *in, int16_t *pcm, int N, int CC, int downsample, int *mem) {
-    const int c0 = TM::W == 1 ? 0 : tm.lane();
-    const int c1 = TM::W == 1 ? CC : imin(tm.lane() + 1, CC);
-    for (int c = c0; c < c1; c++) {
-        const int *x = in[c];
-        int16_t *y = pcm + c;
-        int m = mem[c];
-        if (downsample > 1) {
-            int k = 0;
-            for (int j = 0; j < N; j++) {
-                int t = wadd(x[j], m);
-                m = mul16_32_q15(kPreemphCoef0, t);
-                if (j == k * downsample) { y[k * CC] = (int16_t)sig2word16(t); k++; }
-            }
-        } else {
-            for (int j = 0; j < N; j++) {
-                int t = wadd(x[j], m);
-                m = mul16_32_q15(kPreemphCoef0, t);
-                y[j * CC] = (int16_t)sig2word16(t);
+// deemphasis (celt_decoder.c:185-275, accum = 0) is a 1-pole IIR per channel: strictly order dependent, so it is not run
+// by the stream's warp (30 idle lanes) but by stage C, one THREAD per (stream, channel), over the staged post-filter
+// signal.  x: n samples at 48 kHz; y: int16 PCM with stride CC, decimated by `downsample`; gain = decode gain (Q16, 0 = off,
+// opus_decoder.c:567-577).  Returns the filter memory.
+CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downsample, int m, int gain) {
+    if (downsample > 1) {
+        int k = 0, next = 0;
+        for (int j = 0; j < n; j++) {
+            int t = wadd(x[j], m);
+            m = mul16_32_q15(kPreemphCoef0, t);
+            if (j == next) {
+                int v = sig2word16(t);
+                if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+                y[k * CC] = (int16_t)v;
+                k++;
+                next += downsample;
             }
         }
-        mem[c] = m;
+    } else {
+        int j = 0;
+        // batches of 8 samples: the loads are independent of the recurrence, so they are issued up front (two 16-byte
+        // loads when the pointer allows) and the serial chain runs from registers
+        if ((((uintptr_t)x) & 15) == 0) {
+            for (; j + 8 <= n; j += 8) {
+                int xs[8];
+                const int4 a = *reinterpret_cast<const int4 *>(x + j);
+                const int4 b = *reinterpret_cast<const int4 *>(x + j + 4);
+                xs[0] = a.x; xs[1] = a.y; xs[2] = a.z; xs[3] = a.w; xs[4] = b.x; xs[5] = b.y; xs[6] = b.z; xs[7] = b.w;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    int t = wadd(xs[u], m);
+                    m = mul16_32_q15(kPreemphCoef0, t);
+                    int v = sig2word16(t);
+                    if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+                    y[(j + u) * CC] = (int16_t)v;
+                }
+            }
+        }
+        for (; j < n; j++) {
+            int t = wadd(x[j], m);
+            m = mul16_32_q15(kPreemphCoef0, t);
+            int v = sig2word16(t);
+            if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+            y[j * CC] = (int16_t)v;
+        }
     }
-    tm.sync();
+    return m;
 }
 
 // Shift the synthesis history down by N samples (celt_decoder.c:962-964), team-parallel and overlap-safe:
@@ -244,10 +271,11 @@ CB_DEV void history_shift(TM tm, int *mem, int N) {
     tm.sync();
 }
 
-// Synthesise one received frame from its IR.  pcm: interleaved int16, CC channels.
+// Synthesise one received frame from its IR up to (and excluding) de-emphasis: the post-filtered signal of channel c
+// (N samples at 48 kHz) is staged to sig[c] for stage C.
 // Returns samples per channel at the API rate, or OPUS_INTERNAL_ERROR when the frame overran its bit budget.
 template <class TM>
-CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int16_t *pcm) {
+CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int *const *sig) {
     const int CC = st->channels;
     const int LM = ir.LM, C = ir.C, end = ir.end, start = 0;
     const int M = 1 << LM;
@@ -379,7 +407,12 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
         if (ir.flags & CB_IR_EC_ERROR) st->error = 1;
     }
     tm.sync();
-    deemphasis(tm, out_syn, pcm, N, CC, st->downsample, st->preemph_memD);
+    for (int c = 0; c < CC; c++) {
+        const int *src = out_syn[c];
+        int *dst = sig[c];
+        CB_TEAM_FOR(j, N, tm) dst[j] = src[j];
+    }
+    tm.sync();
     if (ir.flags & CB_IR_OVERRUN) return OPUS_INTERNAL_ERROR_;
     return N / st->downsample;
 }

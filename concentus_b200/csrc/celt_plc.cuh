@@ -8,7 +8,7 @@
 namespace cb {
 
 template <class TM>
-CB_DEV int celt_decode_lost_frame(TM, CbDecState *, SynthScratch &, int16_t *, int) {
+CB_DEV int celt_decode_lost_frame(TM, CbDecState *, SynthScratch &, int *const *, int) {
     return OPUS_UNIMPLEMENTED_;
 }
 

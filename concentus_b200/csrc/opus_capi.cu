@@ -38,15 +38,28 @@ static const uint32_t kDecMagic = 0x0B200DECu;
 // ------------------------------------------------------------------------------------------------
 // Kernels
 // ------------------------------------------------------------------------------------------------
+#ifndef CB_PARSE_THREADS
 #define CB_PARSE_THREADS 128   // stage A block
+#endif
+#ifndef CB_PARSE_MINBLOCKS
+#define CB_PARSE_MINBLOCKS 6   // stage A: min resident blocks per SM (register cap 80)
+#endif
+#ifndef CB_WPB
 #define CB_WPB 4               // stage B: warps (= streams) per block
+#endif
+#ifndef CB_SYNTH_MINBLOCKS
+#define CB_SYNTH_MINBLOCKS 8
+#endif
 
 struct IrView {
     CbPacketIR *pk;      // [n * Fc]
     CbFrameIR *fr;       // [n * Fc * kmax]
     int16_t *X;          // [n * Fc * xstride]
+    int *sig;            // [n * Fc * sigstride] staged post-filter signal for stage C (channel-major per packet)
+    CbSigRange *range;   // [n * Fc]
     int kmax;
     int xstride;         // int16 per packet
+    int sigstride;       // int32 per packet = cap48 * 2
     int Fc;              // packets per stream in this chunk buffer
 };
 
@@ -54,7 +67,7 @@ struct IrView {
 // fold seed (= final range of the previous frame), which each thread recovers for the start of its run by re-parsing the
 // packet before it; inside the run the seed chains naturally.  No decoder state is written here (st->rng is read once per
 // launch for the very first packet of a stream).
-__global__ void __launch_bounds__(CB_PARSE_THREADS)
+__global__ void __launch_bounds__(CB_PARSE_THREADS, CB_PARSE_MINBLOCKS)
 parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, const int64_t *offs, const int32_t *lens, int n, int F,
              int f0, int f1, int call_f0, int R, int cap, int decode_fec, IrView ir, ParseScratch *scratch) {
     const int runs = (f1 - f0 + R - 1) / R;
@@ -87,7 +100,7 @@ parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, cons
         const uint8_t *p = len > 0 ? data + offs[idx] : nullptr;
         CbPacketIR pk;   // built in registers, stored once
         opus_parse_packet(p, len, cap, Fs, seeking ? 0 : decode_fec, ir.kmax, &seed, pk, ir.fr + slot * ir.kmax,
-                          ir.X + slot * ir.xstride, ps);
+                          ir.X + slot * ir.xstride, ps, seeking);
         if (!seeking) ir.pk[slot] = pk;
         if (seeking) {
             bool parsed = false;   // did any frame of this packet run the range decoder (and so set `seed`)?
@@ -107,7 +120,7 @@ parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, cons
 
 // Stage B — synthesis, one warp per stream, packets f0..f1 in order.  PCM row of packet (s,f) starts at
 // pcm[(s*pcm_F + (f-pcm_f0)) * cap * channels].
-__global__ void __launch_bounds__(CB_WPB * 32)
+__global__ void __launch_bounds__(CB_WPB * 32, CB_SYNTH_MINBLOCKS)
 synth_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n, int F, int f0, int f1, int pcm_F, int pcm_f0,
              int cap, int *rets) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -121,9 +134,27 @@ synth_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n,
     for (int f = f0; f < f1; f++) {
         const size_t slot = (size_t)s * ir.Fc + (f - f0);
         int16_t *out = pcm + ((size_t)s * pcm_F + (f - pcm_f0)) * cap * channels;
-        int r = opus_synth_packet(tm, st, S, ir.pk[slot], ir.fr + slot * ir.kmax, ir.X + slot * ir.xstride, out, cap);
+        int r = opus_synth_packet(tm, st, S, ir.pk[slot], ir.fr + slot * ir.kmax, ir.X + slot * ir.xstride, out, cap,
+                                  ir.sig + slot * ir.sigstride, ir.range + slot);
         if (lane == 0) rets[(size_t)s * F + f] = r;
         __syncwarp();
+    }
+}
+
+// Stage C — de-emphasis + decode gain + PCM store, one THREAD per (stream, channel): the 1-pole IIR is order dependent
+// along time but independent across streams and channels, so 32 of them fill a warp.
+__global__ void __launch_bounds__(128)
+deemph_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n, int f0, int f1, int pcm_F, int pcm_f0, int cap) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = t >> 1, c = t & 1;
+    if (s >= n) return;
+    CbDecState *st = pool + slots[s];
+    const int channels = st->channels;
+    if (c >= channels) return;
+    for (int f = f0; f < f1; f++) {
+        const size_t slot = (size_t)s * ir.Fc + (f - f0);
+        int16_t *out = pcm + ((size_t)s * pcm_F + (f - pcm_f0)) * cap * channels;
+        opus_deemph_packet(st, c, ir.sig + slot * ir.sigstride, ir.range[slot], out, cap);
     }
 }
 
@@ -188,17 +219,17 @@ struct Ctx {
     std::mutex mu;
     bool tried = false, ok = false;
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, parse_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, parse_stream = nullptr, synth_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-    cudaEvent_t ev_parse[2] = {nullptr, nullptr}, ev_synth[2] = {nullptr, nullptr}, ev_call = nullptr;
+    cudaEvent_t ev_parse[2] = {nullptr, nullptr}, ev_synth[2] = {nullptr, nullptr}, ev_deemph[2] = {nullptr, nullptr}, ev_call = nullptr;
     CbDecState *pool = nullptr;
     int pool_cap = 0;
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
     DevBuf d_slots, d_data, d_offs, d_lens, d_pcm[2], d_rets, d_stage;
-    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_scratch;
-    size_t ir_budget = (size_t)6 << 30;   // bytes of IR per chunk buffer (env CB200_IR_MB)
-    int run_len = 5;                      // packets per stage-A thread (env CB200_RUN)
+    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_scratch;
+    size_t ir_budget = (size_t)16 << 30;  // bytes of IR + staging per chunk buffer (env CB200_IR_MB)
+    int run_len = 3;                      // packets per stage-A thread (env CB200_RUN)
     PinBuf h_stage, h_slots, h_misc;
     long long launches = 0;
     float last_ms = 0.f;
@@ -221,6 +252,7 @@ bool ctx_init_locked() {
     if (cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&g.parse_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&g.synth_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     cudaEventCreate(&g.ev0);
     cudaEventCreate(&g.ev1);
     for (int i = 0; i < 2; i++) {
@@ -228,13 +260,14 @@ bool ctx_init_locked() {
         cudaEventCreateWithFlags(&g.ev_copy[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g.ev_parse[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g.ev_synth[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g.ev_deemph[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&g.ev_call, cudaEventDisableTiming);
     if (const char *e = getenv("CB200_IR_MB")) g.ir_budget = (size_t)atol(e) << 20;
     if (const char *e = getenv("CB200_RUN")) g.run_len = atoi(e) > 0 ? atoi(e) : 5;
     {
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && g.ir_budget > free_b / 8) g.ir_budget = free_b / 8;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && g.ir_budget > free_b / 10) g.ir_budget = free_b / 10;
     }
     g.smem_per_block = (int)(CB_WPB * sizeof(SynthScratch));
     cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_per_block);
@@ -389,7 +422,7 @@ int sync_states_locked(OpusDecoder **st, int n, bool release) {
 
 // Geometry of one call: chunking of the time axis and the IR buffers behind it.
 struct Plan {
-    int n, F, cap, fec, kmax, xstride, Fc, nchunks, R;
+    int n, F, cap, fec, kmax, xstride, sigstride, Fc, nchunks, R;
 };
 
 bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
@@ -397,8 +430,10 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
     int k = cap / (Fs / 400);
     pl.kmax = k < 1 ? 1 : (k > 48 ? 48 : k);
     pl.xstride = cap * (48000 / Fs) * 2;
+    pl.sigstride = cap * (48000 / Fs) * 2;
     pl.R = g.run_len;
-    const size_t per_packet = sizeof(CbPacketIR) + (size_t)pl.kmax * sizeof(CbFrameIR) + (size_t)pl.xstride * sizeof(int16_t);
+    const size_t per_packet = sizeof(CbPacketIR) + (size_t)pl.kmax * sizeof(CbFrameIR) + (size_t)pl.xstride * sizeof(int16_t) +
+                              (size_t)pl.sigstride * sizeof(int) + sizeof(CbSigRange);
     size_t fc = g.ir_budget / (per_packet * (size_t)n);
     if (fc < 1) fc = 1;
     if (fc > (size_t)F) fc = (size_t)F;
@@ -409,7 +444,8 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
     const size_t slots = (size_t)n * pl.Fc;
     for (int b = 0; b < nb; b++) {
         if (!g.d_irpk[b].reserve(slots * sizeof(CbPacketIR)) || !g.d_irfr[b].reserve(slots * pl.kmax * sizeof(CbFrameIR)) ||
-            !g.d_irx[b].reserve(slots * pl.xstride * sizeof(int16_t)))
+            !g.d_irx[b].reserve(slots * pl.xstride * sizeof(int16_t)) || !g.d_sig[b].reserve(slots * pl.sigstride * sizeof(int)) ||
+            !g.d_range[b].reserve(slots * sizeof(CbSigRange)))
             return false;
     }
     const size_t threads = (size_t)n * ((pl.Fc + pl.R - 1) / pl.R);
@@ -419,30 +455,41 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
 IrView ir_view(const Plan &pl, int b) {
     IrView v;
     v.pk = (CbPacketIR *)g.d_irpk[b].p; v.fr = (CbFrameIR *)g.d_irfr[b].p; v.X = (int16_t *)g.d_irx[b].p;
-    v.kmax = pl.kmax; v.xstride = pl.xstride; v.Fc = pl.Fc;
+    v.sig = (int *)g.d_sig[b].p; v.range = (CbSigRange *)g.d_range[b].p;
+    v.kmax = pl.kmax; v.xstride = pl.xstride; v.sigstride = pl.sigstride; v.Fc = pl.Fc;
     return v;
 }
 
 // Enqueue stage A for chunk c on the parse stream and stage B on the main stream.  PCM goes to pcm_dst laid out with
 // pcm_F packets per stream starting at packet pcm_f0 (the caller decides: whole-call buffer or a chunk buffer).
 void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_data, const int64_t *d_offs, const int32_t *d_lens,
-                   int16_t *pcm_dst, int pcm_F, int pcm_f0, int *d_rets) {
+                   int16_t *pcm_dst, int pcm_F, int pcm_f0, int *d_rets, cudaEvent_t pcm_free = nullptr) {
     const int b = c & 1;
     const int f0 = c * pl.Fc, f1 = (f0 + pl.Fc < pl.F) ? f0 + pl.Fc : pl.F;
     const int runs = (f1 - f0 + pl.R - 1) / pl.R;
     const long long threads = (long long)pl.n * runs;
     IrView v = ir_view(pl, b);
     // stage A(c) may start once stage B(c-2) has drained IR buffer b, and (first chunk) once earlier calls are done
-    if (c == 0) cudaStreamWaitEvent(g.parse_stream, g.ev_call, 0);
+    if (c == 0) {
+        cudaStreamWaitEvent(g.parse_stream, g.ev_call, 0);
+        cudaStreamWaitEvent(g.synth_stream, g.ev_call, 0);
+    }
     if (c >= 2) cudaStreamWaitEvent(g.parse_stream, g.ev_synth[b], 0);
     parse_kernel<<<(unsigned)((threads + CB_PARSE_THREADS - 1) / CB_PARSE_THREADS), CB_PARSE_THREADS, 0, g.parse_stream>>>(
         g.pool, d_slots, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v, (ParseScratch *)g.d_scratch.p);
     cudaEventRecord(g.ev_parse[b], g.parse_stream);
-    cudaStreamWaitEvent(g.stream, g.ev_parse[b], 0);
-    synth_kernel<<<(pl.n + CB_WPB - 1) / CB_WPB, CB_WPB * 32, g.smem_per_block, g.stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, pl.F, f0, f1,
-                                                                                            pcm_F, pcm_f0, pl.cap, d_rets);
-    cudaEventRecord(g.ev_synth[b], g.stream);
-    g.launches += 2;
+    // stage B(c): after A(c); its staging buffer b must have been drained by C(c-2)
+    cudaStreamWaitEvent(g.synth_stream, g.ev_parse[b], 0);
+    if (c >= 2) cudaStreamWaitEvent(g.synth_stream, g.ev_deemph[b], 0);
+    if (pcm_free) cudaStreamWaitEvent(g.synth_stream, pcm_free, 0);   // stage B writes PCM too (leading zero frames)
+    synth_kernel<<<(pl.n + CB_WPB - 1) / CB_WPB, CB_WPB * 32, g.smem_per_block, g.synth_stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, pl.F, f0,
+                                                                                                  f1, pcm_F, pcm_f0, pl.cap, d_rets);
+    cudaEventRecord(g.ev_synth[b], g.synth_stream);
+    // stage C(c) on the main stream (the one the caller synchronises / times)
+    cudaStreamWaitEvent(g.stream, g.ev_synth[b], 0);
+    deemph_kernel<<<(2 * pl.n + 127) / 128, 128, 0, g.stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, f0, f1, pcm_F, pcm_f0, pl.cap);
+    cudaEventRecord(g.ev_deemph[b], g.stream);
+    g.launches += 3;
 }
 
 }  // namespace
@@ -462,6 +509,7 @@ int opus_b200_synchronize(void) {
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.copy_stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(g.parse_stream) != cudaSuccess || cudaStreamSynchronize(g.synth_stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     if (g.launches > 0) cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);   // last span kernel (events on g.stream)
     return OPUS_OK;
 }
@@ -690,7 +738,7 @@ static int decode_span_host_locked(OpusDecoder **st, int n, int F, const unsigne
         const int f0 = c * Fc, f1 = (f0 + Fc < F) ? f0 + Fc : F;
         if (c >= 2) cudaStreamWaitEvent(g.stream, g.ev_copy[b], 0);   // PCM buffer b drained?
         enqueue_chunk(pl, c, (const int *)g.d_slots.p, (const uint8_t *)g.d_data.p, (const int64_t *)g.d_offs.p,
-                      (const int32_t *)g.d_lens.p, (int16_t *)g.d_pcm[b].p, Fc, f0, (int *)g.d_rets.p);
+                      (const int32_t *)g.d_lens.p, (int16_t *)g.d_pcm[b].p, Fc, f0, (int *)g.d_rets.p, c >= 2 ? g.ev_copy[b] : nullptr);
         cudaEventRecord(g.ev_chunk[b], g.stream);
         cudaStreamWaitEvent(g.copy_stream, g.ev_chunk[b], 0);
         // rows of (f1-f0) packets per stream: device pitch Fc*row, host pitch F*row

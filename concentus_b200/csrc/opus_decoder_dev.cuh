@@ -62,7 +62,7 @@ CB_DEV int bandwidth_to_endband(int bw) {   // opus_decoder.c:431-450
 // Nothing here reads or writes decoder state.
 // ---------------------------------------------------------------------------------------------------
 CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int decode_fec, int kmax, unsigned *seed,
-                              CbPacketIR &pk, CbFrameIR *fr, int16_t *Xarea, ParseScratch &ps) {
+                              CbPacketIR &pk, CbFrameIR *fr, int16_t *Xarea, ParseScratch &ps, bool dry) {
     pk.count = 0; pk.lost = 0; pk.frame_size = 0; pk.mode = 0; pk.bandwidth = 0; pk.stream_channels = 0; pk.reserved = 0;
     if (decode_fec < 0 || decode_fec > 1) { pk.ret = OPUS_BAD_ARG_; return; }
     if ((decode_fec || len == 0 || data == nullptr) && cap % (Fs / 400) != 0) { pk.ret = OPUS_BAD_ARG_; return; }
@@ -102,7 +102,7 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
             ir.LM = (uint8_t)LM; ir.C = (uint8_t)C; ir.end = (uint8_t)end;
             ir.rng_final = 0; ir.seed_bands = *seed;
         } else {
-            celt_parse_frame(p, size[i], LM, C, end, seed, ir, Xarea + xoff, ps);
+            celt_parse_frame(p, size[i], LM, C, end, seed, ir, Xarea + xoff, ps, dry);
         }
         xoff += N * C;
         p += size[i];
@@ -113,10 +113,19 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
 // Stage B: consume one packet's IR in stream order.
 // ---------------------------------------------------------------------------------------------------
 
-// opus_decode_frame remainder for one frame (opus_decoder.c:246-252,265-272,452-596)
+// What stage B tells stage C about one packet: which 48 kHz sample range of the packet's staging area holds signal
+// that still has to be de-emphasised (PCM outside it was written by stage B itself: leading zero frames).
+struct CbSigRange {
+    int32_t begin, end;
+};
+
+// opus_decode_frame remainder for one frame (opus_decoder.c:246-252,265-272,452-596).  sig[c] points at this frame's
+// position in the packet's staging area; *staged is set when the frame left signal there.
 template <class TM>
-CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int16_t *pcm, int room) {
+CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int16_t *pcm, int room,
+                            int *const *sig, bool *staged) {
     const int F20 = st->Fs / 50, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
+    *staged = false;
     if (room < F2_5) return OPUS_BUFFER_TOO_SMALL_;
     int frame_size = imin(room, st->Fs / 25 * 3);
     const bool lost = (ir.flags & CB_IR_LOST) != 0;
@@ -142,16 +151,10 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
     if (audiosize > frame_size) return OPUS_BAD_ARG_;
     frame_size = audiosize;
     int celt_ret;
-    if (lost) celt_ret = celt_decode_lost_frame(tm, st, S, pcm, imin(F20, frame_size));
-    else celt_ret = celt_synth_frame(tm, st, S, ir, X, pcm);
-    if (st->decode_gain) {
-        int gain = celt_exp2(s16(mul16_16_p15(21771, st->decode_gain)));   // QCONST16(6.48814081e-4f, 25)
-        CB_TEAM_FOR(i, frame_size * st->channels, tm) {
-            int x = mul16_32_p16(pcm[i], gain);
-            pcm[i] = (int16_t)(x > 32767 ? 32767 : (x < -32767 ? -32767 : x));
-        }
-        tm.sync();
-    }
+    if (lost) celt_ret = celt_decode_lost_frame(tm, st, S, sig, imin(F20, frame_size));
+    else celt_ret = celt_synth_frame(tm, st, S, ir, X, sig);
+    *staged = !(lost && celt_ret < 0);
+    // decode gain (opus_decoder.c:567-577) is applied by stage C when it writes the PCM
     if (tm.lane() == 0) {
         st->rangeFinal = (lost || ir.len <= 1) ? 0 : ir.rng_final;
         st->prev_mode = mode;
@@ -162,40 +165,73 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
 }
 
 // opus_decode_native remainder for one packet (opus_decoder.c:613-627,682-708).  Returns what opus_decode returns.
+// sigbase: the packet's staging area, channel c at sigbase + c*cap48 (cap48 = cap * downsample samples).
 template <class TM>
 CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, const CbPacketIR &pk, const CbFrameIR *fr, int16_t *Xarea,
-                             int16_t *pcm, int cap) {
-    if (pk.ret < 0) return pk.ret;
-    if (pk.lost) {
+                             int16_t *pcm, int cap, int *sigbase, CbSigRange *range) {
+    const int ds = st->downsample;
+    const int cap48 = cap * ds;
+    int sb = 0, se = 0;   // staged range in 48 kHz samples
+    bool any = false;
+    int result;
+    if (pk.ret < 0) {
+        result = pk.ret;
+    } else if (pk.lost) {
         // conceal `cap` samples, frame by frame
         CbFrameIR lostir;
         lostir.flags = CB_IR_LOST; lostir.len = 0; lostir.rng_final = 0;
         int pcm_count = 0;
+        result = 0;
         do {
-            int ret = opus_synth_frame(tm, st, S, lostir, nullptr, pcm + pcm_count * st->channels, cap - pcm_count);
-            if (ret < 0) return ret;
+            int *sig[2] = {sigbase + pcm_count * ds, sigbase + cap48 + pcm_count * ds};
+            bool staged;
+            int ret = opus_synth_frame(tm, st, S, lostir, nullptr, pcm + pcm_count * st->channels, cap - pcm_count, sig, &staged);
+            if (ret < 0) { result = ret; break; }
+            if (staged) { if (!any) sb = pcm_count * ds; any = true; se = (pcm_count + ret) * ds; }
             pcm_count += ret;
         } while (pcm_count < cap);
-        if (tm.lane() == 0) st->last_packet_duration = pcm_count;
+        if (result >= 0) {
+            if (tm.lane() == 0) st->last_packet_duration = pcm_count;
+            tm.sync();
+            result = pcm_count;
+        }
+    } else {
+        if (tm.lane() == 0) {
+            st->mode = pk.mode;
+            st->bandwidth = pk.bandwidth;
+            st->frame_size = pk.frame_size;
+            st->stream_channels = pk.stream_channels;
+        }
         tm.sync();
-        return pcm_count;
+        int nb_samples = 0;
+        result = 0;
+        for (int i = 0; i < pk.count; i++) {
+            int *sig[2] = {sigbase + nb_samples * ds, sigbase + cap48 + nb_samples * ds};
+            bool staged;
+            int ret = opus_synth_frame(tm, st, S, fr[i], Xarea + fr[i].x_off, pcm + nb_samples * st->channels, cap - nb_samples, sig,
+                                       &staged);
+            if (staged) { if (!any) sb = nb_samples * ds; any = true; se = (nb_samples + (ret < 0 ? pk.frame_size : ret)) * ds; }
+            if (ret < 0) { result = ret; break; }
+            nb_samples += ret;
+        }
+        if (result >= 0) {
+            if (tm.lane() == 0) st->last_packet_duration = nb_samples;
+            tm.sync();
+            result = nb_samples;
+        }
     }
-    if (tm.lane() == 0) {
-        st->mode = pk.mode;
-        st->bandwidth = pk.bandwidth;
-        st->frame_size = pk.frame_size;
-        st->stream_channels = pk.stream_channels;
-    }
-    tm.sync();
-    int nb_samples = 0;
-    for (int i = 0; i < pk.count; i++) {
-        int ret = opus_synth_frame(tm, st, S, fr[i], Xarea + fr[i].x_off, pcm + nb_samples * st->channels, cap - nb_samples);
-        if (ret < 0) return ret;
-        nb_samples += ret;
-    }
-    if (tm.lane() == 0) st->last_packet_duration = nb_samples;
-    tm.sync();
-    return nb_samples;
+    if (tm.lane() == 0) { range->begin = any ? sb : 0; range->end = any ? se : 0; }
+    return result;
+}
+
+// Stage C for one packet and one channel: de-emphasis + decode gain + PCM store (celt_decoder.c:185-275).
+CB_DEV void opus_deemph_packet(CbDecState *st, int c, const int *sigbase, const CbSigRange &rg, int16_t *pcm, int cap) {
+    if (rg.end <= rg.begin) return;
+    const int ds = st->downsample, CC = st->channels;
+    const int gain = st->decode_gain ? celt_exp2(s16(mul16_16_p15(21771, st->decode_gain))) : 0;   // QCONST16(6.48814081e-4f, 25)
+    const int *x = sigbase + c * (cap * ds) + rg.begin;
+    int16_t *y = pcm + (rg.begin / ds) * CC + c;
+    st->preemph_memD[c] = deemphasis_channel(x, rg.end - rg.begin, y, CC, ds, st->preemph_memD[c], gain);
 }
 
 }  // namespace cb

@@ -14,7 +14,7 @@ extern "C" {
 int hostsim_dec_state_size(void) { return (int)sizeof(CbDecState); }
 
 // Decode F packets of one stream (packed layout).  cap = pcm capacity per packet (samples per channel).
-// Stage A (parse -> IR) then stage B (synth) per packet, exactly the hand-off the two kernels use.
+// Stage A (parse -> IR), stage B (synth) and stage C (de-emphasis) per packet, exactly the hand-offs the kernels use.
 int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F, int cap, int channels,
                           int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets) {
     CbDecState *st = (CbDecState *)calloc(1, sizeof(CbDecState));
@@ -24,13 +24,24 @@ int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_
     const int kmax = cap / (Fs / 400) < 48 ? cap / (Fs / 400) : 48;
     std::vector<CbFrameIR> fr(kmax > 0 ? kmax : 1);
     std::vector<int16_t> X((size_t)cap * (48000 / Fs) * 2 + 16);
+    std::vector<int> sig((size_t)cap * (48000 / Fs) * 2 + 16);
     cb::SoloTeam tm;
     for (int f = 0; f < F; f++) {
         const uint8_t *p = lens[f] > 0 ? data + offs[f] : nullptr;
         CbPacketIR pk;
         unsigned seed = st->rng;   // chained by stage A in the kernels; equal to st->rng here because B(f-1) has run
-        cb::opus_parse_packet(p, lens[f], cap, Fs, 0, kmax, &seed, pk, fr.data(), X.data(), *ps);
-        int r = cb::opus_synth_packet(tm, st, *S, pk, fr.data(), X.data(), pcm + (size_t)f * cap * channels, cap);
+        // dry pass first (what a run's first thread does to recover its seed): must leave the same final range behind
+        unsigned dry_seed = 12345u;
+        CbPacketIR dry_pk;
+        cb::opus_parse_packet(p, lens[f], cap, Fs, 0, kmax, &dry_seed, dry_pk, fr.data(), X.data(), *ps, true);
+        cb::opus_parse_packet(p, lens[f], cap, Fs, 0, kmax, &seed, pk, fr.data(), X.data(), *ps, false);
+        if (pk.ret >= 0 && !pk.lost && pk.count > 0 && !(fr[pk.count - 1].flags & CB_IR_LOST) && dry_seed != seed) {
+            if (rets) rets[f] = -99;   // dry/full divergence: flag loudly
+            continue;
+        }
+        cb::CbSigRange rg;
+        int r = cb::opus_synth_packet(tm, st, *S, pk, fr.data(), X.data(), pcm + (size_t)f * cap * channels, cap, sig.data(), &rg);
+        for (int c = 0; c < channels; c++) cb::opus_deemph_packet(st, c, sig.data(), rg, pcm + (size_t)f * cap * channels, cap);   // stage C
         if (rets) rets[f] = r;
         if (ranges) ranges[f] = st->rangeFinal;
     }
