@@ -39,7 +39,7 @@ EXPORTS = [
     "opus_packet_get_nb_channels", "opus_packet_get_nb_frames", "opus_packet_get_nb_samples",
     "opus_decoder_get_nb_samples", "opus_strerror", "opus_get_version_string", "opus_decode_batch", "opus_decode_span",
     "opus_decode_span_device", "opus_decoder_sync", "opus_b200_init", "opus_b200_synchronize", "opus_b200_stream",
-    "opus_b200_kernel_launches", "opus_b200_last_kernel_ms",
+    "opus_b200_kernel_launches", "opus_b200_last_kernel_ms", "opus_b200_stage_times",
 ]
 
 
@@ -67,6 +67,7 @@ def lib():
         L.opus_b200_stream.restype = C.c_void_p
         L.opus_b200_kernel_launches.restype = C.c_longlong
         L.opus_b200_last_kernel_ms.restype = C.c_float
+        L.opus_b200_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 

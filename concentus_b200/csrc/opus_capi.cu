@@ -142,7 +142,40 @@ synth_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n,
 }
 
 // Stage C — de-emphasis + decode gain + PCM store, one THREAD per (stream, channel): the 1-pole IIR is order dependent
-// along time but independent across streams and channels, so 32 of them fill a warp.
+// along time but independent across streams and channels, so 32 of them fill a warp.  For the common stereo / 48 kHz case the
+// two channel threads of a stream (an even/odd lane pair) swap halves of each 8-sample batch with shuffles so that each
+// writes 16 contiguous bytes of interleaved PCM instead of eight scattered 2-byte stores.
+__device__ __forceinline__ int deemph_pair_stereo(const int *x, int n, int16_t *pcm_lr, int c, int m, int gain, unsigned pairmask) {
+    // x: this channel's samples (16-byte aligned), pcm_lr: interleaved L/R output (16-byte aligned), n % 8 == 0
+    for (int j = 0; j < n; j += 8) {
+        const int4 a = *reinterpret_cast<const int4 *>(x + j);
+        const int4 b = *reinterpret_cast<const int4 *>(x + j + 4);
+        const int xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned w[4];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            int t = wadd(xs[u], m);
+            m = mul16_32_q15(kPreemphCoef0, t);
+            int v = sig2word16(t);
+            if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+            if (u & 1) w[u >> 1] |= (unsigned)(v & 0xffff) << 16;
+            else w[u >> 1] = (unsigned)(v & 0xffff);
+        }
+        // even lane (L) keeps samples 0..3 and needs R0..R3; odd lane (R) keeps samples 4..7 and needs L4..L7
+        const unsigned o0 = __shfl_xor_sync(pairmask, c == 0 ? w[2] : w[0], 1);
+        const unsigned o1 = __shfl_xor_sync(pairmask, c == 0 ? w[3] : w[1], 1);
+        const unsigned l0 = c == 0 ? w[0] : o0, l1 = c == 0 ? w[1] : o1;   // two L samples per word
+        const unsigned r0 = c == 0 ? o0 : w[2], r1 = c == 0 ? o1 : w[3];   // two R samples per word
+        uint4 out;
+        out.x = __byte_perm(l0, r0, 0x5410);   // L_k   | R_k   << 16
+        out.y = __byte_perm(l0, r0, 0x7632);   // L_k+1 | R_k+1 << 16
+        out.z = __byte_perm(l1, r1, 0x5410);
+        out.w = __byte_perm(l1, r1, 0x7632);
+        *reinterpret_cast<uint4 *>(pcm_lr + (j + (c == 0 ? 0 : 4)) * 2) = out;
+    }
+    return m;
+}
+
 __global__ void __launch_bounds__(128)
 deemph_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n, int f0, int f1, int pcm_F, int pcm_f0, int cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,11 +184,25 @@ deemph_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n
     CbDecState *st = pool + slots[s];
     const int channels = st->channels;
     if (c >= channels) return;
+    const int ds = st->downsample;
+    const int gain = st->decode_gain ? celt_exp2(s16(mul16_16_p15(21771, st->decode_gain))) : 0;   // QCONST16(6.48814081e-4f, 25)
+    const unsigned pairmask = 3u << ((threadIdx.x & 31) & ~1);
+    const bool paired = channels == 2 && ds == 1;
+    int m = st->preemph_memD[c];
     for (int f = f0; f < f1; f++) {
         const size_t slot = (size_t)s * ir.Fc + (f - f0);
         int16_t *out = pcm + ((size_t)s * pcm_F + (f - pcm_f0)) * cap * channels;
-        opus_deemph_packet(st, c, ir.sig + slot * ir.sigstride, ir.range[slot], out, cap);
+        const CbSigRange rg = ir.range[slot];
+        if (rg.end <= rg.begin) continue;
+        const int *x = ir.sig + slot * ir.sigstride + c * (cap * ds) + rg.begin;
+        const int cnt = rg.end - rg.begin;
+        int16_t *y0 = out + (rg.begin / ds) * channels;
+        if (paired && (cnt & 7) == 0 && ((((uintptr_t)x) | ((uintptr_t)y0)) & 15) == 0)
+            m = deemph_pair_stereo(x, cnt, y0, c, m, gain, pairmask);
+        else
+            m = deemphasis_channel(x, cnt, y0 + c, channels, ds, m, gain);
     }
+    st->preemph_memD[c] = m;
 }
 
 // state staging <-> pool
@@ -233,6 +280,12 @@ struct Ctx {
     PinBuf h_stage, h_slots, h_misc;
     long long launches = 0;
     float last_ms = 0.f;
+    // per-stage timing: one event pair per launch, folded into the totals at synchronize time
+    struct Timed { cudaEvent_t a, b; int stage; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> ev_pool;
+    double stage_ms[3] = {0, 0, 0};
+    long long stage_launches[3] = {0, 0, 0};
     int smem_per_block = 0;
 };
 Ctx g;
@@ -249,10 +302,15 @@ bool ctx_init_locked() {
     }
     if (g.device >= ndev) g.device = 0;
     if (cudaSetDevice(g.device) != cudaSuccess) return false;
-    if (cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
-    if (cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
-    if (cudaStreamCreateWithFlags(&g.parse_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
-    if (cudaStreamCreateWithFlags(&g.synth_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    // Measured on B200: giving stages B/C priority interleaves their blocks into the stage A grid and is ~13 % SLOWER
+    // (cache interference); plain FIFO between the streams is the default, CB200_PRIO=1 re-enables the experiment.
+    if (!getenv("CB200_PRIO")) prio_hi = prio_lo;
+    if (cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&g.copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&g.parse_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&g.synth_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return false;
     cudaEventCreate(&g.ev0);
     cudaEventCreate(&g.ev1);
     for (int i = 0; i < 2; i++) {
@@ -420,6 +478,28 @@ int sync_states_locked(OpusDecoder **st, int n, bool release) {
     return OPUS_OK;
 }
 
+cudaEvent_t timing_event() {
+    if (!g.ev_pool.empty()) { cudaEvent_t e = g.ev_pool.back(); g.ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void timing_begin(int stage, cudaStream_t s) {
+    Ctx::Timed t{timing_event(), timing_event(), stage};
+    cudaEventRecord(t.a, s);
+    g.timed.push_back(t);
+}
+void timing_end(cudaStream_t s) { cudaEventRecord(g.timed.back().b, s); }
+void timing_fold() {   // call only when all streams are idle
+    for (auto &t : g.timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { g.stage_ms[t.stage] += ms; g.stage_launches[t.stage]++; }
+        g.ev_pool.push_back(t.a);
+        g.ev_pool.push_back(t.b);
+    }
+    g.timed.clear();
+}
+
 // Geometry of one call: chunking of the time axis and the IR buffers behind it.
 struct Plan {
     int n, F, cap, fec, kmax, xstride, sigstride, Fc, nchunks, R;
@@ -475,19 +555,25 @@ void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_d
         cudaStreamWaitEvent(g.synth_stream, g.ev_call, 0);
     }
     if (c >= 2) cudaStreamWaitEvent(g.parse_stream, g.ev_synth[b], 0);
+    timing_begin(0, g.parse_stream);
     parse_kernel<<<(unsigned)((threads + CB_PARSE_THREADS - 1) / CB_PARSE_THREADS), CB_PARSE_THREADS, 0, g.parse_stream>>>(
         g.pool, d_slots, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v, (ParseScratch *)g.d_scratch.p);
+    timing_end(g.parse_stream);
     cudaEventRecord(g.ev_parse[b], g.parse_stream);
     // stage B(c): after A(c); its staging buffer b must have been drained by C(c-2)
     cudaStreamWaitEvent(g.synth_stream, g.ev_parse[b], 0);
     if (c >= 2) cudaStreamWaitEvent(g.synth_stream, g.ev_deemph[b], 0);
     if (pcm_free) cudaStreamWaitEvent(g.synth_stream, pcm_free, 0);   // stage B writes PCM too (leading zero frames)
+    timing_begin(1, g.synth_stream);
     synth_kernel<<<(pl.n + CB_WPB - 1) / CB_WPB, CB_WPB * 32, g.smem_per_block, g.synth_stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, pl.F, f0,
                                                                                                   f1, pcm_F, pcm_f0, pl.cap, d_rets);
+    timing_end(g.synth_stream);
     cudaEventRecord(g.ev_synth[b], g.synth_stream);
     // stage C(c) on the main stream (the one the caller synchronises / times)
     cudaStreamWaitEvent(g.stream, g.ev_synth[b], 0);
+    timing_begin(2, g.stream);
     deemph_kernel<<<(2 * pl.n + 127) / 128, 128, 0, g.stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, f0, f1, pcm_F, pcm_f0, pl.cap);
+    timing_end(g.stream);
     cudaEventRecord(g.ev_deemph[b], g.stream);
     g.launches += 3;
 }
@@ -510,7 +596,8 @@ int opus_b200_synchronize(void) {
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.copy_stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.parse_stream) != cudaSuccess || cudaStreamSynchronize(g.synth_stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
-    if (g.launches > 0) cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);   // last span kernel (events on g.stream)
+    if (g.launches > 0) cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);   // last call (events on g.stream)
+    timing_fold();
     return OPUS_OK;
 }
 void *opus_b200_stream(void) {
@@ -519,6 +606,17 @@ void *opus_b200_stream(void) {
     return (void *)g.stream;
 }
 long long opus_b200_kernel_launches(void) { return g.launches; }
+// Accumulated device time (ms, CUDA events around every launch on its own stream) and launch count per pipeline stage
+// (0 = parse, 1 = synth, 2 = de-emphasis) since the last reset.  Folded in at synchronisation points.
+int opus_b200_stage_times(double ms[3], long long launches[3], int reset) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    for (int i = 0; i < 3; i++) {
+        if (ms) ms[i] = g.stage_ms[i];
+        if (launches) launches[i] = g.stage_launches[i];
+        if (reset) { g.stage_ms[i] = 0; g.stage_launches[i] = 0; }
+    }
+    return OPUS_OK;
+}
 float opus_b200_last_kernel_ms(void) {
     std::lock_guard<std::mutex> lk(g.mu);
     return g.last_ms;
@@ -749,11 +847,13 @@ static int decode_span_host_locked(OpusDecoder **st, int n, int F, const unsigne
     cudaEventRecord(g.ev1, g.stream);
     cudaMemcpyAsync(ret, g.d_rets.p, sizeof(int) * NF, cudaMemcpyDeviceToHost, g.stream);
     mark_device_newer_locked(st, n);
-    if (cudaStreamSynchronize(g.stream) != cudaSuccess || cudaStreamSynchronize(g.copy_stream) != cudaSuccess) {
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess || cudaStreamSynchronize(g.copy_stream) != cudaSuccess ||
+        cudaStreamSynchronize(g.parse_stream) != cudaSuccess || cudaStreamSynchronize(g.synth_stream) != cudaSuccess) {
         fprintf(stderr, "concentus_b200: CUDA failure in decode span: %s\n", cudaGetErrorString(cudaGetLastError()));
         return OPUS_INTERNAL_ERROR;
     }
     cudaEventElapsedTime(&g.last_ms, g.ev0, g.ev1);
+    timing_fold();
     if (!keep_resident) return sync_states_locked(st, n, true);
     return OPUS_OK;
 }

@@ -137,7 +137,9 @@ int opus_b200_init(int device);            /* select the CUDA device (default 0)
 int opus_b200_synchronize(void);
 void *opus_b200_stream(void);              /* the cudaStream_t the library launches on (for event timing) */
 long long opus_b200_kernel_launches(void); /* number of codec kernels launched so far by this process */
-/* Time of the last span kernel in milliseconds, from CUDA events recorded around it on the library stream. */
+/* Accumulated device time per pipeline stage (0 parse, 1 synth, 2 de-emphasis) in ms and launches, since the last reset. */
+int opus_b200_stage_times(double ms[3], long long launches[3], int reset);
+/* Time of the last span call in milliseconds, from CUDA events recorded around it on the library stream. */
 float opus_b200_last_kernel_ms(void);
 
 #ifdef __cplusplus
