@@ -156,7 +156,7 @@ def run_reference(args, rank, world):
 
 def F_chunk(seconds):
     F = seconds * FS // FRAME
-    for c in (250, 200, 100, 50, 25, 10, 5, 1):
+    for c in (1000, 750, 500, 250, 200, 100, 50, 25, 10, 5, 1):   # packets per e2e call: several pipeline chunks per call
         if F % c == 0:
             return c
     return 1

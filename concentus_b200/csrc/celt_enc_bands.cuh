@@ -1,0 +1,502 @@
+// celt_enc_bands.cuh — encoder side of the band loop: band energies, normalisation, spreading decision, stereo angle,
+// PVQ search and indexing, and quant_all_bands with encode = 1 (no resynthesis: this build has no RESYNTH).
+//
+// Restates opus-fix/celt/bands.c:48-61 (hysteresis_decision), :97-164 (compute_band_energies, normalise_bands), :337-373
+// (intensity_stereo, stereo_split), :428-519 (spreading_decision), the encode branches of :645-1502 (compute_theta,
+// quant_band_n1, quant_partition, quant_band, quant_band_stereo, quant_all_bands), celt/vq.c:70-113 (exp_rotation, dir=+1),
+// :161-325 (alg_quant), :376-408 (stereo_itheta) and celt/cwrs.c:440-461 (icwrs, encode_pulses).
+// Without resynthesis the encoder never folds: lowband, norm, fill and the collapse masks do not influence the bitstream
+// (bands.c:1413-1414 only advances lowband_offset under `resynth`), so they are not carried here.  Scalar code.
+#pragma once
+#include "celt_bands.cuh"
+#include "celt_pitch.cuh"
+
+namespace cb {
+
+// bands.c:48-61
+CB_DEV int hysteresis_decision(int val, const int16_t *thresholds, const int16_t *hysteresis, int N, int prev) {
+    int i;
+    for (i = 0; i < N; i++)
+        if (val < thresholds[i]) break;
+    if (i > prev && val < thresholds[prev] + hysteresis[prev]) i = prev;
+    if (i < prev && val > thresholds[prev - 1] - hysteresis[prev - 1]) i = prev;
+    return i;
+}
+
+// bands.c:97-143.  freq: C*N int32; bandE: [c*21+i]
+CB_DEV_NOINLINE void compute_band_energies(const int *freq, int *bandE, int end, int C, int LM) {
+    const int N = kShortMdct << LM;
+    for (int c = 0; c < C; c++) {
+        for (int i = 0; i < end; i++) {
+            const int lo = kEBands[i] << LM, hi = kEBands[i + 1] << LM;
+            const int *x = freq + c * N;
+            int maxval = maxabs32(x + lo, hi - lo);
+            if (maxval > 0) {
+                int shift = celt_ilog2(maxval) - 14 + (((kLogN[i] >> kBitRes) + LM + 1) >> 1);
+                int sum = 0;
+                if (shift > 0) {
+                    for (int j = lo; j < hi; j++) { int v = s16(x[j] >> shift); sum = mac16_16(sum, v, v); }
+                } else {
+                    for (int j = lo; j < hi; j++) { int v = s16(shl32(x[j], -shift)); sum = mac16_16(sum, v, v); }
+                }
+                bandE[i + c * kNbEBands] = wadd(1, vshr32(celt_sqrt(sum), -shift));
+            } else {
+                bandE[i + c * kNbEBands] = 1;
+            }
+        }
+    }
+}
+
+// bands.c:146-164
+CB_DEV_NOINLINE void normalise_bands(const int *freq, int16_t *X, const int *bandE, int end, int C, int M) {
+    const int N = M * kShortMdct;
+    for (int c = 0; c < C; c++) {
+        for (int i = 0; i < end; i++) {
+            int shift = celt_zlog2(bandE[i + c * kNbEBands]) - 13;
+            int E = s16(vshr32(bandE[i + c * kNbEBands], shift));
+            int g = s16(celt_rcp(shl32(E, 3)));
+            for (int j = M * kEBands[i]; j < M * kEBands[i + 1]; j++)
+                X[j + c * N] = (int16_t)mul16_16_q15(s16(vshr32(freq[j + c * N], shift - 1)), g);
+        }
+    }
+}
+
+// bands.c:428-519
+CB_DEV_NOINLINE int spreading_decision(const int16_t *X, int *average, int last_decision, int *hf_average, int *tapset_decision,
+                                       int update_hf, int end, int C, int M) {
+    int sum = 0, nbBands = 0, hf_sum = 0;
+    const int N0 = M * kShortMdct;
+    if (M * (kEBands[end] - kEBands[end - 1]) <= 8) return kSpreadNone;
+    for (int c = 0; c < C; c++) {
+        for (int i = 0; i < end; i++) {
+            const int16_t *x = X + M * kEBands[i] + c * N0;
+            const int N = M * (kEBands[i + 1] - kEBands[i]);
+            if (N <= 8) continue;
+            int t0 = 0, t1 = 0, t2 = 0;
+            for (int j = 0; j < N; j++) {
+                int x2N = mul16_16(mul16_16_q15(x[j], x[j]), N);
+                if (x2N < 2048) t0++;
+                if (x2N < 512) t1++;
+                if (x2N < 128) t2++;
+            }
+            if (i > kNbEBands - 4) hf_sum += (int)udiv((unsigned)(32 * (t1 + t0)), (unsigned)N);
+            int tmp = (2 * t2 >= N) + (2 * t1 >= N) + (2 * t0 >= N);
+            sum += tmp * 256;
+            nbBands++;
+        }
+    }
+    if (update_hf) {
+        if (hf_sum) hf_sum = (int)udiv((unsigned)hf_sum, (unsigned)(C * (4 - kNbEBands + end)));
+        *hf_average = (*hf_average + hf_sum) >> 1;
+        hf_sum = *hf_average;
+        if (*tapset_decision == 2) hf_sum += 4;
+        else if (*tapset_decision == 0) hf_sum -= 4;
+        if (hf_sum > 22) *tapset_decision = 2;
+        else if (hf_sum > 18) *tapset_decision = 1;
+        else *tapset_decision = 0;
+    }
+    sum = (int)udiv((unsigned)sum, (unsigned)nbBands);
+    sum = (sum + *average) >> 1;
+    *average = sum;
+    sum = (3 * sum + (((3 - last_decision) << 7) + 64) + 2) >> 2;
+    if (sum < 80) return kSpreadAggressive;
+    if (sum < 256) return kSpreadNormal;
+    if (sum < 384) return kSpreadLight;
+    return kSpreadNone;
+}
+
+// vq.c:376-408
+CB_DEV_NOINLINE int stereo_itheta(const int16_t *X, const int16_t *Y, int stereo, int N) {
+    int Emid = 1, Eside = 1;
+    if (stereo) {
+        for (int i = 0; i < N; i++) {
+            int m = s16((X[i] >> 1) + (Y[i] >> 1));
+            int s = s16((X[i] >> 1) - (Y[i] >> 1));
+            Emid = mac16_16(Emid, m, m);
+            Eside = mac16_16(Eside, s, s);
+        }
+    } else {
+        Emid = wadd(Emid, inner_prod16(X, X, N));
+        Eside = wadd(Eside, inner_prod16(Y, Y, N));
+    }
+    int mid = s16(celt_sqrt(Emid));
+    int side = s16(celt_sqrt(Eside));
+    return mul16_16_q15(20861, celt_atan2p(side, mid));   // QCONST16(0.63662f,15)
+}
+
+// bands.c:337-360
+CB_DEV_NOINLINE void intensity_stereo(int16_t *X, const int16_t *Y, const int *bandE, int i, int N) {
+    int shift = celt_zlog2(imax(bandE[i], bandE[i + kNbEBands])) - 13;
+    int left = s16(vshr32(bandE[i], shift));
+    int right = s16(vshr32(bandE[i + kNbEBands], shift));
+    int norm = s16(1 + celt_sqrt(wadd(1, wadd(mul16_16(left, left), mul16_16(right, right)))));
+    int a1 = s16(shl32(left, 14) / norm);
+    int a2 = s16(shl32(right, 14) / norm);
+    for (int j = 0; j < N; j++) X[j] = (int16_t)(mac16_16(mul16_16(a1, X[j]), a2, Y[j]) >> 14);
+}
+// bands.c:362-373
+CB_DEV_NOINLINE void stereo_split(int16_t *X, int16_t *Y, int N) {
+    for (int j = 0; j < N; j++) {
+        int l = mul16_16(23170, X[j]);
+        int r = mul16_16(23170, Y[j]);
+        X[j] = (int16_t)(wadd(l, r) >> 15);
+        Y[j] = (int16_t)(wsub(r, l) >> 15);
+    }
+}
+
+// exp_rotation, encoder direction (vq.c:70-113 with dir = +1)
+CB_DEV void exp_rotation_enc(int16_t *X, int len, int stride, int K, int spread) {
+    if (2 * K >= len || spread == kSpreadNone) return;
+    int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
+    int gain = s16(celt_div(mul16_16(32767, len), len + factor * K));
+    int theta = mul16_16_q15(gain, gain) >> 1;
+    int c = celt_cos_norm(theta);
+    int s = celt_cos_norm(s16(32767 - theta));
+    int stride2 = 0;
+    if (len >= 8 * stride) {
+        stride2 = 1;
+        while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+    }
+    len = (int)udiv((unsigned)len, (unsigned)stride);
+    for (int i = 0; i < stride; i++) {
+        int16_t *x = X + i * len;
+        exp_rotation1(x, len, 1, c, s16(-s));
+        if (stride2) exp_rotation1(x, len, stride2, s, s16(-c));
+    }
+}
+
+// icwrs (cwrs.c:440-456)
+CB_DEV unsigned pvq_encode_index(int n, const int16_t *y) {
+    int j = n - 1;
+    unsigned i = y[j] < 0;
+    int k = iabs(y[j]);
+    do {
+        j--;
+        i += pvq_u(n - j, k);
+        k += iabs(y[j]);
+        if (y[j] < 0) i += pvq_u(n - j, k + 1);
+    } while (j > 0);
+    return i;
+}
+
+// Scratch of the PVQ search: y (doubled pulses), iy (pulses), sign, per band (N <= 176)
+struct PvqScratch {
+    int16_t y[176], iy[176];
+    int8_t sign[176];
+};
+
+// alg_quant (vq.c:161-325), no resynthesis
+CB_DEV_NOINLINE void alg_quant(int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
+    int16_t *y = ps.y, *iy = ps.iy;
+    int8_t *signx = ps.sign;
+    exp_rotation_enc(X, N, B, K, spread);
+    int sum = 0;
+    for (int j = 0; j < N; j++) {
+        if (X[j] > 0) signx[j] = 1;
+        else { signx[j] = -1; X[j] = (int16_t)(-X[j]); }
+        iy[j] = 0;
+        y[j] = 0;
+    }
+    int xy = 0;
+    int yy = 0;   // opus_val16 in the reference: truncated after every update
+    int pulsesLeft = K;
+    if (K > (N >> 1)) {
+        for (int j = 0; j < N; j++) sum = wadd(sum, X[j]);
+        if (sum <= K) {
+            X[0] = 16384;
+            for (int j = 1; j < N; j++) X[j] = 0;
+            sum = 16384;
+        }
+        int rcp = s16(mul16_32_q16(K - 1, celt_rcp(sum)));
+        for (int j = 0; j < N; j++) {
+            int v = mul16_16_q15(X[j], rcp);
+            iy[j] = (int16_t)v;
+            y[j] = (int16_t)v;
+            yy = s16(mac16_16(yy, y[j], y[j]));
+            xy = mac16_16(xy, X[j], y[j]);
+            y[j] = (int16_t)(y[j] * 2);
+            pulsesLeft -= v;
+        }
+    }
+    if (pulsesLeft > N + 3) {
+        int tmp = s16(pulsesLeft);
+        yy = s16(mac16_16(yy, tmp, tmp));
+        yy = s16(mac16_16(yy, tmp, y[0]));
+        iy[0] = (int16_t)(iy[0] + pulsesLeft);
+        pulsesLeft = 0;
+    }
+    for (int i = 0; i < pulsesLeft; i++) {
+        int best_id = 0;
+        int best_num = -32767;
+        int best_den = 0;
+        const int rshift = 1 + celt_ilog2(K - pulsesLeft + i + 1);
+        yy = s16(wadd(yy, 1));
+        for (int j = 0; j < N; j++) {
+            int Rxy = s16(wadd(xy, X[j]) >> rshift);
+            int Ryy = s16(yy + y[j]);
+            Rxy = s16(mul16_16_q15(Rxy, Rxy));
+            if (mul16_16(best_den, Rxy) > mul16_16(Ryy, best_num)) {
+                best_den = Ryy;
+                best_num = Rxy;
+                best_id = j;
+            }
+        }
+        xy = wadd(xy, X[best_id]);
+        yy = s16(yy + y[best_id]);
+        y[best_id] = (int16_t)(y[best_id] + 2);
+        iy[best_id]++;
+    }
+    for (int j = 0; j < N; j++) {
+        X[j] = (int16_t)mul16_16(signx[j], X[j]);
+        if (signx[j] < 0) iy[j] = (int16_t)(-iy[j]);
+    }
+    enc.uint_(pvq_encode_index(N, iy), pvq_v(N, K));
+}
+
+struct EncBandCtx {
+    EcEnc ec;
+    PvqScratch *ps;
+    int16_t *tmp;        // hadamard staging, >= 176 int16
+    const int *bandE;
+    int i, intensity, spread, tf_change;
+    int remaining_bits;
+};
+
+// compute_theta, encoder half (bands.c:645-817)
+CB_DEV void compute_theta_enc(EncBandCtx &ctx, SplitCtx &sctx, int16_t *X, int16_t *Y, int N, int *b, int B, int B0, int LM, int stereo) {
+    EcEnc &ec = ctx.ec;
+    int inv = 0;
+    int pulse_cap = kLogN[ctx.i] + LM * (1 << kBitRes);
+    int offset = (pulse_cap >> 1) - (stereo && N == 2 ? kQThetaOffsetTwoPhase : kQThetaOffset);
+    int qn = compute_qn(N, *b, offset, pulse_cap, stereo);
+    if (stereo && ctx.i >= ctx.intensity) qn = 1;
+    int itheta = stereo_itheta(X, Y, stereo, N);
+    int tell = (int)ec.tell_frac();
+    if (qn != 1) {
+        itheta = (itheta * qn + 8192) >> 14;
+        if (stereo && N > 2) {
+            const int p0 = 3;
+            int x = itheta, x0 = qn / 2;
+            unsigned ft = (unsigned)(p0 * (x0 + 1) + x0);
+            ec.encode((unsigned)(x <= x0 ? p0 * x : (x - 1 - x0) + (x0 + 1) * p0),
+                      (unsigned)(x <= x0 ? p0 * (x + 1) : (x - x0) + (x0 + 1) * p0), ft);
+        } else if (B0 > 1 || stereo) {
+            ec.uint_((unsigned)itheta, (unsigned)qn + 1);
+        } else {
+            int ft = ((qn >> 1) + 1) * ((qn >> 1) + 1);
+            int fs = itheta <= (qn >> 1) ? itheta + 1 : qn + 1 - itheta;
+            int fl = itheta <= (qn >> 1) ? itheta * (itheta + 1) >> 1 : ft - ((qn + 1 - itheta) * (qn + 2 - itheta) >> 1);
+            ec.encode((unsigned)fl, (unsigned)(fl + fs), (unsigned)ft);
+        }
+        itheta = (int)udiv((unsigned)(itheta * 16384), (unsigned)qn);
+        if (stereo) {
+            if (itheta == 0) intensity_stereo(X, Y, ctx.bandE, ctx.i, N);
+            else stereo_split(X, Y, N);
+        }
+    } else if (stereo) {
+        inv = itheta > 8192;
+        if (inv)
+            for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
+        intensity_stereo(X, Y, ctx.bandE, ctx.i, N);
+        if (*b > 2 << kBitRes && ctx.remaining_bits > 2 << kBitRes) ec.bit_logp(inv, 2);
+        else inv = 0;
+        itheta = 0;
+    }
+    int qalloc = (int)ec.tell_frac() - tell;
+    *b -= qalloc;
+    int imid, iside, delta;
+    if (itheta == 0) { imid = 32767; iside = 0; delta = -16384; }
+    else if (itheta == 16384) { imid = 0; iside = 32767; delta = 16384; }
+    else {
+        imid = bitexact_cos(s16(itheta));
+        iside = bitexact_cos(s16(16384 - itheta));
+        delta = frac_mul16((N - 1) << 7, bitexact_log2tan(iside, imid));
+    }
+    sctx.inv = inv; sctx.imid = imid; sctx.iside = iside; sctx.delta = delta; sctx.itheta = itheta; sctx.qalloc = qalloc;
+}
+
+CB_DEV void quant_band_n1_enc(EncBandCtx &ctx, int16_t *X, int16_t *Y) {
+    int16_t *x = X;
+    const int nch = Y != nullptr ? 2 : 1;
+    for (int c = 0; c < nch; c++) {
+        if (ctx.remaining_bits >= 1 << kBitRes) {
+            ctx.ec.bits((unsigned)(x[0] < 0), 1);
+            ctx.remaining_bits -= 1 << kBitRes;
+        }
+        x = Y;
+    }
+}
+
+// quant_partition, encode (bands.c:864-1040) as an explicit walker (see celt_bands.cuh)
+struct EncPartFrame {
+    int16_t *X, *Y;
+    int N, b, B, LM;
+    int mbits, sbits, itheta, rebalance0, mid_first, stage;
+};
+
+CB_DEV void quant_partition_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B, int LM) {
+    EncPartFrame st[5];
+    int sp = 0;
+    st[0].X = X; st[0].N = N; st[0].b = b; st[0].B = B; st[0].LM = LM; st[0].stage = 0;
+    while (sp >= 0) {
+        EncPartFrame &f = st[sp];
+        if (f.stage == 0) {
+            const uint8_t *cache = pulse_cache(ctx.i, f.LM);
+            if (f.LM != -1 && f.b > cache[cache[0]] + 12 && f.N > 2) {
+                SplitCtx s;
+                const int n = f.N >> 1, lm = f.LM - 1, B0 = f.B;
+                const int Bn = (B0 + 1) >> 1;
+                int bb = f.b;
+                f.Y = f.X + n;
+                compute_theta_enc(ctx, s, f.X, f.Y, n, &bb, Bn, B0, lm, 0);
+                int delta = s.delta;
+                const int itheta = s.itheta;
+                if (B0 > 1 && (itheta & 0x3fff)) {
+                    if (itheta > 8192) delta -= delta >> (4 - lm);
+                    else delta = imin(0, delta + (n << kBitRes >> (5 - lm)));
+                }
+                const int mbits = imax(0, imin(bb, (bb - delta) / 2));
+                const int sbits = bb - mbits;
+                ctx.remaining_bits -= s.qalloc;
+                f.mbits = mbits; f.sbits = sbits; f.itheta = itheta; f.rebalance0 = ctx.remaining_bits;
+                f.N = n; f.LM = lm; f.B = Bn;
+                f.mid_first = mbits >= sbits;
+                f.stage = 1;
+                EncPartFrame &c = st[sp + 1];
+                c.N = n; c.B = Bn; c.LM = lm; c.stage = 0;
+                if (f.mid_first) { c.X = f.X; c.b = mbits; }
+                else { c.X = f.Y; c.b = sbits; }
+                sp++;
+            } else {
+                int q = bits2pulses(ctx.i, f.LM, f.b);
+                int curr_bits = pulses2bits(ctx.i, f.LM, q);
+                ctx.remaining_bits -= curr_bits;
+                while (ctx.remaining_bits < 0 && q > 0) {
+                    ctx.remaining_bits += curr_bits;
+                    q--;
+                    curr_bits = pulses2bits(ctx.i, f.LM, q);
+                    ctx.remaining_bits -= curr_bits;
+                }
+                if (q != 0) alg_quant(f.X, f.N, get_pulses(q), ctx.spread, f.B, ctx.ec, *ctx.ps);
+                sp--;
+            }
+        } else if (f.stage == 1) {
+            EncPartFrame &c = st[sp + 1];
+            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
+            if (f.mid_first) {
+                int rebalance = f.mbits - (f.rebalance0 - ctx.remaining_bits);
+                if (rebalance > 3 << kBitRes && f.itheta != 0) f.sbits += rebalance - (3 << kBitRes);
+                c.X = f.Y; c.b = f.sbits;
+            } else {
+                int rebalance = f.sbits - (f.rebalance0 - ctx.remaining_bits);
+                if (rebalance > 3 << kBitRes && f.itheta != 16384) f.mbits += rebalance - (3 << kBitRes);
+                c.X = f.X; c.b = f.mbits;
+            }
+            f.stage = 2;
+            sp++;
+        } else {
+            sp--;
+        }
+    }
+}
+
+// quant_band, encode (bands.c:1044-1170 without the resynthesis tail)
+CB_DEV void quant_band_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B, int LM) {
+    int N_B = N, B0 = B;
+    int recombine = 0;
+    int tf_change = ctx.tf_change;
+    const int longBlocks = B0 == 1;
+    N_B = (int)udiv((unsigned)N_B, (unsigned)B);
+    if (N == 1) { quant_band_n1_enc(ctx, X, nullptr); return; }
+    if (tf_change > 0) recombine = tf_change;
+    for (int k = 0; k < recombine; k++) haar1(X, N >> k, 1 << k);
+    B >>= recombine;
+    N_B <<= recombine;
+    while ((N_B & 1) == 0 && tf_change < 0) {
+        haar1(X, N_B, B);
+        B <<= 1;
+        N_B >>= 1;
+        tf_change++;
+    }
+    B0 = B;
+    if (B0 > 1) deinterleave_hadamard(X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
+    quant_partition_enc(ctx, X, N, b, B, LM);
+}
+
+// quant_all_bands with encode = 1 (bands.c:1337-1502) and quant_band_stereo (bands.c:1176-1335) folded in
+CB_DEV void quant_all_bands_enc(int start, int end, int16_t *X_, int16_t *Y_, const int *bandE, const int *pulses, int shortBlocks,
+                                int spread, int dual_stereo, int intensity, const int *tf_res, int total_bits, int balance,
+                                EcEnc &ec_io, int LM, int codedBands, PvqScratch *ps, int16_t *tmp) {
+    const int M = 1 << LM;
+    const int B = shortBlocks ? M : 1;
+    EncBandCtx ctx;
+    ctx.ec = ec_io; ctx.ps = ps; ctx.tmp = tmp; ctx.bandE = bandE;
+    ctx.intensity = intensity; ctx.spread = spread;
+    for (int i = start; i < end; i++) {
+        ctx.i = i;
+        int16_t *X = X_ + M * kEBands[i];
+        int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;
+        const int N = M * kEBands[i + 1] - M * kEBands[i];
+        const int tell = (int)ctx.ec.tell_frac();
+        if (i != start) balance -= tell;
+        const int remaining_bits = total_bits - tell - 1;
+        ctx.remaining_bits = remaining_bits;
+        int b;
+        if (i <= codedBands - 1) {
+            int curr_balance = sudiv(balance, imin(3, codedBands - i));
+            b = imax(0, imin(16383, imin(remaining_bits + 1, pulses[i] + curr_balance)));
+        } else {
+            b = 0;
+        }
+        ctx.tf_change = tf_res[i];
+        if (dual_stereo && i == intensity) dual_stereo = 0;
+        if (dual_stereo) {
+            quant_band_enc(ctx, X, N, b / 2, B, LM);
+            quant_band_enc(ctx, Y, N, b / 2, B, LM);
+        } else if (Y != nullptr) {
+            if (N == 1) {
+                quant_band_n1_enc(ctx, X, Y);
+            } else {
+                SplitCtx s;
+                int bs = b;
+                compute_theta_enc(ctx, s, X, Y, N, &bs, B, B, LM, 1);
+                if (N == 2) {
+                    int mbits = bs, sbits = 0;
+                    if (s.itheta != 0 && s.itheta != 16384) sbits = 1 << kBitRes;
+                    mbits -= sbits;
+                    const int c = s.itheta > 8192;
+                    ctx.remaining_bits -= s.qalloc + sbits;
+                    int16_t *x2 = c ? Y : X;
+                    int16_t *y2 = c ? X : Y;
+                    if (sbits) {
+                        int sign = wsub(wmul(x2[0], y2[1]), wmul(x2[1], y2[0])) < 0;
+                        ctx.ec.bits((unsigned)sign, 1);
+                    }
+                    quant_band_enc(ctx, x2, N, mbits, B, LM);
+                } else {
+                    int mbits = imax(0, imin(bs, (bs - s.delta) / 2));
+                    int sbits = bs - mbits;
+                    ctx.remaining_bits -= s.qalloc;
+                    int rebalance = ctx.remaining_bits;
+                    if (mbits >= sbits) {
+                        quant_band_enc(ctx, X, N, mbits, B, LM);
+                        rebalance = mbits - (rebalance - ctx.remaining_bits);
+                        if (rebalance > 3 << kBitRes && s.itheta != 0) sbits += rebalance - (3 << kBitRes);
+                        quant_band_enc(ctx, Y, N, sbits, B, LM);
+                    } else {
+                        quant_band_enc(ctx, Y, N, sbits, B, LM);
+                        rebalance = sbits - (rebalance - ctx.remaining_bits);
+                        if (rebalance > 3 << kBitRes && s.itheta != 16384) mbits += rebalance - (3 << kBitRes);
+                        quant_band_enc(ctx, X, N, mbits, B, LM);
+                    }
+                }
+            }
+        } else {
+            quant_band_enc(ctx, X, N, b, B, LM);
+        }
+        balance += pulses[i] + tell;
+    }
+    ec_io = ctx.ec;
+}
+
+}  // namespace cb

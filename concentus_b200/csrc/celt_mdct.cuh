@@ -260,4 +260,64 @@ CB_DEV void imdct_assemble(TM tm, int *out, int B, int shift, const int *fftbuf)
     tm.sync();
 }
 
+// Forward MDCT of one block (mdct.c:121-259): in[N2 + overlap] (windowed fold of the first/last overlap/2 pairs), out with
+// `stride` interleave.  f: scratch for N2 ints (fold result), f2: scratch for N2 ints (N4 complex, FFT buffer).
+template <class TM>
+CB_DEV void mdct_forward(TM tm, const int *in, int *out, int shift, int stride, int *f, int *f2) {
+    const int N2 = (kMaxFrame * 2 >> shift) >> 1;
+    const int N4 = N2 >> 1;
+    int trig_off = 0;
+    for (int i = 0, n = kMaxFrame * 2; i < shift; i++) { n >>= 1; trig_off += n; }
+    const int16_t *t = kMdctTwiddles + trig_off;
+    const int16_t *bitrev = fft_bitrev(shift);
+    const FftPlan &pl = kFftPlan[shift];
+    const int scale_shift = pl.scale_shift - 1;
+    const int ov = kOverlap, q = (ov + 3) >> 2;
+    // window, shuffle, fold (mdct.c:155-203): pair i produces f[2i], f[2i+1]
+    CB_TEAM_FOR(i, N4, tm) {
+        const int *xp1 = in + (ov >> 1) + 2 * i;
+        const int *xp2 = in + N2 - 1 + (ov >> 1) - 2 * i;
+        int re, im;
+        if (i < q) {
+            const int w1 = kWindow120[(ov >> 1) + 2 * i], w2 = kWindow120[(ov >> 1) - 1 - 2 * i];
+            re = wadd(smul(xp1[N2], w2), smul(*xp2, w1));
+            im = wsub(smul(*xp1, w1), smul(xp2[-N2], w2));
+        } else if (i < N4 - q) {
+            re = *xp2;
+            im = *xp1;
+        } else {
+            const int k = i - (N4 - q);
+            const int w1 = kWindow120[2 * k], w2 = kWindow120[ov - 1 - 2 * k];
+            re = wadd(wneg(smul(xp1[-N2], w1)), smul(*xp2, w2));
+            im = wadd(smul(*xp1, w2), smul(xp2[N2], w1));
+        }
+        f[2 * i] = re;
+        f[2 * i + 1] = im;
+    }
+    tm.sync();
+    // pre-rotation with scaling into bit-reversed order (mdct.c:205-227)
+    CB_TEAM_FOR(i, N4, tm) {
+        const int t0 = t[i], t1 = t[N4 + i];
+        const int re = f[2 * i], im = f[2 * i + 1];
+        int yr = wsub(smul(re, t0), smul(im, t1));
+        int yi = wadd(smul(im, t0), smul(re, t1));
+        yr = pshr32(mul16_32_q16(kFftScale, yr), scale_shift);
+        yi = pshr32(mul16_32_q16(kFftScale, yi), scale_shift);
+        const int rev = bitrev[i];
+        f2[2 * rev] = yr;
+        f2[2 * rev + 1] = yi;
+    }
+    tm.sync();
+    fft_inplace(tm, (Cpx *)f2, shift, 1);
+    // post-rotation (mdct.c:233-256)
+    CB_TEAM_FOR(i, N4, tm) {
+        const int fr = f2[2 * i], fi = f2[2 * i + 1];
+        const int yr = wsub(smul(fi, t[N4 + i]), smul(fr, t[i]));
+        const int yi = wadd(smul(fr, t[N4 + i]), smul(fi, t[i]));
+        out[stride * (2 * i)] = yr;
+        out[stride * (N2 - 1 - 2 * i)] = yi;
+    }
+    tm.sync();
+}
+
 }  // namespace cb

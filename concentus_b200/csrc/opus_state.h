@@ -46,3 +46,35 @@ typedef struct CbDecState {
     int16_t lpc[2 * CB_LPC_ORDER];
     int32_t decode_mem[2 * CB_DEC_MEM];
 } CbDecState;
+
+#define CB_COMB_MAXPERIOD 1024
+#define CB_ENC_DELAY_BUF 960   /* MAX_ENCODER_BUFFER (480) x 2 channels, src/opus_encoder.c:58 */
+
+/* Encoder state: Opus layer (src/opus_encoder.c:62-110, CELT-only subset) + CELT layer (celt/celt_encoder.c:60-128). */
+typedef struct CbEncState {
+    /* ---- Opus-layer configuration (survives OPUS_RESET_STATE) ---- */
+    int32_t application, channels, Fs;
+    int32_t force_channels, signal_type, user_bandwidth, max_bandwidth, user_forced_mode;
+    int32_t use_vbr, vbr_constraint, variable_duration, user_bitrate_bps, lsb_depth;
+    int32_t complexity, packet_loss_perc, prediction_disabled, inband_fec, dtx, delay_compensation, encoder_buffer;
+    int32_t voice_ratio, bitrate_bps;
+    /* ---- OPUS_ENCODER_RESET_START ---- */
+    int32_t stream_channels;
+    int32_t hybrid_stereo_width_Q14;
+    int32_t hp_mem[4];
+    int32_t mode, prev_mode, prev_channels, prev_framesize, bandwidth, first;
+    int32_t width_XX, width_XY, width_YY, width_smoothed, width_max_follower;   /* StereoWidthState */
+    int16_t delay_buffer[CB_ENC_DELAY_BUF];
+    uint32_t rangeFinal;
+    /* ---- CELT configuration (celt_encoder.c:62-80) ---- */
+    int32_t upsample, celt_force_intra, celt_disable_pf;
+    /* ---- CELT ENCODER_RESET_START (celt_encoder.c:84-113) ---- */
+    uint32_t rng;
+    int32_t spread_decision, delayedIntra, tonal_average, lastCodedBands, hf_average, tapset_decision;
+    int32_t prefilter_period, prefilter_gain, prefilter_tapset, consec_transient;
+    int32_t preemph_memE[2];
+    int32_t vbr_reservoir, vbr_drift, vbr_offset, vbr_count, overlap_max, stereo_saving, intensity, spec_avg;
+    int32_t in_mem[2 * CB_OVERLAP];
+    int32_t prefilter_mem[2 * CB_COMB_MAXPERIOD];
+    int16_t oldBandE[2 * CB_NB_EBANDS], oldLogE[2 * CB_NB_EBANDS], oldLogE2[2 * CB_NB_EBANDS];
+} CbEncState;
