@@ -37,6 +37,7 @@ struct SoloTeam {
     CB_MEM int max(int v) const { return v; }
     CB_MEM unsigned bor(unsigned v) const { return v; }
     CB_MEM int bcast(int v, int) const { return v; }
+    CB_MEM int exscan(int) const { return 0; }   // exclusive prefix sum over lanes (wrapping)
 };
 
 #if defined(__CUDACC__)
@@ -61,6 +62,15 @@ struct WarpTeam {
         return v;
     }
     CB_MEM int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    CB_MEM int exscan(int v) const {
+        unsigned inc = (unsigned)v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane_ >= o) inc += t;
+        }
+        return (int)(inc - (unsigned)v);
+    }
 };
 #endif
 

@@ -84,6 +84,24 @@ CB_TABLE FftPlan kFftPlan[4] = {
 };
 enum { kFftScale = 17476 };
 
+enum {
+    OPUS_OK_ = 0, OPUS_BAD_ARG_ = -1, OPUS_BUFFER_TOO_SMALL_ = -2, OPUS_INTERNAL_ERROR_ = -3,
+    OPUS_INVALID_PACKET_ = -4, OPUS_UNIMPLEMENTED_ = -5, OPUS_INVALID_STATE_ = -6, OPUS_ALLOC_FAIL_ = -7,
+};
+enum { kBwNarrow = 1101, kBwMedium = 1102, kBwWide = 1103, kBwSuperWide = 1104, kBwFull = 1105 };
+
+// bin (at LM=0 resolution) -> band, from eband5ms
+CB_TABLE uint8_t kBinToBand[100] = {
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 12, 12, 13, 13, 13, 13, 14, 14, 14, 14,
+    15, 15, 15, 15, 15, 15, 16, 16, 16, 16, 16, 16, 17, 17, 17, 17, 17, 17, 17, 17,
+    18, 18, 18, 18, 18, 18, 18, 18, 18, 18, 18, 18,
+    19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19, 19,
+    20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20, 20};
+
+// intensity_thresholds / intensity_histeresis (celt/celt_encoder.c:1973-1977)
+CB_TABLE int16_t kIntensityThresholds[21] = {1, 2, 3, 4, 5, 6, 7, 8, 16, 24, 36, 44, 50, 56, 62, 67, 72, 79, 88, 106, 134};
+CB_TABLE int16_t kIntensityHisteresis[21] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 3, 3, 4, 5, 6, 8, 8};
+
 CB_DEV const int16_t *fft_bitrev(int s) {
     return s == 0 ? kFftBitrev480 : s == 1 ? kFftBitrev240 : s == 2 ? kFftBitrev120 : kFftBitrev60;
 }

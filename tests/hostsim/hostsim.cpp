@@ -51,3 +51,39 @@ int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_
     return 0;
 }
 }
+
+// ---- encoder ----------------------------------------------------------------------------------------------------
+#include "../../concentus_b200/csrc/opus_encoder_dev.cuh"
+
+extern "C" {
+
+int hostsim_enc_state_size(void) { return (int)sizeof(CbEncState); }
+
+// Encode F frames of one stream with the 1-lane team.  cfg = {application, bitrate, vbr, cvbr, complexity, max_bytes,
+// force_channels, bandwidth} (the oracle harness's ref_enc_cfg).  out: F slots of `stride` bytes.
+int hostsim_encode_stream(const int16_t *pcm, int F, int frame_size, int channels, int Fs, const int *cfg, uint8_t *out, int stride,
+                          int32_t *lens, uint32_t *ranges) {
+    CbEncState *st = (CbEncState *)calloc(1, sizeof(CbEncState));
+    cb::EncScratch *S = (cb::EncScratch *)calloc(1, sizeof(cb::EncScratch));
+    if (cb::enc_state_init(st, Fs, channels, cfg[0]) != 0) return -1;
+    int dummy = 0;
+    cb::enc_ctl(st, 4002, cfg[1], &dummy);
+    cb::enc_ctl(st, 4006, cfg[2], &dummy);
+    cb::enc_ctl(st, 4020, cfg[3], &dummy);
+    cb::enc_ctl(st, 4010, cfg[4], &dummy);
+    if (cfg[6]) cb::enc_ctl(st, 4022, cfg[6], &dummy);
+    if (cfg[7]) cb::enc_ctl(st, 4008, cfg[7], &dummy);
+    cb::SoloTeam tm;
+    int rc = 0;
+    for (int f = 0; f < F; f++) {
+        int n = cb::opus_encode_frame(tm, st, *S, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * stride,
+                                      cfg[5] < stride ? cfg[5] : stride);
+        lens[f] = n;
+        if (n < 0) { rc = n; break; }
+        if (ranges) ranges[f] = st->rangeFinal;
+    }
+    free(S);
+    free(st);
+    return rc;
+}
+}
