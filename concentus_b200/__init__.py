@@ -39,8 +39,23 @@ EXPORTS = [
     "opus_packet_get_nb_channels", "opus_packet_get_nb_frames", "opus_packet_get_nb_samples",
     "opus_decoder_get_nb_samples", "opus_strerror", "opus_get_version_string", "opus_decode_batch", "opus_decode_span",
     "opus_decode_span_device", "opus_decoder_sync", "opus_b200_init", "opus_b200_synchronize", "opus_b200_stream",
-    "opus_b200_kernel_launches", "opus_b200_last_kernel_ms", "opus_b200_stage_times",
+    "opus_b200_kernel_launches", "opus_b200_last_kernel_ms", "opus_b200_stage_times", "opus_b200_device_index",
+    "opus_encoder_get_size", "opus_encoder_create", "opus_encoder_init", "opus_encode", "opus_encoder_ctl", "opus_encoder_destroy",
+    "opus_packet_pad", "opus_packet_unpad", "opus_encode_batch", "opus_encode_span", "opus_encode_span_device", "opus_encoder_sync",
+    "opus_b200_enc_synchronize", "opus_b200_enc_kernel_launches", "opus_b200_enc_last_kernel_ms",
 ]
+
+OPUS_APPLICATION_VOIP = 2048
+OPUS_APPLICATION_AUDIO = 2049
+OPUS_APPLICATION_RESTRICTED_LOWDELAY = 2051
+OPUS_AUTO = -1000
+OPUS_SET_BITRATE_REQUEST = 4002
+OPUS_SET_VBR_REQUEST = 4006
+OPUS_SET_BANDWIDTH_REQUEST = 4008
+OPUS_SET_COMPLEXITY_REQUEST = 4010
+OPUS_SET_VBR_CONSTRAINT_REQUEST = 4020
+OPUS_SET_FORCE_CHANNELS_REQUEST = 4022
+OPUS_SET_FORCE_MODE_REQUEST = 11002
 
 
 def lib():
@@ -68,6 +83,20 @@ def lib():
         L.opus_b200_kernel_launches.restype = C.c_longlong
         L.opus_b200_last_kernel_ms.restype = C.c_float
         L.opus_b200_stage_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.opus_encoder_create.restype = C.c_void_p
+        L.opus_encoder_create.argtypes = [C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.opus_encoder_init.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.c_int]
+        L.opus_encoder_destroy.argtypes = [C.c_void_p]
+        L.opus_encoder_destroy.restype = None
+        L.opus_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
+        L.opus_encode_span.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p]
+        L.opus_encode_span_device.argtypes = L.opus_encode_span.argtypes
+        L.opus_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int]
+        L.opus_encoder_sync.argtypes = [C.c_void_p, C.c_int]
+        L.opus_packet_pad.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.opus_packet_unpad.argtypes = [C.c_void_p, C.c_int32]
+        L.opus_b200_enc_kernel_launches.restype = C.c_longlong
+        L.opus_b200_enc_last_kernel_ms.restype = C.c_float
         _lib = L
     return _lib
 
@@ -115,6 +144,68 @@ class DecoderBatch:
         for i in range(self.n):
             if self.handles[i]:
                 L.opus_decoder_destroy(C.c_void_p(self.handles[i]))
+                self.handles[i] = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EncoderBatch:
+    """n independent encoders (same Fs / channels / settings) driven through the batch C ABI."""
+
+    def __init__(self, n, Fs=48000, channels=2, application=OPUS_APPLICATION_RESTRICTED_LOWDELAY, bitrate=OPUS_AUTO, vbr=1, cvbr=1,
+                 complexity=9, force_channels=0, bandwidth=0, force_mode=0):
+        L = lib()
+        self.n, self.Fs, self.channels = n, Fs, channels
+        err = C.c_int(0)
+        self.handles = (C.c_void_p * n)()
+        for i in range(n):
+            h = L.opus_encoder_create(Fs, channels, application, C.byref(err))
+            if not h:
+                raise RuntimeError("opus_encoder_create failed: %d" % err.value)
+            self.handles[i] = h
+            hp = C.c_void_p(h)
+            for req, v in ((OPUS_SET_BITRATE_REQUEST, bitrate), (OPUS_SET_VBR_REQUEST, vbr), (OPUS_SET_VBR_CONSTRAINT_REQUEST, cvbr),
+                           (OPUS_SET_COMPLEXITY_REQUEST, complexity)):
+                rc = L.opus_encoder_ctl(hp, req, C.c_int32(v))
+                if rc != OPUS_OK:
+                    raise RuntimeError("opus_encoder_ctl(%d, %d) -> %d" % (req, v, rc))
+            if force_channels:
+                L.opus_encoder_ctl(hp, OPUS_SET_FORCE_CHANNELS_REQUEST, C.c_int32(force_channels))
+            if bandwidth:
+                L.opus_encoder_ctl(hp, OPUS_SET_BANDWIDTH_REQUEST, C.c_int32(bandwidth))
+            if force_mode:
+                L.opus_encoder_ctl(hp, OPUS_SET_FORCE_MODE_REQUEST, C.c_int32(force_mode))
+
+    def encode_span(self, pcm, F, frame_size, max_data_bytes=1276):
+        """pcm: int16 [n*F*frame_size, channels] (stream-major).  Returns (data uint8 [n*F, max_data_bytes], lens int32 [n*F])."""
+        L = lib()
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.size == self.n * F * frame_size * self.channels
+        data = np.zeros((self.n * F, max_data_bytes), dtype=np.uint8)
+        lens = np.zeros(self.n * F, dtype=np.int32)
+        rc = L.opus_encode_span(self.handles, self.n, F, _p(pcm), frame_size, _p(data), max_data_bytes, _p(lens))
+        if rc != OPUS_OK:
+            raise RuntimeError("opus_encode_span: %s" % L.opus_strerror(rc).decode())
+        return data, lens
+
+    def final_ranges(self):
+        L = lib()
+        out = np.zeros(self.n, dtype=np.uint32)
+        v = C.c_uint32(0)
+        for i in range(self.n):
+            L.opus_encoder_ctl(C.c_void_p(self.handles[i]), OPUS_GET_FINAL_RANGE_REQUEST, C.byref(v))
+            out[i] = v.value
+        return out
+
+    def close(self):
+        L = lib()
+        for i in range(self.n):
+            if self.handles[i]:
+                L.opus_encoder_destroy(C.c_void_p(self.handles[i]))
                 self.handles[i] = None
 
     def __del__(self):

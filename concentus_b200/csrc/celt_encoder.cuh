@@ -69,7 +69,7 @@ struct EncScratch {
     CoarseScratch coarse;
     PvqScratch pvq;
     int16_t had_tmp[176];
-    int16_t pcm_buf[2 * kMaxFrame];                   // Opus layer: DC-rejected (and width-reduced) input of this frame
+    int16_t pcm_buf[2 * (kMaxFrame + 192)];           // Opus layer: delay-compensation samples + DC-rejected input of this frame
     EncVars v;
 };
 

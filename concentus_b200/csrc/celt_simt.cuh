@@ -15,7 +15,7 @@
 #define CB_DEV __device__ __forceinline__
 #define CB_MEM __device__ __forceinline__
 #define CB_MEM_NOINLINE __device__ __noinline__
-#define CB_DEV_NOINLINE __device__ __noinline__
+#define CB_DEV_NOINLINE static __device__ __noinline__
 #define CB_TABLE static __device__ const
 #define CB_CLZ(x) __clz((int)(x))
 #else

@@ -590,6 +590,12 @@ int opus_b200_init(int device) {
     if (!g.tried) g.device = device;
     return ctx_init_locked() ? OPUS_OK : OPUS_INTERNAL_ERROR;
 }
+// The device this process codes on (initialises the runtime); -1 when CUDA is unusable.  Used by the encoder half
+// (opus_enc_capi.cu) so both halves share one device selection.
+int opus_b200_device_index(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return ctx_init_locked() ? g.device : -1;
+}
 int opus_b200_synchronize(void) {
     std::lock_guard<std::mutex> lk(g.mu);
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;

@@ -1,0 +1,553 @@
+// opus_enc_capi.cu — encoder kernels and the encoder half of the C ABI of libconcentus_b200.so (include/opus_b200.h).
+//
+// Boundary: libopus's public encoder API (opus-fix/include/opus.h:171-328, src/opus_encoder.c:150-252,2007-2507) plus our
+// batch / span calls.  Host side = argument checks, ctl, state residency and copies; everything from the Opus-layer rate
+// decisions down to ec_enc_done runs on the device, one warp per stream, F frames per launch (the frames of a stream are
+// serially dependent through the encoder state; streams are independent).
+// There is NO CPU path: if CUDA is unusable every codec call returns OPUS_INTERNAL_ERROR.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/opus_b200.h"
+#include "opus_encoder_dev.cuh"
+
+using namespace cb;
+
+extern "C" int opus_b200_device_index(void);   // opus_capi.cu: the device opus_b200_init selected (initialises the runtime)
+
+// Caller-visible state block: pointer-free and memcpy-able like the reference's (tests/test_opus_encode.c:198,214).
+// Same residency protocol as OpusDecoder (opus_capi.cu).
+struct OpusEncoder {
+    uint32_t magic;
+    int32_t slot;
+    uint64_t gen;
+    int32_t host_current;
+    int32_t reserved;
+    CbEncState st;
+};
+static const uint32_t kEncMagic = 0x0B200E4Cu;
+
+#ifndef CB_ENC_WPB
+#define CB_ENC_WPB 4   // warps (= streams) per block
+#endif
+
+// One warp per stream, frames f0..f1 in order.  PCM of frame (s,f): pcm[(s*F+f)*frame_size*channels]; packet slot:
+// data[(s*F+f)*stride], at most max_bytes are written; rets[s*F+f] = packet length or error.
+__global__ void __launch_bounds__(CB_ENC_WPB * 32)
+encode_span_kernel(CbEncState *pool, const int *slots, EncScratch *scratch, const int16_t *pcm, uint8_t *data, int *rets, int n, int F,
+                   int frame_size, int max_bytes, int stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_ENC_WPB + warp;
+    if (s >= n) return;
+    CbEncState *st = pool + slots[s];
+    EncScratch &S = scratch[s];
+    const int channels = st->channels;
+    WarpTeam tm{lane};
+    for (int f = 0; f < F; f++) {
+        const size_t k = (size_t)s * F + f;
+        const int r = opus_encode_frame(tm, st, S, pcm + k * frame_size * channels, frame_size, data + k * stride, max_bytes);
+        if (lane == 0) rets[k] = r;
+        __syncwarp();
+    }
+}
+
+__global__ void enc_scatter_states_kernel(CbEncState *pool, const int *slots, const CbEncState *stage, int n) {
+    const int words = sizeof(CbEncState) / 4;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int *src = reinterpret_cast<const int *>(stage + k);
+        int *dst = reinterpret_cast<int *>(pool + slots[k]);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+}
+__global__ void enc_gather_states_kernel(const CbEncState *pool, const int *slots, CbEncState *stage, int n) {
+    const int words = sizeof(CbEncState) / 4;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int *src = reinterpret_cast<const int *>(pool + slots[k]);
+        int *dst = reinterpret_cast<int *>(stage + k);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+namespace {
+
+inline int hmin(int a, int b) { return a < b ? a : b; }
+
+struct SlotInfo { const void *owner; uint64_t gen; };
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+};
+struct PinBuf {
+    void *p = nullptr; size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+};
+
+struct EncCtx {
+    std::mutex mu;
+    bool tried = false, ok = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    CbEncState *pool = nullptr;
+    int pool_cap = 0;
+    std::vector<SlotInfo> reg;
+    std::vector<int> free_slots;
+    DevBuf d_slots, d_pcm, d_data, d_rets, d_stage, d_scratch;
+    PinBuf h_stage, h_slots;
+    long long launches = 0;
+    float last_ms = 0.f;
+    double total_ms = 0;
+};
+EncCtx e;
+enum { kStageStates = 128 };
+
+bool ctx_init_locked() {
+    if (e.tried) return e.ok;
+    e.tried = true;
+    const int dev = opus_b200_device_index();
+    if (dev < 0) return false;
+    if (cudaSetDevice(dev) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    cudaEventCreate(&e.ev0);
+    cudaEventCreate(&e.ev1);
+    if (!e.h_stage.reserve(sizeof(CbEncState) * kStageStates) || !e.d_stage.reserve(sizeof(CbEncState) * kStageStates)) return false;
+    e.ok = cudaGetLastError() == cudaSuccess;
+    return e.ok;
+}
+
+bool pool_reserve_locked(int need_total) {
+    if (need_total <= e.pool_cap) return true;
+    int ncap = e.pool_cap ? e.pool_cap : 64;
+    while (ncap < need_total) ncap *= 2;
+    CbEncState *np = nullptr;
+    if (cudaMalloc(&np, sizeof(CbEncState) * (size_t)ncap) != cudaSuccess) return false;
+    if (e.pool) {
+        cudaMemcpyAsync(np, e.pool, sizeof(CbEncState) * (size_t)e.pool_cap, cudaMemcpyDeviceToDevice, e.stream);
+        cudaStreamSynchronize(e.stream);
+        cudaFree(e.pool);
+    }
+    for (int i = ncap - 1; i >= e.pool_cap; i--) e.free_slots.push_back(i);
+    e.reg.resize(ncap, SlotInfo{nullptr, 0});
+    e.pool = np;
+    e.pool_cap = ncap;
+    return true;
+}
+
+inline bool resident(const OpusEncoder *d) {
+    return d->slot >= 0 && d->slot < e.pool_cap && e.reg[d->slot].owner == d && e.reg[d->slot].gen == d->gen;
+}
+
+int make_host_current_locked(OpusEncoder *d) {
+    if (d->host_current) return OPUS_OK;
+    if (d->slot < 0 || d->slot >= e.pool_cap || e.reg[d->slot].gen != d->gen) return OPUS_INVALID_STATE;
+    if (cudaMemcpyAsync(&d->st, e.pool + d->slot, sizeof(CbEncState), cudaMemcpyDeviceToHost, e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    d->host_current = 1;
+    return OPUS_OK;
+}
+
+void release_slot_locked(OpusEncoder *d) {
+    if (d->slot >= 0 && d->slot < e.pool_cap && e.reg[d->slot].owner == d) {
+        e.reg[d->slot].owner = nullptr;
+        e.reg[d->slot].gen++;
+        e.free_slots.push_back(d->slot);
+    }
+    d->slot = -1;
+}
+
+int make_resident_locked(OpusEncoder **st, int n, int *h_slots) {
+    int need_new = 0;
+    for (int i = 0; i < n; i++) {
+        OpusEncoder *d = st[i];
+        if (!d || d->magic != kEncMagic) return OPUS_BAD_ARG;
+        if (!resident(d)) need_new++;
+    }
+    if (n <= 64)
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++)
+                if (st[i] == st[j]) return OPUS_BAD_ARG;
+    const int in_use = e.pool_cap - (int)e.free_slots.size();
+    if (!pool_reserve_locked(in_use + need_new)) return OPUS_ALLOC_FAIL;
+    std::vector<int> up_idx;
+    for (int i = 0; i < n; i++) {
+        OpusEncoder *d = st[i];
+        if (resident(d)) {
+            if (d->host_current) up_idx.push_back(i);
+        } else {
+            if (!d->host_current) {
+                int rc = make_host_current_locked(d);
+                if (rc != OPUS_OK) return rc;
+            }
+            d->slot = e.free_slots.back();
+            e.free_slots.pop_back();
+            e.reg[d->slot].owner = d;
+            d->gen = ++e.reg[d->slot].gen;
+            up_idx.push_back(i);
+        }
+        h_slots[i] = d->slot;
+    }
+    CbEncState *hs = (CbEncState *)e.h_stage.p;
+    if (!e.d_slots.reserve(sizeof(int) * (size_t)(n > kStageStates ? n : kStageStates))) return OPUS_ALLOC_FAIL;
+    for (size_t base = 0; base < up_idx.size(); base += kStageStates) {
+        const int cnt = (int)((up_idx.size() - base) < (size_t)kStageStates ? (up_idx.size() - base) : kStageStates);
+        std::vector<int> sl(cnt);
+        for (int k = 0; k < cnt; k++) {
+            OpusEncoder *d = st[up_idx[base + k]];
+            memcpy(&hs[k], &d->st, sizeof(CbEncState));
+            sl[k] = d->slot;
+        }
+        cudaMemcpyAsync(e.d_stage.p, hs, sizeof(CbEncState) * (size_t)cnt, cudaMemcpyHostToDevice, e.stream);
+        cudaMemcpyAsync(e.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, e.stream);
+        enc_scatter_states_kernel<<<cnt, 256, 0, e.stream>>>(e.pool, (const int *)e.d_slots.p, (const CbEncState *)e.d_stage.p, cnt);
+        if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    }
+    return OPUS_OK;
+}
+
+void mark_device_newer_locked(OpusEncoder **st, int n) {
+    for (int i = 0; i < n; i++) {
+        OpusEncoder *d = st[i];
+        d->gen = ++e.reg[d->slot].gen;
+        d->host_current = 0;
+    }
+}
+
+int sync_states_locked(OpusEncoder **st, int n, bool release) {
+    std::vector<int> idx;
+    for (int i = 0; i < n; i++) {
+        OpusEncoder *d = st[i];
+        if (!d || d->magic != kEncMagic) return OPUS_BAD_ARG;
+        if (!d->host_current) {
+            if (!resident(d)) {
+                int rc = make_host_current_locked(d);
+                if (rc != OPUS_OK) return rc;
+            } else {
+                idx.push_back(i);
+            }
+        }
+    }
+    CbEncState *hs = (CbEncState *)e.h_stage.p;
+    if (!e.d_slots.reserve(sizeof(int) * (size_t)kStageStates)) return OPUS_ALLOC_FAIL;
+    for (size_t base = 0; base < idx.size(); base += kStageStates) {
+        const int cnt = (int)((idx.size() - base) < (size_t)kStageStates ? (idx.size() - base) : kStageStates);
+        std::vector<int> sl(cnt);
+        for (int k = 0; k < cnt; k++) sl[k] = st[idx[base + k]]->slot;
+        cudaMemcpyAsync(e.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, e.stream);
+        enc_gather_states_kernel<<<cnt, 256, 0, e.stream>>>(e.pool, (const int *)e.d_slots.p, (CbEncState *)e.d_stage.p, cnt);
+        cudaMemcpyAsync(hs, e.d_stage.p, sizeof(CbEncState) * (size_t)cnt, cudaMemcpyDeviceToHost, e.stream);
+        if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+        for (int k = 0; k < cnt; k++) {
+            OpusEncoder *d = st[idx[base + k]];
+            memcpy(&d->st, &hs[k], sizeof(CbEncState));
+            d->host_current = 1;
+        }
+    }
+    if (release)
+        for (int i = 0; i < n; i++) release_slot_locked(st[i]);
+    return OPUS_OK;
+}
+
+// Common checks of a span call; all streams must share Fs / channels.
+int check_span(OpusEncoder **st, int n) {
+    for (int i = 0; i < n; i++) {
+        if (!st[i] || st[i]->magic != kEncMagic) return OPUS_BAD_ARG;
+        if (st[i]->st.channels != st[0]->st.channels || st[i]->st.Fs != st[0]->st.Fs) return OPUS_BAD_ARG;
+    }
+    return OPUS_OK;
+}
+
+void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int frame_size, int max_bytes, int stride) {
+    cudaEventRecord(e.ev0, e.stream);
+    encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, 0, e.stream>>>(e.pool, d_slots, (EncScratch *)e.d_scratch.p, d_pcm, d_data,
+                                                                                           d_rets, n, F, frame_size, max_bytes, stride);
+    cudaEventRecord(e.ev1, e.stream);
+    e.launches++;
+}
+
+int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, int frame_size, uint8_t *data, int max_bytes, int stride,
+                            int *ret, bool keep_resident) {
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    int rc = check_span(st, n);
+    if (rc != OPUS_OK) return rc;
+    const int channels = st[0]->st.channels;
+    if (!e.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    int *hsl = (int *)e.h_slots.p;
+    rc = make_resident_locked(st, n, hsl);
+    if (rc != OPUS_OK) return rc;
+    const size_t NF = (size_t)n * F;
+    const size_t pcm_bytes = NF * frame_size * channels * sizeof(int16_t);
+    if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_pcm.reserve(pcm_bytes) || !e.d_data.reserve(NF * stride) ||
+        !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncScratch) * (size_t)n))
+        return OPUS_ALLOC_FAIL;
+    cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
+    cudaMemcpyAsync(e.d_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, e.stream);
+    launch_span((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, frame_size, max_bytes, stride);
+    cudaMemcpyAsync(data, e.d_data.p, NF * stride, cudaMemcpyDeviceToHost, e.stream);
+    cudaMemcpyAsync(ret, e.d_rets.p, sizeof(int) * NF, cudaMemcpyDeviceToHost, e.stream);
+    mark_device_newer_locked(st, n);
+    if (cudaStreamSynchronize(e.stream) != cudaSuccess) {
+        fprintf(stderr, "concentus_b200: CUDA failure in encode span: %s\n", cudaGetErrorString(cudaGetLastError()));
+        return OPUS_INTERNAL_ERROR;
+    }
+    cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1);
+    e.total_ms += e.last_ms;
+    if (!keep_resident) return sync_states_locked(st, n, true);
+    return OPUS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long opus_b200_enc_kernel_launches(void) { return e.launches; }
+float opus_b200_enc_last_kernel_ms(void) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    return e.last_ms;
+}
+int opus_b200_enc_synchronize(void) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    if (e.launches > 0) cudaEventElapsedTime(&e.last_ms, e.ev0, e.ev1);
+    return OPUS_OK;
+}
+
+// ---- lifecycle (opus_encoder.c:150-252,482-510) ----
+int opus_encoder_get_size(int channels) {
+    if (channels < 1 || channels > 2) return 0;
+    return (int)sizeof(OpusEncoder);
+}
+int opus_encoder_init(OpusEncoder *st, opus_int32 Fs, int channels, int application) {
+    if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2) ||
+        (application != OPUS_APPLICATION_VOIP && application != OPUS_APPLICATION_AUDIO && application != OPUS_APPLICATION_RESTRICTED_LOWDELAY))
+        return OPUS_BAD_ARG;
+    memset(st, 0, sizeof(OpusEncoder));
+    st->magic = kEncMagic;
+    st->slot = -1;
+    st->gen = 0;
+    st->host_current = 1;
+    if (enc_state_init(&st->st, Fs, channels, application) != 0) return OPUS_BAD_ARG;
+    return OPUS_OK;
+}
+OpusEncoder *opus_encoder_create(opus_int32 Fs, int channels, int application, int *error) {
+    if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2) ||
+        (application != OPUS_APPLICATION_VOIP && application != OPUS_APPLICATION_AUDIO && application != OPUS_APPLICATION_RESTRICTED_LOWDELAY)) {
+        if (error) *error = OPUS_BAD_ARG;
+        return nullptr;
+    }
+    OpusEncoder *st = (OpusEncoder *)malloc(sizeof(OpusEncoder));
+    if (!st) {
+        if (error) *error = OPUS_ALLOC_FAIL;
+        return nullptr;
+    }
+    int ret = opus_encoder_init(st, Fs, channels, application);
+    if (error) *error = ret;
+    if (ret != OPUS_OK) {
+        free(st);
+        st = nullptr;
+    }
+    return st;
+}
+void opus_encoder_destroy(OpusEncoder *st) {
+    if (!st) return;
+    {
+        std::lock_guard<std::mutex> lk(e.mu);
+        if (e.ok && st->magic == kEncMagic) release_slot_locked(st);
+    }
+    free(st);
+}
+
+// opus_encoder_ctl (opus_encoder.c:2031-2507): every supported request carries one opus_int32 or one pointer to it
+int opus_encoder_ctl(OpusEncoder *st, int request, ...) {
+    va_list ap;
+    va_start(ap, request);
+    {
+        std::lock_guard<std::mutex> lk(e.mu);
+        if (!st->host_current) {
+            if (!ctx_init_locked()) { va_end(ap); return OPUS_INTERNAL_ERROR; }
+            int rc = make_host_current_locked(st);
+            if (rc != OPUS_OK) { va_end(ap); return rc; }
+        }
+    }
+    int ret;
+    if (request == OPUS_RESET_STATE) {
+        ret = enc_ctl(&st->st, request, 0, nullptr);
+    } else if (enc_ctl_is_get(request)) {
+        opus_int32 *p = va_arg(ap, opus_int32 *);
+        if (!p) ret = OPUS_BAD_ARG;
+        else {
+            int v = 0;
+            ret = enc_ctl(&st->st, request, 0, &v);
+            if (ret == OPUS_OK) *p = v;
+        }
+    } else {
+        opus_int32 v = va_arg(ap, opus_int32);
+        int dummy = 0;
+        ret = enc_ctl(&st->st, request, v, &dummy);
+    }
+    va_end(ap);
+    return ret;
+}
+
+// ---- encode ----
+int opus_encode_span_device(OpusEncoder **st, int n, int F, const opus_int16 *d_pcm, int frame_size, unsigned char *d_data,
+                            opus_int32 max_data_bytes, opus_int32 *d_ret) {
+    if (!st || n <= 0 || F <= 0 || frame_size <= 0 || max_data_bytes <= 0) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    int rc = check_span(st, n);
+    if (rc != OPUS_OK) return rc;
+    if (!e.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    int *hsl = (int *)e.h_slots.p;
+    rc = make_resident_locked(st, n, hsl);
+    if (rc != OPUS_OK) return rc;
+    if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_scratch.reserve(sizeof(EncScratch) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
+    launch_span((const int *)e.d_slots.p, d_pcm, d_data, d_ret, n, F, frame_size, hmin(max_data_bytes, 1276), max_data_bytes);
+    mark_device_newer_locked(st, n);
+    if (cudaGetLastError() != cudaSuccess) return OPUS_INTERNAL_ERROR;
+    return OPUS_OK;
+}
+
+int opus_encode_span(OpusEncoder **st, int n, int F, const opus_int16 *pcm, int frame_size, unsigned char *data, opus_int32 max_data_bytes,
+                     opus_int32 *ret) {
+    if (!st || n <= 0 || F <= 0 || frame_size <= 0 || max_data_bytes <= 0 || !pcm || !data || !ret) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(e.mu);
+    return encode_span_host_locked(st, n, F, pcm, frame_size, data, hmin(max_data_bytes, 1276), max_data_bytes, ret, true);
+}
+
+int opus_encode_batch(OpusEncoder **st, const opus_int16 *const *pcm, int frame_size, unsigned char *const *data, opus_int32 max_data_bytes,
+                      opus_int32 *ret, int n) {
+    if (!st || !pcm || !data || !ret || n <= 0) return OPUS_BAD_ARG;
+    if (frame_size <= 0 || max_data_bytes <= 0) {
+        for (int i = 0; i < n; i++) ret[i] = OPUS_BAD_ARG;
+        return OPUS_OK;
+    }
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    const int stride = hmin(max_data_bytes, 1276);
+    for (int i = 0; i < n; i++)
+        if (!st[i] || st[i]->magic != kEncMagic || !pcm[i] || !data[i]) ret[i] = OPUS_BAD_ARG;
+    // group by (Fs, channels): the span kernel wants uniform rows
+    std::vector<char> done(n, 0);
+    for (int i = 0; i < n; i++) {
+        if (done[i] || !st[i] || st[i]->magic != kEncMagic || !pcm[i] || !data[i]) continue;
+        std::vector<int> idx;
+        for (int j = i; j < n; j++)
+            if (!done[j] && st[j] && st[j]->magic == kEncMagic && pcm[j] && data[j] && st[j]->st.channels == st[i]->st.channels &&
+                st[j]->st.Fs == st[i]->st.Fs) {
+                idx.push_back(j);
+                done[j] = 1;
+            }
+        const int m = (int)idx.size(), ch = st[i]->st.channels;
+        // OPUS_SET_EXPERT_FRAME_DURATION: the frame actually coded (opus_encode -> compute_frame_size, opus_encoder.c:2007-2025).
+        // Streams of one group that select different sizes are launched separately.
+        std::vector<int> fsz(m);
+        for (int k = 0; k < m; k++) {
+            if (!st[idx[k]]->host_current && st[idx[k]]->st.variable_duration != 5000) { /* config never changes on the device */ }
+            fsz[k] = frame_size_select(frame_size, st[idx[k]]->st.variable_duration, st[idx[k]]->st.Fs);
+        }
+        std::vector<char> sub_done(m, 0);
+        for (int k0 = 0; k0 < m; k0++) {
+            if (sub_done[k0]) continue;
+            if (fsz[k0] < 0) { ret[idx[k0]] = OPUS_BAD_ARG; sub_done[k0] = 1; continue; }
+            std::vector<int> sub;
+            for (int k = k0; k < m; k++)
+                if (!sub_done[k] && fsz[k] == fsz[k0]) { sub.push_back(idx[k]); sub_done[k] = 1; }
+            const int q = (int)sub.size(), fs = fsz[k0];
+            std::vector<OpusEncoder *> sts(q);
+            std::vector<int16_t> in((size_t)q * fs * ch);
+            std::vector<uint8_t> out((size_t)q * stride);
+            std::vector<int> rets(q);
+            for (int k = 0; k < q; k++) {
+                sts[k] = st[sub[k]];
+                memcpy(in.data() + (size_t)k * fs * ch, pcm[sub[k]], (size_t)fs * ch * sizeof(int16_t));
+            }
+            int rc = encode_span_host_locked(sts.data(), q, 1, in.data(), fs, out.data(), stride, stride, rets.data(), true);
+            if (rc != OPUS_OK) return rc;
+            for (int k = 0; k < q; k++) {
+                ret[sub[k]] = rets[k];
+                if (rets[k] > 0) memcpy(data[sub[k]], out.data() + (size_t)k * stride, (size_t)rets[k]);
+            }
+        }
+    }
+    return OPUS_OK;
+}
+
+int opus_encoder_sync(OpusEncoder **st, int n) {
+    if (!st || n <= 0) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    return sync_states_locked(st, n, true);
+}
+
+// Scalar call = batch of one; the host block is left current so it stays memcpy-able (opus_encoder.c:2007-2025).
+opus_int32 opus_encode(OpusEncoder *st, const opus_int16 *pcm, int analysis_frame_size, unsigned char *data, opus_int32 max_data_bytes) {
+    if (!st || st->magic != kEncMagic || !pcm || !data) return OPUS_BAD_ARG;
+    if (max_data_bytes <= 0) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    // the ctl-visible configuration never changes on the device, so a stale host block still holds it
+    const int frame_size = frame_size_select(analysis_frame_size, st->st.variable_duration, st->st.Fs);
+    if (frame_size < 0) return OPUS_BAD_ARG;
+    const int stride = hmin(max_data_bytes, 1276);
+    std::vector<uint8_t> out((size_t)stride);
+    int r = 0;
+    OpusEncoder *one = st;
+    int rc = encode_span_host_locked(&one, 1, 1, pcm, frame_size, out.data(), stride, stride, &r, false);
+    if (rc != OPUS_OK) return rc;
+    if (r > 0) memcpy(data, out.data(), (size_t)r);
+    return r;
+}
+
+// opus_packet_pad / opus_packet_unpad (repacketizer.c:239-273) for single-frame (code 0 / padded code 3) packets — what
+// this engine's encoder emits.  Multi-frame packets: OPUS_UNIMPLEMENTED (the repacketizer is SURVEY.md §8f rank 2).
+int opus_packet_pad(unsigned char *data, opus_int32 len, opus_int32 new_len) {
+    if (len < 1) return OPUS_BAD_ARG;
+    if (len == new_len) return OPUS_OK;
+    if (len > new_len) return OPUS_BAD_ARG;
+    if ((data[0] & 3) != 0) return OPUS_UNIMPLEMENTED;
+    return packet_pad_single(data, len, new_len);
+}
+opus_int32 opus_packet_unpad(unsigned char *data, opus_int32 len) {
+    if (len < 1) return OPUS_BAD_ARG;
+    if ((data[0] & 3) == 0) return len;
+    if ((data[0] & 3) != 3 || len < 2 || (data[1] & 0x3F) != 1 || (data[1] & 0x80)) return OPUS_UNIMPLEMENTED;
+    int pos = 2, pad = 0;
+    if (data[1] & 0x40) {
+        int p;
+        do {
+            if (pos >= len) return OPUS_INVALID_PACKET;
+            p = data[pos++];
+            pad += p == 255 ? 254 : p;
+        } while (p == 255);
+    }
+    const int payload = len - pos - pad;
+    if (payload < 0) return OPUS_INVALID_PACKET;
+    data[0] &= 0xFC;
+    memmove(data + 1, data + pos, (size_t)payload);
+    return payload + 1;
+}
+
+}  // extern "C"

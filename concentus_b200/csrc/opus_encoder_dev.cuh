@@ -9,10 +9,12 @@
 #pragma once
 #include "celt_encoder.cuh"
 
+#ifndef CB_HD
 #if defined(__CUDACC__)
 #define CB_HD __host__ __device__ inline
 #else
-#define CB_HD inline
+#define CB_HD static inline
+#endif
 #endif
 
 namespace cb {
@@ -194,7 +196,7 @@ CB_DEV int gen_toc(int mode, int framerate, int bandwidth, int channels) {
 
 // opus_packet_pad of a one-frame code-0 packet (repacketizer.c:239-258 -> :102-227): the payload moves up by one byte
 // (plus the padding-length bytes), the packet becomes code 3 with count 1, zero padding follows.
-CB_DEV int packet_pad_single(uint8_t *data, int len, int new_len) {
+CB_HD int packet_pad_single(uint8_t *data, int len, int new_len) {
     if (len < 1) return OPUS_BAD_ARG_;
     if (len == new_len) return OPUS_OK_;
     if (len > new_len) return OPUS_BAD_ARG_;

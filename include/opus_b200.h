@@ -97,6 +97,21 @@ int opus_decode(OpusDecoder *st, const unsigned char *data, opus_int32 len, opus
 int opus_decoder_ctl(OpusDecoder *st, int request, ...);                            /* opus_decoder.c:802 */
 void opus_decoder_destroy(OpusDecoder *st);                                         /* opus_decoder.c:915 */
 
+/* ---- encoder: opus-fix/include/opus.h:171-328, src/opus_encoder.c:150-252,482-510,2007-2507 ----
+ * Scope: frames are coded in MODE_CELT_ONLY (OPUS_APPLICATION_RESTRICTED_LOWDELAY, or
+ * OPUS_APPLICATION_AUDIO when the reference's own mode decision / OPUS_SET_FORCE_MODE picks CELT), 48 kHz, 2.5-20 ms.
+ * A frame the reference would code with SILK/hybrid, OPUS_APPLICATION_VOIP, other API rates and 40/60 ms frames return
+ * OPUS_UNIMPLEMENTED and leave the state untouched. */
+int opus_encoder_get_size(int channels);                                                        /* opus_encoder.c:150 */
+OpusEncoder *opus_encoder_create(opus_int32 Fs, int channels, int application, int *error);     /* opus_encoder.c:482 */
+int opus_encoder_init(OpusEncoder *st, opus_int32 Fs, int channels, int application);           /* opus_encoder.c:164 */
+opus_int32 opus_encode(OpusEncoder *st, const opus_int16 *pcm, int frame_size, unsigned char *data,
+                       opus_int32 max_data_bytes);                                              /* opus_encoder.c:2007 */
+int opus_encoder_ctl(OpusEncoder *st, int request, ...);                                        /* opus_encoder.c:2031 */
+void opus_encoder_destroy(OpusEncoder *st);                                                     /* opus_encoder.c:2509 */
+int opus_packet_pad(unsigned char *data, opus_int32 len, opus_int32 new_len);                   /* repacketizer.c:239 (single-frame packets) */
+opus_int32 opus_packet_unpad(unsigned char *data, opus_int32 len);                              /* repacketizer.c:260 (single-frame packets) */
+
 /* ---- packet helpers: opus-fix/include/opus.h:527-594, src/opus.c:169-352, src/opus_decoder.c:921-981 ---- */
 int opus_packet_parse(const unsigned char *data, opus_int32 len, unsigned char *out_toc, const unsigned char *frames[48],
                       opus_int16 size[48], int *payload_offset);
@@ -132,6 +147,20 @@ int opus_decode_span_device(OpusDecoder **st, int n, int F, const unsigned char 
 /* Write device-resident states back into the caller-visible blocks (memcpy-able again) and release residency. */
 int opus_decoder_sync(OpusDecoder **st, int n);
 
+/* Encoder counterparts.  opus_encode_batch: for i in 0..n-1: ret[i] = opus_encode(st[i], pcm[i], frame_size, data[i],
+ * max_data_bytes).  opus_encode_span: F consecutive frames for each of n streams in one launch; PCM of frame (s,f) is
+ * pcm + (s*F+f)*frame_size*channels, its packet is written at data + (s*F+f)*max_data_bytes (max_data_bytes is both the
+ * size limit of a packet, clamped to 1276 like opus_encoder.c:980, and the slot stride), ret[s*F+f] = packet length or
+ * error.  All streams of a span must share Fs and channel count.  _device: pcm/data/ret are DEVICE pointers, the call only
+ * enqueues; opus_b200_enc_synchronize() waits. */
+int opus_encode_batch(OpusEncoder **st, const opus_int16 *const *pcm, int frame_size, unsigned char *const *data,
+                      opus_int32 max_data_bytes, opus_int32 *ret, int n);
+int opus_encode_span(OpusEncoder **st, int n, int F, const opus_int16 *pcm, int frame_size, unsigned char *data,
+                     opus_int32 max_data_bytes, opus_int32 *ret);
+int opus_encode_span_device(OpusEncoder **st, int n, int F, const opus_int16 *d_pcm, int frame_size, unsigned char *d_data,
+                            opus_int32 max_data_bytes, opus_int32 *d_ret);
+int opus_encoder_sync(OpusEncoder **st, int n);
+
 /* ---- runtime ---- */
 int opus_b200_init(int device);            /* select the CUDA device (default 0); 0 or OPUS_INTERNAL_ERROR */
 int opus_b200_synchronize(void);
@@ -141,6 +170,11 @@ long long opus_b200_kernel_launches(void); /* number of codec kernels launched s
 int opus_b200_stage_times(double ms[3], long long launches[3], int reset);
 /* Time of the last span call in milliseconds, from CUDA events recorded around it on the library stream. */
 float opus_b200_last_kernel_ms(void);
+int opus_b200_device_index(void);         /* device in use, -1 when CUDA is unusable */
+/* encoder half: its own stream */
+int opus_b200_enc_synchronize(void);
+long long opus_b200_enc_kernel_launches(void);
+float opus_b200_enc_last_kernel_ms(void);  /* device time of the last encode span (CUDA events on the encoder stream) */
 
 #ifdef __cplusplus
 }

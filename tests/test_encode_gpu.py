@@ -1,0 +1,185 @@
+"""GPU parity: CUDA encode (through the C ABI of libconcentus_b200.so) vs the oracle (unmodified opus-fix build): packets
+byte-for-byte, packet length per frame, final range after the last frame — the same comparison CSharp/ParityTest makes
+(reference CSharp/ParityTest/TestDriver.cs) and tests/test_opus_encode.c:306 (encoder/decoder final-range agreement)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cb():
+    import concentus_b200 as cb
+    assert cb.lib().opus_b200_init(0) == 0, "CUDA device required: no CPU fallback exists"
+    return cb
+
+
+def _ref_encode(pcm, fs, br, ch, vbr, cvbr, cx, application=O.OPUS_APPLICATION_RESTRICTED_LOWDELAY):
+    d, o, l, r = O.encode_stream(pcm, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx, application=application)
+    return d.reshape(-1, 1276), l, r
+
+
+def _check_group(signals, ch, fs, br, vbr, cvbr, cx, nsec=1, spans=2):
+    """One batch = streams that share every encoder setting; signals = list of (kind, seed)."""
+    cb = _cb()
+    n = len(signals)
+    pcms = [O.test_signal(48000 * nsec, ch, seed, kind) for (kind, seed) in signals]
+    F = pcms[0].shape[0] // fs
+    enc = cb.EncoderBatch(n, 48000, ch, bitrate=br, vbr=vbr, cvbr=cvbr, complexity=cx)
+    allp = np.stack([p[:F * fs].reshape(F, fs * ch) for p in pcms])   # [n, F, fs*ch]
+    data = np.zeros((n, F, 1276), dtype=np.uint8)
+    lens = np.zeros((n, F), dtype=np.int32)
+    cuts = np.linspace(0, F, spans + 1).astype(int)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b == a:
+            continue
+        d, l = enc.encode_span(allp[:, a:b].reshape(-1, ch), b - a, fs)
+        data[:, a:b] = d.reshape(n, b - a, 1276)
+        lens[:, a:b] = l.reshape(n, b - a)
+    fr = enc.final_ranges()
+    enc.close()
+    for s in range(n):
+        rd, rl, rr = _ref_encode(pcms[s], fs, br, ch, vbr, cvbr, cx)
+        tag = (signals[s], ch, fs, br, vbr, cvbr, cx)
+        assert np.array_equal(rl, lens[s]), ("packet lengths", tag, int(np.nonzero(rl != lens[s])[0][0]))
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], data[s, f, :rl[f]]), ("packet bytes", tag, "frame", f)
+        assert int(rr[-1]) == int(fr[s]), ("final range", tag)
+
+
+SIGS = [("music", 11), ("tone", 12), ("clicks", 13), ("noise", 14)]
+
+
+@pytest.mark.parametrize("fs", [120, 240, 480, 960])
+@pytest.mark.parametrize("ch", [1, 2])
+def test_encode_frame_sizes_vbr(fs, ch):
+    _check_group(SIGS, ch, fs, 96000, 1, 0, 10)
+
+
+@pytest.mark.parametrize("br", [32000, 48000, 64000, 128000, 192000, 256000, 510000])
+def test_encode_bitrates_cbr_stereo(br):
+    _check_group(SIGS, 2, 960, br, 0, 0, 10)
+
+
+@pytest.mark.parametrize("br", [32000, 64000, 256000])
+@pytest.mark.parametrize("fs", [120, 480])
+def test_encode_cvbr_mono(br, fs):
+    _check_group(SIGS, 1, fs, br, 1, 1, 10)
+
+
+@pytest.mark.parametrize("cx", [0, 2, 4, 5, 8])
+def test_encode_complexities(cx):
+    _check_group(SIGS, 2, 960, 64000, 1, 1, cx)
+    _check_group(SIGS[:2], 2, 240, 128000, 1, 0, cx)
+
+
+def test_encode_config2_shape_long():
+    """BASELINE configs[2] shape (48 kHz stereo 96 kbps complexity 10, VBR and CBR), long enough for the VBR controller to settle
+    (vbr_count saturates at 970 frames) and for the pre-filter / transient paths to be exercised."""
+    _check_group([("music", 21), ("tone", 22), ("clicks", 23)], 2, 960, 96000, 1, 0, 10, nsec=22, spans=3)
+    _check_group([("music", 24), ("clicks", 25)], 2, 960, 96000, 0, 0, 10, nsec=4, spans=1)
+
+
+def test_encode_many_streams_one_launch():
+    """More streams than one wave of warps: 300 streams x 10 frames, every stream a different signal."""
+    sigs = [(("music", "tone", "clicks", "noise")[i % 4], 1000 + i) for i in range(300)]
+    cb = _cb()
+    ch, fs, F = 2, 960, 10
+    pcms = [O.test_signal(fs * F, ch, seed, kind) for (kind, seed) in sigs]
+    enc = cb.EncoderBatch(len(sigs), 48000, ch, bitrate=96000, vbr=1, cvbr=0, complexity=10)
+    d, l = enc.encode_span(np.concatenate(pcms), F, fs)
+    enc.close()
+    d = d.reshape(len(sigs), F, 1276)
+    l = l.reshape(len(sigs), F)
+    for s in range(len(sigs)):
+        rd, rl, _ = _ref_encode(pcms[s], fs, 96000, ch, 1, 0, 10)
+        assert np.array_equal(rl, l[s]), ("len", sigs[s])
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], d[s, f, :rl[f]]), ("bytes", sigs[s], f)
+
+
+def test_scalar_api_and_state_copy():
+    """opus_encode one frame at a time, a memcpy'd state block continues identically (tests/test_opus_encode.c:198,214),
+    OPUS_RESET_STATE restarts the stream, ctl argument checks (tests/test_opus_api.c)."""
+    cb = _cb()
+    L = cb.lib()
+    ch, fs = 2, 960
+    pcm = O.test_signal(48000, ch, 77, "tone")
+    F = pcm.shape[0] // fs
+    rd, rl, rr = _ref_encode(pcm, fs, 64000, ch, 1, 1, 10)
+    err = C.c_int(0)
+    h = L.opus_encoder_create(48000, ch, cb.OPUS_APPLICATION_RESTRICTED_LOWDELAY, C.byref(err))
+    assert h and err.value == 0
+    hp = C.c_void_p(h)
+    assert L.opus_encoder_ctl(hp, cb.OPUS_SET_BITRATE_REQUEST, C.c_int32(64000)) == 0
+    assert L.opus_encoder_ctl(hp, cb.OPUS_SET_COMPLEXITY_REQUEST, C.c_int32(10)) == 0
+    assert L.opus_encoder_ctl(hp, cb.OPUS_SET_COMPLEXITY_REQUEST, C.c_int32(11)) == cb.OPUS_BAD_ARG
+    assert L.opus_encoder_ctl(hp, 999999, C.c_int32(0)) == cb.OPUS_UNIMPLEMENTED
+    out = np.zeros(1276, dtype=np.uint8)
+    half = F // 2
+    for f in range(half):
+        n = L.opus_encode(hp, O.ptr(pcm[f * fs:(f + 1) * fs]), fs, O.ptr(out), 1276)
+        assert n == rl[f] and np.array_equal(out[:n], rd[f, :n]), f
+        v = C.c_uint32(0)
+        L.opus_encoder_ctl(hp, cb.OPUS_GET_FINAL_RANGE_REQUEST, C.byref(v))
+        assert v.value == int(rr[f])
+    # clone the state block with memcpy, destroy the original, continue on the clone
+    size = L.opus_encoder_get_size(ch)
+    clone = C.create_string_buffer(size)
+    C.memmove(clone, h, size)
+    L.opus_encoder_destroy(hp)
+    cp = C.cast(clone, C.c_void_p)
+    for f in range(half, F):
+        n = L.opus_encode(cp, O.ptr(pcm[f * fs:(f + 1) * fs]), fs, O.ptr(out), 1276)
+        assert n == rl[f] and np.array_equal(out[:n], rd[f, :n]), f
+    # reset: the stream starts over
+    assert L.opus_encoder_ctl(cp, cb.OPUS_RESET_STATE) == 0
+    n = L.opus_encode(cp, O.ptr(pcm[:fs]), fs, O.ptr(out), 1276)
+    assert n == rl[0] and np.array_equal(out[:n], rd[0, :n])
+    # argument errors
+    assert L.opus_encode(cp, O.ptr(pcm[:fs]), 100, O.ptr(out), 1276) == cb.OPUS_BAD_ARG
+    assert L.opus_encode(cp, O.ptr(pcm[:fs]), fs, O.ptr(out), 0) == cb.OPUS_BAD_ARG
+    assert L.opus_encoder_create(44100, 2, cb.OPUS_APPLICATION_AUDIO, C.byref(err)) is None and err.value == cb.OPUS_BAD_ARG
+
+
+def test_encode_decode_roundtrip_on_device():
+    """Our encoder's packets through our decoder: final ranges agree frame by frame (tests/test_opus_encode.c:306) and the PCM
+    equals what the oracle decodes from the oracle's packets."""
+    cb = _cb()
+    ch, fs, F = 2, 960, 50
+    pcm = O.test_signal(fs * F, ch, 5, "music")
+    enc = cb.EncoderBatch(1, 48000, ch, bitrate=128000, vbr=1, cvbr=0, complexity=10)
+    d, l = enc.encode_span(pcm, F, fs)
+    enc.close()
+    offs = (np.arange(F, dtype=np.int64) * 1276)
+    dec = cb.DecoderBatch(1, 48000, ch)
+    out, rets = dec.decode_span(d.reshape(-1), offs, l, F, fs)
+    dec.close()
+    assert (rets == fs).all()
+    rd, rl, _ = _ref_encode(pcm, fs, 128000, ch, 1, 0, 10)
+    rp, _, _ = O.decode_stream(rd.reshape(-1), offs, rl, fs, ch)
+    assert np.array_equal(rp, out)
+
+
+def test_audio_application_forced_celt_and_unimplemented():
+    """OPUS_APPLICATION_AUDIO with OPUS_SET_FORCE_MODE(MODE_CELT_ONLY): 4 ms of look-ahead compensation through the delay buffer.
+    Without forcing, a low-rate frame the reference would hand to SILK returns OPUS_UNIMPLEMENTED and leaves the state alone."""
+    cb = _cb()
+    ch, fs, F = 2, 960, 25
+    pcm = O.test_signal(fs * F, ch, 9, "music")
+    enc = cb.EncoderBatch(1, 48000, ch, application=cb.OPUS_APPLICATION_AUDIO, bitrate=96000, vbr=1, cvbr=1, complexity=10)
+    d, l = enc.encode_span(pcm, F, fs)
+    enc.close()
+    rd, rl, _ = _ref_encode(pcm, fs, 96000, ch, 1, 1, 10, application=O.OPUS_APPLICATION_AUDIO)
+    # the reference picks CELT-only for music-like input at this rate (TOC bit 7)
+    if (rd[:, 0] & 0x80).all():
+        assert np.array_equal(rl, l)
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], d[f, :rl[f]]), f
+    enc = cb.EncoderBatch(1, 48000, 1, application=cb.OPUS_APPLICATION_AUDIO, bitrate=12000, vbr=1, cvbr=1, complexity=10)
+    d, l = enc.encode_span(pcm[:, :1].copy(), F, fs)
+    enc.close()
+    assert (l == cb.OPUS_UNIMPLEMENTED).all()
