@@ -74,7 +74,7 @@ CB_DEV int celt_ilog2(int x) { return ec_ilog((unsigned)x) - 1; }
 CB_DEV int celt_zlog2(int x) { return x <= 0 ? 0 : celt_ilog2(x); }
 
 // isqrt32 (celt/mathops.c:42-66): exact floor(sqrt(v)).
-CB_DEV unsigned isqrt32(unsigned v) {
+CB_MATH unsigned isqrt32(unsigned v) {
     unsigned g = 0;
     int bshift = (ec_ilog(v) - 1) >> 1;
     unsigned b = 1u << bshift;
@@ -88,7 +88,7 @@ CB_DEV unsigned isqrt32(unsigned v) {
 }
 
 // celt_rcp (celt/mathops.c:182-208): Q15 in, Q16 out.
-CB_DEV int celt_rcp(int x) {
+CB_MATH int celt_rcp(int x) {
     int i = celt_ilog2(x);
     int n = s16(vshr32(x, i - 15) - 32768);
     int r = s16(30840 + mul16_16_q15(-15420, n));
@@ -100,7 +100,7 @@ CB_DEV int celt_rcp(int x) {
 CB_DEV int celt_div(int a, int b) { return mul32_32_q31(a, celt_rcp(b)); }
 
 // frac_div32 (celt/mathops.c:70-91)
-CB_DEV int frac_div32(int a, int b) {
+CB_MATH int frac_div32(int a, int b) {
     int shift = celt_ilog2(b) - 29;
     a = vshr32(a, shift);
     b = vshr32(b, shift);
@@ -114,7 +114,7 @@ CB_DEV int frac_div32(int a, int b) {
 }
 
 // celt_rsqrt_norm (celt/mathops.c:94-121): Q16 in [0.25,1), Q14 out.
-CB_DEV int celt_rsqrt_norm(int x) {
+CB_MATH int celt_rsqrt_norm(int x) {
     int n = s16(x - 32768);
     int r = s16(23557 + mul16_16_q15(n, s16(-13490 + mul16_16_q15(n, 6713))));
     int r2 = s16(mul16_16_q15(r, r));
@@ -123,7 +123,7 @@ CB_DEV int celt_rsqrt_norm(int x) {
 }
 
 // celt_sqrt (celt/mathops.c:124-143)
-CB_DEV int celt_sqrt(int x) {
+CB_MATH int celt_sqrt(int x) {
     if (x == 0) return 0;
     if (x >= 1073741824) return 32767;
     int k = (celt_ilog2(x) >> 1) - 7;
@@ -135,13 +135,13 @@ CB_DEV int celt_sqrt(int x) {
 }
 
 // _celt_cos_pi_2 / celt_cos_norm (celt/mathops.c:150-179)
-CB_DEV int celt_cos_pi_2(int x) {
+CB_MATH int celt_cos_pi_2(int x) {
     int x2 = s16(mul16_16_p15(x, x));
     int inner = wadd(-7651, mul16_16_p15(x2, wadd(8277, mul16_16_p15(-626, x2))));
     int v = wadd((32767 - x2), mul16_16_p15(x2, inner));
     return s16(1 + imin(32766, v));
 }
-CB_DEV int celt_cos_norm(int x) {
+CB_MATH int celt_cos_norm(int x) {
     x = x & 0x0001ffff;
     if (x > (1 << 16)) x = (1 << 17) - x;
     if (x & 0x00007fff) {
@@ -154,7 +154,7 @@ CB_DEV int celt_cos_norm(int x) {
 }
 
 // celt_log2 (celt/mathops.h:179-193): Q14 in, Q10 out.
-CB_DEV int celt_log2(int x) {
+CB_MATH int celt_log2(int x) {
     if (x == 0) return -32767;
     int i = celt_ilog2(x);
     int n = s16(vshr32(x, i - 15) - 32768 - 16384);
@@ -168,7 +168,7 @@ CB_DEV int celt_exp2_frac(int x) {
     int frac = shl16(x, 4);
     return s16(16383 + mul16_16_q15(frac, s16(22804 + mul16_16_q15(frac, s16(14819 + mul16_16_q15(10204, frac))))));
 }
-CB_DEV int celt_exp2(int x) {
+CB_MATH int celt_exp2(int x) {
     int integer = s16(x) >> 10;
     if (integer > 14) return 0x7f000000;
     if (integer < -15) return 0;
@@ -180,7 +180,7 @@ CB_DEV int celt_exp2(int x) {
 CB_DEV int celt_atan01(int x) {
     return s16(mul16_16_p15(x, wadd(32767, mul16_16_p15(x, wadd(-21, mul16_16_p15(x, wadd(-11943, mul16_16_p15(4936, x))))))));
 }
-CB_DEV int celt_atan2p(int y, int x) {
+CB_MATH int celt_atan2p(int y, int x) {
     if (y < x) {
         int arg = celt_div(shl32(y, 15), x);
         if (arg >= 32767) arg = 32767;
@@ -193,14 +193,14 @@ CB_DEV int celt_atan2p(int y, int x) {
 }
 
 // bitexact_cos / bitexact_log2tan (celt/bands.c:70-94)
-CB_DEV int bitexact_cos(int x) {
+CB_MATH int bitexact_cos(int x) {
     x = s16(x);
     int tmp = (4096 + x * x) >> 13;
     int x2 = s16(tmp);
     x2 = s16((32767 - x2) + frac_mul16(x2, (-7651 + frac_mul16(x2, (8277 + frac_mul16(-626, x2))))));
     return s16(1 + x2);
 }
-CB_DEV int bitexact_log2tan(int isin, int icos) {
+CB_MATH int bitexact_log2tan(int isin, int icos) {
     int lc = ec_ilog((unsigned)icos);
     int ls = ec_ilog((unsigned)isin);
     icos <<= 15 - lc;

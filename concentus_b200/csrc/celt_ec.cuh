@@ -332,7 +332,7 @@ struct EcEnc {
     // entenc.c:427-445: move the raw-bit tail down to the new end
     CB_MEM void shrink(unsigned size) {
         // memmove semantics: destination is below the source
-        for (unsigned i = 0; i < end_offs; i++) buf[size - end_offs + i] = buf[storage - end_offs + i];
+        CB_NOUNROLL for (unsigned i = 0; i < end_offs; i++) buf[size - end_offs + i] = buf[storage - end_offs + i];
         storage = size;
     }
     // entenc.c:447-508
@@ -359,7 +359,7 @@ struct EcEnc {
             used -= kEcSymBits;
         }
         if (!error) {
-            for (unsigned i = offs; i < storage - end_offs; i++) buf[i] = 0;
+            CB_NOUNROLL for (unsigned i = offs; i < storage - end_offs; i++) buf[i] = 0;
             if (used > 0) {
                 if (end_offs >= storage) error = -1;
                 else {
@@ -383,7 +383,7 @@ struct EcEnc {
             fl = fs;
             fs = EcDec::laplace_freq1(fs, decay);
             int i;
-            for (i = 1; fs > 0 && i < v; i++) {
+            CB_NOUNROLL for (i = 1; fs > 0 && i < v; i++) {
                 fs *= 2;
                 fl += fs + 2 * 1;
                 fs = (fs * (unsigned)decay) >> 15;

@@ -16,7 +16,7 @@ namespace cb {
 // bands.c:48-61
 CB_DEV int hysteresis_decision(int val, const int16_t *thresholds, const int16_t *hysteresis, int N, int prev) {
     int i;
-    for (i = 0; i < N; i++)
+    CB_NOUNROLL for (i = 0; i < N; i++)
         if (val < thresholds[i]) break;
     if (i > prev && val < thresholds[prev] + hysteresis[prev]) i = prev;
     if (i < prev && val > thresholds[prev - 1] - hysteresis[prev - 1]) i = prev;
@@ -26,8 +26,8 @@ CB_DEV int hysteresis_decision(int val, const int16_t *thresholds, const int16_t
 // bands.c:97-143.  freq: C*N int32; bandE: [c*21+i]
 CB_DEV_NOINLINE void compute_band_energies(const int *freq, int *bandE, int end, int C, int LM) {
     const int N = kShortMdct << LM;
-    for (int c = 0; c < C; c++) {
-        for (int i = 0; i < end; i++) {
+    CB_NOUNROLL for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int i = 0; i < end; i++) {
             const int lo = kEBands[i] << LM, hi = kEBands[i + 1] << LM;
             const int *x = freq + c * N;
             int maxval = maxabs32(x + lo, hi - lo);
@@ -35,9 +35,9 @@ CB_DEV_NOINLINE void compute_band_energies(const int *freq, int *bandE, int end,
                 int shift = celt_ilog2(maxval) - 14 + (((kLogN[i] >> kBitRes) + LM + 1) >> 1);
                 int sum = 0;
                 if (shift > 0) {
-                    for (int j = lo; j < hi; j++) { int v = s16(x[j] >> shift); sum = mac16_16(sum, v, v); }
+                    CB_NOUNROLL for (int j = lo; j < hi; j++) { int v = s16(x[j] >> shift); sum = mac16_16(sum, v, v); }
                 } else {
-                    for (int j = lo; j < hi; j++) { int v = s16(shl32(x[j], -shift)); sum = mac16_16(sum, v, v); }
+                    CB_NOUNROLL for (int j = lo; j < hi; j++) { int v = s16(shl32(x[j], -shift)); sum = mac16_16(sum, v, v); }
                 }
                 bandE[i + c * kNbEBands] = wadd(1, vshr32(celt_sqrt(sum), -shift));
             } else {
@@ -50,12 +50,12 @@ CB_DEV_NOINLINE void compute_band_energies(const int *freq, int *bandE, int end,
 // bands.c:146-164
 CB_DEV_NOINLINE void normalise_bands(const int *freq, int16_t *X, const int *bandE, int end, int C, int M) {
     const int N = M * kShortMdct;
-    for (int c = 0; c < C; c++) {
-        for (int i = 0; i < end; i++) {
+    CB_NOUNROLL for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int i = 0; i < end; i++) {
             int shift = celt_zlog2(bandE[i + c * kNbEBands]) - 13;
             int E = s16(vshr32(bandE[i + c * kNbEBands], shift));
             int g = s16(celt_rcp(shl32(E, 3)));
-            for (int j = M * kEBands[i]; j < M * kEBands[i + 1]; j++)
+            CB_NOUNROLL for (int j = M * kEBands[i]; j < M * kEBands[i + 1]; j++)
                 X[j + c * N] = (int16_t)mul16_16_q15(s16(vshr32(freq[j + c * N], shift - 1)), g);
         }
     }
@@ -67,13 +67,13 @@ CB_DEV_NOINLINE int spreading_decision(const int16_t *X, int *average, int last_
     int sum = 0, nbBands = 0, hf_sum = 0;
     const int N0 = M * kShortMdct;
     if (M * (kEBands[end] - kEBands[end - 1]) <= 8) return kSpreadNone;
-    for (int c = 0; c < C; c++) {
-        for (int i = 0; i < end; i++) {
+    CB_NOUNROLL for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int i = 0; i < end; i++) {
             const int16_t *x = X + M * kEBands[i] + c * N0;
             const int N = M * (kEBands[i + 1] - kEBands[i]);
             if (N <= 8) continue;
             int t0 = 0, t1 = 0, t2 = 0;
-            for (int j = 0; j < N; j++) {
+            CB_NOUNROLL for (int j = 0; j < N; j++) {
                 int x2N = mul16_16(mul16_16_q15(x[j], x[j]), N);
                 if (x2N < 2048) t0++;
                 if (x2N < 512) t1++;
@@ -105,47 +105,115 @@ CB_DEV_NOINLINE int spreading_decision(const int16_t *X, int *average, int last_
     return kSpreadNone;
 }
 
+// ---- team-parallel vector kernels of the band loop ----------------------------------------------------------------------
+// The band loop (quant_all_bands_enc below) is executed by EVERY lane of the team with identical (uniform) scalars — range
+// coder included — so no broadcast is needed; only the vector work on X is split over the lanes.  All sums are wrapping
+// 32-bit (order-free), so the split cannot change a bit.  Every function leaves the team synchronised.
+
 // vq.c:376-408
-CB_DEV_NOINLINE int stereo_itheta(const int16_t *X, const int16_t *Y, int stereo, int N) {
-    int Emid = 1, Eside = 1;
+template <class TM>
+CB_DEV_NOINLINE int stereo_itheta(TM tm, const int16_t *X, const int16_t *Y, int stereo, int N) {
+    int em = 0, es = 0;
     if (stereo) {
-        for (int i = 0; i < N; i++) {
+        CB_TEAM_FOR(i, N, tm) {
             int m = s16((X[i] >> 1) + (Y[i] >> 1));
             int s = s16((X[i] >> 1) - (Y[i] >> 1));
-            Emid = mac16_16(Emid, m, m);
-            Eside = mac16_16(Eside, s, s);
+            em = mac16_16(em, m, m);
+            es = mac16_16(es, s, s);
         }
     } else {
-        Emid = wadd(Emid, inner_prod16(X, X, N));
-        Eside = wadd(Eside, inner_prod16(Y, Y, N));
+        CB_TEAM_FOR(i, N, tm) {
+            em = mac16_16(em, X[i], X[i]);
+            es = mac16_16(es, Y[i], Y[i]);
+        }
     }
+    const int Emid = wadd(1, tm.sum(em)), Eside = wadd(1, tm.sum(es));
     int mid = s16(celt_sqrt(Emid));
     int side = s16(celt_sqrt(Eside));
     return mul16_16_q15(20861, celt_atan2p(side, mid));   // QCONST16(0.63662f,15)
 }
 
 // bands.c:337-360
-CB_DEV_NOINLINE void intensity_stereo(int16_t *X, const int16_t *Y, const int *bandE, int i, int N) {
+template <class TM>
+CB_DEV_NOINLINE void intensity_stereo(TM tm, int16_t *X, const int16_t *Y, const int *bandE, int i, int N) {
     int shift = celt_zlog2(imax(bandE[i], bandE[i + kNbEBands])) - 13;
     int left = s16(vshr32(bandE[i], shift));
     int right = s16(vshr32(bandE[i + kNbEBands], shift));
     int norm = s16(1 + celt_sqrt(wadd(1, wadd(mul16_16(left, left), mul16_16(right, right)))));
     int a1 = s16(shl32(left, 14) / norm);
     int a2 = s16(shl32(right, 14) / norm);
-    for (int j = 0; j < N; j++) X[j] = (int16_t)(mac16_16(mul16_16(a1, X[j]), a2, Y[j]) >> 14);
+    CB_TEAM_FOR(j, N, tm) X[j] = (int16_t)(mac16_16(mul16_16(a1, X[j]), a2, Y[j]) >> 14);
+    tm.sync();
 }
 // bands.c:362-373
-CB_DEV_NOINLINE void stereo_split(int16_t *X, int16_t *Y, int N) {
-    for (int j = 0; j < N; j++) {
+template <class TM>
+CB_DEV_NOINLINE void stereo_split(TM tm, int16_t *X, int16_t *Y, int N) {
+    CB_TEAM_FOR(j, N, tm) {
         int l = mul16_16(23170, X[j]);
         int r = mul16_16(23170, Y[j]);
         X[j] = (int16_t)(wadd(l, r) >> 15);
         Y[j] = (int16_t)(wsub(r, l) >> 15);
     }
+    tm.sync();
+}
+template <class TM>
+CB_DEV_NOINLINE void negate_vector(TM tm, int16_t *Y, int N) {
+    CB_TEAM_FOR(j, N, tm) Y[j] = (int16_t)(-Y[j]);
+    tm.sync();
 }
 
-// exp_rotation, encoder direction (vq.c:70-113 with dir = +1)
-CB_DEV void exp_rotation_enc(int16_t *X, int len, int stride, int K, int spread) {
+// haar1 (bands.c:581-594): N0/2 * stride independent butterflies
+template <class TM>
+CB_DEV_NOINLINE void haar1_team(TM tm, int16_t *X, int N0, int stride) {
+    N0 >>= 1;
+    CB_TEAM_FOR(w, N0 * stride, tm) {
+        const int j = w / stride, i = w - j * stride;
+        const int a = stride * 2 * j + i, b = stride * (2 * j + 1) + i;
+        const int t1 = mul16_16(23170, X[a]);
+        const int t2 = mul16_16(23170, X[b]);
+        X[a] = (int16_t)pshr32(wadd(t1, t2), 15);
+        X[b] = (int16_t)pshr32(wsub(t1, t2), 15);
+    }
+    tm.sync();
+}
+// deinterleave_hadamard (bands.c:532-556) through the team scratch
+template <class TM>
+CB_DEV_NOINLINE void deinterleave_hadamard_team(TM tm, int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+    const int N = N0 * stride;
+    const uint8_t *ordery = kOrdery + stride - 2;
+    CB_TEAM_FOR(w, N, tm) {
+        const int j = w / stride, i = w - j * stride;
+        const int row = hadamard ? ordery[i] : i;
+        tmp[row * N0 + j] = X[w];
+    }
+    tm.sync();
+    CB_TEAM_FOR(p, N, tm) X[p] = tmp[p];
+    tm.sync();
+}
+
+// One residue class of exp_rotation1 (vq.c:43-67): the pairs (i, i+stride) with i = r (mod stride) form an independent chain
+CB_DEV void exp_rotation1_chain(int16_t *X, int len, int stride, int c, int s, int r) {
+    const int ms = s16(-s);
+    int i;
+    CB_NOUNROLL for (i = r; i < len - stride; i += stride) {
+        int x1 = X[i], x2 = X[i + stride];
+        X[i + stride] = (int16_t)pshr32(mac16_16(mul16_16(c, x2), s, x1), 15);
+        X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
+    }
+    const int top = len - 2 * stride - 1;
+    if (top >= r) {
+        CB_NOUNROLL for (i = top - ((top - r) % stride); i >= 0; i -= stride) {
+            int x1 = X[i], x2 = X[i + stride];
+            X[i + stride] = (int16_t)pshr32(mac16_16(mul16_16(c, x2), s, x1), 15);
+            X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
+        }
+    }
+}
+
+// exp_rotation, encoder direction (vq.c:70-113 with dir = +1): per block the stride-1 sweep (one chain), then the stride2 sweep
+// (stride2 chains); blocks are independent, so the team runs `stride` resp. `stride*stride2` chains at a time.
+template <class TM>
+CB_DEV_NOINLINE void exp_rotation_enc(TM tm, int16_t *X, int len, int stride, int K, int spread) {
     if (2 * K >= len || spread == kSpreadNone) return;
     int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
     int gain = s16(celt_div(mul16_16(32767, len), len + factor * K));
@@ -158,25 +226,39 @@ CB_DEV void exp_rotation_enc(int16_t *X, int len, int stride, int K, int spread)
         while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
     }
     len = (int)udiv((unsigned)len, (unsigned)stride);
-    for (int i = 0; i < stride; i++) {
-        int16_t *x = X + i * len;
-        exp_rotation1(x, len, 1, c, s16(-s));
-        if (stride2) exp_rotation1(x, len, stride2, s, s16(-c));
+    CB_TEAM_FOR(b, stride, tm) exp_rotation1_chain(X + b * len, len, 1, c, s16(-s), 0);
+    tm.sync();
+    if (stride2) {
+        CB_TEAM_FOR(w, stride * stride2, tm) {
+            const int b = w / stride2, r = w - b * stride2;
+            exp_rotation1_chain(X + b * len, len, stride2, s, s16(-c), r);
+        }
+        tm.sync();
     }
 }
 
-// icwrs (cwrs.c:440-456)
-CB_DEV unsigned pvq_encode_index(int n, const int16_t *y) {
-    int j = n - 1;
-    unsigned i = y[j] < 0;
-    int k = iabs(y[j]);
-    do {
-        j--;
-        i += pvq_u(n - j, k);
-        k += iabs(y[j]);
-        if (y[j] < 0) i += pvq_u(n - j, k + 1);
-    } while (j > 0);
-    return i;
+// icwrs (cwrs.c:440-456) as a sum over positions: with S_j = sum_{m>=j} |y_m| (so S_0 = K),
+//   index = [y_{n-1} < 0] + sum_{j=0}^{n-2} ( U(n-j, S_{j+1}) + [y_j < 0] * U(n-j, S_j + 1) )      (mod 2^32)
+template <class TM>
+CB_DEV_NOINLINE unsigned pvq_encode_index(TM tm, int n, int K, const int16_t *y) {
+    const int per = (n + TM::W - 1) / TM::W;
+    const int first = tm.lane() * per;
+    int local = 0;
+    CB_NOUNROLL for (int j = first; j < first + per && j < n; j++) local += iabs((int)y[j]);
+    int S = K - tm.exscan(local);   // S_first
+    unsigned acc = 0;
+    CB_NOUNROLL for (int j = first; j < first + per && j < n; j++) {
+        const int a = iabs((int)y[j]);
+        const int Snext = S - a;   // S_{j+1}
+        if (j < n - 1) {
+            acc += pvq_u(n - j, Snext);
+            if (y[j] < 0) acc += pvq_u(n - j, S + 1);
+        } else {
+            acc += y[j] < 0;
+        }
+        S = Snext;
+    }
+    return (unsigned)tm.sum((int)acc);
 }
 
 // Scratch of the PVQ search: y (doubled pulses), iy (pulses), sign, per band (N <= 176)
@@ -185,75 +267,113 @@ struct PvqScratch {
     int8_t sign[176];
 };
 
-// alg_quant (vq.c:161-325), no resynthesis
-CB_DEV_NOINLINE void alg_quant(int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
+// best candidate of the greedy search: ratio num/den, ties to the lower index
+struct PvqBest { int num, den, id; };
+CB_DEV bool pvq_better(const PvqBest &a, const PvqBest &b) {
+    const int l = mul16_16(b.den, a.num), r = mul16_16(a.den, b.num);
+    return l > r || (l == r && a.id < b.id);
+}
+
+// alg_quant (vq.c:161-325), no resynthesis.  The greedy search is the encoder's hottest loop (profiles/): every lane scans its
+// share of the N positions in increasing order with the reference's strict '>' test (first maximum wins), then a shuffle tree
+// takes the best of the lanes with ties going to the lower index — the same element the sequential scan selects, because with
+// Ryy > 0 and Rxy >= 0 the cross-multiplied comparison is a strict weak order on the ratios.
+template <class TM>
+CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
     int16_t *y = ps.y, *iy = ps.iy;
     int8_t *signx = ps.sign;
-    exp_rotation_enc(X, N, B, K, spread);
-    int sum = 0;
-    for (int j = 0; j < N; j++) {
-        if (X[j] > 0) signx[j] = 1;
-        else { signx[j] = -1; X[j] = (int16_t)(-X[j]); }
+    exp_rotation_enc(tm, X, N, B, K, spread);
+    CB_TEAM_FOR(j, N, tm) {
+        const int x = X[j];
+        if (x > 0) signx[j] = 1;
+        else { signx[j] = -1; X[j] = (int16_t)(-x); }
         iy[j] = 0;
         y[j] = 0;
     }
+    tm.sync();
     int xy = 0;
     int yy = 0;   // opus_val16 in the reference: truncated after every update
     int pulsesLeft = K;
     if (K > (N >> 1)) {
-        for (int j = 0; j < N; j++) sum = wadd(sum, X[j]);
+        int part = 0;
+        CB_TEAM_FOR(j, N, tm) part = wadd(part, X[j]);
+        int sum = tm.sum(part);
         if (sum <= K) {
-            X[0] = 16384;
-            for (int j = 1; j < N; j++) X[j] = 0;
+            tm.sync();
+            CB_TEAM_FOR(j, N, tm) X[j] = j == 0 ? 16384 : 0;
+            tm.sync();
             sum = 16384;
         }
-        int rcp = s16(mul16_32_q16(K - 1, celt_rcp(sum)));
-        for (int j = 0; j < N; j++) {
-            int v = mul16_16_q15(X[j], rcp);
+        const int rcp = s16(mul16_32_q16(K - 1, celt_rcp(sum)));
+        int pyy = 0, pxy = 0, pk = 0;
+        CB_TEAM_FOR(j, N, tm) {
+            const int v = mul16_16_q15(X[j], rcp);
             iy[j] = (int16_t)v;
-            y[j] = (int16_t)v;
-            yy = s16(mac16_16(yy, y[j], y[j]));
-            xy = mac16_16(xy, X[j], y[j]);
-            y[j] = (int16_t)(y[j] * 2);
-            pulsesLeft -= v;
+            const int yv = s16(v);
+            pyy = mac16_16(pyy, yv, yv);
+            pxy = mac16_16(pxy, X[j], yv);
+            y[j] = (int16_t)(yv * 2);
+            pk += v;
         }
+        yy = s16(tm.sum(pyy));
+        xy = tm.sum(pxy);
+        pulsesLeft -= tm.sum(pk);
+        tm.sync();
     }
     if (pulsesLeft > N + 3) {
         int tmp = s16(pulsesLeft);
         yy = s16(mac16_16(yy, tmp, tmp));
         yy = s16(mac16_16(yy, tmp, y[0]));
-        iy[0] = (int16_t)(iy[0] + pulsesLeft);
+        tm.sync();
+        if (tm.lane() == 0) iy[0] = (int16_t)(iy[0] + pulsesLeft);
+        tm.sync();
         pulsesLeft = 0;
     }
-    for (int i = 0; i < pulsesLeft; i++) {
-        int best_id = 0;
-        int best_num = -32767;
-        int best_den = 0;
+    // shuffle-tree width: lanes >= N hold the sentinel, so only ceil(log2(min(N,W))) levels are needed
+    int levels = 0;
+    while ((1 << levels) < TM::W && (1 << levels) < N) levels++;
+    CB_NOUNROLL for (int i = 0; i < pulsesLeft; i++) {
         const int rshift = 1 + celt_ilog2(K - pulsesLeft + i + 1);
         yy = s16(wadd(yy, 1));
-        for (int j = 0; j < N; j++) {
+        PvqBest best{-32767, 0, 0};
+        CB_TEAM_FOR(j, N, tm) {
             int Rxy = s16(wadd(xy, X[j]) >> rshift);
-            int Ryy = s16(yy + y[j]);
+            const int Ryy = s16(yy + y[j]);
             Rxy = s16(mul16_16_q15(Rxy, Rxy));
-            if (mul16_16(best_den, Rxy) > mul16_16(Ryy, best_num)) {
-                best_den = Ryy;
-                best_num = Rxy;
-                best_id = j;
+            if (mul16_16(best.den, Rxy) > mul16_16(Ryy, best.num)) {
+                best.den = Ryy;
+                best.num = Rxy;
+                best.id = j;
             }
         }
+        CB_NOUNROLL for (int l = 0; l < levels; l++) {
+            PvqBest o;
+            o.num = tm.shfl_xor(best.num, 1 << l);
+            o.den = tm.shfl_xor(best.den, 1 << l);
+            o.id = tm.shfl_xor(best.id, 1 << l);
+            if (pvq_better(o, best)) best = o;
+        }
+        const int best_id = tm.bcast(best.id, 0);
         xy = wadd(xy, X[best_id]);
         yy = s16(yy + y[best_id]);
-        y[best_id] = (int16_t)(y[best_id] + 2);
-        iy[best_id]++;
+        tm.sync();
+        if (tm.lane() == 0) {
+            y[best_id] = (int16_t)(y[best_id] + 2);
+            iy[best_id]++;
+        }
+        tm.sync();
     }
-    for (int j = 0; j < N; j++) {
+    CB_TEAM_FOR(j, N, tm) {
         X[j] = (int16_t)mul16_16(signx[j], X[j]);
         if (signx[j] < 0) iy[j] = (int16_t)(-iy[j]);
     }
-    enc.uint_(pvq_encode_index(N, iy), pvq_v(N, K));
+    tm.sync();
+    enc.uint_(pvq_encode_index(tm, N, K, iy), pvq_v(N, K));
 }
 
+template <class TM>
 struct EncBandCtx {
+    TM tm;
     EcEnc ec;
     PvqScratch *ps;
     int16_t *tmp;        // hadamard staging, >= 176 int16
@@ -263,14 +383,16 @@ struct EncBandCtx {
 };
 
 // compute_theta, encoder half (bands.c:645-817)
-CB_DEV void compute_theta_enc(EncBandCtx &ctx, SplitCtx &sctx, int16_t *X, int16_t *Y, int N, int *b, int B, int B0, int LM, int stereo) {
+template <class TM>
+CB_DEV_NOINLINE void compute_theta_enc(EncBandCtx<TM> &ctx, SplitCtx &sctx, int16_t *X, int16_t *Y, int N, int *b, int B, int B0, int LM, int stereo) {
     EcEnc &ec = ctx.ec;
+    TM tm = ctx.tm;
     int inv = 0;
     int pulse_cap = kLogN[ctx.i] + LM * (1 << kBitRes);
     int offset = (pulse_cap >> 1) - (stereo && N == 2 ? kQThetaOffsetTwoPhase : kQThetaOffset);
     int qn = compute_qn(N, *b, offset, pulse_cap, stereo);
     if (stereo && ctx.i >= ctx.intensity) qn = 1;
-    int itheta = stereo_itheta(X, Y, stereo, N);
+    int itheta = stereo_itheta(tm, X, Y, stereo, N);
     int tell = (int)ec.tell_frac();
     if (qn != 1) {
         itheta = (itheta * qn + 8192) >> 14;
@@ -290,14 +412,15 @@ CB_DEV void compute_theta_enc(EncBandCtx &ctx, SplitCtx &sctx, int16_t *X, int16
         }
         itheta = (int)udiv((unsigned)(itheta * 16384), (unsigned)qn);
         if (stereo) {
-            if (itheta == 0) intensity_stereo(X, Y, ctx.bandE, ctx.i, N);
-            else stereo_split(X, Y, N);
+            tm.sync();
+            if (itheta == 0) intensity_stereo(tm, X, Y, ctx.bandE, ctx.i, N);
+            else stereo_split(tm, X, Y, N);
         }
     } else if (stereo) {
         inv = itheta > 8192;
-        if (inv)
-            for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
-        intensity_stereo(X, Y, ctx.bandE, ctx.i, N);
+        tm.sync();
+        if (inv) negate_vector(tm, Y, N);
+        intensity_stereo(tm, X, Y, ctx.bandE, ctx.i, N);
         if (*b > 2 << kBitRes && ctx.remaining_bits > 2 << kBitRes) ec.bit_logp(inv, 2);
         else inv = 0;
         itheta = 0;
@@ -315,10 +438,11 @@ CB_DEV void compute_theta_enc(EncBandCtx &ctx, SplitCtx &sctx, int16_t *X, int16
     sctx.inv = inv; sctx.imid = imid; sctx.iside = iside; sctx.delta = delta; sctx.itheta = itheta; sctx.qalloc = qalloc;
 }
 
-CB_DEV void quant_band_n1_enc(EncBandCtx &ctx, int16_t *X, int16_t *Y) {
+template <class TM>
+CB_DEV void quant_band_n1_enc(EncBandCtx<TM> &ctx, int16_t *X, int16_t *Y) {
     int16_t *x = X;
     const int nch = Y != nullptr ? 2 : 1;
-    for (int c = 0; c < nch; c++) {
+    CB_NOUNROLL for (int c = 0; c < nch; c++) {
         if (ctx.remaining_bits >= 1 << kBitRes) {
             ctx.ec.bits((unsigned)(x[0] < 0), 1);
             ctx.remaining_bits -= 1 << kBitRes;
@@ -334,7 +458,8 @@ struct EncPartFrame {
     int mbits, sbits, itheta, rebalance0, mid_first, stage;
 };
 
-CB_DEV void quant_partition_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B, int LM) {
+template <class TM>
+CB_DEV void quant_partition_enc(EncBandCtx<TM> &ctx, int16_t *X, int N, int b, int B, int LM) {
     EncPartFrame st[5];
     int sp = 0;
     st[0].X = X; st[0].N = N; st[0].b = b; st[0].B = B; st[0].LM = LM; st[0].stage = 0;
@@ -377,7 +502,7 @@ CB_DEV void quant_partition_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B
                     curr_bits = pulses2bits(ctx.i, f.LM, q);
                     ctx.remaining_bits -= curr_bits;
                 }
-                if (q != 0) alg_quant(f.X, f.N, get_pulses(q), ctx.spread, f.B, ctx.ec, *ctx.ps);
+                if (q != 0) alg_quant(ctx.tm, f.X, f.N, get_pulses(q), ctx.spread, f.B, ctx.ec, *ctx.ps);
                 sp--;
             }
         } else if (f.stage == 1) {
@@ -401,7 +526,8 @@ CB_DEV void quant_partition_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B
 }
 
 // quant_band, encode (bands.c:1044-1170 without the resynthesis tail)
-CB_DEV void quant_band_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B, int LM) {
+template <class TM>
+CB_DEV_NOINLINE void quant_band_enc(EncBandCtx<TM> &ctx, int16_t *X, int N, int b, int B, int LM) {
     int N_B = N, B0 = B;
     int recombine = 0;
     int tf_change = ctx.tf_change;
@@ -409,30 +535,33 @@ CB_DEV void quant_band_enc(EncBandCtx &ctx, int16_t *X, int N, int b, int B, int
     N_B = (int)udiv((unsigned)N_B, (unsigned)B);
     if (N == 1) { quant_band_n1_enc(ctx, X, nullptr); return; }
     if (tf_change > 0) recombine = tf_change;
-    for (int k = 0; k < recombine; k++) haar1(X, N >> k, 1 << k);
+    CB_NOUNROLL for (int k = 0; k < recombine; k++) haar1_team(ctx.tm, X, N >> k, 1 << k);
     B >>= recombine;
     N_B <<= recombine;
     while ((N_B & 1) == 0 && tf_change < 0) {
-        haar1(X, N_B, B);
+        haar1_team(ctx.tm, X, N_B, B);
         B <<= 1;
         N_B >>= 1;
         tf_change++;
     }
     B0 = B;
-    if (B0 > 1) deinterleave_hadamard(X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
+    if (B0 > 1) deinterleave_hadamard_team(ctx.tm, X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
     quant_partition_enc(ctx, X, N, b, B, LM);
 }
 
-// quant_all_bands with encode = 1 (bands.c:1337-1502) and quant_band_stereo (bands.c:1176-1335) folded in
-CB_DEV void quant_all_bands_enc(int start, int end, int16_t *X_, int16_t *Y_, const int *bandE, const int *pulses, int shortBlocks,
+// quant_all_bands with encode = 1 (bands.c:1337-1502) and quant_band_stereo (bands.c:1176-1335) folded in.
+// Called by ALL lanes with uniform arguments; ec_io is updated identically on every lane.
+template <class TM>
+CB_DEV void quant_all_bands_enc(TM tm, int start, int end, int16_t *X_, int16_t *Y_, const int *bandE, const int *pulses, int shortBlocks,
                                 int spread, int dual_stereo, int intensity, const int *tf_res, int total_bits, int balance,
                                 EcEnc &ec_io, int LM, int codedBands, PvqScratch *ps, int16_t *tmp) {
     const int M = 1 << LM;
     const int B = shortBlocks ? M : 1;
-    EncBandCtx ctx;
+    EncBandCtx<TM> ctx;
+    ctx.tm = tm;
     ctx.ec = ec_io; ctx.ps = ps; ctx.tmp = tmp; ctx.bandE = bandE;
     ctx.intensity = intensity; ctx.spread = spread;
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         ctx.i = i;
         int16_t *X = X_ + M * kEBands[i];
         int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;

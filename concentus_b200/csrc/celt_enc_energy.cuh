@@ -11,18 +11,18 @@ namespace cb {
 
 // quant_bands.c:551-572
 CB_DEV void amp2Log2(int effEnd, int end, const int *bandE, int16_t *bandLogE, int C) {
-    for (int c = 0; c < C; c++) {
-        for (int i = 0; i < effEnd; i++)
+    CB_NOUNROLL for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int i = 0; i < effEnd; i++)
             bandLogE[i + c * kNbEBands] = (int16_t)(celt_log2(shl32(bandE[i + c * kNbEBands], 2)) - shl16(kEMeans[i], 6));
-        for (int i = effEnd; i < end; i++) bandLogE[c * kNbEBands + i] = -14336;   // -QCONST16(14.f,DB_SHIFT)
+        CB_NOUNROLL for (int i = effEnd; i < end; i++) bandLogE[c * kNbEBands + i] = -14336;   // -QCONST16(14.f,DB_SHIFT)
     }
 }
 
 // quant_bands.c:144-156
 CB_DEV int loss_distortion(const int16_t *eBands, const int16_t *oldEBands, int start, int end, int C) {
     int dist = 0;
-    for (int c = 0; c < C; c++)
-        for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int c = 0; c < C; c++)
+        CB_NOUNROLL for (int i = start; i < end; i++) {
             int d = (eBands[i + c * kNbEBands] >> 3) - (oldEBands[i + c * kNbEBands] >> 3);
             dist = mac16_16(dist, d, d);
         }
@@ -39,8 +39,8 @@ CB_DEV_NOINLINE int quant_coarse_energy_impl(int start, int end, const int16_t *
     if (tell + 3 <= budget) enc.bit_logp(intra, 3);
     if (intra) { coef = 0; beta = kBetaIntra; }
     else { beta = kBetaCoef[LM]; coef = kPredCoef[LM]; }
-    for (int i = start; i < end; i++) {
-        for (int c = 0; c < C; c++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             const int x = eBands[i + c * kNbEBands];
             const int oldE = imax(-9216, (int)oldEBands[i + c * kNbEBands]);
             const int f = wsub(wsub(shl32(x, 7), pshr32(mul16_16(coef, oldE), 8)), prev[c]);
@@ -99,7 +99,7 @@ CB_DEV_NOINLINE void quant_coarse_energy(int start, int end, int effEnd, const i
     int max_decay = 16384;   // QCONST16(16.f,DB_SHIFT)
     if (end - start > 10) max_decay = s16(imin(max_decay, shl32(nbAvailableBytes, 7)));
     const EcEnc enc_start = enc;
-    for (int i = 0; i < C * kNbEBands; i++) cs.oldE_intra[i] = oldEBands[i];
+    CB_NOUNROLL for (int i = 0; i < C * kNbEBands; i++) cs.oldE_intra[i] = oldEBands[i];
     int badness1 = 0;
     if (two_pass || intra)
         badness1 = quant_coarse_energy_impl(start, end, eBands, cs.oldE_intra, (int)budget, (int)tell, kEProbModel[LM][1],
@@ -111,18 +111,18 @@ CB_DEV_NOINLINE void quant_coarse_energy(int start, int end, int effEnd, const i
         uint8_t *intra_buf = enc_intra.buf + nstart;
         unsigned save = nintra - nstart;
         if (save > sizeof(cs.intra_bits)) save = sizeof(cs.intra_bits);
-        for (unsigned k = 0; k < save; k++) cs.intra_bits[k] = intra_buf[k];
+        CB_NOUNROLL for (unsigned k = 0; k < save; k++) cs.intra_bits[k] = intra_buf[k];
         enc = enc_start;
         const int badness2 = quant_coarse_energy_impl(start, end, eBands, oldEBands, (int)budget, (int)tell, kEProbModel[LM][intra],
                                                       error, enc, C, LM, 0, max_decay);
         if (two_pass && (badness1 < badness2 || (badness1 == badness2 && (int)enc.tell_frac() + intra_bias > tell_intra))) {
             enc = enc_intra;
-            for (unsigned k = 0; k < save; k++) intra_buf[k] = cs.intra_bits[k];
-            for (int i = 0; i < C * kNbEBands; i++) { oldEBands[i] = cs.oldE_intra[i]; error[i] = cs.error_intra[i]; }
+            CB_NOUNROLL for (unsigned k = 0; k < save; k++) intra_buf[k] = cs.intra_bits[k];
+            CB_NOUNROLL for (int i = 0; i < C * kNbEBands; i++) { oldEBands[i] = cs.oldE_intra[i]; error[i] = cs.error_intra[i]; }
             intra = 1;
         }
     } else {
-        for (int i = 0; i < C * kNbEBands; i++) { oldEBands[i] = cs.oldE_intra[i]; error[i] = cs.error_intra[i]; }
+        CB_NOUNROLL for (int i = 0; i < C * kNbEBands; i++) { oldEBands[i] = cs.oldE_intra[i]; error[i] = cs.error_intra[i]; }
     }
     if (intra) *delayedIntra = new_distortion;
     else *delayedIntra = wadd(mul16_32_q15(mul16_16_q15(kPredCoef[LM], kPredCoef[LM]), *delayedIntra), new_distortion);
@@ -130,10 +130,10 @@ CB_DEV_NOINLINE void quant_coarse_energy(int start, int end, int effEnd, const i
 
 // quant_bands.c:369-404
 CB_DEV void quant_fine_energy(int start, int end, int16_t *oldEBands, int16_t *error, const int *fine_quant, EcEnc &enc, int C) {
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         const int frac = s16(1 << fine_quant[i]);
         if (fine_quant[i] <= 0) continue;
-        for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             int q2 = (error[i + c * kNbEBands] + 512) >> (10 - fine_quant[i]);
             if (q2 > frac - 1) q2 = frac - 1;
             if (q2 < 0) q2 = 0;
@@ -148,10 +148,10 @@ CB_DEV void quant_fine_energy(int start, int end, int16_t *oldEBands, int16_t *e
 // quant_bands.c:406-433
 CB_DEV void quant_energy_finalise(int start, int end, int16_t *oldEBands, const int16_t *error, const int *fine_quant,
                                   const int *fine_priority, int bits_left, EcEnc &enc, int C) {
-    for (int prio = 0; prio < 2; prio++) {
-        for (int i = start; i < end && bits_left >= C; i++) {
+    CB_NOUNROLL for (int prio = 0; prio < 2; prio++) {
+        CB_NOUNROLL for (int i = start; i < end && bits_left >= C; i++) {
             if (fine_quant[i] >= kMaxFineBits || fine_priority[i] != prio) continue;
-            for (int c = 0; c < C; c++) {
+            CB_NOUNROLL for (int c = 0; c < C; c++) {
                 int q2 = error[i + c * kNbEBands] < 0 ? 0 : 1;
                 enc.bits((unsigned)q2, 1);
                 int offset = s16((shl16(q2, 10) - 512) >> (fine_quant[i] + 1));
@@ -170,7 +170,7 @@ CB_DEV void tf_encode(int start, int end, int isTransient, int *tf_res, int LM, 
     int tf_select_rsv = LM > 0 && tell + logp + 1 <= budget;
     budget -= tf_select_rsv;
     int curr = 0, tf_changed = 0;
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         if (tell + logp <= budget) {
             enc.bit_logp(tf_res[i] ^ curr, logp);
             tell = (unsigned)enc.tell();
@@ -185,7 +185,7 @@ CB_DEV void tf_encode(int start, int end, int isTransient, int *tf_res, int LM, 
         enc.bit_logp(tf_select, 1);
     else
         tf_select = 0;
-    for (int i = start; i < end; i++) tf_res[i] = kTfSelect[LM][4 * isTransient + 2 * tf_select + tf_res[i]];
+    CB_NOUNROLL for (int i = start; i < end; i++) tf_res[i] = kTfSelect[LM][4 * isTransient + 2 * tf_select + tf_res[i]];
 }
 
 }  // namespace cb

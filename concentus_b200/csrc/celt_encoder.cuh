@@ -43,22 +43,35 @@ struct EncVars {
     int mask_metric[2];
     int tf_select, tf_sum, do_tf, do_spread, do_trim, dual_stereo, alloc_trim;
     int temporal_vbr, maxDepth, tot_boost, total_boost;
+    int anti_collapse_rsv, balance, codedBands;
     int ret;
 };
 
-// Per-stream working set of one frame.  Lives in HBM/L2 next to the state; all of it is dead between frames.
-struct EncScratch {
-    int in[2 * (kMaxFrame + kOverlap)];              // pre-emphasised input + overlap history, per channel
-    int pre[2 * (kCombMaxPeriod + kMaxFrame)];       // pre-filter history + new samples, per channel
-    int freq[2 * kMaxFrame];                          // MDCT output
-    int mdct_f[kMaxFrame], mdct_f2[kMaxFrame];        // MDCT fold / FFT buffers (one block at a time)
-    int16_t X[2 * kMaxFrame];                         // normalised spectrum
-    int16_t pitch_raw[(kCombMaxPeriod + kMaxFrame) / 2], pitch_buf[(kCombMaxPeriod + kMaxFrame) / 2];
-    int16_t x_lp4[kMaxFrame / 4], y_lp4[(kMaxFrame + kCombMaxPeriod) / 4];
-    int xcorr[kCombMaxPeriod / 2];
-    int yy_lookup[kCombMaxPeriod / 2 + 1];
-    int16_t ttmp[2 * (kMaxFrame + kOverlap)];         // transient_analysis work, per channel
-    int16_t tf_tmp[kMaxFrame], tf_tmp1[kMaxFrame];    // tf_analysis work
+// Per-stream working set of one frame, split by temperature.
+//   EncShared — per-warp SHARED memory (~11 KB): everything lane 0 walks serially or the team hits repeatedly, overlaid by
+//               phase (the phases of a frame are strictly sequential), plus the band-sized arrays and the frame scalars.
+//   EncGlobal — HBM/L2: the three big sample buffers, touched only by coalesced team-wide passes.
+struct EncShared {
+    union Phase {
+        int16_t pcm_buf[2 * (kMaxFrame + 192)];       // Opus layer: delay-compensation samples + DC-rejected input of this frame
+        struct {                                       // pitch pre-filter analysis
+            int16_t pitch_buf[(kCombMaxPeriod + kMaxFrame) / 2];
+            int16_t x_lp4[kMaxFrame / 4], y_lp4[(kMaxFrame + kCombMaxPeriod) / 4];
+            union {
+                int16_t pitch_raw[(kCombMaxPeriod + kMaxFrame) / 2];
+                struct { int xcorr[kCombMaxPeriod / 2]; int yy_lookup[kCombMaxPeriod / 2 + 1]; } c;
+            } a;
+        } pf;
+        int tin[2 * (kMaxFrame + kOverlap)];          // transient_analysis: staged input (int32), rewritten in place as int16
+        int fft[kMaxFrame];                            // MDCT: one channel's FFT buffer (all short blocks at once)
+        struct {                                       // normalised spectrum and what works on it
+            int16_t X[2 * kMaxFrame];
+            union {
+                struct { int16_t tf_tmp[kMaxFrame], tf_tmp1[kMaxFrame]; } tf;
+                struct { PvqScratch pvq; int16_t had_tmp[176]; } q;
+            } w;
+        } x;
+    } u;
     int metric[kNbEBands];
     int bandE[2 * kNbEBands];
     int16_t bandLogE[2 * kNbEBands], bandLogE2[2 * kNbEBands], error[2 * kNbEBands];
@@ -67,10 +80,12 @@ struct EncScratch {
     int tf_res[kNbEBands], offsets[kNbEBands], cap[kNbEBands], fine_quant[kNbEBands], pulses[kNbEBands], fine_priority[kNbEBands];
     AllocScratch alloc;
     CoarseScratch coarse;
-    PvqScratch pvq;
-    int16_t had_tmp[176];
-    int16_t pcm_buf[2 * (kMaxFrame + 192)];           // Opus layer: delay-compensation samples + DC-rejected input of this frame
     EncVars v;
+};
+struct EncGlobal {
+    int in[2 * (kMaxFrame + kOverlap)];              // pre-emphasised input + overlap history, per channel
+    int pre[2 * (kCombMaxPeriod + kMaxFrame)];       // pre-filter history + new samples, per channel
+    int freq[2 * kMaxFrame];                          // MDCT output
 };
 
 // ---- team reductions ---------------------------------------------------------------------------------------------
@@ -124,7 +139,7 @@ struct AllocEncIo {
 
 // pitch_downsample (pitch.c:147-217): x0/x1 -> x_out[len/2] (x_raw: staging of the same size).
 template <class TM>
-CB_DEV void pitch_downsample_team(TM tm, const int *x0, const int *x1, int len, int C, int16_t *x_raw, int16_t *x_out) {
+CB_DEV_NOINLINE void pitch_downsample_team(TM tm, const int *x0, const int *x1, int len, int C, int16_t *x_raw, int16_t *x_out) {
     int maxabs = team_maxabs32(tm, x0, len);
     if (C == 2) maxabs = imax(maxabs, team_maxabs32(tm, x1, len));
     if (maxabs < 1) maxabs = 1;
@@ -178,18 +193,18 @@ CB_DEV void pitch_downsample_team(TM tm, const int *x0, const int *x1, int len, 
     if (sh <= 0) ac[0] = wadd(ac[0], shl32(1, -sh));
     if (ac[0] < 268435456) {
         int shift2 = 29 - ec_ilog((unsigned)ac[0]);
-        for (int i = 0; i <= 4; i++) ac[i] = shl32(ac[i], shift2);
+        CB_NOUNROLL for (int i = 0; i <= 4; i++) ac[i] = shl32(ac[i], shift2);
     } else if (ac[0] >= 536870912) {
         int shift2 = 1;
         if (ac[0] >= 1073741824) shift2++;
-        for (int i = 0; i <= 4; i++) ac[i] = ac[i] >> shift2;
+        CB_NOUNROLL for (int i = 0; i <= 4; i++) ac[i] = ac[i] >> shift2;
     }
     ac[0] = wadd(ac[0], ac[0] >> 13);
-    for (int i = 1; i <= 4; i++) ac[i] = wsub(ac[i], mul16_32_q15(2 * i * i, ac[i]));
+    CB_NOUNROLL for (int i = 1; i <= 4; i++) ac[i] = wsub(ac[i], mul16_32_q15(2 * i * i, ac[i]));
     int16_t lpc[4];
     celt_lpc(lpc, ac, 4);
     int tmp = 32767;
-    for (int i = 0; i < 4; i++) {
+    CB_NOUNROLL for (int i = 0; i < 4; i++) {
         tmp = s16(mul16_16_q15(29491, tmp));
         lpc[i] = (int16_t)mul16_16_q15(lpc[i], tmp);
     }
@@ -214,7 +229,7 @@ CB_DEV void pitch_downsample_team(TM tm, const int *x0, const int *x1, int len, 
 
 // pitch_search (pitch.c:260-369)
 template <class TM>
-CB_DEV int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t *y, int len, int max_pitch, int16_t *x_lp4, int16_t *y_lp4,
+CB_DEV_NOINLINE int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t *y, int len, int max_pitch, int16_t *x_lp4, int16_t *y_lp4,
                              int *xcorr) {
     const int lag = len + max_pitch;
     int best_pitch[2] = {0, 0};
@@ -238,7 +253,7 @@ CB_DEV int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t *y, int l
         const int n = len >> 2, np = max_pitch >> 2;
         CB_TEAM_FOR(i, np, tm) {
             int s = 0;
-            for (int j = 0; j < n; j++) s = mac16_16(s, x_lp4[j], y_lp4[i + j]);
+            CB_NOUNROLL for (int j = 0; j < n; j++) s = mac16_16(s, x_lp4[j], y_lp4[i + j]);
             xcorr[i] = s;
             maxcorr = imax(maxcorr, s);
         }
@@ -251,7 +266,7 @@ CB_DEV int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t *y, int l
     maxcorr = 1;
     CB_TEAM_FOR(i, max_pitch >> 1, tm) xcorr[i] = 0;
     tm.sync();
-    for (int i = 0; i < max_pitch >> 1; i++) {
+    CB_NOUNROLL for (int i = 0; i < max_pitch >> 1; i++) {
         if (iabs(i - 2 * best_pitch[0]) > 2 && iabs(i - 2 * best_pitch[1]) > 2) continue;
         int s = 0;
         CB_TEAM_FOR(j, len >> 1, tm) s = wadd(s, mul16_16(x_lp[j], y[i + j]) >> shift);
@@ -273,7 +288,7 @@ CB_DEV int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t *y, int l
 
 // remove_doubling (pitch.c:372-505).  opus-fix keeps g, g0 32-bit (pitch.c:376,416-420).
 template <class TM>
-CB_DEV int remove_doubling_team(TM tm, const int16_t *x, int maxperiod, int minperiod, int N, int *T0_, int prev_period, int prev_gain,
+CB_DEV_NOINLINE int remove_doubling_team(TM tm, const int16_t *x, int maxperiod, int minperiod, int N, int *T0_, int prev_period, int prev_gain,
                                 int *yy_lookup) {
     const int minperiod0 = minperiod;
     maxperiod /= 2; minperiod /= 2; *T0_ /= 2; prev_period /= 2; N /= 2;
@@ -293,10 +308,10 @@ CB_DEV int remove_doubling_team(TM tm, const int16_t *x, int maxperiod, int minp
         const int per = (maxperiod + TM::W - 1) / TM::W;
         const int first = 1 + tm.lane() * per;
         int local = 0;
-        for (int i = first; i < first + per && i <= maxperiod; i++)
+        CB_NOUNROLL for (int i = first; i < first + per && i <= maxperiod; i++)
             local = wsub(wadd(local, mul16_16(x[-i], x[-i])), mul16_16(x[N - i], x[N - i]));
         int yy = wadd(xx, tm.exscan(local));
-        for (int i = first; i < first + per && i <= maxperiod; i++) {
+        CB_NOUNROLL for (int i = first; i < first + per && i <= maxperiod; i++) {
             yy = wsub(wadd(yy, mul16_16(x[-i], x[-i])), mul16_16(x[N - i], x[N - i]));
             yy_lookup[i] = imax(0, yy);
         }
@@ -312,7 +327,7 @@ CB_DEV int remove_doubling_team(TM tm, const int16_t *x, int maxperiod, int minp
         int t = vshr32(x2y2, 2 * (sh - 7));
         g = g0 = vshr32(mul16_32_q15(celt_rsqrt_norm(t), xy), sh + 1);
     }
-    for (int k = 2; k <= 15; k++) {
+    CB_NOUNROLL for (int k = 2; k <= 15; k++) {
         int T1 = (int)udiv((unsigned)(2 * T0 + k), (unsigned)(2 * k));
         if (T1 < minperiod) break;
         int T1b;
@@ -371,7 +386,7 @@ CB_DEV int remove_doubling_team(TM tm, const int16_t *x, int maxperiod, int minp
 
 // comb_filter with y != x (celt.c:183-244), every output sample independent
 template <class TM>
-CB_DEV void comb_filter_fir_team(TM tm, int *y, const int *x, int T0, int T1, int N, int g0, int g1, int tapset0, int tapset1, int overlap) {
+CB_DEV_NOINLINE void comb_filter_fir_team(TM tm, int *y, const int *x, int T0, int T1, int N, int g0, int g1, int tapset0, int tapset1, int overlap) {
     if (g0 == 0 && g1 == 0) {
         CB_TEAM_FOR(i, N, tm) y[i] = x[i];
         return;
@@ -410,12 +425,15 @@ CB_TABLE uint8_t kInvTable[128] = {
     6, 6, 6, 6, 6, 6, 6, 6, 6, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
     4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2};
 
-CB_DEV_NOINLINE int transient_channel(const int *in, int len, int16_t *tmp) {
+// xin: the channel's input already shifted down by SIG_SHIFT (int32, shared memory); the int16 work vector is written IN PLACE
+// over it (element i of the int16 view trails element i of the int32 view, so no unread input is overwritten).
+CB_DEV_NOINLINE int transient_channel(int *xin, int len) {
+    int16_t *tmp = reinterpret_cast<int16_t *>(xin);
     const int len2 = len / 2;
     int mem0 = 0, mem1 = 0;
     int mxv = 0, mnv = 0;
-    for (int i = 0; i < len; i++) {
-        int x = in[i] >> 12;
+    CB_NOUNROLL for (int i = 0; i < len; i++) {
+        int x = xin[i];
         int y = wadd(mem0, x);
         mem0 = wsub(wadd(mem1, y), shl32(x, 1));
         mem1 = wsub(x, y >> 1);
@@ -429,11 +447,11 @@ CB_DEV_NOINLINE int transient_channel(const int *in, int len, int16_t *tmp) {
         // (count & 31) of the zero-extended value, truncated to 16 bits
         int shift = 14 - celt_ilog2(1 + imax(mxv, -mnv));
         if (shift != 0)
-            for (int i = 0; i < len; i++) tmp[i] = (int16_t)((unsigned)(uint16_t)tmp[i] << (shift & 31));
+            CB_NOUNROLL for (int i = 0; i < len; i++) tmp[i] = (int16_t)((unsigned)(uint16_t)tmp[i] << (shift & 31));
     }
     int mean = 0;
     mem0 = 0;
-    for (int i = 0; i < len2; i++) {
+    CB_NOUNROLL for (int i = 0; i < len2; i++) {
         int x2 = s16(pshr32(wadd(mul16_16(tmp[2 * i], tmp[2 * i]), mul16_16(tmp[2 * i + 1], tmp[2 * i + 1])), 16));
         mean = wadd(mean, x2);
         int v = s16(mem0 + pshr32(x2 - mem0, 4));
@@ -442,7 +460,7 @@ CB_DEV_NOINLINE int transient_channel(const int *in, int len, int16_t *tmp) {
     }
     mem0 = 0;
     int maxE = 0;
-    for (int i = len2 - 1; i >= 0; i--) {
+    CB_NOUNROLL for (int i = len2 - 1; i >= 0; i--) {
         int v = s16(mem0 + pshr32(tmp[i] - mem0, 3));
         tmp[i] = (int16_t)v;
         mem0 = v;
@@ -451,7 +469,7 @@ CB_DEV_NOINLINE int transient_channel(const int *in, int len, int16_t *tmp) {
     mean = mul16_16(celt_sqrt(mean), celt_sqrt(mul16_16(maxE, len2 >> 1)));
     const int norm = shl32(len2, 6 + 14) / wadd(1, mean >> 1);
     int unmask = 0;
-    for (int i = 12; i < len2 - 5; i += 4) {
+    CB_NOUNROLL for (int i = 12; i < len2 - 5; i += 4) {
         int id = imax(0, imin(127, mul16_32_q15(tmp[i] + 1, norm)));
         unmask += kInvTable[id];
     }
@@ -464,15 +482,15 @@ CB_DEV int patch_transient_decision(const int16_t *newE, const int16_t *oldE, in
     int spread_old[26];
     if (C == 1) {
         spread_old[start] = oldE[start];
-        for (int i = start + 1; i < end; i++) spread_old[i] = s16(imax(spread_old[i - 1] - 1024, (int)oldE[i]));
+        CB_NOUNROLL for (int i = start + 1; i < end; i++) spread_old[i] = s16(imax(spread_old[i - 1] - 1024, (int)oldE[i]));
     } else {
         spread_old[start] = imax((int)oldE[start], (int)oldE[start + kNbEBands]);
-        for (int i = start + 1; i < end; i++)
+        CB_NOUNROLL for (int i = start + 1; i < end; i++)
             spread_old[i] = s16(imax(spread_old[i - 1] - 1024, imax((int)oldE[i], (int)oldE[i + kNbEBands])));
     }
-    for (int i = end - 2; i >= start; i--) spread_old[i] = s16(imax(spread_old[i], spread_old[i + 1] - 1024));
-    for (int c = 0; c < C; c++)
-        for (int i = imax(2, start); i < end - 1; i++) {
+    CB_NOUNROLL for (int i = end - 2; i >= start; i--) spread_old[i] = s16(imax(spread_old[i], spread_old[i + 1] - 1024));
+    CB_NOUNROLL for (int c = 0; c < C; c++)
+        CB_NOUNROLL for (int i = imax(2, start); i < end - 1; i++) {
             int x1 = imax(0, (int)newE[i + c * kNbEBands]);
             int x2 = imax(0, spread_old[i]);
             mean_diff = wadd(mean_diff, imax(0, x1 - x2));
@@ -484,24 +502,24 @@ CB_DEV int patch_transient_decision(const int16_t *newE, const int16_t *oldE, in
 // ---- tf_analysis (celt_encoder.c:539-712) -------------------------------------------------------------------------
 CB_DEV int l1_metric(const int16_t *tmp, int N, int LM, int bias) {
     int L1 = 0;
-    for (int i = 0; i < N; i++) L1 += iabs((int)tmp[i]);
+    CB_NOUNROLL for (int i = 0; i < N; i++) L1 += iabs((int)tmp[i]);
     return mac16_32_q15(L1, LM * bias, L1);
 }
 
 // metric of one band (the per-band body of tf_analysis, :580-640); tmp / tmp_1: this band's N int16 of scratch
 CB_DEV_NOINLINE int tf_band_metric(const int16_t *Xb, int N, int narrow, int isTransient, int LM, int bias, int16_t *tmp, int16_t *tmp_1,
                                    int *tf_sum_term) {
-    for (int j = 0; j < N; j++) tmp[j] = Xb[j];
+    CB_NOUNROLL for (int j = 0; j < N; j++) tmp[j] = Xb[j];
     int L1 = l1_metric(tmp, N, isTransient ? LM : 0, bias);
     int best_L1 = L1;
     int best_level = 0;
     if (isTransient && !narrow) {
-        for (int j = 0; j < N; j++) tmp_1[j] = tmp[j];
+        CB_NOUNROLL for (int j = 0; j < N; j++) tmp_1[j] = tmp[j];
         haar1(tmp_1, N >> LM, 1 << LM);
         L1 = l1_metric(tmp_1, N, LM + 1, bias);
         if (L1 < best_L1) { best_L1 = L1; best_level = -1; }
     }
-    for (int k = 0; k < LM + !(isTransient || narrow); k++) {
+    CB_NOUNROLL for (int k = 0; k < LM + !(isTransient || narrow); k++) {
         int B = isTransient ? LM - k - 1 : k + 1;
         haar1(tmp, N >> k, 1 << k);
         L1 = l1_metric(tmp, N, B, bias);
@@ -518,10 +536,10 @@ CB_DEV_NOINLINE int tf_viterbi(const int *metric, int len, int isTransient, int 
     int path0[kNbEBands], path1[kNbEBands];
     int selcost[2];
     int tf_select = 0;
-    for (int sel = 0; sel < 2; sel++) {
+    CB_NOUNROLL for (int sel = 0; sel < 2; sel++) {
         int cost0 = 0;
         int cost1 = isTransient ? 0 : lambda;
-        for (int i = 1; i < len; i++) {
+        CB_NOUNROLL for (int i = 1; i < len; i++) {
             int curr0 = imin(cost0, cost1 + lambda);
             int curr1 = imin(cost0 + lambda, cost1);
             cost0 = curr0 + iabs(metric[i] - 2 * kTfSelect[LM][4 * isTransient + 2 * sel + 0]);
@@ -532,7 +550,7 @@ CB_DEV_NOINLINE int tf_viterbi(const int *metric, int len, int isTransient, int 
     if (selcost[1] < selcost[0] && isTransient) tf_select = 1;
     int cost0 = 0;
     int cost1 = isTransient ? 0 : lambda;
-    for (int i = 1; i < len; i++) {
+    CB_NOUNROLL for (int i = 1; i < len; i++) {
         int curr0, curr1;
         int from0 = cost0, from1 = cost1 + lambda;
         if (from0 < from1) { curr0 = from0; path0[i] = 0; }
@@ -545,7 +563,7 @@ CB_DEV_NOINLINE int tf_viterbi(const int *metric, int len, int isTransient, int 
         cost1 = curr1 + iabs(metric[i] - 2 * kTfSelect[LM][4 * isTransient + 2 * tf_select + 1]);
     }
     tf_res[len - 1] = cost0 < cost1 ? 0 : 1;
-    for (int i = len - 2; i >= 0; i--) tf_res[i] = tf_res[i + 1] == 1 ? path1[i + 1] : path0[i + 1];
+    CB_NOUNROLL for (int i = len - 2; i >= 0; i--) tf_res[i] = tf_res[i + 1] == 1 ? path1[i + 1] : path0[i + 1];
     return tf_select;
 }
 
@@ -572,47 +590,47 @@ CB_DEV_NOINLINE int dynalloc_analysis(const int16_t *bandLogE, const int16_t *ba
     const int nb = kNbEBands;
     int tot_boost = 0;
     int16_t follower[2 * kNbEBands], noise_floor[kNbEBands];
-    for (int i = 0; i < nb; i++) offsets[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < nb; i++) offsets[i] = 0;
     int maxDepth = -32666;
-    for (int i = 0; i < end; i++)
+    CB_NOUNROLL for (int i = 0; i < end; i++)
         noise_floor[i] = (int16_t)(mul16_16(64, kLogN[i]) + 512 + shl16(9 - lsb_depth, 10) - shl16(kEMeans[i], 6) + mul16_16(6, (i + 5) * (i + 5)));
-    for (int c = 0; c < C; c++)
-        for (int i = 0; i < end; i++) maxDepth = imax(maxDepth, (int)bandLogE[c * nb + i] - noise_floor[i]);
+    CB_NOUNROLL for (int c = 0; c < C; c++)
+        CB_NOUNROLL for (int i = 0; i < end; i++) maxDepth = imax(maxDepth, (int)bandLogE[c * nb + i] - noise_floor[i]);
     maxDepth = s16(maxDepth);
     if (effectiveBytes > 50 && LM >= 1) {
         int last = 0;
-        for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             int16_t *f = &follower[c * nb];
             const int16_t *e2 = &bandLogE2[c * nb];
             f[0] = e2[0];
-            for (int i = 1; i < end; i++) {
+            CB_NOUNROLL for (int i = 1; i < end; i++) {
                 if (e2[i] > e2[i - 1] + 512) last = i;
                 f[i] = (int16_t)imin(f[i - 1] + 1536, (int)e2[i]);
             }
-            for (int i = last - 1; i >= 0; i--) f[i] = (int16_t)imin((int)f[i], imin(f[i + 1] + 2048, (int)e2[i]));
+            CB_NOUNROLL for (int i = last - 1; i >= 0; i--) f[i] = (int16_t)imin((int)f[i], imin(f[i + 1] + 2048, (int)e2[i]));
             const int offset = 1024;
-            for (int i = 2; i < end - 2; i++) f[i] = (int16_t)imax((int)f[i], median_of_5(&e2[i - 2]) - offset);
+            CB_NOUNROLL for (int i = 2; i < end - 2; i++) f[i] = (int16_t)imax((int)f[i], median_of_5(&e2[i - 2]) - offset);
             int tmp = median_of_3(&e2[0]) - offset;
             f[0] = (int16_t)imax((int)f[0], tmp);
             f[1] = (int16_t)imax((int)f[1], tmp);
             tmp = median_of_3(&e2[end - 3]) - offset;
             f[end - 2] = (int16_t)imax((int)f[end - 2], tmp);
             f[end - 1] = (int16_t)imax((int)f[end - 1], tmp);
-            for (int i = 0; i < end; i++) f[i] = (int16_t)imax((int)f[i], (int)noise_floor[i]);
+            CB_NOUNROLL for (int i = 0; i < end; i++) f[i] = (int16_t)imax((int)f[i], (int)noise_floor[i]);
         }
         if (C == 2) {
-            for (int i = start; i < end; i++) {
+            CB_NOUNROLL for (int i = start; i < end; i++) {
                 follower[nb + i] = (int16_t)imax((int)follower[nb + i], follower[i] - 4096);
                 follower[i] = (int16_t)imax((int)follower[i], follower[nb + i] - 4096);
                 follower[i] = (int16_t)((imax(0, bandLogE[i] - follower[i]) + imax(0, bandLogE[nb + i] - follower[nb + i])) >> 1);
             }
         } else {
-            for (int i = start; i < end; i++) follower[i] = (int16_t)imax(0, bandLogE[i] - follower[i]);
+            CB_NOUNROLL for (int i = start; i < end; i++) follower[i] = (int16_t)imax(0, bandLogE[i] - follower[i]);
         }
         // surround_dynalloc is all zero here: follower[i] = MAX16(follower[i], 0) is the identity for these non-negative values
         if ((!vbr || constrained_vbr) && !isTransient)
-            for (int i = start; i < end; i++) follower[i] = (int16_t)(follower[i] >> 1);
-        for (int i = start; i < end; i++) {
+            CB_NOUNROLL for (int i = start; i < end; i++) follower[i] = (int16_t)(follower[i] >> 1);
+        CB_NOUNROLL for (int i = start; i < end; i++) {
             if (i < 8) follower[i] = (int16_t)(follower[i] * 2);
             if (i >= 12) follower[i] = (int16_t)(follower[i] >> 1);
             follower[i] = (int16_t)imin((int)follower[i], 4096);
@@ -681,20 +699,20 @@ CB_DEV_NOINLINE int compute_vbr(int base_target, int LM, int bitrate, int lastCo
 
 // ---- alloc_trim_analysis (celt_encoder.c:756-838) & stereo_analysis (:840-870), team reductions over X -------------
 template <class TM>
-CB_DEV int alloc_trim_analysis_team(TM tm, const int16_t *X, const int16_t *bandLogE, int end, int LM, int C, int N0, int *stereo_saving,
+CB_DEV_NOINLINE int alloc_trim_analysis_team(TM tm, const int16_t *X, const int16_t *bandLogE, int end, int LM, int C, int N0, int *stereo_saving,
                                     int tf_estimate, int intensity) {
     int diff = 0;
     int trim = 1280;
     if (C == 2) {
         int sum = 0;
-        for (int i = 0; i < 8; i++) {
+        CB_NOUNROLL for (int i = 0; i < 8; i++) {
             int partial = team_inner16(tm, &X[kEBands[i] << LM], &X[N0 + (kEBands[i] << LM)], band_width(i) << LM);
             sum = s16(sum + s16(partial >> 18));
         }
         sum = mul16_16_q15(4096, sum);
         sum = imin(1024, iabs(sum));
         int minXC = sum;
-        for (int i = 8; i < intensity; i++) {
+        CB_NOUNROLL for (int i = 8; i < intensity; i++) {
             int partial = team_inner16(tm, &X[kEBands[i] << LM], &X[N0 + (kEBands[i] << LM)], band_width(i) << LM);
             minXC = imin(minXC, iabs(s16(partial >> 18)));
         }
@@ -706,8 +724,8 @@ CB_DEV int alloc_trim_analysis_team(TM tm, const int16_t *X, const int16_t *band
         trim = s16(trim + imax(-1024, mul16_16_q15(24576, logXC)));
         *stereo_saving = s16(imin(*stereo_saving + 64, -(logXC2 >> 1)));
     }
-    for (int c = 0; c < C; c++)
-        for (int i = 0; i < end - 1; i++) diff += bandLogE[i + c * kNbEBands] * (2 + 2 * i - end);
+    CB_NOUNROLL for (int c = 0; c < C; c++)
+        CB_NOUNROLL for (int i = 0; i < end - 1; i++) diff += bandLogE[i + c * kNbEBands] * (2 + 2 * i - end);
     diff /= C * (end - 1);
     trim = s16(trim - imax(-512, imin(512, ((diff + 1024) >> 2) / 6)));
     trim = s16(trim - 2 * (tf_estimate >> 6));
@@ -734,13 +752,13 @@ CB_DEV int stereo_analysis_team(TM tm, const int16_t *X, int LM, int N0) {
 
 // spreading_decision (bands.c:428-519): threshold counts per band as one packed team sum
 template <class TM>
-CB_DEV int spreading_decision_team(TM tm, const int16_t *X, int *average, int last_decision, int *hf_average, int *tapset_decision,
+CB_DEV_NOINLINE int spreading_decision_team(TM tm, const int16_t *X, int *average, int last_decision, int *hf_average, int *tapset_decision,
                                    int update_hf, int end, int C, int M) {
     int sum = 0, nbBands = 0, hf_sum = 0;
     const int N0 = M * kShortMdct;
     if (M * (kEBands[end] - kEBands[end - 1]) <= 8) return kSpreadNone;
-    for (int c = 0; c < C; c++) {
-        for (int i = 0; i < end; i++) {
+    CB_NOUNROLL for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int i = 0; i < end; i++) {
             const int16_t *x = X + M * kEBands[i] + c * N0;
             const int N = M * (kEBands[i + 1] - kEBands[i]);
             if (N <= 8) continue;
@@ -779,14 +797,66 @@ CB_DEV int spreading_decision_team(TM tm, const int16_t *X, int *average, int la
 
 // ---- transform + band energies (team) --------------------------------------------------------------------------------
 
+// clt_mdct_forward (mdct.c:121-259) for the B blocks of one channel at once: window/fold and pre-rotation are fused and write
+// straight into the shared FFT buffer in bit-reversed order, one batched FFT, post-rotation writes the interleaved output.
+// in: the channel's B*N2 + overlap samples (HBM); out: freq of this channel, coefficient k of block b at out[b + k*B].
+template <class TM>
+CB_DEV void mdct_forward_blocks(TM tm, const int *in, int *out, int shift, int B, int *fftbuf) {
+    const int N2 = (kMaxFrame * 2 >> shift) >> 1;
+    const int N4 = N2 >> 1;
+    int trig_off = 0;
+    CB_NOUNROLL for (int i = 0, n = kMaxFrame * 2; i < shift; i++) { n >>= 1; trig_off += n; }
+    const int16_t *t = kMdctTwiddles + trig_off;
+    const int16_t *bitrev = fft_bitrev(shift);
+    const int scale_shift = kFftPlan[shift].scale_shift - 1;
+    const int ov = kOverlap, q = (ov + 3) >> 2;
+    CB_TEAM_FOR(w, B * N4, tm) {
+        const int b = w / N4, i = w - b * N4;
+        const int *xp1 = in + b * N2 + (ov >> 1) + 2 * i;
+        const int *xp2 = in + b * N2 + N2 - 1 + (ov >> 1) - 2 * i;
+        int re, im;
+        if (i < q) {
+            const int w1 = kWindow120[(ov >> 1) + 2 * i], w2 = kWindow120[(ov >> 1) - 1 - 2 * i];
+            re = wadd(smul(xp1[N2], w2), smul(*xp2, w1));
+            im = wsub(smul(*xp1, w1), smul(xp2[-N2], w2));
+        } else if (i < N4 - q) {
+            re = *xp2;
+            im = *xp1;
+        } else {
+            const int k = i - (N4 - q);
+            const int w1 = kWindow120[2 * k], w2 = kWindow120[ov - 1 - 2 * k];
+            re = wadd(wneg(smul(xp1[-N2], w1)), smul(*xp2, w2));
+            im = wadd(smul(*xp1, w2), smul(xp2[N2], w1));
+        }
+        const int t0 = t[i], t1 = t[N4 + i];
+        int yr = wsub(smul(re, t0), smul(im, t1));
+        int yi = wadd(smul(im, t0), smul(re, t1));
+        yr = pshr32(mul16_32_q16(kFftScale, yr), scale_shift);
+        yi = pshr32(mul16_32_q16(kFftScale, yi), scale_shift);
+        const int rev = bitrev[i];
+        fftbuf[b * N2 + 2 * rev] = yr;
+        fftbuf[b * N2 + 2 * rev + 1] = yi;
+    }
+    tm.sync();
+    fft_inplace(tm, (Cpx *)fftbuf, shift, B);
+    CB_TEAM_FOR(w, B * N4, tm) {
+        const int b = w / N4, i = w - b * N4;
+        const int fr = fftbuf[b * N2 + 2 * i], fi = fftbuf[b * N2 + 2 * i + 1];
+        const int yr = wsub(smul(fi, t[N4 + i]), smul(fr, t[i]));
+        const int yi = wadd(smul(fr, t[N4 + i]), smul(fi, t[i]));
+        out[b + B * (2 * i)] = yr;
+        out[b + B * (N2 - 1 - 2 * i)] = yi;
+    }
+    tm.sync();
+}
+
 // compute_mdcts (celt_encoder.c:418-461), upsample == 1
 template <class TM>
-CB_DEV void compute_mdcts_team(TM tm, int shortBlocks, const int *in, int *freq, int C, int CC, int LM, int *f, int *f2) {
+CB_DEV_NOINLINE void compute_mdcts_team(TM tm, int shortBlocks, const int *in, int *freq, int C, int CC, int LM, int *fftbuf) {
     int B, N, shift;
     if (shortBlocks) { B = shortBlocks; N = kShortMdct; shift = kMaxLM; }
     else { B = 1; N = kShortMdct << LM; shift = kMaxLM - LM; }
-    for (int c = 0; c < CC; c++)
-        for (int b = 0; b < B; b++) mdct_forward(tm, in + c * (B * N + kOverlap) + b * N, &freq[b + c * N * B], shift, B, f, f2);
+    CB_NOUNROLL for (int c = 0; c < CC; c++) mdct_forward_blocks(tm, in + c * (B * N + kOverlap), freq + c * N * B, shift, B, fftbuf);
     if (CC == 2 && C == 1) {
         CB_TEAM_FOR(i, B * N, tm) freq[i] = wadd(freq[i] >> 1, freq[B * N + i] >> 1);
         tm.sync();
@@ -795,10 +865,10 @@ CB_DEV void compute_mdcts_team(TM tm, int shortBlocks, const int *in, int *freq,
 
 // compute_band_energies (bands.c:97-143) + amp2Log2 (quant_bands.c:551-572)
 template <class TM>
-CB_DEV void band_energies_team(TM tm, const int *freq, int *bandE, int16_t *bandLogE, int effEnd, int end, int C, int LM) {
+CB_DEV_NOINLINE void band_energies_team(TM tm, const int *freq, int *bandE, int16_t *bandLogE, int effEnd, int end, int C, int LM) {
     const int N = kShortMdct << LM;
-    for (int c = 0; c < C; c++) {
-        for (int i = 0; i < effEnd; i++) {
+    CB_NOUNROLL for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int i = 0; i < effEnd; i++) {
             const int lo = kEBands[i] << LM, hi = kEBands[i + 1] << LM;
             const int *x = freq + c * N;
             const int maxval = team_maxabs32(tm, x + lo, hi - lo);
@@ -820,14 +890,14 @@ CB_DEV void band_energies_team(TM tm, const int *freq, int *bandE, int16_t *band
             }
         }
         if (tm.lane() == 0)
-            for (int i = effEnd; i < end; i++) bandLogE[c * kNbEBands + i] = -14336;
+            CB_NOUNROLL for (int i = effEnd; i < end; i++) bandLogE[c * kNbEBands + i] = -14336;
     }
     tm.sync();
 }
 
 // normalise_bands (bands.c:146-164)
 template <class TM>
-CB_DEV void normalise_bands_team(TM tm, const int *freq, int16_t *X, const int *bandE, int end, int C, int M, int LM, int16_t *band_g,
+CB_DEV_NOINLINE void normalise_bands_team(TM tm, const int *freq, int16_t *X, const int *bandE, int end, int C, int M, int LM, int16_t *band_g,
                                  int8_t *band_shift) {
     const int N = M * kShortMdct;
     CB_TEAM_FOR(k, C * kNbEBands, tm) {
@@ -852,11 +922,13 @@ CB_DEV void normalise_bands_team(TM tm, const int *freq, int16_t *X, const int *
 // ---- the frame -------------------------------------------------------------------------------------------------------
 
 // celt_encode_with_ec (celt_encoder.c:1379-2273).  `pcm`: CC-interleaved int16, frame_size samples per channel (48 kHz).
+// `st` holds the head of the state (CB_ENC_HEAD_BYTES, possibly a shared-memory copy), `gst` the full block in HBM (only its
+// sample histories are touched).  `pcm` may live in S.u.pcm_buf: it is dead before the first overlay is written.
 // S.v.ec must hold the range coder the Opus layer initialised (and shrank to nbCompressedBytes).  Returns (on every lane)
 // the number of payload bytes, or a negative error.
 template <class TM>
-CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEncCfg &cfg, const int16_t *pcm, int frame_size,
-                             int nbCompressedBytes_in) {
+CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &S, EncGlobal &G, const CeltEncCfg &cfg, const int16_t *pcm,
+                             int frame_size, int nbCompressedBytes_in) {
     EncVars &V = S.v;
     const bool L0 = tm.lane() == 0;
     const int CC = st->channels;
@@ -865,7 +937,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
     const int end = cfg.end;
     const int effEnd = end;   // effEBands == 21 in the 48 kHz mode
     int LM;
-    for (LM = 0; LM <= kMaxLM; LM++)
+    CB_NOUNROLL for (LM = 0; LM <= kMaxLM; LM++)
         if (kShortMdct << LM == frame_size) break;
     if (LM > kMaxLM || nbCompressedBytes_in < 2) return OPUS_BAD_ARG_;
     const int M = 1 << LM;
@@ -919,8 +991,8 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
         tm.sync();
         if (L0) st->overlap_max = b;
     }
-    for (int c = 0; c < CC; c++) {
-        int *inp = S.in + c * (N + ov) + ov;
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
+        int *inp = G.in + c * (N + ov) + ov;
         const int m0 = st->preemph_memE[c];
         CB_TEAM_FOR(i, N, tm) {
             const int x = pcm[CC * i + c];
@@ -958,21 +1030,21 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
 
     // ---- pitch pre-filter (run_prefilter, :1067-1192) ----
     {
-        int *pre0 = S.pre, *pre1 = S.pre + (N + kCombMaxPeriod);
-        for (int c = 0; c < CC; c++) {
+        int *pre0 = G.pre, *pre1 = G.pre + (N + kCombMaxPeriod);
+        CB_NOUNROLL for (int c = 0; c < CC; c++) {
             int *pre = c ? pre1 : pre0;
-            CB_TEAM_FOR(i, kCombMaxPeriod, tm) pre[i] = st->prefilter_mem[c * kCombMaxPeriod + i];
-            CB_TEAM_FOR(i, N, tm) pre[kCombMaxPeriod + i] = S.in[c * (N + ov) + ov + i];
+            CB_TEAM_FOR(i, kCombMaxPeriod, tm) pre[i] = gst->prefilter_mem[c * kCombMaxPeriod + i];
+            CB_TEAM_FOR(i, N, tm) pre[kCombMaxPeriod + i] = G.in[c * (N + ov) + ov + i];
         }
         tm.sync();
         int pitch_index, gain1;
         const int prev_period = st->prefilter_period, prev_gain = st->prefilter_gain, prev_tapset = st->prefilter_tapset;
         if (V.enabled) {
-            pitch_downsample_team(tm, pre0, pre1, kCombMaxPeriod + N, CC, S.pitch_raw, S.pitch_buf);
-            pitch_index = pitch_search_team(tm, S.pitch_buf + (kCombMaxPeriod >> 1), S.pitch_buf, N, kCombMaxPeriod - 3 * kCombMinPeriod,
-                                            S.x_lp4, S.y_lp4, S.xcorr);
+            pitch_downsample_team(tm, pre0, pre1, kCombMaxPeriod + N, CC, S.u.pf.a.pitch_raw, S.u.pf.pitch_buf);
+            pitch_index = pitch_search_team(tm, S.u.pf.pitch_buf + (kCombMaxPeriod >> 1), S.u.pf.pitch_buf, N, kCombMaxPeriod - 3 * kCombMinPeriod,
+                                            S.u.pf.x_lp4, S.u.pf.y_lp4, S.u.pf.a.c.xcorr);
             pitch_index = kCombMaxPeriod - pitch_index;
-            gain1 = remove_doubling_team(tm, S.pitch_buf, kCombMaxPeriod, kCombMinPeriod, N, &pitch_index, prev_period, prev_gain, S.yy_lookup);
+            gain1 = remove_doubling_team(tm, S.u.pf.pitch_buf, kCombMaxPeriod, kCombMinPeriod, N, &pitch_index, prev_period, prev_gain, S.u.pf.a.c.yy_lookup);
             if (pitch_index > kCombMaxPeriod - 2) pitch_index = kCombMaxPeriod - 2;
             gain1 = s16(mul16_16_q15(22938, gain1));
             if (cfg.loss_rate > 2) gain1 = gain1 >> 1;
@@ -1001,14 +1073,14 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
         }
         const int pp = V.prefilter_period0;
         const int tapset1 = V.prefilter_tapset;
-        for (int c = 0; c < CC; c++) {
+        CB_NOUNROLL for (int c = 0; c < CC; c++) {
             int *pre = c ? pre1 : pre0;
-            int *inc = S.in + c * (N + ov);
-            CB_TEAM_FOR(i, ov, tm) inc[i] = st->in_mem[c * ov + i];
+            int *inc = G.in + c * (N + ov);
+            CB_TEAM_FOR(i, ov, tm) inc[i] = gst->in_mem[c * ov + i];
             comb_filter_fir_team(tm, inc + ov, pre + kCombMaxPeriod, pp, pitch_index, N, -prev_gain, -gain1, prev_tapset, tapset1, ov);
             tm.sync();
-            CB_TEAM_FOR(i, ov, tm) st->in_mem[c * ov + i] = inc[N + i];
-            CB_TEAM_FOR(i, kCombMaxPeriod, tm) st->prefilter_mem[c * kCombMaxPeriod + i] = pre[N + i];
+            CB_TEAM_FOR(i, ov, tm) gst->in_mem[c * ov + i] = inc[N + i];
+            CB_TEAM_FOR(i, kCombMaxPeriod, tm) gst->prefilter_mem[c * kCombMaxPeriod + i] = pre[N + i];
         }
         tm.sync();
         if (L0) {
@@ -1031,14 +1103,16 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
 
     // ---- transient analysis (:1642-1657): one lane per channel ----
     if (cfg.complexity >= 1) {
-        for (int c = tm.lane(); c < CC; c += TM::W) V.mask_metric[c] = transient_channel(S.in + c * (N + ov), N + ov, S.ttmp + c * (N + ov));
+        CB_TEAM_FOR(i, CC * (N + ov), tm) S.u.tin[i] = G.in[i] >> 12;
+        tm.sync();
+        CB_NOUNROLL for (int c = tm.lane(); c < CC; c += TM::W) V.mask_metric[c] = transient_channel(S.u.tin + c * (N + ov), N + ov);
     }
     tm.sync();
     if (L0) {
         int isTransient = 0, shortBlocks = 0, tf_estimate = 0, tf_chan = 0, transient_got_disabled = 0;
         if (cfg.complexity >= 1) {
             int mask_metric = 0;
-            for (int c = 0; c < CC; c++)
+            CB_NOUNROLL for (int c = 0; c < CC; c++)
                 if (V.mask_metric[c] > mask_metric) { tf_chan = c; mask_metric = V.mask_metric[c]; }
             isTransient = mask_metric > 200;
             const int tf_max = imax(0, s16(celt_sqrt(27 * mask_metric)) - 42);
@@ -1058,13 +1132,13 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
 
     // ---- MDCT, band energies (:1660-1690) ----
     if (V.secondMdct) {
-        compute_mdcts_team(tm, 0, S.in, S.freq, C, CC, LM, S.mdct_f, S.mdct_f2);
-        band_energies_team(tm, S.freq, S.bandE, S.bandLogE2, effEnd, end, C, LM);
+        compute_mdcts_team(tm, 0, G.in, G.freq, C, CC, LM, S.u.fft);
+        band_energies_team(tm, G.freq, S.bandE, S.bandLogE2, effEnd, end, C, LM);
         CB_TEAM_FOR(i, C * kNbEBands, tm) S.bandLogE2[i] = (int16_t)(S.bandLogE2[i] + (shl16(LM, 10) >> 1));
         tm.sync();
     }
-    compute_mdcts_team(tm, V.shortBlocks, S.in, S.freq, C, CC, LM, S.mdct_f, S.mdct_f2);
-    band_energies_team(tm, S.freq, S.bandE, S.bandLogE, effEnd, end, C, LM);
+    compute_mdcts_team(tm, V.shortBlocks, G.in, G.freq, C, CC, LM, S.u.fft);
+    band_energies_team(tm, G.freq, S.bandE, S.bandLogE, effEnd, end, C, LM);
 
     // ---- temporal VBR, bandLogE2, transient patch (:1803-1848) ----
     if (L0) {
@@ -1073,7 +1147,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
             int follow = -10240;
             int frame_avg = 0;
             const int offset = V.shortBlocks ? (shl16(LM, 10) >> 1) : 0;
-            for (int i = start; i < end; i++) {
+            CB_NOUNROLL for (int i = start; i < end; i++) {
                 follow = s16(imax(follow - 1024, S.bandLogE[i] - offset));
                 if (C == 2) follow = s16(imax(follow, S.bandLogE[i + kNbEBands] - offset));
                 frame_avg += follow;
@@ -1085,7 +1159,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
             V.temporal_vbr = temporal_vbr;
         }
         if (!V.secondMdct)
-            for (int i = 0; i < C * kNbEBands; i++) S.bandLogE2[i] = S.bandLogE[i];
+            CB_NOUNROLL for (int i = 0; i < C * kNbEBands; i++) S.bandLogE2[i] = S.bandLogE[i];
         V.patch = 0;
         if (LM > 0 && V.ec.tell() + 3 <= V.total_bits && !V.isTransient && cfg.complexity >= 5) {
             if (patch_transient_decision(S.bandLogE, st->oldBandE, start, end, C)) {
@@ -1097,8 +1171,8 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
     }
     tm.sync();
     if (V.patch) {
-        compute_mdcts_team(tm, V.shortBlocks, S.in, S.freq, C, CC, LM, S.mdct_f, S.mdct_f2);
-        band_energies_team(tm, S.freq, S.bandE, S.bandLogE, effEnd, end, C, LM);
+        compute_mdcts_team(tm, V.shortBlocks, G.in, G.freq, C, CC, LM, S.u.fft);
+        band_energies_team(tm, G.freq, S.bandE, S.bandLogE, effEnd, end, C, LM);
         CB_TEAM_FOR(i, C * kNbEBands, tm) S.bandLogE2[i] = (int16_t)(S.bandLogE2[i] + (shl16(LM, 10) >> 1));
         if (L0) V.tf_estimate = 3277;
         tm.sync();
@@ -1112,20 +1186,20 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
         V.do_tf = V.effectiveBytes >= 15 * C && start == 0 && cfg.complexity >= 2;
     }
     // ---- band normalisation (:1856) ----
-    normalise_bands_team(tm, S.freq, S.X, S.bandE, effEnd, C, M, LM, S.band_g, S.band_shift);
+    normalise_bands_team(tm, G.freq, S.u.x.X, S.bandE, effEnd, C, M, LM, S.band_g, S.band_shift);
 
     // ---- tf_analysis (:1858-1880): one band per lane ----
     const int isTransient = V.isTransient;
     const int shortBlocks = V.shortBlocks;
     if (V.do_tf) {
         const int bias = mul16_16_q14(1311, imax(-4096, 8192 - V.tf_estimate));
-        const int16_t *Xc = S.X + V.tf_chan * N;
+        const int16_t *Xc = S.u.x.X + V.tf_chan * N;
         int tf_sum = 0;
         CB_TEAM_FOR(i, effEnd, tm) {
             const int lo = kEBands[i] << LM;
             const int Nb = band_width(i) << LM;
             int term;
-            S.metric[i] = tf_band_metric(Xc + lo, Nb, band_width(i) == 1, isTransient, LM, bias, S.tf_tmp + lo, S.tf_tmp1 + lo, &term);
+            S.metric[i] = tf_band_metric(Xc + lo, Nb, band_width(i) == 1, isTransient, LM, bias, S.u.x.w.tf.tf_tmp + lo, S.u.x.w.tf.tf_tmp1 + lo, &term);
             tf_sum += term;
         }
         tf_sum = tm.sum(tf_sum);
@@ -1138,12 +1212,12 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
             else lambda = 3;
             lambda *= 2;
             V.tf_select = tf_viterbi(S.metric, effEnd, isTransient, S.tf_res, lambda, LM);
-            for (int i = effEnd; i < end; i++) S.tf_res[i] = S.tf_res[effEnd - 1];
+            CB_NOUNROLL for (int i = effEnd; i < end; i++) S.tf_res[i] = S.tf_res[effEnd - 1];
             V.tf_sum = tf_sum;
         }
     } else if (L0) {
         V.tf_sum = 0;
-        for (int i = 0; i < end; i++) S.tf_res[i] = isTransient;
+        CB_NOUNROLL for (int i = 0; i < end; i++) S.tf_res[i] = isTransient;
         V.tf_select = 0;
     }
     // ---- coarse energy, tf flags (:1882-1889) ----
@@ -1167,7 +1241,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
     if (V.do_spread) {
         int average = st->tonal_average, hf_average = st->hf_average, tapset_decision = st->tapset_decision;
         const int last = st->spread_decision;
-        const int dec = spreading_decision_team(tm, S.X, &average, last, &hf_average, &tapset_decision, V.pf_on && !shortBlocks, effEnd, C, M);
+        const int dec = spreading_decision_team(tm, S.u.x.X, &average, last, &hf_average, &tapset_decision, V.pf_on && !shortBlocks, effEnd, C, M);
         tm.sync();
         if (L0) {
             st->tonal_average = average; st->hf_average = hf_average; st->tapset_decision = tapset_decision;
@@ -1187,13 +1261,13 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
         int total_bits = V.total_bits << kBitRes;
         int total_boost = 0;
         int tell = (int)ec.tell_frac();
-        for (int i = start; i < end; i++) {
+        CB_NOUNROLL for (int i = start; i < end; i++) {
             const int width = C * band_width(i) << LM;
             const int quanta = imin(width << kBitRes, imax(6 << kBitRes, width));
             int loop_logp = dynalloc_logp;
             int boost = 0;
             int j;
-            for (j = 0; tell + (loop_logp << kBitRes) < total_bits - total_boost && boost < S.cap[i]; j++) {
+            CB_NOUNROLL for (j = 0; tell + (loop_logp << kBitRes) < total_bits - total_boost && boost < S.cap[i]; j++) {
                 const int flag = j < S.offsets[i];
                 ec.bit_logp(flag, (unsigned)loop_logp);
                 tell = (int)ec.tell_frac();
@@ -1214,7 +1288,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
     tm.sync();
     int dual_stereo = 0;
     if (C == 2) {
-        if (LM != 0) dual_stereo = stereo_analysis_team(tm, S.X, LM, N);
+        if (LM != 0) dual_stereo = stereo_analysis_team(tm, S.u.x.X, LM, N);
         if (L0) {
             st->intensity = hysteresis_decision(s16(V.equiv_rate / 1000), kIntensityThresholds, kIntensityHisteresis, 21, st->intensity);
             st->intensity = imin(end, imax(start, st->intensity));
@@ -1224,7 +1298,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
     int alloc_trim = 5;
     if (V.do_trim) {
         int stereo_saving = st->stereo_saving;
-        alloc_trim = alloc_trim_analysis_team(tm, S.X, S.bandLogE, end, LM, C, N, &stereo_saving, V.tf_estimate, st->intensity);
+        alloc_trim = alloc_trim_analysis_team(tm, S.u.x.X, S.bandLogE, end, LM, C, N, &stereo_saving, V.tf_estimate, st->intensity);
         tm.sync();
         if (L0) st->stereo_saving = stereo_saving;
     }
@@ -1295,32 +1369,50 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, EncScratch &S, const CeltEnc
         if (st->lastCodedBands) st->lastCodedBands = imin(st->lastCodedBands + 1, imax(st->lastCodedBands - 1, codedBands));
         else st->lastCodedBands = codedBands;
         quant_fine_energy(start, end, st->oldBandE, S.error, S.fine_quant, ec, C);
-        quant_all_bands_enc(start, end, S.X, C == 2 ? S.X + N : nullptr, S.bandE, S.pulses, shortBlocks, st->spread_decision, dual_stereo,
-                            st->intensity, S.tf_res, nbCompressedBytes * (8 << kBitRes) - anti_collapse_rsv, balance, ec, LM, codedBands,
-                            &S.pvq, S.had_tmp);
+        V.ec = ec;
+        V.nbCompressedBytes = nbCompressedBytes;
+        V.anti_collapse_rsv = anti_collapse_rsv;
+        V.balance = balance;
+        V.codedBands = codedBands;
+        V.dual_stereo = dual_stereo;
+    }
+    tm.sync();
+    // ---- residual quantisation (:2208): every lane walks the band loop with identical scalars, vector work is split ----
+    {
+        EcEnc ec = V.ec;
+        quant_all_bands_enc(tm, start, end, S.u.x.X, C == 2 ? S.u.x.X + N : nullptr, S.bandE, S.pulses, shortBlocks, st->spread_decision,
+                            V.dual_stereo, st->intensity, S.tf_res, V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, ec, LM,
+                            V.codedBands, &S.u.x.w.q.pvq, S.u.x.w.q.had_tmp);
+        tm.sync();
+        if (L0) V.ec = ec;
+    }
+    if (L0) {
+        EcEnc ec = V.ec;
+        const int nbCompressedBytes = V.nbCompressedBytes;
+        const int anti_collapse_rsv = V.anti_collapse_rsv;
         if (anti_collapse_rsv > 0) {
             const int anti_collapse_on = st->consec_transient < 2;
             ec.bits((unsigned)anti_collapse_on, 1);
         }
         quant_energy_finalise(start, end, st->oldBandE, S.error, S.fine_quant, S.fine_priority, nbCompressedBytes * 8 - ec.tell(), ec, C);
         if (V.silence)
-            for (int i = 0; i < C * kNbEBands; i++) st->oldBandE[i] = -28672;
+            CB_NOUNROLL for (int i = 0; i < C * kNbEBands; i++) st->oldBandE[i] = -28672;
         st->prefilter_period = V.pitch_index;
         st->prefilter_gain = V.gain1;
         st->prefilter_tapset = V.prefilter_tapset;
         if (CC == 2 && C == 1)
-            for (int i = 0; i < kNbEBands; i++) st->oldBandE[kNbEBands + i] = st->oldBandE[i];
+            CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) st->oldBandE[kNbEBands + i] = st->oldBandE[i];
         if (!isTransient) {
-            for (int i = 0; i < CC * kNbEBands; i++) { st->oldLogE2[i] = st->oldLogE[i]; st->oldLogE[i] = st->oldBandE[i]; }
+            CB_NOUNROLL for (int i = 0; i < CC * kNbEBands; i++) { st->oldLogE2[i] = st->oldLogE[i]; st->oldLogE[i] = st->oldBandE[i]; }
         } else {
-            for (int i = 0; i < CC * kNbEBands; i++) st->oldLogE[i] = (int16_t)imin((int)st->oldLogE[i], (int)st->oldBandE[i]);
+            CB_NOUNROLL for (int i = 0; i < CC * kNbEBands; i++) st->oldLogE[i] = (int16_t)imin((int)st->oldLogE[i], (int)st->oldBandE[i]);
         }
-        for (int c = 0; c < CC; c++) {
-            for (int i = 0; i < start; i++) {
+        CB_NOUNROLL for (int c = 0; c < CC; c++) {
+            CB_NOUNROLL for (int i = 0; i < start; i++) {
                 st->oldBandE[c * kNbEBands + i] = 0;
                 st->oldLogE[c * kNbEBands + i] = st->oldLogE2[c * kNbEBands + i] = -28672;
             }
-            for (int i = end; i < kNbEBands; i++) {
+            CB_NOUNROLL for (int i = end; i < kNbEBands; i++) {
                 st->oldBandE[c * kNbEBands + i] = 0;
                 st->oldLogE[c * kNbEBands + i] = st->oldLogE2[c * kNbEBands + i] = -28672;
             }

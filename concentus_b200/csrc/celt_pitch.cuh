@@ -12,24 +12,24 @@ namespace cb {
 
 CB_DEV int inner_prod16(const int16_t *x, const int16_t *y, int n) {
     int s = 0;
-    for (int i = 0; i < n; i++) s = mac16_16(s, x[i], y[i]);
+    CB_NOUNROLL for (int i = 0; i < n; i++) s = mac16_16(s, x[i], y[i]);
     return s;
 }
 CB_DEV int maxabs16(const int16_t *x, int n) {
     int mx = 0, mn = 0;
-    for (int i = 0; i < n; i++) { mx = imax(mx, x[i]); mn = imin(mn, x[i]); }
+    CB_NOUNROLL for (int i = 0; i < n; i++) { mx = imax(mx, x[i]); mn = imin(mn, x[i]); }
     return imax(mx, -mn);
 }
 CB_DEV int maxabs32(const int *x, int n) {
     int mx = 0, mn = 0;
-    for (int i = 0; i < n; i++) { mx = imax(mx, x[i]); mn = imin(mn, x[i]); }
+    CB_NOUNROLL for (int i = 0; i < n; i++) { mx = imax(mx, x[i]); mn = imin(mn, x[i]); }
     return imax(mx, wneg(mn));
 }
 
 // celt_pitch_xcorr (pitch.c:225-258): xcorr[i] = sum_j x[j]*y[i+j]; returns max(1, max_i xcorr[i])
 CB_DEV_NOINLINE int pitch_xcorr(const int16_t *x, const int16_t *y, int *xcorr, int len, int max_pitch) {
     int maxcorr = 1;
-    for (int i = 0; i < max_pitch; i++) {
+    CB_NOUNROLL for (int i = 0; i < max_pitch; i++) {
         int s = inner_prod16(x, y + i, len);
         xcorr[i] = s;
         maxcorr = imax(maxcorr, s);
@@ -41,15 +41,15 @@ CB_DEV_NOINLINE int pitch_xcorr(const int16_t *x, const int16_t *y, int *xcorr, 
 CB_DEV_NOINLINE void celt_lpc(int16_t *out, const int *ac, int p) {
     int lpc[kLpcOrder];
     int error = ac[0];
-    for (int i = 0; i < p; i++) lpc[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < p; i++) lpc[i] = 0;
     if (ac[0] != 0) {
-        for (int i = 0; i < p; i++) {
+        CB_NOUNROLL for (int i = 0; i < p; i++) {
             int rr = 0;
-            for (int j = 0; j < i; j++) rr = wadd(rr, mul32_32_q31(lpc[j], ac[i - j]));
+            CB_NOUNROLL for (int j = 0; j < i; j++) rr = wadd(rr, mul32_32_q31(lpc[j], ac[i - j]));
             rr = wadd(rr, ac[i + 1] >> 3);
             int r = wneg(frac_div32(shl32(rr, 3), error));
             lpc[i] = r >> 3;
-            for (int j = 0; j < (i + 1) >> 1; j++) {
+            CB_NOUNROLL for (int j = 0; j < (i + 1) >> 1; j++) {
                 int t1 = lpc[j], t2 = lpc[i - 1 - j];
                 lpc[j] = wadd(t1, mul32_32_q31(r, t2));
                 lpc[i - 1 - j] = wadd(t2, mul32_32_q31(r, t1));
@@ -58,7 +58,7 @@ CB_DEV_NOINLINE void celt_lpc(int16_t *out, const int *ac, int p) {
             if (error < (ac[0] >> 10)) break;
         }
     }
-    for (int i = 0; i < p; i++) out[i] = (int16_t)round16(lpc[i], 16);
+    CB_NOUNROLL for (int i = 0; i < p; i++) out[i] = (int16_t)round16(lpc[i], 16);
 }
 
 // _celt_autocorr (celt_lpc.c:232-328).  xx: scratch for n int16.  Returns the shift.
@@ -68,8 +68,8 @@ CB_DEV_NOINLINE int celt_autocorr(const int16_t *x, int *ac, const int16_t *wind
     if (overlap == 0) {
         xptr = x;
     } else {
-        for (int i = 0; i < n; i++) xx[i] = x[i];
-        for (int i = 0; i < overlap; i++) {
+        CB_NOUNROLL for (int i = 0; i < n; i++) xx[i] = x[i];
+        CB_NOUNROLL for (int i = 0; i < overlap; i++) {
             xx[i] = (int16_t)mul16_16_q15(x[i], window[i]);
             xx[n - i - 1] = (int16_t)mul16_16_q15(x[n - i - 1], window[i]);
         }
@@ -79,35 +79,35 @@ CB_DEV_NOINLINE int celt_autocorr(const int16_t *x, int *ac, const int16_t *wind
     {
         int ac0 = 1 + (n << 7);
         if (n & 1) ac0 = wadd(ac0, mul16_16(xptr[0], xptr[0]) >> 9);
-        for (int i = (n & 1); i < n; i += 2) {
+        CB_NOUNROLL for (int i = (n & 1); i < n; i += 2) {
             ac0 = wadd(ac0, mul16_16(xptr[i], xptr[i]) >> 9);
             ac0 = wadd(ac0, mul16_16(xptr[i + 1], xptr[i + 1]) >> 9);
         }
         shift = celt_ilog2(ac0) - 30 + 10;
         shift = shift / 2;
         if (shift > 0) {
-            for (int i = 0; i < n; i++) xx[i] = (int16_t)pshr32(xptr[i], shift);
+            CB_NOUNROLL for (int i = 0; i < n; i++) xx[i] = (int16_t)pshr32(xptr[i], shift);
             xptr = xx;
         } else {
             shift = 0;
         }
     }
     pitch_xcorr(xptr, xptr, ac, fastN, lag + 1);
-    for (int k = 0; k <= lag; k++) {
+    CB_NOUNROLL for (int k = 0; k <= lag; k++) {
         int d = 0;
-        for (int i = k + fastN; i < n; i++) d = mac16_16(d, xptr[i], xptr[i - k]);
+        CB_NOUNROLL for (int i = k + fastN; i < n; i++) d = mac16_16(d, xptr[i], xptr[i - k]);
         ac[k] = wadd(ac[k], d);
     }
     shift = 2 * shift;
     if (shift <= 0) ac[0] = wadd(ac[0], shl32(1, -shift));
     if (ac[0] < 268435456) {
         int shift2 = 29 - ec_ilog((unsigned)ac[0]);
-        for (int i = 0; i <= lag; i++) ac[i] = shl32(ac[i], shift2);
+        CB_NOUNROLL for (int i = 0; i <= lag; i++) ac[i] = shl32(ac[i], shift2);
         shift -= shift2;
     } else if (ac[0] >= 536870912) {
         int shift2 = 1;
         if (ac[0] >= 1073741824) shift2++;
-        for (int i = 0; i <= lag; i++) ac[i] = ac[i] >> shift2;
+        CB_NOUNROLL for (int i = 0; i <= lag; i++) ac[i] = ac[i] >> shift2;
         shift += shift2;
     }
     return shift;
@@ -122,21 +122,21 @@ CB_DEV_NOINLINE void pitch_downsample(const int *x0, const int *x1, int16_t *x_l
     if (shift < 0) shift = 0;
     if (C == 2) shift++;
     const int half = len >> 1;
-    for (int i = 1; i < half; i++) x_lp[i] = (int16_t)((wadd(wadd(x0[2 * i - 1], x0[2 * i + 1]) >> 1, x0[2 * i]) >> 1) >> shift);
+    CB_NOUNROLL for (int i = 1; i < half; i++) x_lp[i] = (int16_t)((wadd(wadd(x0[2 * i - 1], x0[2 * i + 1]) >> 1, x0[2 * i]) >> 1) >> shift);
     x_lp[0] = (int16_t)((wadd(x0[1] >> 1, x0[0]) >> 1) >> shift);
     if (C == 2) {
-        for (int i = 1; i < half; i++)
+        CB_NOUNROLL for (int i = 1; i < half; i++)
             x_lp[i] = (int16_t)(x_lp[i] + (int16_t)((wadd(wadd(x1[2 * i - 1], x1[2 * i + 1]) >> 1, x1[2 * i]) >> 1) >> shift));
         x_lp[0] = (int16_t)(x_lp[0] + (int16_t)((wadd(x1[1] >> 1, x1[0]) >> 1) >> shift));
     }
     int ac[5];
     celt_autocorr(x_lp, ac, nullptr, 0, 4, half, xx);
     ac[0] = wadd(ac[0], ac[0] >> 13);
-    for (int i = 1; i <= 4; i++) ac[i] = wsub(ac[i], mul16_32_q15(2 * i * i, ac[i]));
+    CB_NOUNROLL for (int i = 1; i <= 4; i++) ac[i] = wsub(ac[i], mul16_32_q15(2 * i * i, ac[i]));
     int16_t lpc[4];
     celt_lpc(lpc, ac, 4);
     int tmp = 32767;
-    for (int i = 0; i < 4; i++) {
+    CB_NOUNROLL for (int i = 0; i < 4; i++) {
         tmp = s16(mul16_16_q15(29491, tmp));   // QCONST16(.9f,15)
         lpc[i] = (int16_t)mul16_16_q15(lpc[i], tmp);
     }
@@ -149,7 +149,7 @@ CB_DEV_NOINLINE void pitch_downsample(const int *x0, const int *x1, int16_t *x_l
     lpc2[4] = (int16_t)mul16_16_q15(c1, lpc[3]);
     // celt_fir5, in place (mem = previous INPUT samples)
     int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
-    for (int i = 0; i < half; i++) {
+    CB_NOUNROLL for (int i = 0; i < half; i++) {
         const int xi = x_lp[i];
         int sum = shl32(xi, 12);
         sum = mac16_16(sum, lpc2[0], m0);
@@ -170,8 +170,8 @@ CB_DEV_NOINLINE void find_best_pitch(const int *xcorr, const int16_t *y, int len
     const int xshift = celt_ilog2(maxcorr) - 14;
     best_pitch[0] = 0;
     best_pitch[1] = 1;
-    for (int j = 0; j < len; j++) Syy = wadd(Syy, mul16_16(y[j], y[j]) >> yshift);
-    for (int i = 0; i < max_pitch; i++) {
+    CB_NOUNROLL for (int j = 0; j < len; j++) Syy = wadd(Syy, mul16_16(y[j], y[j]) >> yshift);
+    CB_NOUNROLL for (int i = 0; i < max_pitch; i++) {
         if (xcorr[i] > 0) {
             int xcorr16 = s16(vshr32(xcorr[i], xshift));
             int num = s16(mul16_16_q15(xcorr16, xcorr16));
@@ -194,14 +194,14 @@ CB_DEV_NOINLINE void pitch_search(const int16_t *x_lp, const int16_t *y, int len
                                   int16_t *y_lp4, int *xcorr) {
     const int lag = len + max_pitch;
     int best_pitch[2] = {0, 0};
-    for (int j = 0; j < len >> 2; j++) x_lp4[j] = x_lp[2 * j];
-    for (int j = 0; j < lag >> 2; j++) y_lp4[j] = y[2 * j];
+    CB_NOUNROLL for (int j = 0; j < len >> 2; j++) x_lp4[j] = x_lp[2 * j];
+    CB_NOUNROLL for (int j = 0; j < lag >> 2; j++) y_lp4[j] = y[2 * j];
     const int xmax = maxabs16(x_lp4, len >> 2);
     const int ymax = maxabs16(y_lp4, lag >> 2);
     int shift = celt_ilog2(imax(1, imax(xmax, ymax))) - 11;
     if (shift > 0) {
-        for (int j = 0; j < len >> 2; j++) x_lp4[j] = (int16_t)(x_lp4[j] >> shift);
-        for (int j = 0; j < lag >> 2; j++) y_lp4[j] = (int16_t)(y_lp4[j] >> shift);
+        CB_NOUNROLL for (int j = 0; j < len >> 2; j++) x_lp4[j] = (int16_t)(x_lp4[j] >> shift);
+        CB_NOUNROLL for (int j = 0; j < lag >> 2; j++) y_lp4[j] = (int16_t)(y_lp4[j] >> shift);
         shift *= 2;
     } else {
         shift = 0;
@@ -209,11 +209,11 @@ CB_DEV_NOINLINE void pitch_search(const int16_t *x_lp, const int16_t *y, int len
     int maxcorr = pitch_xcorr(x_lp4, y_lp4, xcorr, len >> 2, max_pitch >> 2);
     find_best_pitch(xcorr, y_lp4, len >> 2, max_pitch >> 2, best_pitch, 0, maxcorr);
     maxcorr = 1;
-    for (int i = 0; i < max_pitch >> 1; i++) {
+    CB_NOUNROLL for (int i = 0; i < max_pitch >> 1; i++) {
         xcorr[i] = 0;
         if (iabs(i - 2 * best_pitch[0]) > 2 && iabs(i - 2 * best_pitch[1]) > 2) continue;
         int sum = 0;
-        for (int j = 0; j < len >> 1; j++) sum = wadd(sum, mul16_16(x_lp[j], y[i + j]) >> shift);
+        CB_NOUNROLL for (int j = 0; j < len >> 1; j++) sum = wadd(sum, mul16_16(x_lp[j], y[i + j]) >> shift);
         xcorr[i] = imax(-1, sum);
         maxcorr = imax(maxcorr, sum);
     }
@@ -243,10 +243,10 @@ CB_DEV_NOINLINE int remove_doubling(const int16_t *x, int maxperiod, int minperi
     int T, T0;
     T = T0 = *T0_;
     int xx = 0, xy = 0;
-    for (int i = 0; i < N; i++) { xx = mac16_16(xx, x[i], x[i]); xy = mac16_16(xy, x[i], x[i - T0]); }
+    CB_NOUNROLL for (int i = 0; i < N; i++) { xx = mac16_16(xx, x[i], x[i]); xy = mac16_16(xy, x[i], x[i - T0]); }
     yy_lookup[0] = xx;
     int yy = xx;
-    for (int i = 1; i <= maxperiod; i++) {
+    CB_NOUNROLL for (int i = 1; i <= maxperiod; i++) {
         yy = wsub(wadd(yy, mul16_16(x[-i], x[-i])), mul16_16(x[N - i], x[N - i]));
         yy_lookup[i] = imax(0, yy);
     }
@@ -259,7 +259,7 @@ CB_DEV_NOINLINE int remove_doubling(const int16_t *x, int maxperiod, int minperi
         int t = vshr32(x2y2, 2 * (sh - 7));
         g = g0 = vshr32(mul16_32_q15(celt_rsqrt_norm(t), xy), sh + 1);
     }
-    for (int k = 2; k <= 15; k++) {
+    CB_NOUNROLL for (int k = 2; k <= 15; k++) {
         int T1 = (int)udiv((unsigned)(2 * T0 + k), (unsigned)(2 * k));
         if (T1 < minperiod) break;
         int T1b;
@@ -271,7 +271,7 @@ CB_DEV_NOINLINE int remove_doubling(const int16_t *x, int maxperiod, int minperi
         }
         int xy2 = 0;
         xy = 0;
-        for (int i = 0; i < N; i++) { xy = mac16_16(xy, x[i], x[i - T1]); xy2 = mac16_16(xy2, x[i], x[i - T1b]); }
+        CB_NOUNROLL for (int i = 0; i < N; i++) { xy = mac16_16(xy, x[i], x[i - T1]); xy2 = mac16_16(xy2, x[i], x[i - T1b]); }
         xy = wadd(xy, xy2);
         yy = wadd(yy_lookup[T1], yy_lookup[T1b]);
         int g1;
@@ -297,7 +297,7 @@ CB_DEV_NOINLINE int remove_doubling(const int16_t *x, int maxperiod, int minperi
     if (best_yy <= best_xy) pg = 32767;
     else pg = s16(frac_div32(best_xy, wadd(best_yy, 1)) >> 16);
     int xc[3];
-    for (int k = 0; k < 3; k++) xc[k] = inner_prod16(x, x - (T + k - 1), N);
+    CB_NOUNROLL for (int k = 0; k < 3; k++) xc[k] = inner_prod16(x, x - (T + k - 1), N);
     int offset;
     if (wsub(xc[2], xc[0]) > mul16_32_q15(22938, wsub(xc[1], xc[0]))) offset = 1;
     else if (wsub(xc[0], xc[2]) > mul16_32_q15(22938, wsub(xc[1], xc[2]))) offset = -1;
@@ -311,7 +311,7 @@ CB_DEV_NOINLINE int remove_doubling(const int16_t *x, int maxperiod, int minperi
 // comb_filter, y != x (celt.c:183-244): a plain FIR over x's history.  window == nullptr <=> overlap == 0.
 CB_DEV_NOINLINE void comb_filter_fir(int *y, const int *x, int T0, int T1, int N, int g0, int g1, int tapset0, int tapset1, int overlap) {
     if (g0 == 0 && g1 == 0) {
-        for (int i = 0; i < N; i++) y[i] = x[i];
+        CB_NOUNROLL for (int i = 0; i < N; i++) y[i] = x[i];
         return;
     }
     const int g00 = s16(mul16_16_p15(g0, kCombGains[tapset0][0]));
@@ -322,7 +322,7 @@ CB_DEV_NOINLINE void comb_filter_fir(int *y, const int *x, int T0, int T1, int N
     const int g12 = s16(mul16_16_p15(g1, kCombGains[tapset1][2]));
     if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
     int i;
-    for (i = 0; i < overlap; i++) {
+    CB_NOUNROLL for (i = 0; i < overlap; i++) {
         int f = s16(mul16_16_q15(kWindow120[i], kWindow120[i]));
         int nf = 32767 - f;
         int v = x[i];
@@ -335,10 +335,10 @@ CB_DEV_NOINLINE void comb_filter_fir(int *y, const int *x, int T0, int T1, int N
         y[i] = v;
     }
     if (g1 == 0) {
-        for (; i < N; i++) y[i] = x[i];
+        CB_NOUNROLL for (; i < N; i++) y[i] = x[i];
         return;
     }
-    for (; i < N; i++) {
+    CB_NOUNROLL for (; i < N; i++) {
         int v = x[i];
         v = wadd(v, mul16_32_q15(g10, x[i - T1]));
         v = wadd(v, mul16_32_q15(g11, wadd(x[i - T1 + 1], x[i - T1 - 1])));

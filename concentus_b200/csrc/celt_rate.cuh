@@ -18,11 +18,11 @@ CB_DEV int get_pulses(int i) { return i < 8 ? i : (8 + (i & 7)) << ((i >> 3) - 1
 
 CB_DEV const uint8_t *pulse_cache(int band, int LM) { return kCacheBits + kCacheIndex[(LM + 1) * kNbEBands + band]; }
 
-CB_DEV int bits2pulses(int band, int LM, int bits) {
+CB_MATH int bits2pulses(int band, int LM, int bits) {
     const uint8_t *cache = pulse_cache(band, LM);
     int lo = 0, hi = cache[0];
     bits--;
-    for (int i = 0; i < kLogMaxPseudo; i++) {
+    CB_NOUNROLL for (int i = 0; i < kLogMaxPseudo; i++) {
         int mid = (lo + hi + 1) >> 1;
         if ((int)cache[mid] >= bits) hi = mid;
         else lo = mid;
@@ -35,7 +35,7 @@ CB_DEV int pulses2bits(int band, int LM, int pulses) {
 }
 
 CB_DEV void init_caps(int *cap, int LM, int C) {
-    for (int i = 0; i < kNbEBands; i++) {
+    CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) {
         int N = band_width(i) << LM;
         cap[i] = (kCacheCaps[kNbEBands * (2 * LM + C - 1) + i] + 64) * C * N >> 2;
     }
@@ -76,7 +76,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
             total -= dual_stereo_rsv;
         }
     }
-    for (int j = start; j < end; j++) {
+    CB_NOUNROLL for (int j = start; j < end; j++) {
         int w = band_width(j);
         thresh[j] = imax(C << kBitRes, (3 * w << LM << kBitRes) >> 4);
         trim_offset[j] = C * w * (alloc_trim - 5 - LM) * (end - j - 1) * (1 << (LM + kBitRes)) >> 6;
@@ -86,7 +86,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
     do {
         int done = 0, psum = 0;
         int mid = (lo + hi) >> 1;
-        for (int j = end; j-- > start;) {
+        CB_NOUNROLL for (int j = end; j-- > start;) {
             int bitsj = C * band_width(j) * kAllocVectors[mid * len + j] << LM >> 2;
             if (bitsj > 0) bitsj = imax(0, bitsj + trim_offset[j]);
             bitsj += offsets[j];
@@ -101,7 +101,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
         else lo = mid + 1;
     } while (lo <= hi);
     hi = lo--;
-    for (int j = start; j < end; j++) {
+    CB_NOUNROLL for (int j = start; j < end; j++) {
         int w = band_width(j);
         int b1 = C * w * kAllocVectors[lo * len + j] << LM >> 2;
         int b2 = hi >= kNbAllocVectors ? cap[j] : C * w * kAllocVectors[hi * len + j] << LM >> 2;
@@ -123,11 +123,11 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
     int psum;
     lo = 0;
     hi = 1 << kAllocSteps;
-    for (int i = 0; i < kAllocSteps; i++) {
+    CB_NOUNROLL for (int i = 0; i < kAllocSteps; i++) {
         int mid = (lo + hi) >> 1;
         int done = 0;
         psum = 0;
-        for (int j = end; j-- > start;) {
+        CB_NOUNROLL for (int j = end; j-- > start;) {
             int tmp = bits1[j] + (mid * bits2[j] >> kAllocSteps);
             if (tmp >= thresh[j] || done) {
                 done = 1;
@@ -142,7 +142,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
     psum = 0;
     {
         int done = 0;
-        for (int j = end; j-- > start;) {
+        CB_NOUNROLL for (int j = end; j-- > start;) {
             int tmp = bits1[j] + (lo * bits2[j] >> kAllocSteps);
             if (tmp < thresh[j] && !done) {
                 tmp = tmp >= alloc_floor ? alloc_floor : 0;
@@ -156,7 +156,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
     }
     // band skipping, from the top
     int codedBands;
-    for (codedBands = end;; codedBands--) {
+    CB_NOUNROLL for (codedBands = end;; codedBands--) {
         int j = codedBands - 1;
         if (j <= skip_start) {
             total += skip_rsv;
@@ -199,8 +199,8 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
         int span = kEBands[codedBands] - kEBands[start];
         int percoeff = (int)udiv((unsigned)left, (unsigned)span);
         left -= span * percoeff;
-        for (int j = start; j < codedBands; j++) bits[j] += percoeff * band_width(j);
-        for (int j = start; j < codedBands; j++) {
+        CB_NOUNROLL for (int j = start; j < codedBands; j++) bits[j] += percoeff * band_width(j);
+        CB_NOUNROLL for (int j = start; j < codedBands; j++) {
             int tmp = imin(left, band_width(j));
             bits[j] += tmp;
             left -= tmp;
@@ -208,7 +208,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
     }
     int balance = 0;
     int j;
-    for (j = start; j < codedBands; j++) {
+    CB_NOUNROLL for (j = start; j < codedBands; j++) {
         int N0 = band_width(j);
         int N = N0 << LM;
         int bit = bits[j] + balance;
@@ -244,7 +244,7 @@ CB_DEV int compute_allocation(Io io, AllocScratch &sc, int start, int end, const
         balance = excess;
     }
     *balance_out = balance;
-    for (; j < end; j++) {
+    CB_NOUNROLL for (; j < end; j++) {
         ebits[j] = bits[j] >> stereo >> kBitRes;
         bits[j] = 0;
         fine_priority[j] = ebits[j] < 1;

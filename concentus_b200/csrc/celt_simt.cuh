@@ -18,6 +18,15 @@
 #define CB_DEV_NOINLINE static __device__ __noinline__
 #define CB_TABLE static __device__ const
 #define CB_CLZ(x) __clz((int)(x))
+// Medium-sized helpers (polynomial math, allocation look-ups): inlined where a kernel is dominated by them (decoder stages),
+// real calls where instruction-cache footprint matters more (CB_SMALL_CODE: the encoder kernel, profiles/r1_enc_*).
+#if defined(CB_SMALL_CODE)
+#define CB_MATH static __device__ __noinline__
+#define CB_NOUNROLL _Pragma("unroll 1")
+#else
+#define CB_MATH __device__ __forceinline__
+#define CB_NOUNROLL
+#endif
 #else
 #define CB_DEV static inline
 #define CB_MEM inline
@@ -25,6 +34,8 @@
 #define CB_DEV_NOINLINE static
 #define CB_TABLE static const
 #define CB_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
+#define CB_MATH static inline
+#define CB_NOUNROLL
 #endif
 
 namespace cb {
@@ -38,6 +49,7 @@ struct SoloTeam {
     CB_MEM unsigned bor(unsigned v) const { return v; }
     CB_MEM int bcast(int v, int) const { return v; }
     CB_MEM int exscan(int) const { return 0; }   // exclusive prefix sum over lanes (wrapping)
+    CB_MEM int shfl_xor(int v, int) const { return v; }
 };
 
 #if defined(__CUDACC__)
@@ -62,6 +74,7 @@ struct WarpTeam {
         return v;
     }
     CB_MEM int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    CB_MEM int shfl_xor(int v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
     CB_MEM int exscan(int v) const {
         unsigned inc = (unsigned)v;
 #pragma unroll
@@ -77,4 +90,4 @@ struct WarpTeam {
 }  // namespace cb
 
 // for (i over [0,n)) distributed over the team
-#define CB_TEAM_FOR(i, n, tm) for (int i = (tm).lane(); i < (n); i += (tm).W)
+#define CB_TEAM_FOR(i, n, tm) CB_NOUNROLL for (int i = (tm).lane(); i < (n); i += (tm).W)

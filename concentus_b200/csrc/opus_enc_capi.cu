@@ -5,6 +5,7 @@
 // decisions down to ec_enc_done runs on the device, one warp per stream, F frames per launch (the frames of a stream are
 // serially dependent through the encoder state; streams are independent).
 // There is NO CPU path: if CUDA is unusable every codec call returns OPUS_INTERNAL_ERROR.
+#define CB_SMALL_CODE 1   // see celt_simt.cuh: the encoder kernel is instruction-cache bound when everything is inlined
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -34,27 +35,43 @@ struct OpusEncoder {
 static const uint32_t kEncMagic = 0x0B200E4Cu;
 
 #ifndef CB_ENC_WPB
-#define CB_ENC_WPB 4   // warps (= streams) per block
+#define CB_ENC_WPB 2          // warps (= streams) per block
+#endif
+#ifndef CB_ENC_MINBLOCKS
+#define CB_ENC_MINBLOCKS 7    // resident blocks per SM: 14 streams per SM, 2,072 per B200 -> 4,096 streams = 2 full waves
 #endif
 
-// One warp per stream, frames f0..f1 in order.  PCM of frame (s,f): pcm[(s*F+f)*frame_size*channels]; packet slot:
+// Shared memory of one warp: the frame working set plus the head of the stream's state (scalars + band-energy histories),
+// which stays on chip for the whole span and is written back once at the end.
+struct EncWarpSmem {
+    EncShared S;
+    int head[CB_ENC_HEAD_BYTES / 4];
+};
+
+// One warp per stream, frames 0..F-1 in order.  PCM of frame (s,f): pcm[(s*F+f)*frame_size*channels]; packet slot:
 // data[(s*F+f)*stride], at most max_bytes are written; rets[s*F+f] = packet length or error.
-__global__ void __launch_bounds__(CB_ENC_WPB * 32)
-encode_span_kernel(CbEncState *pool, const int *slots, EncScratch *scratch, const int16_t *pcm, uint8_t *data, int *rets, int n, int F,
+__global__ void __launch_bounds__(CB_ENC_WPB * 32, CB_ENC_MINBLOCKS)
+encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const int16_t *pcm, uint8_t *data, int *rets, int n, int F,
                    int frame_size, int max_bytes, int stride) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_ENC_WPB + warp;
     if (s >= n) return;
-    CbEncState *st = pool + slots[s];
-    EncScratch &S = scratch[s];
+    EncWarpSmem &W = reinterpret_cast<EncWarpSmem *>(smem_raw)[warp];
+    CbEncState *gst = pool + slots[s];
+    for (int i = lane; i < CB_ENC_HEAD_BYTES / 4; i += 32) W.head[i] = reinterpret_cast<const int *>(gst)[i];
+    __syncwarp();
+    CbEncState *st = reinterpret_cast<CbEncState *>(W.head);   // only the head fields are valid through this pointer
+    EncGlobal &G = scratch[s];
     const int channels = st->channels;
     WarpTeam tm{lane};
     for (int f = 0; f < F; f++) {
         const size_t k = (size_t)s * F + f;
-        const int r = opus_encode_frame(tm, st, S, pcm + k * frame_size * channels, frame_size, data + k * stride, max_bytes);
+        const int r = opus_encode_frame(tm, st, gst, W.S, G, pcm + k * frame_size * channels, frame_size, data + k * stride, max_bytes);
         if (lane == 0) rets[k] = r;
         __syncwarp();
     }
+    for (int i = lane; i < CB_ENC_HEAD_BYTES / 4; i += 32) reinterpret_cast<int *>(gst)[i] = W.head[i];
 }
 
 __global__ void enc_scatter_states_kernel(CbEncState *pool, const int *slots, const CbEncState *stage, int n) {
@@ -132,6 +149,8 @@ bool ctx_init_locked() {
     cudaEventCreate(&e.ev0);
     cudaEventCreate(&e.ev1);
     if (!e.h_stage.reserve(sizeof(CbEncState) * kStageStates) || !e.d_stage.reserve(sizeof(CbEncState) * kStageStates)) return false;
+    cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CB_ENC_WPB * sizeof(EncWarpSmem)));
+    cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     e.ok = cudaGetLastError() == cudaSuccess;
     return e.ok;
 }
@@ -279,7 +298,7 @@ int check_span(OpusEncoder **st, int n) {
 
 void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int frame_size, int max_bytes, int stride) {
     cudaEventRecord(e.ev0, e.stream);
-    encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, 0, e.stream>>>(e.pool, d_slots, (EncScratch *)e.d_scratch.p, d_pcm, d_data,
+    encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, CB_ENC_WPB * sizeof(EncWarpSmem), e.stream>>>(e.pool, d_slots, (EncGlobal *)e.d_scratch.p, d_pcm, d_data,
                                                                                            d_rets, n, F, frame_size, max_bytes, stride);
     cudaEventRecord(e.ev1, e.stream);
     e.launches++;
@@ -298,7 +317,7 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
     const size_t NF = (size_t)n * F;
     const size_t pcm_bytes = NF * frame_size * channels * sizeof(int16_t);
     if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_pcm.reserve(pcm_bytes) || !e.d_data.reserve(NF * stride) ||
-        !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncScratch) * (size_t)n))
+        !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n))
         return OPUS_ALLOC_FAIL;
     cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
     cudaMemcpyAsync(e.d_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, e.stream);
@@ -422,7 +441,7 @@ int opus_encode_span_device(OpusEncoder **st, int n, int F, const opus_int16 *d_
     int *hsl = (int *)e.h_slots.p;
     rc = make_resident_locked(st, n, hsl);
     if (rc != OPUS_OK) return rc;
-    if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_scratch.reserve(sizeof(EncScratch) * (size_t)n)) return OPUS_ALLOC_FAIL;
+    if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n)) return OPUS_ALLOC_FAIL;
     cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
     launch_span((const int *)e.d_slots.p, d_pcm, d_data, d_ret, n, F, frame_size, hmin(max_data_bytes, 1276), max_data_bytes);
     mark_device_newer_locked(st, n);

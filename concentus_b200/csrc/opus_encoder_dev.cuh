@@ -32,21 +32,21 @@ CB_HD void enc_state_reset_celt(CbEncState *st) {
     st->preemph_memE[0] = st->preemph_memE[1] = 0;
     st->vbr_reservoir = 0; st->vbr_drift = 0; st->vbr_offset = 0; st->vbr_count = 0;
     st->overlap_max = 0; st->stereo_saving = 0; st->intensity = 0; st->spec_avg = 0;
-    for (int i = 0; i < 2 * CB_OVERLAP; i++) st->in_mem[i] = 0;
-    for (int i = 0; i < 2 * CB_COMB_MAXPERIOD; i++) st->prefilter_mem[i] = 0;
-    for (int i = 0; i < 2 * CB_NB_EBANDS; i++) { st->oldBandE[i] = 0; st->oldLogE[i] = st->oldLogE2[i] = -28672; }
+    CB_NOUNROLL for (int i = 0; i < 2 * CB_OVERLAP; i++) st->in_mem[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < 2 * CB_COMB_MAXPERIOD; i++) st->prefilter_mem[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < 2 * CB_NB_EBANDS; i++) { st->oldBandE[i] = 0; st->oldLogE[i] = st->oldLogE2[i] = -28672; }
 }
 // Opus OPUS_RESET_STATE (opus_encoder.c:2437-2458)
 CB_HD void enc_state_reset(CbEncState *st) {
     st->stream_channels = st->channels;
     st->hybrid_stereo_width_Q14 = 1 << 14;
-    for (int i = 0; i < 4; i++) st->hp_mem[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < 4; i++) st->hp_mem[i] = 0;
     st->mode = CB_MODE_HYBRID;
     st->prev_mode = 0; st->prev_channels = 0; st->prev_framesize = 0;
     st->bandwidth = 1105;
     st->first = 1;
     st->width_XX = st->width_XY = st->width_YY = 0; st->width_smoothed = 0; st->width_max_follower = 0;
-    for (int i = 0; i < CB_ENC_DELAY_BUF; i++) st->delay_buffer[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < CB_ENC_DELAY_BUF; i++) st->delay_buffer[i] = 0;
     st->rangeFinal = 0;
     enc_state_reset_celt(st);
 }
@@ -209,21 +209,21 @@ CB_HD int packet_pad_single(uint8_t *data, int len, int new_len) {
         nb_255s = (pad_amount - 1) / 255;
         hdr += nb_255s + 1;
     }
-    for (int i = payload - 1; i >= 0; i--) data[hdr + i] = data[1 + i];   // memmove upwards
+    CB_NOUNROLL for (int i = payload - 1; i >= 0; i--) data[hdr + i] = data[1 + i];   // memmove upwards
     data[0] = (uint8_t)((data[0] & 0xFC) | 0x3);
     data[1] = (uint8_t)(1 | (pad_amount != 0 ? 0x40 : 0));
     if (pad_amount != 0) {
-        for (int i = 0; i < nb_255s; i++) data[2 + i] = 255;
+        CB_NOUNROLL for (int i = 0; i < nb_255s; i++) data[2 + i] = 255;
         data[2 + nb_255s] = (uint8_t)(pad_amount - 255 * nb_255s - 1);
     }
-    for (int i = hdr + payload; i < new_len; i++) data[i] = 0;
+    CB_NOUNROLL for (int i = hdr + payload; i < new_len; i++) data[i] = 0;
     return OPUS_OK_;
 }
 
 // dc_reject (opus_encoder.c:362-385) for one channel: two cascaded one-pole sections, order dependent
 CB_DEV_NOINLINE void dc_reject_channel(const int16_t *in, int16_t *out, int32_t *hp_mem, int len, int channels, int c, int shift) {
     int m0 = hp_mem[2 * c], m1 = hp_mem[2 * c + 1];
-    for (int i = 0; i < len; i++) {
+    CB_NOUNROLL for (int i = 0; i < len; i++) {
         const int x = shl32(in[channels * i + c], 15);
         const int tmp = wsub(x, m0);
         m0 = wadd(m0, pshr32(wsub(x, m0), shift));
@@ -250,7 +250,7 @@ CB_DEV void compute_stereo_width_team(TM tm, const int16_t *pcm, int frame_size,
         const int i = 4 * g;
         if (i < frame_size - 3) {
             int pxx = 0, pxy = 0, pyy = 0;
-            for (int k = 0; k < 4; k++) {
+            CB_NOUNROLL for (int k = 0; k < 4; k++) {
                 const int x = pcm[2 * (i + k)], y = pcm[2 * (i + k) + 1];
                 pxx += mul16_16(x, x) >> 2;
                 pxy += mul16_16(x, y) >> 2;
@@ -306,9 +306,11 @@ CB_TABLE int32_t kBwThreshStereoVoice[8] = {11000, 1000, 14000, 1000, 21000, 200
 CB_TABLE int32_t kBwThreshStereoMusic[8] = {12000, 1000, 18000, 2000, 21000, 2000, 30000, 2000};
 
 // opus_encode_native (opus_encoder.c:938-2005), MODE_CELT_ONLY path.  pcm: frame_size x channels int16; out: >= out_data_bytes.
+// st: head of the state (maybe a shared-memory copy), gst: the full block in HBM (delay buffer and sample histories).
 // Returns (uniformly on all lanes) the packet length or a negative error code.
 template <class TM>
-CB_DEV int opus_encode_frame(TM tm, CbEncState *st, EncScratch &S, const int16_t *pcm, int frame_size, uint8_t *out, int out_data_bytes) {
+CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &S, EncGlobal &G, const int16_t *pcm, int frame_size, uint8_t *out,
+                             int out_data_bytes) {
     const bool L0 = tm.lane() == 0;
     const int Fs = st->Fs, channels = st->channels;
     int max_data_bytes = imin(1276, out_data_bytes);
@@ -409,7 +411,7 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, EncScratch &S, const int16_t
         if (channels == 2 && st->force_channels != 1) { voice_t = kBwThreshStereoVoice; music_t = kBwThreshStereoMusic; }
         else { voice_t = kBwThreshMonoVoice; music_t = kBwThreshMonoMusic; }
         int thr[8];
-        for (int i = 0; i < 8; i++) thr[i] = music_t[i] + ((voice_est * voice_est * (voice_t[i] - music_t[i])) >> 14);
+        CB_NOUNROLL for (int i = 0; i < 8; i++) thr[i] = music_t[i] + ((voice_est * voice_est * (voice_t[i] - music_t[i])) >> 14);
         bandwidth = 1105;
         do {
             int threshold = thr[2 * (bandwidth - 1102)];
@@ -428,12 +430,15 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, EncScratch &S, const int16_t
     const int bytes_target = imin(max_data_bytes, bitrate_bps * frame_size / (Fs * 8)) - 1;
 
     // ---- commit point: from here on the frame is coded ----
-    int16_t *pcm_buf = S.pcm_buf;
-    CB_TEAM_FOR(i, total_buffer * channels, tm) pcm_buf[i] = st->delay_buffer[(st->encoder_buffer - total_buffer) * channels + i];
+    int16_t *pcm_buf = S.u.pcm_buf;
+    CB_TEAM_FOR(i, total_buffer * channels, tm) pcm_buf[i] = gst->delay_buffer[(st->encoder_buffer - total_buffer) * channels + i];
     {
+        // stage the frame in shared memory (coalesced), then filter it in place: one lane per channel, order dependent
+        int16_t *dst = pcm_buf + total_buffer * channels;
+        CB_TEAM_FOR(i, frame_size * channels, tm) dst[i] = pcm[i];
+        tm.sync();
         const int shift = celt_ilog2(Fs / (3 * 3));
-        for (int c = tm.lane(); c < channels; c += TM::W)
-            dc_reject_channel(pcm, pcm_buf + total_buffer * channels, st->hp_mem, frame_size, channels, c, shift);
+        CB_NOUNROLL for (int c = tm.lane(); c < channels; c += TM::W) dc_reject_channel(dst, dst, st->hp_mem, frame_size, channels, c, shift);
     }
     tm.sync();
     // delay buffer (opus_encoder.c:1773-1781)
@@ -442,16 +447,16 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, EncScratch &S, const int16_t
         if (channels * (eb - (frame_size + total_buffer)) > 0) {
             const int keep = channels * (eb - frame_size - total_buffer);
             // the move overlaps itself: stage through registers in two passes of the whole team
-            for (int base = 0; base < keep; base += TM::W) {
+            CB_NOUNROLL for (int base = 0; base < keep; base += TM::W) {
                 const int i = base + tm.lane();
-                const int v = i < keep ? st->delay_buffer[channels * frame_size + i] : 0;
+                const int v = i < keep ? gst->delay_buffer[channels * frame_size + i] : 0;
                 tm.sync();
-                if (i < keep) st->delay_buffer[i] = (int16_t)v;
+                if (i < keep) gst->delay_buffer[i] = (int16_t)v;
                 tm.sync();
             }
-            CB_TEAM_FOR(i, (frame_size + total_buffer) * channels, tm) st->delay_buffer[keep + i] = pcm_buf[i];
+            CB_TEAM_FOR(i, (frame_size + total_buffer) * channels, tm) gst->delay_buffer[keep + i] = pcm_buf[i];
         } else {
-            CB_TEAM_FOR(i, eb * channels, tm) st->delay_buffer[i] = pcm_buf[(frame_size + total_buffer - eb) * channels + i];
+            CB_TEAM_FOR(i, eb * channels, tm) gst->delay_buffer[i] = pcm_buf[(frame_size + total_buffer - eb) * channels + i];
         }
         tm.sync();
     }
@@ -503,7 +508,7 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, EncScratch &S, const int16_t
     tm.sync();
     int ret = 0;
     // "If false, we already busted the budget" cannot happen here: nothing has been coded before the CELT frame
-    ret = celt_encode_frame(tm, st, S, cfg, pcm_buf, frame_size, nb_compr_bytes);
+    ret = celt_encode_frame(tm, st, gst, S, G, cfg, pcm_buf, frame_size, nb_compr_bytes);
     if (ret < 0) return OPUS_INTERNAL_ERROR_;
     if (L0) {
         out[0] = (uint8_t)gen_toc(mode, Fs / frame_size, curr_bandwidth, stream_channels);

@@ -3,6 +3,7 @@
 // memcpy'd, relocated and snapshotted exactly like the reference's states
 // (opus-fix/tests/test_opus_decode.c:84-95, src/opus_decoder.c:55-79, celt/celt_decoder.c:67-100).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #define CB_NB_EBANDS 21
@@ -50,7 +51,9 @@ typedef struct CbDecState {
 #define CB_COMB_MAXPERIOD 1024
 #define CB_ENC_DELAY_BUF 960   /* MAX_ENCODER_BUFFER (480) x 2 channels, src/opus_encoder.c:58 */
 
-/* Encoder state: Opus layer (src/opus_encoder.c:62-110, CELT-only subset) + CELT layer (celt/celt_encoder.c:60-128). */
+/* Encoder state: Opus layer (src/opus_encoder.c:62-110, CELT-only subset) + CELT layer (celt/celt_encoder.c:60-128).
+ * Layout: everything small comes first (the "head": scalars and the three band-energy histories, CB_ENC_HEAD_BYTES) so a
+ * kernel can keep it in shared memory for a whole span; the sample histories (the "tail") stay in HBM. */
 typedef struct CbEncState {
     /* ---- Opus-layer configuration (survives OPUS_RESET_STATE) ---- */
     int32_t application, channels, Fs;
@@ -64,7 +67,6 @@ typedef struct CbEncState {
     int32_t hp_mem[4];
     int32_t mode, prev_mode, prev_channels, prev_framesize, bandwidth, first;
     int32_t width_XX, width_XY, width_YY, width_smoothed, width_max_follower;   /* StereoWidthState */
-    int16_t delay_buffer[CB_ENC_DELAY_BUF];
     uint32_t rangeFinal;
     /* ---- CELT configuration (celt_encoder.c:62-80) ---- */
     int32_t upsample, celt_force_intra, celt_disable_pf;
@@ -74,7 +76,11 @@ typedef struct CbEncState {
     int32_t prefilter_period, prefilter_gain, prefilter_tapset, consec_transient;
     int32_t preemph_memE[2];
     int32_t vbr_reservoir, vbr_drift, vbr_offset, vbr_count, overlap_max, stereo_saving, intensity, spec_avg;
+    int16_t oldBandE[2 * CB_NB_EBANDS], oldLogE[2 * CB_NB_EBANDS], oldLogE2[2 * CB_NB_EBANDS];
+    int32_t head_pad;                                    /* keeps the tail 8-byte aligned */
+    /* ---- tail: sample histories (HBM) ---- */
     int32_t in_mem[2 * CB_OVERLAP];
     int32_t prefilter_mem[2 * CB_COMB_MAXPERIOD];
-    int16_t oldBandE[2 * CB_NB_EBANDS], oldLogE[2 * CB_NB_EBANDS], oldLogE2[2 * CB_NB_EBANDS];
+    int16_t delay_buffer[CB_ENC_DELAY_BUF];
 } CbEncState;
+#define CB_ENC_HEAD_BYTES ((int)offsetof(CbEncState, in_mem))

@@ -64,7 +64,8 @@ int hostsim_enc_state_size(void) { return (int)sizeof(CbEncState); }
 int hostsim_encode_stream(const int16_t *pcm, int F, int frame_size, int channels, int Fs, const int *cfg, uint8_t *out, int stride,
                           int32_t *lens, uint32_t *ranges) {
     CbEncState *st = (CbEncState *)calloc(1, sizeof(CbEncState));
-    cb::EncScratch *S = (cb::EncScratch *)calloc(1, sizeof(cb::EncScratch));
+    cb::EncShared *S = (cb::EncShared *)calloc(1, sizeof(cb::EncShared));
+    cb::EncGlobal *G = (cb::EncGlobal *)calloc(1, sizeof(cb::EncGlobal));
     if (cb::enc_state_init(st, Fs, channels, cfg[0]) != 0) return -1;
     int dummy = 0;
     cb::enc_ctl(st, 4002, cfg[1], &dummy);
@@ -76,12 +77,13 @@ int hostsim_encode_stream(const int16_t *pcm, int F, int frame_size, int channel
     cb::SoloTeam tm;
     int rc = 0;
     for (int f = 0; f < F; f++) {
-        int n = cb::opus_encode_frame(tm, st, *S, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * stride,
+        int n = cb::opus_encode_frame(tm, st, st, *S, *G, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * stride,
                                       cfg[5] < stride ? cfg[5] : stride);
         lens[f] = n;
         if (n < 0) { rc = n; break; }
         if (ranges) ranges[f] = st->rangeFinal;
     }
+    free(G);
     free(S);
     free(st);
     return rc;
