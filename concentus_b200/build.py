@@ -11,7 +11,11 @@ SRCS = [os.path.join(HERE, "csrc", "opus_capi.cu"), os.path.join(HERE, "csrc", "
 OBJDIR = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libconcentus_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+EXTRA = os.environ.get("CB200_DEFS", "").split()   # e.g. "-DCB_ENC_WPB=7 -DCB_PHASE_SYNC=1" (A/B builds only)
+if os.environ.get("CB200_OUT"):
+    OUT = os.environ["CB200_OUT"]
+    OBJDIR = OUT + ".obj"
+FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
 
 def _newest_src():

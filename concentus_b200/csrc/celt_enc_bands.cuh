@@ -562,6 +562,7 @@ CB_DEV void quant_all_bands_enc(TM tm, int start, int end, int16_t *X_, int16_t 
     ctx.ec = ec_io; ctx.ps = ps; ctx.tmp = tmp; ctx.bandE = bandE;
     ctx.intensity = intensity; ctx.spread = spread;
     CB_NOUNROLL for (int i = start; i < end; i++) {
+        tm.phase();   // one per band, kNbEBands per frame (balanced below): co-resident streams walk the band loop together
         ctx.i = i;
         int16_t *X = X_ + M * kEBands[i];
         int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;
@@ -625,6 +626,7 @@ CB_DEV void quant_all_bands_enc(TM tm, int start, int end, int16_t *X_, int16_t 
         }
         balance += pulses[i] + tell;
     }
+    CB_NOUNROLL for (int i = end - start; i < kNbEBands; i++) tm.phase();
     ec_io = ctx.ec;
 }
 

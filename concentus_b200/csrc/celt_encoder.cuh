@@ -21,6 +21,7 @@
 
 namespace cb {
 
+enum { kEncPhases = 7 + 2 + kNbEBands };   // tm.phase() calls per coded frame (celt_encode_frame)
 enum { kBitrateMax = -1, kOpusAuto = -1000, kFramesizeArg = 5000, kFramesizeVariable = 5010 };
 
 // What the Opus layer sets on the CELT encoder before a frame (celt_encoder_ctl calls, src/opus_encoder.c:1715-1770)
@@ -939,7 +940,10 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     int LM;
     CB_NOUNROLL for (LM = 0; LM <= kMaxLM; LM++)
         if (kShortMdct << LM == frame_size) break;
-    if (LM > kMaxLM || nbCompressedBytes_in < 2) return OPUS_BAD_ARG_;
+    if (LM > kMaxLM || nbCompressedBytes_in < 2) {
+        for (int i = 0; i < kEncPhases; i++) tm.phase();
+        return OPUS_BAD_ARG_;
+    }
     const int M = 1 << LM;
     const int N = M * kShortMdct;
     const int ov = kOverlap;
@@ -1028,6 +1032,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     tm.sync();
 
+    tm.phase();
     // ---- pitch pre-filter (run_prefilter, :1067-1192) ----
     {
         int *pre0 = G.pre, *pre1 = G.pre + (N + kCombMaxPeriod);
@@ -1041,9 +1046,11 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         const int prev_period = st->prefilter_period, prev_gain = st->prefilter_gain, prev_tapset = st->prefilter_tapset;
         if (V.enabled) {
             pitch_downsample_team(tm, pre0, pre1, kCombMaxPeriod + N, CC, S.u.pf.a.pitch_raw, S.u.pf.pitch_buf);
+            tm.phase();
             pitch_index = pitch_search_team(tm, S.u.pf.pitch_buf + (kCombMaxPeriod >> 1), S.u.pf.pitch_buf, N, kCombMaxPeriod - 3 * kCombMinPeriod,
                                             S.u.pf.x_lp4, S.u.pf.y_lp4, S.u.pf.a.c.xcorr);
             pitch_index = kCombMaxPeriod - pitch_index;
+            tm.phase();
             gain1 = remove_doubling_team(tm, S.u.pf.pitch_buf, kCombMaxPeriod, kCombMinPeriod, N, &pitch_index, prev_period, prev_gain, S.u.pf.a.c.yy_lookup);
             if (pitch_index > kCombMaxPeriod - 2) pitch_index = kCombMaxPeriod - 2;
             gain1 = s16(mul16_16_q15(22938, gain1));
@@ -1051,6 +1058,8 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
             if (cfg.loss_rate > 4) gain1 = gain1 >> 1;
             if (cfg.loss_rate > 8) gain1 = 0;
         } else {
+            tm.phase();
+            tm.phase();
             gain1 = 0;
             pitch_index = kCombMinPeriod;
         }
@@ -1101,6 +1110,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         }
     }
 
+    tm.phase();
     // ---- transient analysis (:1642-1657): one lane per channel ----
     if (cfg.complexity >= 1) {
         CB_TEAM_FOR(i, CC * (N + ov), tm) S.u.tin[i] = G.in[i] >> 12;
@@ -1130,6 +1140,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     tm.sync();
 
+    tm.phase();
     // ---- MDCT, band energies (:1660-1690) ----
     if (V.secondMdct) {
         compute_mdcts_team(tm, 0, G.in, G.freq, C, CC, LM, S.u.fft);
@@ -1185,6 +1196,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         }
         V.do_tf = V.effectiveBytes >= 15 * C && start == 0 && cfg.complexity >= 2;
     }
+    tm.phase();
     // ---- band normalisation (:1856) ----
     normalise_bands_team(tm, G.freq, S.u.x.X, S.bandE, effEnd, C, M, LM, S.band_g, S.band_shift);
 
@@ -1220,6 +1232,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         CB_NOUNROLL for (int i = 0; i < end; i++) S.tf_res[i] = isTransient;
         V.tf_select = 0;
     }
+    tm.phase();
     // ---- coarse energy, tf flags (:1882-1889) ----
     if (L0) {
         EcEnc ec = V.ec;
@@ -1303,6 +1316,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         if (L0) st->stereo_saving = stereo_saving;
     }
 
+    tm.phase();
     // ---- rate control, allocation, quantisation, packing: lane 0 (:1992-2262) ----
     if (L0) {
         EcEnc ec = V.ec;
@@ -1377,6 +1391,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         V.dual_stereo = dual_stereo;
     }
     tm.sync();
+    tm.phase();
     // ---- residual quantisation (:2208): every lane walks the band loop with identical scalars, vector work is split ----
     {
         EcEnc ec = V.ec;

@@ -50,6 +50,7 @@ struct SoloTeam {
     CB_MEM int bcast(int v, int) const { return v; }
     CB_MEM int exscan(int) const { return 0; }   // exclusive prefix sum over lanes (wrapping)
     CB_MEM int shfl_xor(int v, int) const { return v; }
+    CB_MEM void phase() const {}
 };
 
 #if defined(__CUDACC__)
@@ -75,6 +76,14 @@ struct WarpTeam {
     }
     CB_MEM int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
     CB_MEM int shfl_xor(int v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
+    // Phase boundary of a frame: with CB_PHASE_SYNC the warps of a block (each on its own stream) wait for each other here,
+    // so that co-resident warps execute the same region of a kernel much larger than the instruction cache.  EVERY warp of the
+    // block must pass the same number of phase() calls per frame (see kEncPhases).
+#if defined(CB_PHASE_SYNC)
+    CB_MEM void phase() const { __syncthreads(); }
+#else
+    CB_MEM void phase() const {}
+#endif
     CB_MEM int exscan(int v) const {
         unsigned inc = (unsigned)v;
 #pragma unroll

@@ -5,6 +5,9 @@
 // decisions down to ec_enc_done runs on the device, one warp per stream, F frames per launch (the frames of a stream are
 // serially dependent through the encoder state; streams are independent).
 // There is NO CPU path: if CUDA is unusable every codec call returns OPUS_INTERNAL_ERROR.
+#if !defined(CB_NO_PHASE_SYNC) && !defined(CB_PHASE_SYNC)
+#define CB_PHASE_SYNC 1      // see the block-shape note below
+#endif
 #define CB_SMALL_CODE 1   // see celt_simt.cuh: the encoder kernel is instruction-cache bound when everything is inlined
 #include <cuda_runtime.h>
 
@@ -34,11 +37,18 @@ struct OpusEncoder {
 };
 static const uint32_t kEncMagic = 0x0B200E4Cu;
 
+// Block shape (measured on B200, profiles/r1_enc_*): ONE block of 14 warps per SM, the warps phase-synchronised
+// (celt_simt.cuh WarpTeam::phase).  The kernel is ~250 KB of SASS against a 32 KB L1.5 instruction cache: with free-running
+// warps 35-70 % of the issue slots were lost to instruction fetch; letting the 14 streams of an SM walk the frame in step
+// doubled the throughput.  2,072 streams are resident per B200, so 4,096 streams are two full waves.
 #ifndef CB_ENC_WPB
-#define CB_ENC_WPB 2          // warps (= streams) per block
+#define CB_ENC_WPB 14         // warps (= streams) per block
 #endif
 #ifndef CB_ENC_MINBLOCKS
-#define CB_ENC_MINBLOCKS 7    // resident blocks per SM: 14 streams per SM, 2,072 per B200 -> 4,096 streams = 2 full waves
+#define CB_ENC_MINBLOCKS 1
+#endif
+#if !defined(CB_NO_PHASE_SYNC) && !defined(CB_PHASE_SYNC)
+#define CB_PHASE_SYNC 1
 #endif
 
 // Shared memory of one warp: the frame working set plus the head of the stream's state (scalars + band-energy histories),
@@ -56,7 +66,12 @@ encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_ENC_WPB + warp;
-    if (s >= n) return;
+    if (s >= n) {
+#if defined(CB_PHASE_SYNC)
+        for (int f = 0; f < F * kEncPhases; f++) __syncthreads();   // keep the block's phase barriers balanced
+#endif
+        return;
+    }
     EncWarpSmem &W = reinterpret_cast<EncWarpSmem *>(smem_raw)[warp];
     CbEncState *gst = pool + slots[s];
     for (int i = lane; i < CB_ENC_HEAD_BYTES / 4; i += 32) W.head[i] = reinterpret_cast<const int *>(gst)[i];

@@ -305,6 +305,11 @@ CB_TABLE int32_t kBwThreshMonoMusic[8] = {12000, 1000, 15000, 1000, 18000, 2000,
 CB_TABLE int32_t kBwThreshStereoVoice[8] = {11000, 1000, 14000, 1000, 21000, 2000, 28000, 2000};
 CB_TABLE int32_t kBwThreshStereoMusic[8] = {12000, 1000, 18000, 2000, 21000, 2000, 30000, 2000};
 
+template <class TM>
+CB_DEV void skip_phases(TM tm) {
+    for (int i = 0; i < kEncPhases; i++) tm.phase();
+}
+
 // opus_encode_native (opus_encoder.c:938-2005), MODE_CELT_ONLY path.  pcm: frame_size x channels int16; out: >= out_data_bytes.
 // st: head of the state (maybe a shared-memory copy), gst: the full block in HBM (delay buffer and sample histories).
 // Returns (uniformly on all lanes) the packet length or a negative error code.
@@ -317,8 +322,8 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     // frame_size has been through frame_size_select() on the host (opus_encode, opus_encoder.c:2007-2025)
     if ((!st->variable_duration && 400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs && 25 * frame_size != Fs &&
          50 * frame_size != 3 * Fs) || 400 * frame_size < Fs || max_data_bytes <= 0)
-        return OPUS_BAD_ARG_;
-    if (Fs != 48000) return OPUS_UNIMPLEMENTED_;
+        { skip_phases(tm); return OPUS_BAD_ARG_; }
+    if (Fs != 48000) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }
     const int delay_compensation = st->application == kAppLowdelay ? 0 : st->delay_compensation;
     const int lsb_depth = imin(16, st->lsb_depth);
     const int total_buffer = delay_compensation;
@@ -378,6 +383,7 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         }
         if (!st->use_vbr) ret = max_data_bytes;
         tm.sync();
+        skip_phases(tm);
         return ret;
     }
     equiv_rate = bitrate_bps - (40 * stream_channels + 20) * (Fs / frame_size - 50);
@@ -400,10 +406,10 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     if (mode != CB_MODE_CELT_ONLY && frame_size < Fs / 100) mode = CB_MODE_CELT_ONLY;
     if (max_data_bytes < (frame_rate > 50 ? 12000 : 8000) * frame_size / (Fs * 8)) mode = CB_MODE_CELT_ONLY;
-    if (mode != CB_MODE_CELT_ONLY) return OPUS_UNIMPLEMENTED_;                 // SILK / hybrid: not in this engine
-    if (st->prev_mode > 0 && st->prev_mode != CB_MODE_CELT_ONLY) return OPUS_UNIMPLEMENTED_;
-    if (st->application == kAppVoip) return OPUS_UNIMPLEMENTED_;               // hp_cutoff (SILK biquad) path
-    if (frame_size > Fs / 50) return OPUS_UNIMPLEMENTED_;                      // 40/60 ms repacketised frames
+    if (mode != CB_MODE_CELT_ONLY) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }                 // SILK / hybrid: not in this engine
+    if (st->prev_mode > 0 && st->prev_mode != CB_MODE_CELT_ONLY) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }
+    if (st->application == kAppVoip) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }               // hp_cutoff (SILK biquad) path
+    if (frame_size > Fs / 50) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }                      // 40/60 ms repacketised frames
     // bandwidth (opus_encoder.c:1229-1292)
     int bandwidth;
     {
