@@ -15,7 +15,8 @@ import pytest
 import oracle_lib as O
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not os.path.basename(p).startswith("enc_"))
+GOLDEN_ENC = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "enc_*.npz")))
 HAVE_REF = os.path.exists(O.REF_SO) or os.path.isdir("/root/reference/opus-fix")
 needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built and reference sources absent")
 
@@ -29,7 +30,27 @@ def _hostsim():
     hs = C.CDLL(so)
     hs.hostsim_decode_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+    hs.hostsim_encode_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p]
     return hs
+
+
+def _hostsim_encode(hs, pcm, fs, br, ch, vbr, cvbr, cx, application=O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, max_bytes=1275):
+    """The encoder headers compiled for the CPU with a 1-lane team (tests/hostsim).  Returns (packets [F,1276], lens, ranges)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    F = pcm.shape[0] // fs
+    out = np.zeros((F, 1276), dtype=np.uint8)
+    lens = np.zeros(F, dtype=np.int32)
+    rng = np.zeros(F, dtype=np.uint32)
+    cfg = np.array([application, br, vbr, cvbr, cx, max_bytes, 0, 0], dtype=np.int32)
+    hs.hostsim_encode_stream(O.ptr(pcm), F, fs, ch, 48000, O.ptr(cfg), O.ptr(out), 1276, O.ptr(lens), O.ptr(rng))
+    return out, lens, rng
+
+
+def _same_packets(g_data, g_offs, g_lens, out, lens):
+    if not np.array_equal(g_lens, lens):
+        return False
+    return all(np.array_equal(g_data[g_offs[f]:g_offs[f] + g_lens[f]], out[f, :g_lens[f]]) for f in range(len(lens)))
 
 
 def _hostsim_decode(hs, data, offs, lens, fs, ch):
@@ -113,6 +134,106 @@ def test_hostsim_vs_oracle_mini_sweep():
                     assert np.array_equal(rret, hret) and np.array_equal(rr, hr) and np.array_equal(rp, hp), (kind, ch, fs, br)
 
 
+# ---- encoder --------------------------------------------------------------------------------------------------------
+
+@needs_ref
+@pytest.mark.parametrize("path", GOLDEN_ENC, ids=[os.path.basename(p)[:-4] for p in GOLDEN_ENC])
+def test_oracle_reproduces_encoder_golden(path):
+    g = np.load(path)
+    d, o, l, r = O.encode_stream(g["pcm"], int(g["frame_size"]), int(g["bitrate"]), int(g["channels"]), vbr=int(g["vbr"]),
+                                 cvbr=int(g["cvbr"]), complexity=int(g["complexity"]))
+    assert _same_packets(g["data"], g["offs"], g["lens"], d.reshape(-1, 1276), l)
+    assert np.array_equal(r, g["enc_ranges"])
+    # and the reference decoder agrees with the encoder on every final range (tests/test_opus_encode.c:306)
+    _, dr, _ = O.decode_stream(g["data"], g["offs"], g["lens"], int(g["frame_size"]), int(g["channels"]))
+    assert np.array_equal(dr, g["enc_ranges"])
+
+
+@pytest.mark.parametrize("path", GOLDEN_ENC, ids=[os.path.basename(p)[:-4] for p in GOLDEN_ENC])
+def test_hostsim_encoder_matches_golden(path):
+    g = np.load(path)
+    out, lens, rng = _hostsim_encode(_hostsim(), g["pcm"], int(g["frame_size"]), int(g["bitrate"]), int(g["channels"]), int(g["vbr"]),
+                                     int(g["cvbr"]), int(g["complexity"]))
+    assert _same_packets(g["data"], g["offs"], g["lens"], out, lens)
+    assert np.array_equal(rng, g["enc_ranges"])
+
+
+@needs_ref
+def test_hostsim_encoder_vs_oracle_mini_sweep():
+    """BASELINE configs[3] in miniature: frame size x channels x bitrate x CBR/VBR/CVBR x complexity x signal kind."""
+    hs = _hostsim()
+    rs = np.random.RandomState(11)
+    cases = [(k, ch, fs, br, m, cx) for k in ("music", "tone", "clicks", "noise") for ch in (1, 2) for fs in (120, 240, 480, 960)
+             for br in (32000, 48000, 64000, 96000, 128000, 192000, 256000, 510000) for m in ((0, 0), (1, 0), (1, 1)) for cx in (0, 5, 10)]
+    for i in rs.permutation(len(cases))[:120]:
+        kind, ch, fs, br, (vbr, cvbr), cx = cases[i]
+        x = O.test_signal(24000, ch, 300 + int(i), kind)
+        d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx)
+        out, lens, rng = _hostsim_encode(hs, x, fs, br, ch, vbr, cvbr, cx)
+        assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), cases[i]
+
+
+@needs_ref
+def test_hostsim_encoder_long_vbr_and_audio_application():
+    """The VBR controller settles over ~970 frames (vbr_count); OPUS_APPLICATION_AUDIO adds 4 ms of delay compensation."""
+    hs = _hostsim()
+    x = O.test_signal(48000 * 21, 2, 5, "music")
+    d, o, l, r = O.encode_stream(x, 960, 96000, 2, vbr=1, cvbr=1, complexity=10)
+    out, lens, rng = _hostsim_encode(hs, x, 960, 96000, 2, 1, 1, 10)
+    assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng)
+    for (ch, fs, br) in ((2, 960, 96000), (2, 240, 128000), (2, 960, 24000)):
+        x = O.test_signal(48000, ch, 6, "music")
+        d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=1, complexity=10, application=O.OPUS_APPLICATION_AUDIO)
+        assert (d.reshape(-1, 1276)[:, 0] & 0x80).all()      # the reference itself picks CELT-only here
+        out, lens, rng = _hostsim_encode(hs, x, fs, br, ch, 1, 1, 10, application=O.OPUS_APPLICATION_AUDIO)
+        assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (ch, fs, br)
+
+
+def test_encoder_host_api_ctl_and_padding():
+    """Host-side half of the encoder C ABI: sizes, init argument checks, ctl set/get round trips and range checks
+    (opus-fix/tests/test_opus_api.c encoder section), opus_packet_pad / unpad against the reference's."""
+    import concentus_b200 as cb
+    L = cb.lib()
+    assert L.opus_encoder_get_size(0) == 0 and L.opus_encoder_get_size(3) == 0
+    for ch in (1, 2):
+        assert 2048 < L.opus_encoder_get_size(ch) <= (1 << 17)
+    err = C.c_int(0)
+    assert L.opus_encoder_create(48000, 2, 1234, C.byref(err)) is None and err.value == cb.OPUS_BAD_ARG
+    assert L.opus_encoder_create(48000, 3, cb.OPUS_APPLICATION_AUDIO, C.byref(err)) is None and err.value == cb.OPUS_BAD_ARG
+    h = L.opus_encoder_create(48000, 2, cb.OPUS_APPLICATION_RESTRICTED_LOWDELAY, C.byref(err))
+    assert h and err.value == 0
+    hp = C.c_void_p(h)
+    v = C.c_int32(0)
+    for (setr, getr, good, bad) in ((4002, 4003, 96000, 0), (4010, 4011, 7, 11), (4006, 4007, 0, 2), (4020, 4021, 0, 2), (4022, 4023, 1, 3),
+                                    (4004, 4005, 1104, 1100), (4014, 4015, 20, 101), (4036, 4037, 16, 7), (4042, 4043, 1, 2), (4024, 4025, 3002, 5)):
+        assert L.opus_encoder_ctl(hp, setr, C.c_int32(good)) == 0, setr
+        assert L.opus_encoder_ctl(hp, getr, C.byref(v)) == 0 and v.value == good, getr
+        assert L.opus_encoder_ctl(hp, setr, C.c_int32(bad)) == cb.OPUS_BAD_ARG, setr
+        assert L.opus_encoder_ctl(hp, getr, None) == cb.OPUS_BAD_ARG
+    assert L.opus_encoder_ctl(hp, 4002, C.c_int32(5000000)) == 0 and L.opus_encoder_ctl(hp, 4003, C.byref(v)) == 0 and v.value == 600000
+    assert L.opus_encoder_ctl(hp, 4027, C.byref(v)) == 0 and v.value == 120                      # lookahead, restricted low delay
+    assert L.opus_encoder_ctl(hp, 4029, C.byref(v)) == 0 and v.value == 48000
+    assert L.opus_encoder_ctl(hp, 4000, C.c_int32(cb.OPUS_APPLICATION_AUDIO)) == 0                # allowed before the first frame
+    assert L.opus_encoder_ctl(hp, 4027, C.byref(v)) == 0 and v.value == 120 + 192
+    assert L.opus_encoder_ctl(hp, 31337, C.c_int32(0)) == cb.OPUS_UNIMPLEMENTED
+    before = C.string_at(h, L.opus_encoder_get_size(2))
+    assert L.opus_encoder_ctl(hp, cb.OPUS_RESET_STATE) == 0
+    L.opus_encoder_destroy(hp)
+    assert len(before) == L.opus_encoder_get_size(2)
+    # padding: a code-0 packet grown to every size up to +600 bytes, and back
+    pk = np.zeros(1276, dtype=np.uint8)
+    pk[:40] = np.arange(40) + 0xF8
+    for new_len in (40, 41, 42, 100, 295, 296, 297, 640):
+        a = pk.copy()
+        assert L.opus_packet_pad(O.ptr(a), 40, new_len) == 0
+        if HAVE_REF:
+            b = pk.copy()
+            assert O.ref().opus_packet_pad(O.ptr(b), 40, new_len) == 0
+            assert np.array_equal(a[:new_len], b[:new_len]), new_len
+        assert L.opus_packet_unpad(O.ptr(a), new_len) == 40 and np.array_equal(a[:40], pk[:40])
+    assert L.opus_packet_pad(O.ptr(pk), 40, 39) == cb.OPUS_BAD_ARG
+
+
 def test_hostsim_garbage_packets_do_not_crash_and_match_oracle():
     hs = _hostsim()
     rs = np.random.RandomState(5)
@@ -188,6 +309,11 @@ def test_product_fails_loudly_without_cuda():
             "r=L.opus_decode(C.c_void_p(h), p.ctypes.data_as(C.c_void_p), 4, o.ctypes.data_as(C.c_void_p), 960, 0); print(r, L.opus_b200_init(0))")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
     assert out.stdout.split() == ["-3", "-3"], (out.stdout, out.stderr)
+    code = ("import ctypes as C, numpy as np, concentus_b200 as cb; L=cb.lib(); e=C.c_int(0);"
+            "h=L.opus_encoder_create(48000,2,2051,C.byref(e)); x=np.zeros(1920,dtype=np.int16); o=np.zeros(1276,dtype=np.uint8);"
+            "r=L.opus_encode(C.c_void_p(h), x.ctypes.data_as(C.c_void_p), 960, o.ctypes.data_as(C.c_void_p), 1276); print(r)")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.stdout.split() == ["-3"], (out.stdout, out.stderr)
 
 
 def _gloo_worker(rank, world, port, q):
