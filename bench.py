@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — CELT decode throughput (audio-seconds per wall-second, x realtime) on N B200s.
+"""bench.py — CELT decode (headline) and encode throughput (audio-seconds per wall-second, x realtime) on N B200s.
 
 Workload (BASELINE.json configs[1]): 4,096 independent 48 kHz stereo 64 kbps (CBR) 20 ms CELT streams, 60 s each,
 per GPU.  One "step" = one pass over that whole batch (245,760 audio-seconds per GPU).  Streams are sharded
@@ -11,6 +11,9 @@ Arms
                        e2e   : host (pinned) packets in, host PCM out through opus_decode_span (H2D + D2H inside the timing)
   --impl reference   the UNMODIFIED opus-fix C build (oracle/_ref), one stream per thread on all host cores, on a bounded
                      sample of the same workload.
+
+The same JSON line carries an "encode" object for BASELINE.json configs[2] (4,096 streams, 48 kHz stereo, 96 kbps VBR,
+complexity 10) with its own value / e2e / roofline / cpu_baseline, measured the same way through opus_encode_span(_device).
 
 Input packets are synthetic: produced by the reference encoder (restricted-lowdelay, 64 kbps CBR, complexity 10) from the
 generate_music / tone / clicks test signals — `--base` distinct 60 s programmes, replicated across the streams with
@@ -144,7 +147,15 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         t += step()
     val = n * seconds * args.steps / t
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
+    enc_ref = None
+    if not args.no_encode:
+        ne = min(args.streams, max(cores * 16, 64))
+        ev, et = reference_encode(args, cores, ne, min(args.enc_seconds, 6))
+        enc_ref = {"metric": "CELT encode audio-sec per sec (x realtime), 48k stereo", "value": ev, "unit": "x realtime",
+                   "config": encode_workload_config(args, world),
+                   "cpu_baseline": {"value": ev, "unit": "x realtime", "cores": cores, "kind": "reference",
+                                    "sample": "%d streams x %d s, opus-fix -O2, one stream per thread, %.1f s wall" % (ne, min(args.enc_seconds, 6), et)}}
+    line = {"impl": "reference", "encode": enc_ref, "metric": METRIC, "value": val, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args, world),
@@ -152,6 +163,159 @@ def run_reference(args, rank, world):
                              "sample": "%d streams x %d s (of %d streams per GPU), opus-fix -O2, one stream per thread" % (n, seconds, args.streams)},
             "e2e": {"value": val, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+ENC_BITRATE = 96000
+
+
+def encode_programmes(nbase, seconds):
+    """nbase distinct PCM programmes [nbase, seconds*FS, CH] for the encoder bench (music / tone / clicks mix)."""
+    import oracle_lib as O
+    kinds = ["music", "tone", "clicks", "music"]
+    seg = min(10, seconds) * FS
+    out = np.zeros((nbase, seconds * FS, CH), dtype=np.int16)
+    for b in range(nbase):
+        x = O.test_signal(seg, CH, 7331 + b, kinds[b % len(kinds)])
+        reps = (seconds * FS + len(x) - 1) // len(x)
+        out[b] = np.tile(x, (reps, 1))[:seconds * FS]
+    return out
+
+
+def encode_workload_config(args, world):
+    return {"workload": "batched CELT encode: %d independent 48 kHz stereo 96 kbps VBR complexity-10 20 ms streams per GPU, %d s each "
+                        "(BASELINE.json configs[2])" % (args.streams, args.enc_seconds),
+            "streams_per_gpu": args.streams, "seconds_per_stream": args.enc_seconds, "frame_ms": 20, "bitrate": ENC_BITRATE, "complexity": 10,
+            "vbr": 1, "parallelism": "streams sharded over %d GPU(s), host partitioning, no collective" % world,
+            "l2": "PCM in per step (%.1f GB) >> 126 MB L2, no flush needed" % (args.streams * args.enc_seconds * FS * CH * 2 / 1e9)}
+
+
+def reference_encode(args, cores, n, seconds):
+    """The unmodified opus-fix encoder on n streams x seconds, one stream per thread.  Returns (x realtime, wall s)."""
+    import oracle_lib as O
+    F = seconds * FS // FRAME
+    base = encode_programmes(min(args.base, n), seconds)
+    pcm = np.ascontiguousarray(base[np.arange(n) % base.shape[0]])
+    out = np.zeros((n, F, 1276), dtype=np.uint8)
+    lens = np.zeros((n, F), dtype=np.int32)
+    cfg = O.RefEncCfg(O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, ENC_BITRATE, 1, 0, 10, 1276, 0, 0)
+    t = O.ref().ref_encode_streams_mt(n, F, cores, O.ptr(pcm), FRAME, CH, FS, C.byref(cfg), O.ptr(out), 1276, O.ptr(lens), None)
+    assert (lens > 2).all()
+    return n * seconds / t, t
+
+
+def bench_encode(args, L, cb, torch, dev, local, world, dist, rank, cores, peaks):
+    """BASELINE.json configs[2] through opus_encode_span_device (value) and opus_encode_span (e2e)."""
+    S, seconds = args.streams, args.enc_seconds
+    F = seconds * FS // FRAME
+    nbase = min(args.base, S)
+    base = encode_programmes(nbase, seconds)
+    d_base = torch.from_numpy(base).to(dev)                                  # [nbase, T, CH]
+    prog = torch.arange(S, device=dev) % nbase
+    rot = ((torch.arange(S, device=dev) // nbase) * 37 * FRAME) % (seconds * FS)
+    d_pcm = torch.empty((S, seconds * FS, CH), dtype=torch.int16, device=dev)
+    for s0 in range(0, S, 256):                                              # rotated copies, built on the device in slabs
+        s1 = min(S, s0 + 256)
+        idx = (torch.arange(seconds * FS, device=dev)[None, :] + rot[s0:s1, None]) % (seconds * FS)
+        d_pcm[s0:s1] = d_base[prog[s0:s1, None], idx]
+    del d_base
+    stride = 1276
+    d_data = torch.zeros((S * F * stride,), dtype=torch.uint8, device=dev)
+    d_ret = torch.zeros((S * F,), dtype=torch.int32, device=dev)
+    enc = cb.EncoderBatch(S, FS, CH, bitrate=ENC_BITRATE, vbr=1, cvbr=0, complexity=10)
+    estream = torch.cuda.ExternalStream(L.opus_b200_enc_stream(), device=dev)
+
+    def step_value():
+        rc = L.opus_encode_span_device(enc.handles, S, F, C.c_void_p(d_pcm.data_ptr()), FRAME, C.c_void_p(d_data.data_ptr()), stride,
+                                       C.c_void_p(d_ret.data_ptr()))
+        assert rc == 0, rc
+
+    def barrier():
+        torch.cuda.synchronize()
+        L.opus_b200_enc_synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step_value()
+    barrier()
+    assert bool((d_ret > 2).all().item()), "encode returned errors"
+    mean_len = float(d_ret.float().mean().item())
+    launches0 = L.opus_b200_enc_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(estream)
+    for _ in range(args.steps):
+        step_value()
+    e1.record(estream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(L.opus_b200_enc_kernel_launches() - launches0)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * S * seconds * args.steps / (ms / 1e3)
+    # roofline: one launch per step; algorithmic bytes = PCM in + packet bytes out (SURVEY.md 8d: 3,840 + len per frame)
+    algo = float(S) * F * (FRAME * CH * 2 + mean_len)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kms = ms / max(launches, 1)
+    achieved = algo / (kms / 1e3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "encode_traffic.json")))
+        traffic = tj["dram_bytes_per_frame"]["encode_span_kernel"] * S * F
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "encode_span_kernel", "kernel_ms_per_launch": kms, "algorithmic_bytes_per_launch": algo,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "note": "integer-issue / latency bound (one warp per stream, frames serial within a stream); limiter evidence under profiles/"}
+    # e2e: pinned host PCM in, host packets out, one opus_encode_span call per second of audio
+    e2e = None
+    if not args.no_e2e:
+        del d_data
+        torch.cuda.empty_cache()
+        fc = FS // FRAME
+        h_pcm = torch.empty((S, fc * FRAME, CH), dtype=torch.int16).pin_memory()
+        h_pcm.copy_(d_pcm[:, :fc * FRAME].cpu())
+        h_data = torch.empty((S * fc * stride,), dtype=torch.uint8).pin_memory()
+        h_ret = torch.empty((S * fc,), dtype=torch.int32).pin_memory()
+        enc2 = cb.EncoderBatch(S, FS, CH, bitrate=ENC_BITRATE, vbr=1, cvbr=0, complexity=10)
+
+        def step_e2e():
+            for c in range(seconds):
+                rc = L.opus_encode_span(enc2.handles, S, fc, C.c_void_p(h_pcm.data_ptr()), FRAME, C.c_void_p(h_data.data_ptr()), stride,
+                                        C.c_void_p(h_ret.data_ptr()))
+                assert rc == 0, rc
+        for _ in range(max(1, args.warmup - 2)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        ems = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        assert bool((h_ret > 2).all().item())
+        e2e = {"value": world * S * seconds * args.steps / (ems / 1e3), "unit": "x realtime",
+               "h2d_bytes_per_step": int(seconds * h_pcm.numel() * 2), "d2h_bytes_per_step": int(seconds * (h_data.numel() + h_ret.numel() * 4)),
+               "ms_per_step": ems / args.steps,
+               "api": "opus_encode_span, %d calls of %d frames x %d streams per step, pinned host buffers, wall clock" % (seconds, fc, S)}
+        enc2.close()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n = min(S, max(cores * 16, 64))
+        v, t = reference_encode(args, cores, n, min(seconds, 6))
+        cpu = {"value": v, "unit": "x realtime", "cores": cores, "kind": "reference",
+               "sample": "%d streams x %d s of the same programmes, opus-fix -O2 build, one stream per thread, %.1f s wall" % (n, min(seconds, 6), t)}
+    enc.close()
+    del d_pcm
+    torch.cuda.empty_cache()
+    return {"metric": "CELT encode audio-sec per sec (x realtime), 48k stereo", "value": value, "unit": "x realtime", "ms_per_step": ms / args.steps,
+            "mean_packet_bytes": mean_len, "config": encode_workload_config(args, world), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu}
 
 
 def F_chunk(seconds):
@@ -181,6 +345,8 @@ def main():
     ap.add_argument("--base", type=int, default=64, help="distinct programmes encoded by the oracle")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-encode", action="store_true")
+    ap.add_argument("--enc-seconds", type=int, default=6, help="audio seconds per stream per encode step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -338,13 +504,19 @@ def main():
         cpu = {"value": n * seconds / t, "unit": "x realtime", "cores": cores, "kind": "reference",
                "sample": "first %d of the %d streams x %d s, opus-fix -O2 build, one stream per thread, %.1f s wall" % (n, S, seconds, t)}
 
+    dec.close()
+    del d_blob
+    torch.cuda.empty_cache()
+    encode = None
+    if not args.no_encode:
+        encode = bench_encode(args, L, cb, torch, dev, local, world, dist, rank, cores, peaks)
+        launches += encode["gpu_launches"]
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, "encode": encode}
         print(json.dumps(line), flush=True)
-    dec.close()
     if dist is not None:
         dist.destroy_process_group()
 

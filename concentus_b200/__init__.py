@@ -42,7 +42,7 @@ EXPORTS = [
     "opus_b200_kernel_launches", "opus_b200_last_kernel_ms", "opus_b200_stage_times", "opus_b200_device_index",
     "opus_encoder_get_size", "opus_encoder_create", "opus_encoder_init", "opus_encode", "opus_encoder_ctl", "opus_encoder_destroy",
     "opus_packet_pad", "opus_packet_unpad", "opus_encode_batch", "opus_encode_span", "opus_encode_span_device", "opus_encoder_sync",
-    "opus_b200_enc_synchronize", "opus_b200_enc_kernel_launches", "opus_b200_enc_last_kernel_ms",
+    "opus_b200_enc_synchronize", "opus_b200_enc_stream", "opus_b200_enc_kernel_launches", "opus_b200_enc_last_kernel_ms",
 ]
 
 OPUS_APPLICATION_VOIP = 2048
@@ -96,6 +96,7 @@ def lib():
         L.opus_packet_pad.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.opus_packet_unpad.argtypes = [C.c_void_p, C.c_int32]
         L.opus_b200_enc_kernel_launches.restype = C.c_longlong
+        L.opus_b200_enc_stream.restype = C.c_void_p
         L.opus_b200_enc_last_kernel_ms.restype = C.c_float
         _lib = L
     return _lib

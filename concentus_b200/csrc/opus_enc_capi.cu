@@ -355,6 +355,11 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
 extern "C" {
 
 long long opus_b200_enc_kernel_launches(void) { return e.launches; }
+void *opus_b200_enc_stream(void) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return nullptr;
+    return (void *)e.stream;
+}
 float opus_b200_enc_last_kernel_ms(void) {
     std::lock_guard<std::mutex> lk(e.mu);
     return e.last_ms;

@@ -173,6 +173,7 @@ float opus_b200_last_kernel_ms(void);
 int opus_b200_device_index(void);         /* device in use, -1 when CUDA is unusable */
 /* encoder half: its own stream */
 int opus_b200_enc_synchronize(void);
+void *opus_b200_enc_stream(void);          /* the cudaStream_t the encoder launches on */
 long long opus_b200_enc_kernel_launches(void);
 float opus_b200_enc_last_kernel_ms(void);  /* device time of the last encode span (CUDA events on the encoder stream) */
 
