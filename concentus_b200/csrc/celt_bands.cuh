@@ -38,8 +38,8 @@ struct SplitCtx {
 // haar1 (bands.c:581-594)
 CB_DEV_NOINLINE void haar1(int16_t *X, int N0, int stride) {
     N0 >>= 1;
-    for (int i = 0; i < stride; i++)
-        for (int j = 0; j < N0; j++) {
+    CB_NOUNROLL for (int i = 0; i < stride; i++)
+        CB_NOUNROLL for (int j = 0; j < N0; j++) {
             int a = stride * 2 * j + i, b = stride * (2 * j + 1) + i;
             int t1 = mul16_16(23170, X[a]);
             int t2 = mul16_16(23170, X[b]);
@@ -52,26 +52,26 @@ CB_DEV_NOINLINE void haar1(int16_t *X, int N0, int stride) {
 CB_DEV_NOINLINE void deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
     const int N = N0 * stride;
     const uint8_t *ordery = kOrdery + stride - 2;
-    for (int i = 0; i < stride; i++) {
+    CB_NOUNROLL for (int i = 0; i < stride; i++) {
         const int row = hadamard ? ordery[i] : i;
-        for (int j = 0; j < N0; j++) tmp[row * N0 + j] = X[j * stride + i];
+        CB_NOUNROLL for (int j = 0; j < N0; j++) tmp[row * N0 + j] = X[j * stride + i];
     }
-    for (int p = 0; p < N; p++) X[p] = tmp[p];
+    CB_NOUNROLL for (int p = 0; p < N; p++) X[p] = tmp[p];
 }
 CB_DEV_NOINLINE void interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
     const int N = N0 * stride;
     const uint8_t *ordery = kOrdery + stride - 2;
-    for (int i = 0; i < stride; i++) {
+    CB_NOUNROLL for (int i = 0; i < stride; i++) {
         const int row = hadamard ? ordery[i] : i;
-        for (int j = 0; j < N0; j++) tmp[j * stride + i] = X[row * N0 + j];
+        CB_NOUNROLL for (int j = 0; j < N0; j++) tmp[j * stride + i] = X[row * N0 + j];
     }
-    for (int p = 0; p < N; p++) X[p] = tmp[p];
+    CB_NOUNROLL for (int p = 0; p < N; p++) X[p] = tmp[p];
 }
 
 // stereo_merge (bands.c:375-424)
 CB_DEV_NOINLINE void stereo_merge(int16_t *X, int16_t *Y, int mid, int N) {
     int xp = 0, side = 0;
-    for (int j = 0; j < N; j++) {
+    CB_NOUNROLL for (int j = 0; j < N; j++) {
         xp = mac16_16(xp, Y[j], X[j]);
         side = mac16_16(side, Y[j], Y[j]);
     }
@@ -80,7 +80,7 @@ CB_DEV_NOINLINE void stereo_merge(int16_t *X, int16_t *Y, int mid, int N) {
     int El = wsub(wadd(mul16_16(mid2, mid2), side), wmul(2, xp));
     int Er = wadd(wadd(mul16_16(mid2, mid2), side), wmul(2, xp));
     if (Er < 161061 || El < 161061) {   // QCONST32(6e-4f, 28)
-        for (int j = 0; j < N; j++) Y[j] = X[j];
+        CB_NOUNROLL for (int j = 0; j < N; j++) Y[j] = X[j];
         return;
     }
     int kl = celt_ilog2(El) >> 1;
@@ -91,7 +91,7 @@ CB_DEV_NOINLINE void stereo_merge(int16_t *X, int16_t *Y, int mid, int N) {
     int rgain = celt_rsqrt_norm(t);
     if (kl < 7) kl = 7;
     if (kr < 7) kr = 7;
-    for (int j = 0; j < N; j++) {
+    CB_NOUNROLL for (int j = 0; j < N; j++) {
         int l = s16(mul16_16_p15(mid, X[j]));
         int r = Y[j];
         X[j] = (int16_t)pshr32(mul16_16(lgain, s16(l - r)), kl + 1);
@@ -185,7 +185,7 @@ CB_DEV void compute_theta(BandCtx &ctx, SplitCtx &sctx, int N, int *b, int B, in
 CB_DEV unsigned quant_band_n1(BandCtx &ctx, int16_t *X, int16_t *Y, int16_t *lowband_out) {
     int16_t *x = X;
     const int nch = Y != nullptr ? 2 : 1;
-    for (int c = 0; c < nch; c++) {
+    CB_NOUNROLL for (int c = 0; c < nch; c++) {
         int sign = 0;
         if (ctx.remaining_bits >= 1 << kBitRes) {
             sign = (int)ctx.ec.bits(1);
@@ -217,17 +217,17 @@ CB_DEV unsigned partition_leaf(BandCtx &ctx, int16_t *X, int N, int b, int B, co
         const unsigned cm_mask = (1u << B) - 1;
         fill &= (int)cm_mask;
         if (!fill) {
-            for (int j = 0; j < N; j++) X[j] = 0;
+            CB_NOUNROLL for (int j = 0; j < N; j++) X[j] = 0;
         } else {
             unsigned sd = ctx.seed;
             if (lowband == nullptr) {
-                for (int j = 0; j < N; j++) {
+                CB_NOUNROLL for (int j = 0; j < N; j++) {
                     sd = lcg_rand(sd);
                     X[j] = (int16_t)((int)sd >> 20);
                 }
                 cm = cm_mask;
             } else {
-                for (int j = 0; j < N; j++) {
+                CB_NOUNROLL for (int j = 0; j < N; j++) {
                     sd = lcg_rand(sd);
                     int t = (sd & 0x8000) ? 4 : -4;   // QCONST16(1.0f/256, 10)
                     X[j] = (int16_t)(lowband[j] + t);
@@ -338,10 +338,10 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     if (tf_change > 0) recombine = tf_change;
     if (ctx.dry) lowband = nullptr;
     if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
-        for (int j = 0; j < N; j++) lowband_scratch[j] = lowband[j];
+        CB_NOUNROLL for (int j = 0; j < N; j++) lowband_scratch[j] = lowband[j];
         lowband = lowband_scratch;
     }
-    for (int k = 0; k < recombine; k++) {
+    CB_NOUNROLL for (int k = 0; k < recombine; k++) {
         if (lowband) haar1(lowband, N >> k, 1 << k);
         fill = kBitInterleave[fill & 0xF] | kBitInterleave[fill >> 4] << 2;
     }
@@ -366,20 +366,20 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     if (B0 > 1) interleave_hadamard(X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
     N_B = N_B0;
     B = B0;
-    for (int k = 0; k < time_divide; k++) {
+    CB_NOUNROLL for (int k = 0; k < time_divide; k++) {
         B >>= 1;
         N_B <<= 1;
         cm |= cm >> B;
         haar1(X, N_B, B);
     }
-    for (int k = 0; k < recombine; k++) {
+    CB_NOUNROLL for (int k = 0; k < recombine; k++) {
         cm = kBitDeinterleave[cm];
         haar1(X, N0 >> k, 1 << k);
     }
     B <<= recombine;
     if (lowband_out) {
         const int n = s16(celt_sqrt(shl32(N0, 22)));
-        for (int j = 0; j < N0; j++) lowband_out[j] = (int16_t)mul16_16_q15(n, X[j]);
+        CB_NOUNROLL for (int j = 0; j < N0; j++) lowband_out[j] = (int16_t)mul16_16_q15(n, X[j]);
     }
     cm &= (1u << B) - 1;
     return cm;
@@ -404,7 +404,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
     ctx.tmp = tmp;
     ctx.intensity = intensity; ctx.spread = spread; ctx.seed = *seed;
     ctx.dry = dry;
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         ctx.i = i;
         const int last = (i == end - 1);
         int16_t *X = X_ + M * kEBands[i];
@@ -446,7 +446,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
         if (dual_stereo && i == intensity) {
             dual_stereo = 0;
             const int n = dry ? 0 : M * kEBands[i] - norm_offset;
-            for (int j = 0; j < n; j++) norm[j] = (int16_t)((norm[j] + norm2[j]) >> 1);
+            CB_NOUNROLL for (int j = 0; j < n; j++) norm[j] = (int16_t)((norm[j] + norm2[j]) >> 1);
         }
         int16_t *lb = effective_lowband != -1 ? norm + effective_lowband : nullptr;
         int16_t *lb_out = last ? nullptr : norm + M * kEBands[i] - norm_offset;
@@ -492,7 +492,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
             mode = kMono; npass = 1;
         }
         unsigned cm_acc = 0;
-        for (int pass = 0; pass < npass; pass++) {
+        CB_NOUNROLL for (int pass = 0; pass < npass; pass++) {
             int16_t *px, *plb, *plb_out, *pscratch;
             int pb, pgain, pfill;
             if (mode == kMono) {
@@ -548,7 +548,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
             stereo_merge(X, Y, s.imid, N);
         }
         if (!dry && (mode == kStereo || mode == kStereoN2) && s.inv)
-            for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
+            CB_NOUNROLL for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
         if (npass > 0 && mode != kDual) x_cm = y_cm = cm_acc;
         collapse_masks[i * C + 0] = (uint8_t)x_cm;
         collapse_masks[i * C + C - 1] = (uint8_t)y_cm;
@@ -563,7 +563,7 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
 template <class TM>
 CB_DEV void anti_collapse(TM tm, int16_t *X_, const uint8_t *collapse_masks, int LM, int C, int size, int start, int end,
                           const int16_t *logE, const int16_t *prev1logE, const int16_t *prev2logE, const int16_t *pulses, unsigned seed) {
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         int N0 = band_width(i);
         int depth = (int)udiv((unsigned)(1 + pulses[i]), (unsigned)N0) >> LM;
         int thresh32 = celt_exp2(s16(-shl16(depth, 10 - kBitRes))) >> 1;
@@ -572,7 +572,7 @@ CB_DEV void anti_collapse(TM tm, int16_t *X_, const uint8_t *collapse_masks, int
         int shift = celt_ilog2(t) >> 1;
         t = shl32(t, (7 - shift) << 1);
         int sqrt_1 = celt_rsqrt_norm(t);
-        for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             int prev1 = prev1logE[c * kNbEBands + i];
             int prev2 = prev2logE[c * kNbEBands + i];
             if (C == 1) {
@@ -594,10 +594,10 @@ CB_DEV void anti_collapse(TM tm, int16_t *X_, const uint8_t *collapse_masks, int
             int16_t *X = X_ + c * size + (kEBands[i] << LM);
             int renormalize = 0;
             const unsigned mask = collapse_masks[i * C + c];
-            for (int k = 0; k < 1 << LM; k++) {
+            CB_NOUNROLL for (int k = 0; k < 1 << LM; k++) {
                 if (!(mask & (1u << k))) {
                     // every lane steps the generator so the seed stays team-uniform; lane j%W stores slot j
-                    for (int j = 0; j < N0; j++) {
+                    CB_NOUNROLL for (int j = 0; j < N0; j++) {
                         seed = lcg_rand(seed);
                         if ((j % TM::W) == tm.lane()) X[(j << LM) + k] = (int16_t)((seed & 0x8000) ? r : -r);
                     }

@@ -73,7 +73,7 @@ CB_DEV void celt_parse_frame(const uint8_t *data, int len, int LM, int C, int en
     }
     const int shortBlocks = isTransient ? M : 0;
     const int intra_ener = tell + 3 <= total_bits ? dec.bit_logp(3) : 0;
-    for (int i = 0; i < 2 * kNbEBands; i++) { ir.qi[i] = 0; ir.eoff[i] = 0; }
+    CB_NOUNROLL for (int i = 0; i < 2 * kNbEBands; i++) { ir.qi[i] = 0; ir.eoff[i] = 0; }
     decode_coarse_symbols(start, end, intra_ener, dec, C, LM, ir.qi);
     tf_decode(start, end, isTransient, tf_res, LM, dec);
     tell = dec.tell();
@@ -83,7 +83,7 @@ CB_DEV void celt_parse_frame(const uint8_t *data, int len, int LM, int C, int en
     int dynalloc_logp = 6;
     total_bits <<= kBitRes;
     tell = (int)dec.tell_frac();
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         int width = C * band_width(i) << LM;
         int quanta = imin(width << kBitRes, imax(6 << kBitRes, width));
         int loop_logp = dynalloc_logp;
@@ -127,7 +127,7 @@ CB_DEV void celt_parse_frame(const uint8_t *data, int len, int LM, int C, int en
     ir.flags = (uint8_t)((silence ? CB_IR_SILENCE : 0) | (isTransient ? CB_IR_TRANSIENT : 0) | (intra_ener ? CB_IR_INTRA : 0) |
                          (anti_collapse_on ? CB_IR_ANTICOLLAPSE : 0) | (dec.error ? CB_IR_EC_ERROR : 0) |
                          (dec.tell() > 8 * len ? CB_IR_OVERRUN : 0));
-    for (int i = 0; i < kNbEBands; i++) ir.pulses[i] = (int16_t)(i < end ? pulses[i] : 0);
+    CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) ir.pulses[i] = (int16_t)(i < end ? pulses[i] : 0);
     *seed = dec.rng;
 }
 
@@ -159,7 +159,7 @@ CB_DEV void comb_filter_inplace(TM tm, int *x, int T0, int T1, int N, int g0, in
     // "off" period is 0 in the bitstream — so it is skipped and does not bound the run length.
     const int Tmin = imin(g0 != 0 ? T0 : kCombMaxPeriod, g1 != 0 ? T1 : kCombMaxPeriod);
     const int G = imin(TM::W, Tmin - 2);
-    for (int base = 0; base < overlap; base += G) {
+    CB_NOUNROLL for (int base = 0; base < overlap; base += G) {
         int i = base + tm.lane();
         if (tm.lane() < G && i < overlap) {
             int f = s16(mul16_16_q15(kWindow120[i], kWindow120[i]));
@@ -180,7 +180,7 @@ CB_DEV void comb_filter_inplace(TM tm, int *x, int T0, int T1, int N, int g0, in
         tm.sync();
     }
     if (g1 == 0) return;
-    for (int base = overlap; base < N; base += G) {
+    CB_NOUNROLL for (int base = overlap; base < N; base += G) {
         int i = base + tm.lane();
         if (tm.lane() < G && i < N) {
             int v = x[i];
@@ -200,7 +200,7 @@ CB_DEV void comb_filter_inplace(TM tm, int *x, int T0, int T1, int N, int g0, in
 CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downsample, int m, int gain) {
     if (downsample > 1) {
         int k = 0, next = 0;
-        for (int j = 0; j < n; j++) {
+        CB_NOUNROLL for (int j = 0; j < n; j++) {
             int t = wadd(x[j], m);
             m = mul16_32_q15(kPreemphCoef0, t);
             if (j == next) {
@@ -216,13 +216,13 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
         // batches of 8 samples: the loads are independent of the recurrence, so they are issued up front (two 16-byte
         // loads when the pointer allows) and the serial chain runs from registers
         if ((((uintptr_t)x) & 15) == 0) {
-            for (; j + 8 <= n; j += 8) {
+            CB_NOUNROLL for (; j + 8 <= n; j += 8) {
                 int xs[8];
                 const int4 a = *reinterpret_cast<const int4 *>(x + j);
                 const int4 b = *reinterpret_cast<const int4 *>(x + j + 4);
                 xs[0] = a.x; xs[1] = a.y; xs[2] = a.z; xs[3] = a.w; xs[4] = b.x; xs[5] = b.y; xs[6] = b.z; xs[7] = b.w;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
+                CB_NOUNROLL for (int u = 0; u < 8; u++) {
                     int t = wadd(xs[u], m);
                     m = mul16_32_q15(kPreemphCoef0, t);
                     int v = sig2word16(t);
@@ -231,7 +231,7 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
                 }
             }
         }
-        for (; j < n; j++) {
+        CB_NOUNROLL for (; j < n; j++) {
             int t = wadd(x[j], m);
             m = mul16_32_q15(kPreemphCoef0, t);
             int v = sig2word16(t);
@@ -247,7 +247,7 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
 template <class TM>
 CB_DEV void history_shift(TM tm, int *mem, int N) {
     const int count = kDecBuf - N + kOverlap / 2;
-    for (int base = 0; base < count; base += TM::W) {
+    CB_NOUNROLL for (int base = 0; base < count; base += TM::W) {
         int i = base + tm.lane();
         int v = 0;
         if (i < count) v = mem[i + N];
@@ -268,7 +268,7 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
     const int N = M * kShortMdct;
     const int silence = ir.flags & CB_IR_SILENCE, isTransient = (ir.flags & CB_IR_TRANSIENT) != 0;
     int *decode_mem[2], *out_syn[2];
-    for (int c = 0; c < CC; c++) {
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
         decode_mem[c] = st->decode_mem + c * CB_DEC_MEM;
         out_syn[c] = decode_mem[c] + kDecBuf - N;
     }
@@ -278,14 +278,14 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
     // ---- energies: prediction recurrence is serial over bands, tiny -> lane 0 ----
     if (tm.lane() == 0) {
         if (C == 1)
-            for (int i = 0; i < kNbEBands; i++) oldBandE[i] = (int16_t)imax(oldBandE[i], oldBandE[kNbEBands + i]);
+            CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) oldBandE[i] = (int16_t)imax(oldBandE[i], oldBandE[kNbEBands + i]);
         apply_coarse_energy(start, end, oldBandE, ir.qi, (ir.flags & CB_IR_INTRA) != 0, C, LM);
-        for (int c = 0; c < C; c++)
-            for (int i = start; i < end; i++)
+        CB_NOUNROLL for (int c = 0; c < C; c++)
+            CB_NOUNROLL for (int i = start; i < end; i++)
                 oldBandE[c * kNbEBands + i] = (int16_t)(oldBandE[c * kNbEBands + i] + ir.eoff[c * kNbEBands + i]);
     }
     tm.sync();
-    for (int c = 0; c < CC; c++) history_shift(tm, decode_mem[c], N);
+    CB_NOUNROLL for (int c = 0; c < CC; c++) history_shift(tm, decode_mem[c], N);
     if (ir.flags & CB_IR_ANTICOLLAPSE)
         anti_collapse(tm, X, ir.collapse, LM, C, N, start, end, oldBandE, oldLogE, oldLogE2, ir.pulses, ir.seed_bands);
     if (silence) {
@@ -333,7 +333,7 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
             return mode == 0 ? v0 : mode == 1 ? v1 : (wadd(v0, v1) >> 1);
         };
         const int npass = (CC == 2 && C == 2) ? 2 : 1;
-        for (int p = 0; p < npass; p++) {
+        CB_NOUNROLL for (int p = 0; p < npass; p++) {
             const int mode = (CC == 1 && C == 2) ? 2 : p;
             imdct_compute(tm, [&](int j) { return freq(mode, j); }, B, shift, S.fft);
             imdct_assemble(tm, out_syn[p], B, shift, S.fft);
@@ -345,7 +345,7 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
     const int pf_period = imax(st->postfilter_period, kCombMinPeriod);
     const int pf_period_old = imax(st->postfilter_period_old, kCombMinPeriod);
     const int postfilter_pitch = ir.pf_pitch, postfilter_gain = ir.pf_gain, postfilter_tapset = ir.pf_tapset;
-    for (int c = 0; c < CC; c++) {
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
         comb_filter_inplace(tm, out_syn[c], pf_period_old, pf_period, kShortMdct, st->postfilter_gain_old, st->postfilter_gain,
                             st->postfilter_tapset_old, st->postfilter_tapset, kOverlap);
         if (LM != 0)
@@ -367,23 +367,23 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
         }
         // ---- energy history (celt_decoder.c:1027-1062) ----
         if (C == 1)
-            for (int i = 0; i < kNbEBands; i++) oldBandE[kNbEBands + i] = oldBandE[i];
+            CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) oldBandE[kNbEBands + i] = oldBandE[i];
         if (!isTransient) {
             const int max_inc = st->loss_count < 10 ? M : 1024;   // M*QCONST16(0.001f,DB_SHIFT) ; QCONST16(1.f,DB_SHIFT)
-            for (int i = 0; i < 2 * kNbEBands; i++) {
+            CB_NOUNROLL for (int i = 0; i < 2 * kNbEBands; i++) {
                 oldLogE2[i] = oldLogE[i];
                 oldLogE[i] = oldBandE[i];
                 backgroundLogE[i] = (int16_t)imin(backgroundLogE[i] + max_inc, (int)oldBandE[i]);
             }
         } else {
-            for (int i = 0; i < 2 * kNbEBands; i++) oldLogE[i] = (int16_t)imin(oldLogE[i], oldBandE[i]);
+            CB_NOUNROLL for (int i = 0; i < 2 * kNbEBands; i++) oldLogE[i] = (int16_t)imin(oldLogE[i], oldBandE[i]);
         }
-        for (int c = 0; c < 2; c++) {
-            for (int i = 0; i < start; i++) {
+        CB_NOUNROLL for (int c = 0; c < 2; c++) {
+            CB_NOUNROLL for (int i = 0; i < start; i++) {
                 oldBandE[c * kNbEBands + i] = 0;
                 oldLogE[c * kNbEBands + i] = oldLogE2[c * kNbEBands + i] = -28672;
             }
-            for (int i = end; i < kNbEBands; i++) {
+            CB_NOUNROLL for (int i = end; i < kNbEBands; i++) {
                 oldBandE[c * kNbEBands + i] = 0;
                 oldLogE[c * kNbEBands + i] = oldLogE2[c * kNbEBands + i] = -28672;
             }
@@ -393,7 +393,7 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
         if (ir.flags & CB_IR_EC_ERROR) st->error = 1;
     }
     tm.sync();
-    for (int c = 0; c < CC; c++) {
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
         const int *src = out_syn[c];
         int *dst = sig[c];
         CB_TEAM_FOR(j, N, tm) dst[j] = src[j];

@@ -17,8 +17,8 @@ namespace cb {
 CB_DEV void decode_coarse_symbols(int start, int end, int intra, EcDec &dec, int C, int LM, int16_t *qi_out) {
     const uint8_t *prob = kEProbModel[LM][intra];
     const int budget = (int)dec.storage * 8;
-    for (int i = start; i < end; i++) {
-        for (int c = 0; c < C; c++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             int qi;
             int tell = dec.tell();
             if (budget - tell >= 15) {
@@ -44,8 +44,8 @@ CB_DEV void apply_coarse_energy(int start, int end, int16_t *oldE, const int16_t
     int coef, beta;
     if (intra) { coef = 0; beta = kBetaIntra; }
     else { beta = kBetaCoef[LM]; coef = kPredCoef[LM]; }
-    for (int i = start; i < end; i++) {
-        for (int c = 0; c < C; c++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             int q = shl32((int)qi_in[i + c * kNbEBands], 10);
             int16_t *e = &oldE[i + c * kNbEBands];
             int old = imax(-9216, (int)*e);   // -QCONST16(9.f, DB_SHIFT)
@@ -59,9 +59,9 @@ CB_DEV void apply_coarse_energy(int start, int end, int16_t *oldE, const int16_t
 
 // unquant_fine_energy (quant_bands.c:500-521): offsets accumulated into eoff
 CB_DEV void decode_fine_energy(int start, int end, const int *fine_quant, EcDec &dec, int C, int16_t *eoff) {
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         if (fine_quant[i] <= 0) continue;
-        for (int c = 0; c < C; c++) {
+        CB_NOUNROLL for (int c = 0; c < C; c++) {
             int q2 = (int)dec.bits((unsigned)fine_quant[i]);
             int offset = s16(s16((shl32(q2, 10) + 512) >> fine_quant[i]) - 512);
             eoff[i + c * kNbEBands] = (int16_t)(eoff[i + c * kNbEBands] + offset);
@@ -72,10 +72,10 @@ CB_DEV void decode_fine_energy(int start, int end, const int *fine_quant, EcDec 
 // unquant_energy_finalise (quant_bands.c:523-549)
 CB_DEV void decode_energy_finalise(int start, int end, const int *fine_quant, const int *fine_priority, int bits_left, EcDec &dec,
                                    int C, int16_t *eoff) {
-    for (int prio = 0; prio < 2; prio++) {
-        for (int i = start; i < end && bits_left >= C; i++) {
+    CB_NOUNROLL for (int prio = 0; prio < 2; prio++) {
+        CB_NOUNROLL for (int i = start; i < end && bits_left >= C; i++) {
             if (fine_quant[i] >= kMaxFineBits || fine_priority[i] != prio) continue;
-            for (int c = 0; c < C; c++) {
+            CB_NOUNROLL for (int c = 0; c < C; c++) {
                 int q2 = (int)dec.bits(1);
                 int offset = s16((shl16(q2, 10) - 512) >> (fine_quant[i] + 1));
                 eoff[i + c * kNbEBands] = (int16_t)(eoff[i + c * kNbEBands] + offset);
@@ -93,7 +93,7 @@ CB_DEV void tf_decode(int start, int end, int isTransient, int *tf_res, int LM, 
     int tf_select_rsv = LM > 0 && tell + logp + 1 <= budget;
     budget -= tf_select_rsv;
     int tf_changed = 0, curr = 0;
-    for (int i = start; i < end; i++) {
+    CB_NOUNROLL for (int i = start; i < end; i++) {
         if (tell + logp <= budget) {
             curr ^= dec.bit_logp(logp);
             tell = (unsigned)dec.tell();
@@ -105,7 +105,7 @@ CB_DEV void tf_decode(int start, int end, int isTransient, int *tf_res, int LM, 
     int tf_select = 0;
     if (tf_select_rsv && kTfSelect[LM][4 * isTransient + 0 + tf_changed] != kTfSelect[LM][4 * isTransient + 2 + tf_changed])
         tf_select = dec.bit_logp(1);
-    for (int i = start; i < end; i++) tf_res[i] = kTfSelect[LM][4 * isTransient + 2 * tf_select + tf_res[i]];
+    CB_NOUNROLL for (int i = start; i < end; i++) tf_res[i] = kTfSelect[LM][4 * isTransient + 2 * tf_select + tf_res[i]];
 }
 
 }  // namespace cb

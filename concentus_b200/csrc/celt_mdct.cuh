@@ -38,7 +38,7 @@ template <class TM>
 CB_DEV void fft_inplace(TM tm, Cpx *buf, int s, int nblocks) {
     const FftPlan &pl = kFftPlan[s];
     const int nfft = pl.nfft;
-    for (int st = 0; st < pl.nstages; st++) {
+    CB_NOUNROLL for (int st = 0; st < pl.nstages; st++) {
         const int p = pl.radix[st];
         const int m = pl.m[st];
         const int mm = p * m;
@@ -186,7 +186,7 @@ CB_DEV void imdct_compute(TM tm, FreqFn freq, int B, int shift, int *fftbuf) {
     const int N2 = (kMaxFrame * 2 >> shift) >> 1;   // coefficients per block (= NB)
     const int N4 = N2 >> 1;
     int trig_off = 0;
-    for (int i = 0, n = kMaxFrame * 2; i < shift; i++) { n >>= 1; trig_off += n; }
+    CB_NOUNROLL for (int i = 0, n = kMaxFrame * 2; i < shift; i++) { n >>= 1; trig_off += n; }
     const int16_t *t = kMdctTwiddles + trig_off;
     const int16_t *bitrev = fft_bitrev(shift);
     // pre-rotate straight into bit-reversed order (mdct.c:283-303)
@@ -267,7 +267,7 @@ CB_DEV void mdct_forward(TM tm, const int *in, int *out, int shift, int stride, 
     const int N2 = (kMaxFrame * 2 >> shift) >> 1;
     const int N4 = N2 >> 1;
     int trig_off = 0;
-    for (int i = 0, n = kMaxFrame * 2; i < shift; i++) { n >>= 1; trig_off += n; }
+    CB_NOUNROLL for (int i = 0, n = kMaxFrame * 2; i < shift; i++) { n >>= 1; trig_off += n; }
     const int16_t *t = kMdctTwiddles + trig_off;
     const int16_t *bitrev = fft_bitrev(shift);
     const FftPlan &pl = kFftPlan[shift];

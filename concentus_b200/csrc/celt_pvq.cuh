@@ -40,7 +40,7 @@ CB_DEV_NOINLINE int pvq_decode_index(int n, int k, unsigned i, int16_t *y) {
                 do p = pvq_row(--k, n);
                 while (p > i);
             } else {
-                for (p = kPvqU[rown + k]; p > i; p = kPvqU[rown + k]) k--;
+                CB_NOUNROLL for (p = kPvqU[rown + k]; p > i; p = kPvqU[rown + k]) k--;
             }
             i -= p;
             val = s16((k0 - k + s) ^ s);
@@ -87,12 +87,12 @@ CB_DEV_NOINLINE int pvq_decode_index(int n, int k, unsigned i, int16_t *y) {
 // exp_rotation1 (vq.c:43-67): forward then backward in-place Givens sweep — order dependent.
 CB_DEV_NOINLINE void exp_rotation1(int16_t *X, int len, int stride, int c, int s) {
     int ms = s16(-s);
-    for (int i = 0; i < len - stride; i++) {
+    CB_NOUNROLL for (int i = 0; i < len - stride; i++) {
         int x1 = X[i], x2 = X[i + stride];
         X[i + stride] = (int16_t)pshr32(mac16_16(mul16_16(c, x2), s, x1), 15);
         X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
     }
-    for (int i = len - 2 * stride - 1; i >= 0; i--) {
+    CB_NOUNROLL for (int i = len - 2 * stride - 1; i >= 0; i--) {
         int x1 = X[i], x2 = X[i + stride];
         X[i + stride] = (int16_t)pshr32(mac16_16(mul16_16(c, x2), s, x1), 15);
         X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
@@ -113,7 +113,7 @@ CB_DEV void exp_rotation_dec(int16_t *X, int len, int stride, int K, int spread)
         while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
     }
     len = (int)udiv((unsigned)len, (unsigned)stride);
-    for (int i = 0; i < stride; i++) {
+    CB_NOUNROLL for (int i = 0; i < stride; i++) {
         int16_t *x = X + i * len;
         if (stride2) exp_rotation1(x, len, stride2, s, c);
         exp_rotation1(x, len, 1, c, s);
@@ -137,21 +137,21 @@ CB_DEV unsigned alg_unquant(int16_t *X, int N, int K, int spread, int B, EcDec &
     // normalise_residual (vq.c:117-136) fused with extract_collapse_mask (vq.c:139-157)
     unsigned mask = 0;
     if (B <= 1) {
-        for (int i = 0; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);
+        CB_NOUNROLL for (int i = 0; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);
         mask = 1;
     } else {
         const int N0 = (int)udiv((unsigned)N, (unsigned)B);
         int i = 0;
-        for (int blk = 0; blk < B; blk++) {
+        CB_NOUNROLL for (int blk = 0; blk < B; blk++) {
             int any = 0;
-            for (int j = 0; j < N0; j++, i++) {
+            CB_NOUNROLL for (int j = 0; j < N0; j++, i++) {
                 int v = iy[i];
                 any |= v;
                 X[i] = (int16_t)pshr32(mul16_16(g, v), k + 1);
             }
             mask |= (unsigned)(any != 0) << blk;
         }
-        for (; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);
+        CB_NOUNROLL for (; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);
     }
     exp_rotation_dec(X, N, B, K, spread);
     return mask;

@@ -6,6 +6,7 @@
 // loop -> IR in HBM) and synth_kernel (one warp per stream: energies, anti-collapse, IMDCT, post-filter, de-emphasis,
 // all persistent state).  Time chunks are double-buffered so stage A of chunk c+1 overlaps stage B of chunk c.
 // There is NO CPU path: if CUDA is unusable every codec call returns OPUS_INTERNAL_ERROR.
+#define CB_SMALL_CODE 1   // celt_simt.cuh: real calls for the medium-sized helpers and no loop unrolling — the decoder stages were 50-55 % instruction-fetch stalled with everything inlined (profiles/r1_dec_*), +30 % throughput
 #include <cuda_runtime.h>
 
 #include <cstdarg>

@@ -20,12 +20,12 @@ CB_HD void dec_state_reset_celt(CbDecState *st) {
     st->postfilter_gain = st->postfilter_gain_old = 0;
     st->postfilter_tapset = st->postfilter_tapset_old = 0;
     st->preemph_memD[0] = st->preemph_memD[1] = 0;
-    for (int i = 0; i < 2 * CB_NB_EBANDS; i++) {
+    CB_NOUNROLL for (int i = 0; i < 2 * CB_NB_EBANDS; i++) {
         st->oldEBands[i] = 0; st->backgroundLogE[i] = 0;
         st->oldLogE[i] = st->oldLogE2[i] = -28672;
     }
-    for (int i = 0; i < 2 * CB_LPC_ORDER; i++) st->lpc[i] = 0;
-    for (int i = 0; i < 2 * CB_DEC_MEM; i++) st->decode_mem[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < 2 * CB_LPC_ORDER; i++) st->lpc[i] = 0;
+    CB_NOUNROLL for (int i = 0; i < 2 * CB_DEC_MEM; i++) st->decode_mem[i] = 0;
 }
 // OPUS_RESET_STATE of the Opus decoder (opus_decoder.c:873-887)
 CB_HD void dec_state_reset(CbDecState *st) {
@@ -92,7 +92,7 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     while ((kShortMdct << LM) != N && LM < kMaxLM) LM++;
     const uint8_t *p = data + offset;
     int xoff = 0;
-    for (int i = 0; i < count; i++) {
+    CB_NOUNROLL for (int i = 0; i < count; i++) {
         CbFrameIR &ir = fr[i];
         ir.x_off = xoff;
         if (size[i] <= 1) {
@@ -205,7 +205,7 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, const CbPac
         tm.sync();
         int nb_samples = 0;
         result = 0;
-        for (int i = 0; i < pk.count; i++) {
+        CB_NOUNROLL for (int i = 0; i < pk.count; i++) {
             int *sig[2] = {sigbase + nb_samples * ds, sigbase + cap48 + nb_samples * ds};
             bool staged;
             int ret = opus_synth_frame(tm, st, S, fr[i], Xarea + fr[i].x_off, pcm + nb_samples * st->channels, cap - nb_samples, sig,

@@ -109,7 +109,7 @@ CB_HD int pkt_parse(const uint8_t *data, int len, int self_delimited, uint8_t *o
         cbr = !(ch & 0x80);
         if (!cbr) {
             last_size = len;
-            for (i = 0; i < count - 1; i++) {
+            CB_NOUNROLL for (i = 0; i < count - 1; i++) {
                 bytes = pkt_parse_size(data, len, size + i);
                 len -= bytes;
                 if (size[i] < 0 || size[i] > len) return -4;
@@ -120,7 +120,7 @@ CB_HD int pkt_parse(const uint8_t *data, int len, int self_delimited, uint8_t *o
         } else if (!self_delimited) {
             last_size = len / count;
             if (last_size * count != len) return -4;
-            for (i = 0; i < count - 1; i++) size[i] = (int16_t)last_size;
+            CB_NOUNROLL for (i = 0; i < count - 1; i++) size[i] = (int16_t)last_size;
         }
         break;
     }
@@ -132,7 +132,7 @@ CB_HD int pkt_parse(const uint8_t *data, int len, int self_delimited, uint8_t *o
         data += bytes;
         if (cbr) {
             if (size[count - 1] * count > len) return -4;
-            for (i = 0; i < count - 1; i++) size[i] = size[count - 1];
+            CB_NOUNROLL for (i = 0; i < count - 1; i++) size[i] = size[count - 1];
         } else if (bytes + size[count - 1] > last_size) {
             return -4;
         }
@@ -141,7 +141,7 @@ CB_HD int pkt_parse(const uint8_t *data, int len, int self_delimited, uint8_t *o
         size[count - 1] = (int16_t)last_size;
     }
     if (payload_offset) *payload_offset = (int)(data - data0);
-    for (i = 0; i < count; i++) data += size[i];
+    CB_NOUNROLL for (i = 0; i < count; i++) data += size[i];
     if (packet_offset) *packet_offset = pad + (int)(data - data0);
     if (out_toc) *out_toc = toc;
     return count;
