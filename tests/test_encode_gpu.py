@@ -183,3 +183,39 @@ def test_audio_application_forced_celt_and_unimplemented():
     d, l = enc.encode_span(pcm[:, :1].copy(), F, fs)
     enc.close()
     assert (l == cb.OPUS_UNIMPLEMENTED).all()
+
+
+def test_mixed_settings_in_one_launch():
+    """BASELINE configs[4] in miniature: one span launch over streams that differ in bitrate, CBR/VBR/CVBR and complexity
+    (per-stream settings live in each stream's own state block; only Fs, channel count and frame size are shared)."""
+    cb = _cb()
+    L = cb.lib()
+    ch, fs, F = 2, 960, 25
+    rs = np.random.RandomState(3)
+    rates = [32000, 48000, 64000, 96000, 128000, 192000, 256000, 510000]
+    cfgs = [(rates[rs.randint(8)], [(0, 0), (1, 0), (1, 1)][rs.randint(3)], [0, 5, 10][rs.randint(3)]) for _ in range(48)]
+    pcms = [O.test_signal(fs * F, ch, 9000 + i, ("music", "tone", "clicks", "noise")[i % 4]) for i in range(len(cfgs))]
+    enc = cb.EncoderBatch(len(cfgs), 48000, ch)
+    for i, (br, (vbr, cvbr), cx) in enumerate(cfgs):
+        hp = C.c_void_p(enc.handles[i])
+        for req, v in ((cb.OPUS_SET_BITRATE_REQUEST, br), (cb.OPUS_SET_VBR_REQUEST, vbr), (cb.OPUS_SET_VBR_CONSTRAINT_REQUEST, cvbr),
+                       (cb.OPUS_SET_COMPLEXITY_REQUEST, cx)):
+            assert L.opus_encoder_ctl(hp, req, C.c_int32(v)) == 0
+    d, l = enc.encode_span(np.concatenate(pcms), F, fs)
+    enc.close()
+    d = d.reshape(len(cfgs), F, 1276)
+    l = l.reshape(len(cfgs), F)
+    # decode everything in one launch too and compare with the oracle's decode of the oracle's packets
+    offs = np.arange(len(cfgs) * F, dtype=np.int64) * 1276
+    dec = cb.DecoderBatch(len(cfgs), 48000, ch)
+    out, rets = dec.decode_span(d.reshape(-1), offs, l.reshape(-1), F, fs)
+    dec.close()
+    assert (rets == fs).all()
+    out = out.reshape(len(cfgs), F * fs, ch)
+    for i, (br, (vbr, cvbr), cx) in enumerate(cfgs):
+        rd, rl, _ = _ref_encode(pcms[i], fs, br, ch, vbr, cvbr, cx)
+        assert np.array_equal(rl, l[i]), ("len", i, cfgs[i])
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], d[i, f, :rl[f]]), ("bytes", i, cfgs[i], f)
+        rp, _, _ = O.decode_stream(rd.reshape(-1), np.arange(F, dtype=np.int64) * 1276, rl, fs, ch)
+        assert np.array_equal(rp, out[i]), ("pcm", i, cfgs[i])
