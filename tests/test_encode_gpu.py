@@ -18,7 +18,7 @@ def _cb():
 
 
 def _ref_encode(pcm, fs, br, ch, vbr, cvbr, cx, application=O.OPUS_APPLICATION_RESTRICTED_LOWDELAY):
-    d, o, l, r = O.encode_stream(pcm, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx, application=application)
+    d, o, l, r = O.encode_stream(pcm, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx, application=application, max_bytes=1276)
     return d.reshape(-1, 1276), l, r
 
 
