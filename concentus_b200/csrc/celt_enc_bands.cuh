@@ -191,22 +191,30 @@ CB_DEV_NOINLINE void deinterleave_hadamard_team(TM tm, int16_t *X, int16_t *tmp,
     tm.sync();
 }
 
-// One residue class of exp_rotation1 (vq.c:43-67): the pairs (i, i+stride) with i = r (mod stride) form an independent chain
+// One residue class of exp_rotation1 (vq.c:43-67): the pairs (i, i+stride) with i = r (mod stride) form an independent chain.
+// Each sweep carries the element it shares with the next pair in a register: one load and one store per step.
 CB_DEV void exp_rotation1_chain(int16_t *X, int len, int stride, int c, int s, int r) {
     const int ms = s16(-s);
-    int i;
-    CB_NOUNROLL for (i = r; i < len - stride; i += stride) {
-        int x1 = X[i], x2 = X[i + stride];
-        X[i + stride] = (int16_t)pshr32(mac16_16(mul16_16(c, x2), s, x1), 15);
-        X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
+    if (r < len - stride) {
+        int i = r;
+        int x1 = X[i];
+        CB_NOUNROLL for (; i < len - stride; i += stride) {
+            const int x2 = X[i + stride];
+            X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
+            x1 = s16(pshr32(mac16_16(mul16_16(c, x2), s, x1), 15));
+        }
+        X[i] = (int16_t)x1;
     }
     const int top = len - 2 * stride - 1;
     if (top >= r) {
-        CB_NOUNROLL for (i = top - ((top - r) % stride); i >= 0; i -= stride) {
-            int x1 = X[i], x2 = X[i + stride];
+        int i = top - ((top - r) % stride);
+        int x2 = X[i + stride];
+        CB_NOUNROLL for (; i >= 0; i -= stride) {
+            const int x1 = X[i];
             X[i + stride] = (int16_t)pshr32(mac16_16(mul16_16(c, x2), s, x1), 15);
-            X[i] = (int16_t)pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15);
+            x2 = s16(pshr32(mac16_16(mul16_16(c, x1), ms, x2), 15));
         }
+        X[i + stride] = (int16_t)x2;
     }
 }
 
@@ -278,11 +286,84 @@ CB_DEV bool pvq_better(const PvqBest &a, const PvqBest &b) {
 // share of the N positions in increasing order with the reference's strict '>' test (first maximum wins), then a shuffle tree
 // takes the best of the lanes with ties going to the lower index — the same element the sequential scan selects, because with
 // Ryy > 0 and Rxy >= 0 the cross-multiplied comparison is a strict weak order on the ratios.
+// alg_quant for N <= team width: position j lives in lane j's registers (|X|, y, iy, sign), nothing touches shared memory
+// until the pulse vector is handed to the indexer.  Same arithmetic and tie-breaking as the general version below.
+template <class TM>
+CB_DEV_NOINLINE void alg_quant_small(TM tm, int16_t *X, int N, int K, EcEnc &enc, PvqScratch &ps) {
+    const int j = tm.lane();
+    const bool active = j < N;
+    int xj = active ? (int)X[j] : 0;
+    const int sgn = xj > 0 ? 1 : -1;
+    if (xj <= 0) xj = s16(-xj);
+    int yj = 0, iyj = 0;
+    int xy = 0, yy = 0;
+    int pulsesLeft = K;
+    if (K > (N >> 1)) {
+        int sum = tm.sum(xj);
+        if (sum <= K) {
+            xj = j == 0 ? 16384 : 0;
+            sum = 16384;
+        }
+        const int rcp = s16(mul16_32_q16(K - 1, celt_rcp(sum)));
+        const int v = mul16_16_q15(xj, rcp);
+        iyj = v;
+        const int yv = s16(v);
+        yy = s16(tm.sum(mul16_16(yv, yv)));
+        xy = tm.sum(mul16_16(xj, yv));
+        yj = s16(yv * 2);
+        pulsesLeft -= tm.sum(v);
+    }
+    if (pulsesLeft > N + 3) {
+        const int tmp = s16(pulsesLeft);
+        const int y0 = tm.bcast(yj, 0);
+        yy = s16(mac16_16(yy, tmp, tmp));
+        yy = s16(mac16_16(yy, tmp, y0));
+        if (j == 0) iyj += pulsesLeft;
+        pulsesLeft = 0;
+    }
+    int levels = 0;
+    while ((1 << levels) < N) levels++;
+    CB_NOUNROLL for (int i = 0; i < pulsesLeft; i++) {
+        const int rshift = 1 + celt_ilog2(K - pulsesLeft + i + 1);
+        yy = s16(wadd(yy, 1));
+        PvqBest best{-32767, 0, j};
+        if (active) {
+            int Rxy = s16(wadd(xy, xj) >> rshift);
+            best.den = s16(yy + yj);
+            best.num = s16(mul16_16_q15(Rxy, Rxy));
+        }
+        CB_NOUNROLL for (int l = 0; l < levels; l++) {
+            PvqBest o;
+            o.num = tm.shfl_xor(best.num, 1 << l);
+            o.den = tm.shfl_xor(best.den, 1 << l);
+            o.id = tm.shfl_xor(best.id, 1 << l);
+            if (pvq_better(o, best)) best = o;
+        }
+        const int best_id = tm.bcast(best.id, 0);
+        xy = wadd(xy, tm.bcast(xj, best_id));
+        yy = s16(yy + tm.bcast(yj, best_id));
+        if (j == best_id) {
+            yj = s16(yj + 2);
+            iyj++;
+        }
+    }
+    if (active) {
+        X[j] = (int16_t)mul16_16(sgn, xj);
+        ps.iy[j] = (int16_t)(sgn < 0 ? -iyj : iyj);
+    }
+    tm.sync();
+    enc.uint_(pvq_encode_index(tm, N, K, ps.iy), pvq_v(N, K));
+}
+
 template <class TM>
 CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
     int16_t *y = ps.y, *iy = ps.iy;
     int8_t *signx = ps.sign;
     exp_rotation_enc(tm, X, N, B, K, spread);
+    if (TM::W > 1 && N <= TM::W) {
+        alg_quant_small(tm, X, N, K, enc, ps);
+        return;
+    }
     CB_TEAM_FOR(j, N, tm) {
         const int x = X[j];
         if (x > 0) signx[j] = 1;

@@ -41,7 +41,7 @@ struct EncVars {
     int silence, tell, enabled;
     int pf_on, pitch_index, gain1, qg, prefilter_tapset, prefilter_period0;
     int isTransient, shortBlocks, transient_got_disabled, tf_estimate, tf_chan, secondMdct, patch;
-    int mask_metric[2];
+    int mask_metric[2], tr_scratch[4];
     int tf_select, tf_sum, do_tf, do_spread, do_trim, dual_stereo, alloc_trim;
     int temporal_vbr, maxDepth, tot_boost, total_boost;
     int anti_collapse_rsv, balance, codedBands;
@@ -228,10 +228,67 @@ CB_DEV_NOINLINE void pitch_downsample_team(TM tm, const int *x0, const int *x1, 
     tm.sync();
 }
 
+// find_best_pitch (pitch.c:45-103), team version.  The reference walks every lag i with a running window energy
+//   Syy_0 = 1 + sum_{j<len} (y[j]^2 >> yshift),  Syy_{i+1} = max(1, Syy_i + (y[i+len]^2 >> yshift) - (y[i]^2 >> yshift))
+// and tests a candidate only where xcorr[i] > 0.  The window energy is a prefix sum (wrapping adds, order-free); the team builds
+// it once, verifies that the max(1, .) clamp can never engage (min over all lags >= 1 — it is 1 + a sum of non-negative terms
+// unless 32-bit wrap-around interferes) and then only the candidate lags are visited, in increasing order, with the reference's
+// comparisons.  If the clamp could engage the reference's sequential walk is used instead (never observed).
+// `cand`/`ncand`: sorted lags to visit, or ncand < 0 for "every lag".  syy: scratch for max_pitch + 1 ints.
+template <class TM>
+CB_DEV_NOINLINE void find_best_pitch_team(TM tm, const int *xcorr, const int16_t *y, int len, int max_pitch, int *best_pitch, int yshift,
+                                          int maxcorr, const int *cand, int ncand, int *syy) {
+    int part = 0;
+    CB_TEAM_FOR(j, len, tm) part = wadd(part, mul16_16(y[j], y[j]) >> yshift);
+    const int syy0 = wadd(1, tm.sum(part));
+    // exclusive prefix of d[i] = (y[i+len]^2 >> ys) - (y[i]^2 >> ys), lane-contiguous chunks
+    const int per = (max_pitch + TM::W - 1) / TM::W;
+    const int first = tm.lane() * per;
+    int local = 0;
+    CB_NOUNROLL for (int i = first; i < first + per && i < max_pitch; i++)
+        local = wadd(local, wsub(mul16_16(y[i + len], y[i + len]) >> yshift, mul16_16(y[i], y[i]) >> yshift));
+    int run = wadd(syy0, tm.exscan(local));
+    int mn = 0x7fffffff;
+    CB_NOUNROLL for (int i = first; i < first + per && i < max_pitch; i++) {
+        syy[i] = run;
+        mn = imin(mn, run);
+        run = wadd(run, wsub(mul16_16(y[i + len], y[i + len]) >> yshift, mul16_16(y[i], y[i]) >> yshift));
+    }
+    mn = ~tm.max(~mn);
+    tm.sync();
+    if (mn < 1) {   // the clamp would change the walk: do exactly what the reference does
+        find_best_pitch(xcorr, y, len, max_pitch, best_pitch, yshift, maxcorr);
+        return;
+    }
+    int best_num[2] = {-1, -1};
+    int best_den[2] = {0, 0};
+    const int xshift = celt_ilog2(maxcorr) - 14;
+    best_pitch[0] = 0;
+    best_pitch[1] = 1;
+    const int nvisit = ncand < 0 ? max_pitch : ncand;
+    CB_NOUNROLL for (int k = 0; k < nvisit; k++) {
+        const int i = ncand < 0 ? k : cand[k];
+        const int xc = xcorr[i];
+        if (xc > 0) {
+            const int Syy = syy[i];
+            int xcorr16 = s16(vshr32(xc, xshift));
+            int num = s16(mul16_16_q15(xcorr16, xcorr16));
+            if (mul16_32_q15(num, best_den[1]) > mul16_32_q15(best_num[1], Syy)) {
+                if (mul16_32_q15(num, best_den[0]) > mul16_32_q15(best_num[0], Syy)) {
+                    best_num[1] = best_num[0]; best_den[1] = best_den[0]; best_pitch[1] = best_pitch[0];
+                    best_num[0] = num; best_den[0] = Syy; best_pitch[0] = i;
+                } else {
+                    best_num[1] = num; best_den[1] = Syy; best_pitch[1] = i;
+                }
+            }
+        }
+    }
+}
+
 // pitch_search (pitch.c:260-369)
 template <class TM>
 CB_DEV_NOINLINE int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t *y, int len, int max_pitch, int16_t *x_lp4, int16_t *y_lp4,
-                             int *xcorr) {
+                             int *xcorr, int *syy) {
     const int lag = len + max_pitch;
     int best_pitch[2] = {0, 0};
     CB_TEAM_FOR(j, len >> 2, tm) x_lp4[j] = x_lp[2 * j];
@@ -248,27 +305,67 @@ CB_DEV_NOINLINE int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t 
     } else {
         shift = 0;
     }
-    // coarse search, 4x decimated: one lag per lane
+    // coarse search, 4x decimated (celt_pitch_xcorr): each lane owns 8 CONSECUTIVE lags and slides an 8-sample register window
+    // over y, so a tap costs one broadcast load of x, one load of y and 8 multiply-adds (244 lags = 31 lanes x 8).
+    // y_lp4 is read up to 7 + 3 entries past its valid part (inside its array); those sums belong to lags >= np and are dropped.
     int maxcorr = 1;
     {
         const int n = len >> 2, np = max_pitch >> 2;
-        CB_TEAM_FOR(i, np, tm) {
-            int s = 0;
-            CB_NOUNROLL for (int j = 0; j < n; j++) s = mac16_16(s, x_lp4[j], y_lp4[i + j]);
-            xcorr[i] = s;
-            maxcorr = imax(maxcorr, s);
+        CB_NOUNROLL for (int blk = tm.lane(); blk * 8 < np; blk += TM::W) {
+            const int16_t *yb = y_lp4 + blk * 8;
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+            int w0 = yb[0], w1 = yb[1], w2 = yb[2], w3 = yb[3], w4 = yb[4], w5 = yb[5], w6 = yb[6], w7;
+            int j = 0;
+#define CB_XC_TAP(W0, W1, W2, W3, W4, W5, W6, W7)                                                          \
+    {                                                                                                      \
+        const int xj = x_lp4[j];                                                                           \
+        W7 = yb[j + 7];                                                                                    \
+        a0 += xj * W0; a1 += xj * W1; a2 += xj * W2; a3 += xj * W3; a4 += xj * W4; a5 += xj * W5; a6 += xj * W6; a7 += xj * W7; \
+        j++;                                                                                               \
+    }
+            CB_NOUNROLL for (; j + 8 <= n;) {
+                CB_XC_TAP(w0, w1, w2, w3, w4, w5, w6, w7)
+                CB_XC_TAP(w1, w2, w3, w4, w5, w6, w7, w0)
+                CB_XC_TAP(w2, w3, w4, w5, w6, w7, w0, w1)
+                CB_XC_TAP(w3, w4, w5, w6, w7, w0, w1, w2)
+                CB_XC_TAP(w4, w5, w6, w7, w0, w1, w2, w3)
+                CB_XC_TAP(w5, w6, w7, w0, w1, w2, w3, w4)
+                CB_XC_TAP(w6, w7, w0, w1, w2, w3, w4, w5)
+                CB_XC_TAP(w7, w0, w1, w2, w3, w4, w5, w6)
+            }
+            CB_NOUNROLL for (; j < n;) {   // tail (frame sizes whose len/4 is not a multiple of 8): slide by hand
+                CB_XC_TAP(w0, w1, w2, w3, w4, w5, w6, w7)
+                w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
+            }
+#undef CB_XC_TAP
+            const int acc[8] = {a0, a1, a2, a3, a4, a5, a6, a7};
+            for (int k = 0; k < 8; k++)
+                if (blk * 8 + k < np) {
+                    xcorr[blk * 8 + k] = acc[k];
+                    maxcorr = imax(maxcorr, acc[k]);
+                }
         }
         maxcorr = tm.max(maxcorr);
         tm.sync();
     }
-    find_best_pitch(xcorr, y_lp4, len >> 2, max_pitch >> 2, best_pitch, 0, maxcorr);
+    find_best_pitch_team(tm, xcorr, y_lp4, len >> 2, max_pitch >> 2, best_pitch, 0, maxcorr, nullptr, -1, syy);
     tm.sync();   // xcorr is rewritten below
-    // finer search, 2x decimated, around the two candidates (at most 10 lags): lanes split the taps
+    // finer search, 2x decimated, around the two candidates (at most 10 lags, visited in increasing order): lanes split the taps
+    int cand[10];
+    int ncand = 0;
+    {
+        const int c0 = 2 * best_pitch[0], c1 = 2 * best_pitch[1];
+        const int lo = imin(c0, c1), hi = imax(c0, c1);
+        for (int d = -2; d <= 2; d++)
+            if (lo + d >= 0 && lo + d < (max_pitch >> 1)) cand[ncand++] = lo + d;
+        for (int d = -2; d <= 2; d++)
+            if (hi + d >= 0 && hi + d < (max_pitch >> 1) && hi + d > lo + 2) cand[ncand++] = hi + d;
+    }
     maxcorr = 1;
     CB_TEAM_FOR(i, max_pitch >> 1, tm) xcorr[i] = 0;
     tm.sync();
-    CB_NOUNROLL for (int i = 0; i < max_pitch >> 1; i++) {
-        if (iabs(i - 2 * best_pitch[0]) > 2 && iabs(i - 2 * best_pitch[1]) > 2) continue;
+    CB_NOUNROLL for (int k = 0; k < ncand; k++) {
+        const int i = cand[k];
         int s = 0;
         CB_TEAM_FOR(j, len >> 1, tm) s = wadd(s, mul16_16(x_lp[j], y[i + j]) >> shift);
         s = tm.sum(s);
@@ -276,7 +373,7 @@ CB_DEV_NOINLINE int pitch_search_team(TM tm, const int16_t *x_lp, const int16_t 
         maxcorr = imax(maxcorr, s);
     }
     tm.sync();
-    find_best_pitch(xcorr, y, len >> 1, max_pitch >> 1, best_pitch, shift + 1, maxcorr);
+    find_best_pitch_team(tm, xcorr, y, len >> 1, max_pitch >> 1, best_pitch, shift + 1, maxcorr, cand, ncand, syy);
     int offset = 0;
     if (best_pitch[0] > 0 && best_pitch[0] < (max_pitch >> 1) - 1) {
         int a = xcorr[best_pitch[0] - 1], b = xcorr[best_pitch[0]], c = xcorr[best_pitch[0] + 1];
@@ -426,55 +523,86 @@ CB_TABLE uint8_t kInvTable[128] = {
     6, 6, 6, 6, 6, 6, 6, 6, 6, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
     4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 3, 2};
 
-// xin: the channel's input already shifted down by SIG_SHIFT (int32, shared memory); the int16 work vector is written IN PLACE
-// over it (element i of the int16 view trails element i of the int32 view, so no unread input is overwritten).
-CB_DEV_NOINLINE int transient_channel(int *xin, int len) {
-    int16_t *tmp = reinterpret_cast<int16_t *>(xin);
+// transient_analysis (celt_encoder.c:227-378), split by what is order dependent:
+//   A  lane per channel : the high-pass recurrence (floor() inside the feedback: not a linear scan) + max/min of its output
+//   B  whole team       : normalisation shift and the pairwise energies x2[i] (independent), their sum `mean`
+//   C  lane per channel : forward (post-echo) and backward (pre-echo) one-pole followers over x2, maxE
+//   D  whole team       : the inverse-table sum over every fourth follower value
+// tin: per channel `len` int32 (input >> SIG_SHIFT, staged in shared memory).  Stage A rewrites the first half of a channel's
+// block in place as int16 (element i of the int16 view trails element i of the int32 view); x2 and the followers live in the
+// second half.  sc: 4 ints of team-shared scratch.  mask_metric[c] receives the channel's metric.
+template <class TM>
+CB_DEV_NOINLINE void transient_analysis_team(TM tm, int *tin, int len, int CC, int *sc, int *mask_metric) {
     const int len2 = len / 2;
-    int mem0 = 0, mem1 = 0;
-    int mxv = 0, mnv = 0;
-    CB_NOUNROLL for (int i = 0; i < len; i++) {
-        int x = xin[i];
-        int y = wadd(mem0, x);
-        mem0 = wsub(wadd(mem1, y), shl32(x, 1));
-        mem1 = wsub(x, y >> 1);
-        int t = i < 12 ? 0 : s16(y >> 2);
-        tmp[i] = (int16_t)t;
-        mxv = imax(mxv, t);
-        mnv = imin(mnv, t);
+    CB_NOUNROLL for (int c = tm.lane(); c < CC; c += TM::W) {
+        const int *xin = tin + c * len;
+        int16_t *tmp = reinterpret_cast<int16_t *>(tin + c * len);
+        int mem0 = 0, mem1 = 0, mxv = 0, mnv = 0;
+        CB_NOUNROLL for (int i = 0; i < len; i++) {
+            const int x = xin[i];
+            const int y = wadd(mem0, x);
+            mem0 = wsub(wadd(mem1, y), shl32(x, 1));
+            mem1 = wsub(x, y >> 1);
+            const int t = i < 12 ? 0 : s16(y >> 2);
+            tmp[i] = (int16_t)t;
+            mxv = imax(mxv, t);
+            mnv = imin(mnv, t);
+        }
+        sc[c] = 14 - celt_ilog2(1 + imax(mxv, -mnv));
     }
-    {
+    tm.sync();
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
+        const int16_t *tmp = reinterpret_cast<const int16_t *>(tin + c * len);
+        int16_t *x2buf = reinterpret_cast<int16_t *>(tin + c * len) + len;
         // SHL16 with a NEGATIVE count (maxabs == 32768) is what the reference's C expression does on x86: a 32-bit shift by
         // (count & 31) of the zero-extended value, truncated to 16 bits
-        int shift = 14 - celt_ilog2(1 + imax(mxv, -mnv));
-        if (shift != 0)
-            CB_NOUNROLL for (int i = 0; i < len; i++) tmp[i] = (int16_t)((unsigned)(uint16_t)tmp[i] << (shift & 31));
+        const int shift = sc[c];
+        int part = 0;
+        CB_TEAM_FOR(i, len2, tm) {
+            int a = tmp[2 * i], b = tmp[2 * i + 1];
+            if (shift != 0) {
+                a = (int16_t)((unsigned)(uint16_t)a << (shift & 31));
+                b = (int16_t)((unsigned)(uint16_t)b << (shift & 31));
+            }
+            const int x2 = s16(pshr32(wadd(mul16_16(a, a), mul16_16(b, b)), 16));
+            x2buf[i] = (int16_t)x2;
+            part = wadd(part, x2);
+        }
+        const int mean = tm.sum(part);
+        if (tm.lane() == 0) sc[2 + c] = mean;
     }
-    int mean = 0;
-    mem0 = 0;
-    CB_NOUNROLL for (int i = 0; i < len2; i++) {
-        int x2 = s16(pshr32(wadd(mul16_16(tmp[2 * i], tmp[2 * i]), mul16_16(tmp[2 * i + 1], tmp[2 * i + 1])), 16));
-        mean = wadd(mean, x2);
-        int v = s16(mem0 + pshr32(x2 - mem0, 4));
-        tmp[i] = (int16_t)v;
-        mem0 = v;
+    tm.sync();
+    CB_NOUNROLL for (int c = tm.lane(); c < CC; c += TM::W) {
+        int16_t *f = reinterpret_cast<int16_t *>(tin + c * len) + len;
+        int mem0 = 0;
+        CB_NOUNROLL for (int i = 0; i < len2; i++) {
+            mem0 = s16(mem0 + pshr32(f[i] - mem0, 4));
+            f[i] = (int16_t)mem0;
+        }
+        mem0 = 0;
+        int maxE = 0;
+        CB_NOUNROLL for (int i = len2 - 1; i >= 0; i--) {
+            mem0 = s16(mem0 + pshr32(f[i] - mem0, 3));
+            f[i] = (int16_t)mem0;
+            maxE = imax(maxE, mem0);
+        }
+        sc[c] = maxE;
     }
-    mem0 = 0;
-    int maxE = 0;
-    CB_NOUNROLL for (int i = len2 - 1; i >= 0; i--) {
-        int v = s16(mem0 + pshr32(tmp[i] - mem0, 3));
-        tmp[i] = (int16_t)v;
-        mem0 = v;
-        maxE = imax(maxE, mem0);
+    tm.sync();
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
+        const int16_t *f = reinterpret_cast<const int16_t *>(tin + c * len) + len;
+        const int mean = mul16_16(celt_sqrt(sc[2 + c]), celt_sqrt(mul16_16(sc[c], len2 >> 1)));
+        const int norm = shl32(len2, 6 + 14) / wadd(1, mean >> 1);
+        const int cnt = (len2 - 5 - 12 + 3) / 4;   // i = 12, 16, ... < len2 - 5
+        int part = 0;
+        CB_TEAM_FOR(k, cnt, tm) {
+            const int id = imax(0, imin(127, mul16_32_q15(f[12 + 4 * k] + 1, norm)));
+            part += kInvTable[id];
+        }
+        const int unmask = tm.sum(part);
+        if (tm.lane() == 0) mask_metric[c] = 64 * unmask * 4 / (6 * (len2 - 17));
     }
-    mean = mul16_16(celt_sqrt(mean), celt_sqrt(mul16_16(maxE, len2 >> 1)));
-    const int norm = shl32(len2, 6 + 14) / wadd(1, mean >> 1);
-    int unmask = 0;
-    CB_NOUNROLL for (int i = 12; i < len2 - 5; i += 4) {
-        int id = imax(0, imin(127, mul16_32_q15(tmp[i] + 1, norm)));
-        unmask += kInvTable[id];
-    }
-    return 64 * unmask * 4 / (6 * (len2 - 17));
+    tm.sync();
 }
 
 // patch_transient_decision (celt_encoder.c:380-414)
@@ -1048,7 +1176,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
             pitch_downsample_team(tm, pre0, pre1, kCombMaxPeriod + N, CC, S.u.pf.a.pitch_raw, S.u.pf.pitch_buf);
             tm.phase();
             pitch_index = pitch_search_team(tm, S.u.pf.pitch_buf + (kCombMaxPeriod >> 1), S.u.pf.pitch_buf, N, kCombMaxPeriod - 3 * kCombMinPeriod,
-                                            S.u.pf.x_lp4, S.u.pf.y_lp4, S.u.pf.a.c.xcorr);
+                                            S.u.pf.x_lp4, S.u.pf.y_lp4, S.u.pf.a.c.xcorr, S.u.pf.a.c.yy_lookup);
             pitch_index = kCombMaxPeriod - pitch_index;
             tm.phase();
             gain1 = remove_doubling_team(tm, S.u.pf.pitch_buf, kCombMaxPeriod, kCombMinPeriod, N, &pitch_index, prev_period, prev_gain, S.u.pf.a.c.yy_lookup);
@@ -1115,7 +1243,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     if (cfg.complexity >= 1) {
         CB_TEAM_FOR(i, CC * (N + ov), tm) S.u.tin[i] = G.in[i] >> 12;
         tm.sync();
-        CB_NOUNROLL for (int c = tm.lane(); c < CC; c += TM::W) V.mask_metric[c] = transient_channel(S.u.tin + c * (N + ov), N + ov);
+        transient_analysis_team(tm, S.u.tin, N + ov, CC, V.tr_scratch, V.mask_metric);
     }
     tm.sync();
     if (L0) {
