@@ -643,7 +643,9 @@ CB_DEV void quant_all_bands_enc(TM tm, int start, int end, int16_t *X_, int16_t 
     ctx.ec = ec_io; ctx.ps = ps; ctx.tmp = tmp; ctx.bandE = bandE;
     ctx.intensity = intensity; ctx.spread = spread;
     CB_NOUNROLL for (int i = start; i < end; i++) {
+#if !defined(CB_NO_BAND_PHASE)
         tm.phase();   // one per band, kNbEBands per frame (balanced below): co-resident streams walk the band loop together
+#endif
         ctx.i = i;
         int16_t *X = X_ + M * kEBands[i];
         int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;
@@ -707,7 +709,9 @@ CB_DEV void quant_all_bands_enc(TM tm, int start, int end, int16_t *X_, int16_t 
         }
         balance += pulses[i] + tell;
     }
+#if !defined(CB_NO_BAND_PHASE)
     CB_NOUNROLL for (int i = end - start; i < kNbEBands; i++) tm.phase();
+#endif
     ec_io = ctx.ec;
 }
 

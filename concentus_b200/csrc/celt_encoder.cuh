@@ -21,7 +21,11 @@
 
 namespace cb {
 
-enum { kEncPhases = 7 + 2 + kNbEBands };   // tm.phase() calls per coded frame (celt_encode_frame)
+#if defined(CB_NO_BAND_PHASE)
+enum { kEncPhases = 7 + 2 };
+#else
+enum { kEncPhases = 7 + 2 + kNbEBands };
+#endif   // tm.phase() calls per coded frame (celt_encode_frame)
 enum { kBitrateMax = -1, kOpusAuto = -1000, kFramesizeArg = 5000, kFramesizeVariable = 5010 };
 
 // What the Opus layer sets on the CELT encoder before a frame (celt_encoder_ctl calls, src/opus_encoder.c:1715-1770)

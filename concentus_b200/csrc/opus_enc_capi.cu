@@ -165,7 +165,10 @@ bool ctx_init_locked() {
     cudaEventCreate(&e.ev1);
     if (!e.h_stage.reserve(sizeof(CbEncState) * kStageStates) || !e.d_stage.reserve(sizeof(CbEncState) * kStageStates)) return false;
     cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CB_ENC_WPB * sizeof(EncWarpSmem)));
-    cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#ifndef CB_ENC_CARVEOUT
+#define CB_ENC_CARVEOUT 70   // % of the 228 KB: the block needs 157 KB of shared memory; the rest stays L1 for stacks and tables
+#endif
+    cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, CB_ENC_CARVEOUT);
     e.ok = cudaGetLastError() == cudaSuccess;
     return e.ok;
 }
