@@ -245,8 +245,8 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
 // Shift the synthesis history down by N samples (celt_decoder.c:962-964), team-parallel and overlap-safe:
 // each chunk is read by all lanes before any lane writes it, and destinations trail sources by N >= 120.
 template <class TM>
-CB_DEV void history_shift(TM tm, int *mem, int N) {
-    const int count = kDecBuf - N + kOverlap / 2;
+CB_DEV void history_shift(TM tm, int *mem, int N, int count = -1) {
+    if (count < 0) count = kDecBuf - N + kOverlap / 2;
     CB_NOUNROLL for (int base = 0; base < count; base += TM::W) {
         int i = base + tm.lane();
         int v = 0;
@@ -257,47 +257,17 @@ CB_DEV void history_shift(TM tm, int *mem, int N) {
     tm.sync();
 }
 
-// Synthesise one received frame from its IR up to (and excluding) de-emphasis: the post-filtered signal of channel c
-// (N samples at 48 kHz) is staged to sig[c] for stage C.
-// Returns samples per channel at the API rate, or OPUS_INTERNAL_ERROR when the frame overran its bit budget.
+// celt_synthesis (celt_decoder.c:280-350) with denormalise_bands (bands.c:169-238) fused into the IMDCT pre-rotation.
+// X: C*N normalised spectrum; out_syn[c]: synthesis target (tail of the channel's history).
 template <class TM>
-CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int *const *sig) {
-    const int CC = st->channels;
-    const int LM = ir.LM, C = ir.C, end = ir.end, start = 0;
+CB_DEV void celt_synthesis_team(TM tm, SynthScratch &S, const int16_t *X, int *const *out_syn, const int16_t *oldBandE, int start, int effEnd,
+                                int C, int CC, int isTransient, int LM, int downsample, int silence) {
     const int M = 1 << LM;
     const int N = M * kShortMdct;
-    const int silence = ir.flags & CB_IR_SILENCE, isTransient = (ir.flags & CB_IR_TRANSIENT) != 0;
-    int *decode_mem[2], *out_syn[2];
-    CB_NOUNROLL for (int c = 0; c < CC; c++) {
-        decode_mem[c] = st->decode_mem + c * CB_DEC_MEM;
-        out_syn[c] = decode_mem[c] + kDecBuf - N;
-    }
-    const int effEnd = imin(end, kNbEBands);
-    int16_t *oldBandE = st->oldEBands, *oldLogE = st->oldLogE, *oldLogE2 = st->oldLogE2, *backgroundLogE = st->backgroundLogE;
-
-    // ---- energies: prediction recurrence is serial over bands, tiny -> lane 0 ----
-    if (tm.lane() == 0) {
-        if (C == 1)
-            CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) oldBandE[i] = (int16_t)imax(oldBandE[i], oldBandE[kNbEBands + i]);
-        apply_coarse_energy(start, end, oldBandE, ir.qi, (ir.flags & CB_IR_INTRA) != 0, C, LM);
-        CB_NOUNROLL for (int c = 0; c < C; c++)
-            CB_NOUNROLL for (int i = start; i < end; i++)
-                oldBandE[c * kNbEBands + i] = (int16_t)(oldBandE[c * kNbEBands + i] + ir.eoff[c * kNbEBands + i]);
-    }
-    tm.sync();
-    CB_NOUNROLL for (int c = 0; c < CC; c++) history_shift(tm, decode_mem[c], N);
-    if (ir.flags & CB_IR_ANTICOLLAPSE)
-        anti_collapse(tm, X, ir.collapse, LM, C, N, start, end, oldBandE, oldLogE, oldLogE2, ir.pulses, ir.seed_bands);
-    if (silence) {
-        CB_TEAM_FOR(i, C * kNbEBands, tm) oldBandE[i] = -28672;   // -QCONST16(28.f,DB_SHIFT)
-        tm.sync();
-    }
-
-    // ---- celt_synthesis (celt_decoder.c:280-350) with denormalise_bands (bands.c:169-238) fused in ----
     {
         int bstart = start, bend = effEnd;
         int bound = M * kEBands[bend];
-        if (st->downsample != 1) bound = imin(bound, N / st->downsample);
+        if (downsample != 1) bound = imin(bound, N / downsample);
         if (silence) { bound = 0; bstart = bend = 0; }
         const int lo = M * kEBands[bstart];
         CB_TEAM_FOR(w, C * kNbEBands, tm) {   // per-band gain/shift (bands.c:195-227)
@@ -340,6 +310,46 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
             if (CC == 2 && C == 1) imdct_assemble(tm, out_syn[1], B, shift, S.fft);   // mono stream into two channels
         }
     }
+}
+
+// Synthesise one received frame from its IR up to (and excluding) de-emphasis: the post-filtered signal of channel c
+// (N samples at 48 kHz) is staged to sig[c] for stage C.
+// Returns samples per channel at the API rate, or OPUS_INTERNAL_ERROR when the frame overran its bit budget.
+template <class TM>
+CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int *const *sig) {
+    const int CC = st->channels;
+    const int LM = ir.LM, C = ir.C, end = ir.end, start = 0;
+    const int M = 1 << LM;
+    const int N = M * kShortMdct;
+    const int silence = ir.flags & CB_IR_SILENCE, isTransient = (ir.flags & CB_IR_TRANSIENT) != 0;
+    int *decode_mem[2], *out_syn[2];
+    CB_NOUNROLL for (int c = 0; c < CC; c++) {
+        decode_mem[c] = st->decode_mem + c * CB_DEC_MEM;
+        out_syn[c] = decode_mem[c] + kDecBuf - N;
+    }
+    const int effEnd = imin(end, kNbEBands);
+    int16_t *oldBandE = st->oldEBands, *oldLogE = st->oldLogE, *oldLogE2 = st->oldLogE2, *backgroundLogE = st->backgroundLogE;
+
+    // ---- energies: prediction recurrence is serial over bands, tiny -> lane 0 ----
+    if (tm.lane() == 0) {
+        if (C == 1)
+            CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) oldBandE[i] = (int16_t)imax(oldBandE[i], oldBandE[kNbEBands + i]);
+        apply_coarse_energy(start, end, oldBandE, ir.qi, (ir.flags & CB_IR_INTRA) != 0, C, LM);
+        CB_NOUNROLL for (int c = 0; c < C; c++)
+            CB_NOUNROLL for (int i = start; i < end; i++)
+                oldBandE[c * kNbEBands + i] = (int16_t)(oldBandE[c * kNbEBands + i] + ir.eoff[c * kNbEBands + i]);
+    }
+    tm.sync();
+    CB_NOUNROLL for (int c = 0; c < CC; c++) history_shift(tm, decode_mem[c], N);
+    if (ir.flags & CB_IR_ANTICOLLAPSE)
+        anti_collapse(tm, X, ir.collapse, LM, C, N, start, end, oldBandE, oldLogE, oldLogE2, ir.pulses, ir.seed_bands);
+    if (silence) {
+        CB_TEAM_FOR(i, C * kNbEBands, tm) oldBandE[i] = -28672;   // -QCONST16(28.f,DB_SHIFT)
+        tm.sync();
+    }
+
+    // ---- celt_synthesis (celt_decoder.c:280-350) with denormalise_bands (bands.c:169-238) fused in ----
+    celt_synthesis_team(tm, S, X, out_syn, oldBandE, start, effEnd, C, CC, isTransient, LM, st->downsample, silence);
 
     // ---- post-filter (celt_decoder.c:1001-1025) ----
     const int pf_period = imax(st->postfilter_period, kCombMinPeriod);

@@ -76,54 +76,18 @@ parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, cons
     if (t >= n * runs) return;
     const int s = t / runs, r = t - s * runs;
     const CbDecState *st = pool + slots[s];
-    const int Fs = st->Fs;
     ParseScratch &ps = scratch[t];
     const int first = f0 + r * R;
     const int last = first + R < f1 ? first + R : f1;
-    const size_t slot0 = (size_t)s * ir.Fc + (first - f0);
-    // One loop, one call site of the (large) packet parser.  While `seeking`, f walks BACK from first-1 looking for the
-    // nearest packet that sets the fold seed (errors and losses do not), parsing into the run's first IR slot as scratch;
-    // then f walks forward over the run proper.
-    unsigned seed = 0;
-    bool seeking = first > call_f0;
-    if (!seeking) seed = st->rng;
-    int f = seeking ? first - 1 : first;
-    while (seeking || f < last) {
-        if (seeking && f < call_f0) {
-            seed = st->rng;
-            seeking = false;
-            f = first;
-            continue;
-        }
-        const size_t idx = (size_t)s * F + f;
-        const size_t slot = seeking ? slot0 : (size_t)s * ir.Fc + (f - f0);
-        const int len = lens[idx];
-        const uint8_t *p = len > 0 ? data + offs[idx] : nullptr;
-        CbPacketIR pk;   // built in registers, stored once
-        opus_parse_packet(p, len, cap, Fs, seeking ? 0 : decode_fec, ir.kmax, &seed, pk, ir.fr + slot * ir.kmax,
-                          ir.X + slot * ir.xstride, ps, seeking);
-        if (!seeking) ir.pk[slot] = pk;
-        if (seeking) {
-            bool parsed = false;   // did any frame of this packet run the range decoder (and so set `seed`)?
-            if (pk.ret >= 0 && !pk.lost)
-                for (int i = 0; i < pk.count; i++) parsed |= !(ir.fr[slot * ir.kmax + i].flags & CB_IR_LOST);
-            if (parsed) {
-                seeking = false;
-                f = first;
-            } else {
-                f--;
-            }
-        } else {
-            f++;
-        }
-    }
+    opus_parse_run(st, data, offs + (size_t)s * F, lens + (size_t)s * F, call_f0, first, last, cap, decode_fec, ir.kmax, ir.xstride,
+                   ir.pk + (size_t)s * ir.Fc, ir.fr + (size_t)s * ir.Fc * ir.kmax, ir.X + (size_t)s * ir.Fc * ir.xstride, f0, ps);
 }
 
 // Stage B — synthesis, one warp per stream, packets f0..f1 in order.  PCM row of packet (s,f) starts at
 // pcm[(s*pcm_F + (f-pcm_f0)) * cap * channels].
 __global__ void __launch_bounds__(CB_WPB * 32, CB_SYNTH_MINBLOCKS)
 synth_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n, int F, int f0, int f1, int pcm_F, int pcm_f0,
-             int cap, int *rets) {
+             int cap, int *rets, PlcScratch *plc) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_WPB + warp;
@@ -135,7 +99,7 @@ synth_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n,
     for (int f = f0; f < f1; f++) {
         const size_t slot = (size_t)s * ir.Fc + (f - f0);
         int16_t *out = pcm + ((size_t)s * pcm_F + (f - pcm_f0)) * cap * channels;
-        int r = opus_synth_packet(tm, st, S, ir.pk[slot], ir.fr + slot * ir.kmax, ir.X + slot * ir.xstride, out, cap,
+        int r = opus_synth_packet(tm, st, S, plc[s], ir.pk[slot], ir.fr + slot * ir.kmax, ir.X + slot * ir.xstride, out, cap,
                                   ir.sig + slot * ir.sigstride, ir.range + slot);
         if (lane == 0) rets[(size_t)s * F + f] = r;
         __syncwarp();
@@ -275,7 +239,7 @@ struct Ctx {
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
     DevBuf d_slots, d_data, d_offs, d_lens, d_pcm[2], d_rets, d_stage;
-    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_scratch;
+    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_scratch, d_plc;
     size_t ir_budget = (size_t)16 << 30;  // bytes of IR + staging per chunk buffer (env CB200_IR_MB)
     int run_len = 3;                      // packets per stage-A thread (env CB200_RUN)
     PinBuf h_stage, h_slots, h_misc;
@@ -530,6 +494,7 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
             return false;
     }
     const size_t threads = (size_t)n * ((pl.Fc + pl.R - 1) / pl.R);
+    if (!g.d_plc.reserve((size_t)n * sizeof(PlcScratch))) return false;   // concealment scratch, one per stream (lost frames only)
     return g.d_scratch.reserve(threads * sizeof(ParseScratch));
 }
 
@@ -567,7 +532,7 @@ void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_d
     if (pcm_free) cudaStreamWaitEvent(g.synth_stream, pcm_free, 0);   // stage B writes PCM too (leading zero frames)
     timing_begin(1, g.synth_stream);
     synth_kernel<<<(pl.n + CB_WPB - 1) / CB_WPB, CB_WPB * 32, g.smem_per_block, g.synth_stream>>>(g.pool, d_slots, v, pcm_dst, pl.n, pl.F, f0,
-                                                                                                  f1, pcm_F, pcm_f0, pl.cap, d_rets);
+                                                                                                  f1, pcm_F, pcm_f0, pl.cap, d_rets, (PlcScratch *)g.d_plc.p);
     timing_end(g.synth_stream);
     cudaEventRecord(g.ev_synth[b], g.synth_stream);
     // stage C(c) on the main stream (the one the caller synchronises / times)

@@ -58,15 +58,68 @@ CB_DEV int bandwidth_to_endband(int bw) {   // opus_decoder.c:431-450
 
 // ---------------------------------------------------------------------------------------------------
 // Stage A: one packet -> IR.  `cap` = PCM capacity for this packet (samples per channel at Fs), kmax = frame IR
-// slots per packet.  *seed: fold/noise seed chained from frame to frame (previous frame's final rng).
-// Nothing here reads or writes decoder state.
+// slots per packet.  Nothing here reads or writes decoder state.
+//
+// What a frame's parse needs from the past is the fold/noise seed st->rng.  A received frame sets it to its final range;
+// pitch-based concealment leaves it alone; NOISE-based concealment (the 6th and later consecutive lost frame,
+// celt_decoder.c:446,470-489) steps the LCG once per synthesised coefficient.  SeedTrack carries exactly the decoder state
+// that decides this — the seed, the loss streak (st->loss_count), the frame size / bandwidth the last packet set and whether
+// any packet was decoded yet (st->prev_mode != 0) — so stage A can follow it through lost packets without stage B.
 // ---------------------------------------------------------------------------------------------------
-CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int decode_fec, int kmax, unsigned *seed,
+struct SeedTrack {
+    unsigned seed;
+    int streak;       // st->loss_count
+    int fs_last;      // st->frame_size (API rate)
+    int bw_last;      // st->bandwidth
+    int have_mode;    // st->prev_mode != 0
+    int channels;     // decoder output channels (constant)
+};
+
+// One concealment frame of `audiosize` samples (API rate): what celt_decode_lost does to (rng, loss_count).
+CB_DEV bool track_lost_frame(SeedTrack &tr, int audiosize, int Fs) {
+    const int N = audiosize * (48000 / Fs);
+    int LM;
+    for (LM = 0; LM <= kMaxLM; LM++)
+        if (kShortMdct << LM == N) break;
+    if (LM > kMaxLM) return false;   // celt_decode_with_ec rejects the size: OPUS_BAD_ARG, state untouched
+    if (tr.streak >= 5) {
+        const int effEnd = imin(bandwidth_to_endband(tr.bw_last), kNbEBands);
+        const int steps = tr.channels * (kEBands[effEnd] << LM);
+        unsigned sd = tr.seed;
+        CB_NOUNROLL for (int k = 0; k < steps; k++) sd = lcg_rand(sd);
+        tr.seed = sd;
+    }
+    tr.streak++;
+    return true;
+}
+// The frame size opus_decode_frame conceals when `room` samples are left (opus_decoder.c:244-300); 0 = nothing is concealed.
+CB_DEV int lost_audiosize(const SeedTrack &tr, int room, int Fs) {
+    const int F20 = Fs / 50, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
+    if (room < F2_5) return -1;
+    int audiosize = imin(imin(room, Fs / 25 * 3), tr.fs_last);
+    if (tr.have_mode && audiosize < F20) {
+        if (audiosize > F10) audiosize = F10;
+        else if (audiosize > F5 && audiosize < F10) audiosize = F5;
+    }
+    return audiosize;
+}
+// A wholly lost packet: opus_decode_native's concealment loop over `cap` samples (opus_decoder.c:613-627)
+CB_DEV void track_lost_packet(SeedTrack &tr, int cap, int Fs) {
+    int pcm_count = 0;
+    do {
+        const int a = lost_audiosize(tr, cap - pcm_count, Fs);
+        if (a <= 0) break;
+        if (tr.have_mode && !track_lost_frame(tr, a, Fs)) break;
+        pcm_count += a;
+    } while (pcm_count < cap);
+}
+
+CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int decode_fec, int kmax, SeedTrack &tr,
                               CbPacketIR &pk, CbFrameIR *fr, int16_t *Xarea, ParseScratch &ps, bool dry) {
     pk.count = 0; pk.lost = 0; pk.frame_size = 0; pk.mode = 0; pk.bandwidth = 0; pk.stream_channels = 0; pk.reserved = 0;
     if (decode_fec < 0 || decode_fec > 1) { pk.ret = OPUS_BAD_ARG_; return; }
     if ((decode_fec || len == 0 || data == nullptr) && cap % (Fs / 400) != 0) { pk.ret = OPUS_BAD_ARG_; return; }
-    if (len == 0 || data == nullptr) { pk.ret = 0; pk.lost = 1; return; }
+    if (len == 0 || data == nullptr) { pk.ret = 0; pk.lost = 1; track_lost_packet(tr, cap, Fs); return; }
     if (len < 0) { pk.ret = OPUS_BAD_ARG_; return; }
     const int packet_mode = pkt_mode(data);
     const int packet_frame_size = pkt_samples_per_frame(data, Fs);
@@ -76,7 +129,7 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     const int count = pkt_parse(data, len, 0, &toc, size, &offset, nullptr);
     if (count < 0) { pk.ret = count; return; }
     if (packet_mode != CB_MODE_CELT_ONLY) { pk.ret = OPUS_UNIMPLEMENTED_; return; }   // scope edge: no SILK / hybrid
-    if (decode_fec) { pk.ret = 0; pk.lost = 1; return; }   // CELT carries no in-band FEC (opus_decoder.c:655-657)
+    if (decode_fec) { pk.ret = 0; pk.lost = 1; track_lost_packet(tr, cap, Fs); return; }   // CELT carries no in-band FEC (opus_decoder.c:655-657)
     if (count * packet_frame_size > cap) { pk.ret = OPUS_BUFFER_TOO_SMALL_; return; }
     if (count > kmax) { pk.ret = OPUS_BUFFER_TOO_SMALL_; return; }   // cannot happen when kmax = cap / (Fs/400)
     pk.ret = 0;
@@ -85,6 +138,8 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     pk.mode = (int16_t)packet_mode;
     pk.bandwidth = (int16_t)pkt_bandwidth(data);
     pk.stream_channels = (int16_t)pkt_nb_channels(data);
+    tr.fs_last = packet_frame_size;
+    tr.bw_last = pk.bandwidth;
     const int C = pk.stream_channels;
     const int end = bandwidth_to_endband(pk.bandwidth);
     const int N = packet_frame_size * (48000 / Fs);   // CELT frame length at 48 kHz
@@ -92,20 +147,74 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     while ((kShortMdct << LM) != N && LM < kMaxLM) LM++;
     const uint8_t *p = data + offset;
     int xoff = 0;
+    int nb_samples = 0;
     CB_NOUNROLL for (int i = 0; i < count; i++) {
         CbFrameIR &ir = fr[i];
         ir.x_off = xoff;
         if (size[i] <= 1) {
-            // concealment frame: no symbols; the seed passes through (pitch PLC leaves st->rng alone)
+            // concealment frame inside a received packet (opus_decoder.c:246-252): no symbols
             ir.flags = CB_IR_LOST;
             ir.len = size[i];
             ir.LM = (uint8_t)LM; ir.C = (uint8_t)C; ir.end = (uint8_t)end;
-            ir.rng_final = 0; ir.seed_bands = *seed;
+            ir.rng_final = 0; ir.seed_bands = tr.seed;
+            const int a = lost_audiosize(tr, cap - nb_samples, Fs);
+            if (a > 0 && tr.have_mode) track_lost_frame(tr, a, Fs);
+            nb_samples += a > 0 ? a : 0;
         } else {
-            celt_parse_frame(p, size[i], LM, C, end, seed, ir, Xarea + xoff, ps, dry);
+            celt_parse_frame(p, size[i], LM, C, end, &tr.seed, ir, Xarea + xoff, ps, dry);
+            tr.streak = 0;
+            tr.have_mode = 1;
+            nb_samples += packet_frame_size;
         }
         xoff += N * C;
         p += size[i];
+    }
+}
+
+// One stage-A work item: packets [first, last) of one stream (a "run").  st = the stream's state as it was when the launch
+// began (stage B of this launch has not run yet), call_f0 = first packet of the call, f0 = first packet of the chunk whose IR
+// arrays pk_s / fr_s / X_s (already offset to this stream) are being filled: packet f goes to slot f - f0.
+// Two phases around ONE call site of the (large) packet parser.  Seeking: f walks BACK from first-1 to the nearest packet
+// that holds a received frame (it fixes seed, loss streak, frame size and bandwidth: SeedTrack), dry-parsing into the run's
+// first IR slot as scratch; then f walks FORWARD — dry over the lost / rejected packets up to the run, for real over the run.
+CB_DEV void opus_parse_run(const CbDecState *st, const uint8_t *data, const int64_t *offs_s, const int32_t *lens_s, int call_f0, int first,
+                           int last, int cap, int decode_fec, int kmax, int xstride, CbPacketIR *pk_s, CbFrameIR *fr_s, int16_t *X_s, int f0,
+                           ParseScratch &ps) {
+    const int Fs = st->Fs;
+    const size_t slot0 = (size_t)(first - f0);
+    SeedTrack tr;
+    tr.seed = st->rng; tr.streak = st->loss_count; tr.fs_last = st->frame_size; tr.bw_last = st->bandwidth;
+    tr.have_mode = st->prev_mode != 0; tr.channels = st->channels;
+    bool seeking = first > call_f0;
+    int f = seeking ? first - 1 : first;
+    while (f < last) {
+        if (seeking && f < call_f0) {   // nothing received since the call began: the state is the context
+            tr.seed = st->rng; tr.streak = st->loss_count; tr.fs_last = st->frame_size; tr.bw_last = st->bandwidth;
+            tr.have_mode = st->prev_mode != 0;
+            seeking = false;
+            f = call_f0;
+            continue;
+        }
+        const bool dry = f < first;
+        const size_t slot = dry ? slot0 : (size_t)(f - f0);
+        const int len = lens_s[f];
+        const uint8_t *p = len > 0 ? data + offs_s[f] : nullptr;
+        CbPacketIR pk;   // built in registers, stored once
+        opus_parse_packet(p, len, cap, Fs, dry ? 0 : decode_fec, kmax, tr, pk, fr_s + slot * kmax, X_s + slot * xstride, ps, dry);
+        if (!dry) pk_s[slot] = pk;
+        if (seeking) {
+            bool parsed = false;   // did any frame of this packet run the range decoder?
+            if (pk.ret >= 0 && !pk.lost)
+                for (int i = 0; i < pk.count; i++) parsed |= !(fr_s[slot * kmax + i].flags & CB_IR_LOST);
+            if (parsed) {
+                seeking = false;   // tr now holds the context after this packet: walk forward from the next one
+                f++;
+            } else {
+                f--;
+            }
+        } else {
+            f++;
+        }
     }
 }
 
@@ -122,7 +231,7 @@ struct CbSigRange {
 // opus_decode_frame remainder for one frame (opus_decoder.c:246-252,265-272,452-596).  sig[c] points at this frame's
 // position in the packet's staging area; *staged is set when the frame left signal there.
 template <class TM>
-CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFrameIR &ir, int16_t *X, int16_t *pcm, int room,
+CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, PlcScratch &P, const CbFrameIR &ir, int16_t *X, int16_t *pcm, int room,
                             int *const *sig, bool *staged) {
     const int F20 = st->Fs / 50, F10 = F20 >> 1, F5 = F10 >> 1, F2_5 = F5 >> 1;
     *staged = false;
@@ -151,7 +260,7 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
     if (audiosize > frame_size) return OPUS_BAD_ARG_;
     frame_size = audiosize;
     int celt_ret;
-    if (lost) celt_ret = celt_decode_lost_frame(tm, st, S, sig, imin(F20, frame_size));
+    if (lost) celt_ret = celt_decode_lost_frame(tm, st, S, P, sig, imin(F20, frame_size), bandwidth_to_endband(st->bandwidth));
     else celt_ret = celt_synth_frame(tm, st, S, ir, X, sig);
     *staged = !(lost && celt_ret < 0);
     // decode gain (opus_decoder.c:567-577) is applied by stage C when it writes the PCM
@@ -167,7 +276,7 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
 // opus_decode_native remainder for one packet (opus_decoder.c:613-627,682-708).  Returns what opus_decode returns.
 // sigbase: the packet's staging area, channel c at sigbase + c*cap48 (cap48 = cap * downsample samples).
 template <class TM>
-CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, const CbPacketIR &pk, const CbFrameIR *fr, int16_t *Xarea,
+CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, PlcScratch &P, const CbPacketIR &pk, const CbFrameIR *fr, int16_t *Xarea,
                              int16_t *pcm, int cap, int *sigbase, CbSigRange *range) {
     const int ds = st->downsample;
     const int cap48 = cap * ds;
@@ -185,7 +294,7 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, const CbPac
         do {
             int *sig[2] = {sigbase + pcm_count * ds, sigbase + cap48 + pcm_count * ds};
             bool staged;
-            int ret = opus_synth_frame(tm, st, S, lostir, nullptr, pcm + pcm_count * st->channels, cap - pcm_count, sig, &staged);
+            int ret = opus_synth_frame(tm, st, S, P, lostir, nullptr, pcm + pcm_count * st->channels, cap - pcm_count, sig, &staged);
             if (ret < 0) { result = ret; break; }
             if (staged) { if (!any) sb = pcm_count * ds; any = true; se = (pcm_count + ret) * ds; }
             pcm_count += ret;
@@ -208,7 +317,7 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, const CbPac
         CB_NOUNROLL for (int i = 0; i < pk.count; i++) {
             int *sig[2] = {sigbase + nb_samples * ds, sigbase + cap48 + nb_samples * ds};
             bool staged;
-            int ret = opus_synth_frame(tm, st, S, fr[i], Xarea + fr[i].x_off, pcm + nb_samples * st->channels, cap - nb_samples, sig,
+            int ret = opus_synth_frame(tm, st, S, P, fr[i], Xarea + fr[i].x_off, pcm + nb_samples * st->channels, cap - nb_samples, sig,
                                        &staged);
             if (staged) { if (!any) sb = nb_samples * ds; any = true; se = (nb_samples + (ret < 0 ? pk.frame_size : ret)) * ds; }
             if (ret < 0) { result = ret; break; }

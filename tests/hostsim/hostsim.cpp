@@ -17,34 +17,39 @@ int hostsim_dec_state_size(void) { return (int)sizeof(CbDecState); }
 // Stage A (parse -> IR), stage B (synth) and stage C (de-emphasis) per packet, exactly the hand-offs the kernels use.
 int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F, int cap, int channels,
                           int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets) {
+    // Emulates the kernels' schedule: the call is cut into chunks of Fc packets; for a chunk, stage A runs first for every run
+    // of R packets from the state as it stood when the chunk began (each run reconstructing its own context), then stages B
+    // and C consume the chunk in order.  (The kernels use the state at CALL start for all chunks and walk back across chunk
+    // boundaries inside the call; a chunk here is therefore a "call".)
+    const int Fc = 16, R = 3;
     CbDecState *st = (CbDecState *)calloc(1, sizeof(CbDecState));
     cb::SynthScratch *S = (cb::SynthScratch *)calloc(1, sizeof(cb::SynthScratch));
     cb::ParseScratch *ps = (cb::ParseScratch *)calloc(1, sizeof(cb::ParseScratch));
+    cb::PlcScratch *plc = (cb::PlcScratch *)calloc(1, sizeof(cb::PlcScratch));
     if (cb::dec_state_init(st, Fs, channels) != 0) return -1;
-    const int kmax = cap / (Fs / 400) < 48 ? cap / (Fs / 400) : 48;
-    std::vector<CbFrameIR> fr(kmax > 0 ? kmax : 1);
-    std::vector<int16_t> X((size_t)cap * (48000 / Fs) * 2 + 16);
+    const int kmax = cap / (Fs / 400) < 48 ? (cap / (Fs / 400) > 0 ? cap / (Fs / 400) : 1) : 48;
+    const int xstride = cap * (48000 / Fs) * 2 + 16;
+    std::vector<CbPacketIR> pk(Fc);
+    std::vector<CbFrameIR> fr((size_t)Fc * kmax);
+    std::vector<int16_t> X((size_t)Fc * xstride);
     std::vector<int> sig((size_t)cap * (48000 / Fs) * 2 + 16);
     cb::SoloTeam tm;
-    for (int f = 0; f < F; f++) {
-        const uint8_t *p = lens[f] > 0 ? data + offs[f] : nullptr;
-        CbPacketIR pk;
-        unsigned seed = st->rng;   // chained by stage A in the kernels; equal to st->rng here because B(f-1) has run
-        // dry pass first (what a run's first thread does to recover its seed): must leave the same final range behind
-        unsigned dry_seed = 12345u;
-        CbPacketIR dry_pk;
-        cb::opus_parse_packet(p, lens[f], cap, Fs, 0, kmax, &dry_seed, dry_pk, fr.data(), X.data(), *ps, true);
-        cb::opus_parse_packet(p, lens[f], cap, Fs, 0, kmax, &seed, pk, fr.data(), X.data(), *ps, false);
-        if (pk.ret >= 0 && !pk.lost && pk.count > 0 && !(fr[pk.count - 1].flags & CB_IR_LOST) && dry_seed != seed) {
-            if (rets) rets[f] = -99;   // dry/full divergence: flag loudly
-            continue;
+    for (int f0 = 0; f0 < F; f0 += Fc) {
+        const int f1 = f0 + Fc < F ? f0 + Fc : F;
+        for (int first = f0; first < f1; first += R)   // stage A, run by run, any order
+            cb::opus_parse_run(st, data, offs, lens, f0, first, first + R < f1 ? first + R : f1, cap, 0, kmax, xstride, pk.data(), fr.data(),
+                               X.data(), f0, *ps);
+        for (int f = f0; f < f1; f++) {                // stages B and C
+            const int slot = f - f0;
+            cb::CbSigRange rg;
+            int r = cb::opus_synth_packet(tm, st, *S, *plc, pk[slot], fr.data() + (size_t)slot * kmax, X.data() + (size_t)slot * xstride,
+                                          pcm + (size_t)f * cap * channels, cap, sig.data(), &rg);
+            for (int c = 0; c < channels; c++) cb::opus_deemph_packet(st, c, sig.data(), rg, pcm + (size_t)f * cap * channels, cap);
+            if (rets) rets[f] = r;
+            if (ranges) ranges[f] = st->rangeFinal;
         }
-        cb::CbSigRange rg;
-        int r = cb::opus_synth_packet(tm, st, *S, pk, fr.data(), X.data(), pcm + (size_t)f * cap * channels, cap, sig.data(), &rg);
-        for (int c = 0; c < channels; c++) cb::opus_deemph_packet(st, c, sig.data(), rg, pcm + (size_t)f * cap * channels, cap);   // stage C
-        if (rets) rets[f] = r;
-        if (ranges) ranges[f] = st->rangeFinal;
     }
+    free(plc);
     free(ps);
     free(S);
     free(st);

@@ -234,6 +234,35 @@ def test_encoder_host_api_ctl_and_padding():
     assert L.opus_packet_pad(O.ptr(pk), 40, 39) == cb.OPUS_BAD_ARG
 
 
+@needs_ref
+@pytest.mark.parametrize("pattern", ["single", "burst", "random", "toc_only", "start_lost"])
+def test_hostsim_packet_loss_concealment_vs_oracle(pattern):
+    """celt_decode_lost (pitch-based and, after 5 losses, noise-based) through the host simulation of the stage-B code."""
+    hs = _hostsim()
+    cases = [("music", 2, 960, 64000), ("tone", 2, 960, 96000), ("tone", 1, 480, 48000), ("clicks", 2, 240, 128000), ("music", 1, 120, 64000)]
+    for k, (kind, ch, fs, br) in enumerate(cases):
+        x = O.test_signal(48000, ch, 40 + k, kind)
+        d, o, l, _ = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=0)
+        d, o = O.pack(d, o, l)
+        l = l.copy()
+        F = len(l)
+        rs = np.random.RandomState(k)
+        if pattern == "single":
+            l[10::17] = 0
+        elif pattern == "burst":
+            for f in range(12, F, 40):
+                l[f:f + 8] = 0
+        elif pattern == "random":
+            l[rs.rand(F) < 0.2] = 0
+        elif pattern == "toc_only":
+            l[9::13] = 1
+        else:
+            l[:3] = 0
+        rp, rr, rret = O.decode_stream(d, o, l, fs, ch)
+        hp, hr, hret = _hostsim_decode(hs, d, o, l, fs, ch)
+        assert np.array_equal(rret, hret) and np.array_equal(rr, hr) and np.array_equal(rp, hp), (pattern, kind, ch, fs)
+
+
 def test_hostsim_garbage_packets_do_not_crash_and_match_oracle():
     hs = _hostsim()
     rs = np.random.RandomState(5)

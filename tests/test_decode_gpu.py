@@ -126,3 +126,73 @@ def test_error_codes_and_scope_edge():
     assert L.opus_decode(C.c_void_p(h), None, 0, O.ptr(out), 960, 0) == 960
     assert not out[:960].any()
     L.opus_decoder_destroy(C.c_void_p(h))
+
+
+def _lossy(lens, pattern, seed):
+    """Mark packets lost (len 0 -> opus_decode(NULL)) or cut to a bare TOC (len 1 -> PLC as well, opus_decoder.c:246-252)."""
+    l = lens.copy()
+    F = len(l)
+    rs = np.random.RandomState(seed)
+    if pattern == "single":
+        l[10::17] = 0
+    elif pattern == "burst":                     # 8 in a row: pitch-based for 5 frames, then noise-based (celt_decoder.c:446)
+        for f in range(12, F, 40):
+            l[f:f + 8] = 0
+    elif pattern == "random":
+        l[rs.rand(F) < 0.2] = 0
+    elif pattern == "toc_only":
+        l[9::13] = 1
+    elif pattern == "start_lost":
+        l[:3] = 0
+    return l
+
+
+@pytest.mark.parametrize("pattern", ["single", "burst", "random", "toc_only", "start_lost"])
+def test_packet_loss_concealment(pattern):
+    """celt_decode_lost (celt_decoder.c:415-711) through the batch API: NULL / TOC-only packets inside received streams, the
+    way tests/test_opus_decode.c:125-132 and opus_demo -loss drive it.  PCM, return codes and final ranges vs the oracle."""
+    cb = _cb()
+    cases = [("music", 2, 960, 64000), ("tone", 2, 960, 96000), ("tone", 1, 480, 48000), ("clicks", 2, 240, 128000),
+             ("music", 1, 120, 64000), ("noise", 2, 960, 128000)]
+    for k, (kind, ch, fs, br) in enumerate(cases):
+        x = O.test_signal(48000, ch, 40 + k, kind)
+        d, o, l, _ = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=0)
+        d, o = O.pack(d, o, l)
+        l = _lossy(l, pattern, k)
+        F = len(l)
+        rp, rr, rret = O.decode_stream(d, o, l, fs, ch)
+        dec = cb.DecoderBatch(1, 48000, ch)
+        F1 = F // 3                                   # two launches: the concealment state crosses a launch boundary
+        p1, r1 = dec.decode_span(d, o[:F1], l[:F1], F1, fs)
+        p2, r2 = dec.decode_span(d, o[F1:], l[F1:], F - F1, fs)
+        fr = dec.final_ranges()
+        dec.close()
+        assert np.array_equal(np.concatenate([r1, r2]), rret), (pattern, kind, ch, fs)
+        got = np.concatenate([p1, p2])
+        bad = np.nonzero((rp.reshape(F, -1) != got.reshape(F, -1)).any(axis=1))[0]
+        assert bad.size == 0, (pattern, kind, ch, fs, "first bad frame", int(bad[0]), "lost", np.nonzero(l <= 1)[0][:6].tolist())
+        assert int(rr[-1]) == int(fr[0])
+
+
+def test_scalar_api_null_packet_and_fec_flag():
+    """opus_decode(st, NULL, 0, ...) and decode_fec=1 on a CELT packet (no in-band FEC: concealment, opus_decoder.c:655-657)."""
+    cb = _cb()
+    L = cb.lib()
+    x = O.test_signal(48000, 2, 3, "tone")
+    d, o, l, _ = O.encode_stream(x, 960, 64000)
+    F = len(l)
+    err = C.c_int(0)
+    h = L.opus_decoder_create(48000, 2, C.byref(err))
+    out = np.zeros((960, 2), dtype=np.int16)
+    l2 = l.copy()
+    l2[5] = 0
+    l2[20:22] = 0
+    rp, rr, rret = O.decode_stream(d, o, l2, 960, 2)
+    for f in range(F):
+        if l2[f] == 0:
+            r = L.opus_decode(C.c_void_p(h), None, 0, O.ptr(out), 960, 0)
+        else:
+            pkt = d[o[f]:o[f] + l[f]].copy()
+            r = L.opus_decode(C.c_void_p(h), O.ptr(pkt), int(l[f]), O.ptr(out), 960, 0)
+        assert r == 960 and np.array_equal(out, rp[f * 960:(f + 1) * 960]), f
+    L.opus_decoder_destroy(C.c_void_p(h))
