@@ -79,7 +79,12 @@ struct WarpTeam {
     // Phase boundary of a frame: with CB_PHASE_SYNC the warps of a block (each on its own stream) wait for each other here,
     // so that co-resident warps execute the same region of a kernel much larger than the instruction cache.  EVERY warp of the
     // block must pass the same number of phase() calls per frame (see kEncPhases).
-#if defined(CB_PHASE_SYNC)
+#if defined(CB_PHASE_SYNC) && defined(CB_PHASE_GROUP)
+    // sub-block groups of CB_PHASE_GROUP warps on named barriers 1..15 (A/B knob: less waiting, more code positions in flight)
+    CB_MEM void phase() const {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / CB_PHASE_GROUP), "r"(CB_PHASE_GROUP * 32) : "memory");
+    }
+#elif defined(CB_PHASE_SYNC)
     CB_MEM void phase() const { __syncthreads(); }
 #else
     CB_MEM void phase() const {}

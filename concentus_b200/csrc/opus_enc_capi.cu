@@ -68,7 +68,10 @@ encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const
     const int s = blockIdx.x * CB_ENC_WPB + warp;
     if (s >= n) {
 #if defined(CB_PHASE_SYNC)
-        for (int f = 0; f < F * kEncPhases; f++) __syncthreads();   // keep the block's phase barriers balanced
+        {
+            WarpTeam idle{lane};
+            for (int f = 0; f < F * kEncPhases; f++) idle.phase();   // keep the block's phase barriers balanced
+        }
 #endif
         return;
     }
