@@ -711,15 +711,23 @@ CB_DEV void mdct_forward_blocks(TM tm, const int *in, int *out, int shift, int B
     tm.sync();
 }
 
-// compute_mdcts (celt_encoder.c:418-461), upsample == 1
+// compute_mdcts (celt_encoder.c:418-461)
 template <class TM>
-CB_DEV_NOINLINE void compute_mdcts_team(TM tm, int shortBlocks, const int *in, int *freq, int C, int CC, int LM, int *fftbuf) {
+CB_DEV_NOINLINE void compute_mdcts_team(TM tm, int shortBlocks, const int *in, int *freq, int C, int CC, int LM, int upsample, int *fftbuf) {
     int B, N, shift;
     if (shortBlocks) { B = shortBlocks; N = kShortMdct; shift = kMaxLM; }
     else { B = 1; N = kShortMdct << LM; shift = kMaxLM - LM; }
     CB_NOUNROLL for (int c = 0; c < CC; c++) mdct_forward_blocks(tm, in + c * (B * N + kOverlap), freq + c * N * B, shift, B, fftbuf);
     if (CC == 2 && C == 1) {
         CB_TEAM_FOR(i, B * N, tm) freq[i] = wadd(freq[i] >> 1, freq[B * N + i] >> 1);
+        tm.sync();
+    }
+    if (upsample != 1) {   // API rate below 48 kHz: the zero-stuffed input's images above the original Nyquist are dropped
+        const int bound = B * N / upsample;
+        CB_TEAM_FOR(w, C * B * N, tm) {
+            const int i = w % (B * N);
+            freq[w] = i < bound ? wmul(freq[w], upsample) : 0;
+        }
         tm.sync();
     }
 }
@@ -782,15 +790,18 @@ CB_DEV_NOINLINE void normalise_bands_team(TM tm, const int *freq, int16_t *X, co
 
 // ---- the frame -------------------------------------------------------------------------------------------------------
 
-// celt_encode_with_ec (celt_encoder.c:1379-2273).  `pcm`: CC-interleaved int16, frame_size samples per channel (48 kHz).
+// celt_encode_with_ec (celt_encoder.c:1379-2273).  `pcm`: CC-interleaved int16, frame_size_api samples per channel at the API rate
+// (st->upsample = 48000 / Fs: below 48 kHz the input is zero-stuffed in the pre-emphasis, :490-533).
 // `st` holds the head of the state (CB_ENC_HEAD_BYTES, possibly a shared-memory copy), `gst` the full block in HBM (only its
 // sample histories are touched).  `pcm` may live in S.u.pcm_buf: it is dead before the first overlay is written.
 // S.v.ec must hold the range coder the Opus layer initialised (and shrank to nbCompressedBytes).  Returns (on every lane)
 // the number of payload bytes, or a negative error.
 template <class TM>
 CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &S, EncGlobal &G, const CeltEncCfg &cfg, const int16_t *pcm,
-                             int frame_size, int nbCompressedBytes_in) {
+                             int frame_size_api, int nbCompressedBytes_in) {
     EncVars &V = S.v;
+    const int upsample = st->upsample;
+    const int frame_size = frame_size_api * upsample;
     const bool L0 = tm.lane() == 0;
     const int CC = st->channels;
     const int C = cfg.C;
@@ -849,8 +860,8 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     int sample_max;
     {
         const int old_overlap_max = st->overlap_max;
-        const int a = team_maxabs16(tm, pcm, C * (N - ov));
-        const int b = team_maxabs16(tm, pcm + C * (N - ov), C * ov);
+        const int a = team_maxabs16(tm, pcm, C * (N - ov) / upsample);
+        const int b = team_maxabs16(tm, pcm + C * (N - ov) / upsample, C * ov / upsample);
         sample_max = imax(imax(old_overlap_max, a), b);
         tm.sync();
         if (L0) st->overlap_max = b;
@@ -858,13 +869,22 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     CB_NOUNROLL for (int c = 0; c < CC; c++) {
         int *inp = G.in + c * (N + ov) + ov;
         const int m0 = st->preemph_memE[c];
-        CB_TEAM_FOR(i, N, tm) {
-            const int x = pcm[CC * i + c];
-            const int m = i == 0 ? m0 : mul16_16(kPreemphCoef0, pcm[CC * (i - 1) + c]) >> 3;
-            inp[i] = wsub(shl32(x, 12), m);
+        if (upsample == 1) {
+            CB_TEAM_FOR(i, N, tm) {
+                const int x = pcm[CC * i + c];
+                const int m = i == 0 ? m0 : mul16_16(kPreemphCoef0, pcm[CC * (i - 1) + c]) >> 3;
+                inp[i] = wsub(shl32(x, 12), m);
+            }
+        } else {
+            CB_TEAM_FOR(i, N, tm) {   // x[k] = pcm[k / upsample] when k is a multiple of upsample, else 0
+                const int x = i % upsample == 0 ? (int)pcm[CC * (i / upsample) + c] : 0;
+                const int xp = i == 0 ? 0 : ((i - 1) % upsample == 0 ? (int)pcm[CC * ((i - 1) / upsample) + c] : 0);
+                const int m = i == 0 ? m0 : mul16_16(kPreemphCoef0, xp) >> 3;
+                inp[i] = wsub(shl32(x, 12), m);
+            }
         }
         tm.sync();
-        if (L0) st->preemph_memE[c] = mul16_16(kPreemphCoef0, pcm[CC * (N - 1) + c]) >> 3;
+        if (L0) st->preemph_memE[c] = upsample == 1 ? mul16_16(kPreemphCoef0, pcm[CC * (N - 1) + c]) >> 3 : 0;
     }
     if (L0) {
         EcEnc ec = V.ec;
@@ -1003,12 +1023,12 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     tm.phase();
     // ---- MDCT, band energies (:1660-1690) ----
     if (V.secondMdct) {
-        compute_mdcts_team(tm, 0, G.in, G.freq, C, CC, LM, S.u.fft);
+        compute_mdcts_team(tm, 0, G.in, G.freq, C, CC, LM, upsample, S.u.fft);
         band_energies_team(tm, G.freq, S.bandE, S.bandLogE2, effEnd, end, C, LM);
         CB_TEAM_FOR(i, C * kNbEBands, tm) S.bandLogE2[i] = (int16_t)(S.bandLogE2[i] + (shl16(LM, 10) >> 1));
         tm.sync();
     }
-    compute_mdcts_team(tm, V.shortBlocks, G.in, G.freq, C, CC, LM, S.u.fft);
+    compute_mdcts_team(tm, V.shortBlocks, G.in, G.freq, C, CC, LM, upsample, S.u.fft);
     band_energies_team(tm, G.freq, S.bandE, S.bandLogE, effEnd, end, C, LM);
 
     // ---- temporal VBR, bandLogE2, transient patch (:1803-1848) ----
@@ -1042,7 +1062,7 @@ CB_DEV int celt_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     tm.sync();
     if (V.patch) {
-        compute_mdcts_team(tm, V.shortBlocks, G.in, G.freq, C, CC, LM, S.u.fft);
+        compute_mdcts_team(tm, V.shortBlocks, G.in, G.freq, C, CC, LM, upsample, S.u.fft);
         band_energies_team(tm, G.freq, S.bandE, S.bandLogE, effEnd, end, C, LM);
         CB_TEAM_FOR(i, C * kNbEBands, tm) S.bandLogE2[i] = (int16_t)(S.bandLogE2[i] + (shl16(LM, 10) >> 1));
         if (L0) V.tf_estimate = 3277;

@@ -281,15 +281,17 @@ CB_DEV void compute_stereo_width_team(TM tm, const int16_t *pcm, int frame_size,
     w.width = s16(imin(32767, 20 * w.max_follower));
 }
 
-// stereo_fade (opus_encoder.c:411-441), in place, 48 kHz
+// stereo_fade (opus_encoder.c:411-441), in place
 template <class TM>
-CB_DEV void stereo_fade_team(TM tm, int16_t *buf, int g1, int g2, int frame_size) {
+CB_DEV void stereo_fade_team(TM tm, int16_t *buf, int g1, int g2, int frame_size, int Fs) {
+    const int inc = 48000 / Fs;
+    const int overlap = kOverlap / inc;
     g1 = s16(32767 - g1);
     g2 = s16(32767 - g2);
     CB_TEAM_FOR(i, frame_size, tm) {
         int g = g2;
-        if (i < kOverlap) {
-            const int w = s16(mul16_16_q15(kWindow120[i], kWindow120[i]));
+        if (i < overlap) {
+            const int w = s16(mul16_16_q15(kWindow120[i * inc], kWindow120[i * inc]));
             g = s16(mac16_16(mul16_16(w, g2), 32767 - w, g1) >> 15);
         }
         int diff = s16(((int)buf[i * 2] - (int)buf[i * 2 + 1]) >> 1);
@@ -323,7 +325,6 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     if ((!st->variable_duration && 400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs && 25 * frame_size != Fs &&
          50 * frame_size != 3 * Fs) || 400 * frame_size < Fs || max_data_bytes <= 0)
         { skip_phases(tm); return OPUS_BAD_ARG_; }
-    if (Fs != 48000) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }
     const int delay_compensation = st->application == kAppLowdelay ? 0 : st->delay_compensation;
     const int lsb_depth = imin(16, st->lsb_depth);
     const int total_buffer = delay_compensation;
@@ -431,6 +432,11 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     if (bandwidth > st->max_bandwidth) bandwidth = st->max_bandwidth;
     if (st->user_bandwidth != kOpusAuto) bandwidth = st->user_bandwidth;
+    // nothing above the Nyquist rate of the input (opus_encoder.c:1308-1315)
+    if (Fs <= 24000 && bandwidth > 1104) bandwidth = 1104;
+    if (Fs <= 16000 && bandwidth > 1103) bandwidth = 1103;
+    if (Fs <= 12000 && bandwidth > 1102) bandwidth = 1102;
+    if (Fs <= 8000 && bandwidth > 1101) bandwidth = 1101;
     if (bandwidth == 1102) bandwidth = 1103;   // CELT has no mediumband
     const int curr_bandwidth = bandwidth;
     const int bytes_target = imin(max_data_bytes, bitrate_bps * frame_size / (Fs * 8)) - 1;
@@ -472,7 +478,7 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         int g1 = st->hybrid_stereo_width_Q14, g2 = stereoWidth_Q14;
         g1 = g1 == 16384 ? 32767 : shl16(g1, 1);
         g2 = g2 == 16384 ? 32767 : shl16(g2, 1);
-        stereo_fade_team(tm, pcm_buf, g1, g2, frame_size);
+        stereo_fade_team(tm, pcm_buf, g1, g2, frame_size, Fs);
         if (L0) st->hybrid_stereo_width_Q14 = stereoWidth_Q14;
     }
     CeltEncCfg cfg;

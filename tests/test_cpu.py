@@ -189,6 +189,31 @@ def test_hostsim_encoder_long_vbr_and_audio_application():
         assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (ch, fs, br)
 
 
+@needs_ref
+def test_hostsim_encoder_other_api_rates():
+    """Encoder at 8/12/16/24 kHz API rates, both applications, every frame size."""
+    hs = _hostsim()
+    n = 0
+    for Fs in (8000, 12000, 16000, 24000):
+        for ch in (1, 2):
+            for ms in (2.5, 5, 10, 20):
+                br, vbr, cvbr = ((24000, 1, 1), (64000, 0, 0), (128000, 1, 0))[n % 3]
+                app = (O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, O.OPUS_APPLICATION_AUDIO)[n % 2]
+                fs = int(Fs * ms / 1000)
+                x = O.test_signal(Fs // 2, ch, 70 + n, ("music", "tone", "clicks", "noise")[n % 4])
+                n += 1
+                d, o, l, r = O.encode_stream(x, fs, br, ch, Fs=Fs, vbr=vbr, cvbr=cvbr, complexity=10, application=app, max_bytes=1276)
+                if not (d.reshape(-1, 1276)[:, 0] & 0x80).all():
+                    continue
+                F = x.shape[0] // fs
+                out = np.zeros((F, 1276), dtype=np.uint8)
+                lens = np.zeros(F, dtype=np.int32)
+                rng = np.zeros(F, dtype=np.uint32)
+                cfg = np.array([app, br, vbr, cvbr, 10, 1276, 0, 0], dtype=np.int32)
+                hs.hostsim_encode_stream(O.ptr(np.ascontiguousarray(x)), F, fs, ch, Fs, O.ptr(cfg), O.ptr(out), 1276, O.ptr(lens), O.ptr(rng))
+                assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (Fs, ch, ms, br, app)
+
+
 def test_encoder_host_api_ctl_and_padding():
     """Host-side half of the encoder C ABI: sizes, init argument checks, ctl set/get round trips and range checks
     (opus-fix/tests/test_opus_api.c encoder section), opus_packet_pad / unpad against the reference's."""
