@@ -91,6 +91,7 @@ struct EncGlobal {
     int in[2 * (kMaxFrame + kOverlap)];              // pre-emphasised input + overlap history, per channel
     int pre[2 * (kCombMaxPeriod + kMaxFrame)];       // pre-filter history + new samples, per channel
     int freq[2 * kMaxFrame];                          // MDCT output
+    uint8_t tmp_data[3 * 1276];                       // 40/60 ms frames: the 20 ms sub-packets before repacketisation
 };
 
 // Encoder-side compute_allocation hooks (rate.c:346-364,391-411)

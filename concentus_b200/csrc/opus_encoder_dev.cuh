@@ -8,6 +8,7 @@
 // than 48 kHz and frames longer than 20 ms return OPUS_UNIMPLEMENTED and leave the state untouched — there is no CPU path.
 #pragma once
 #include "celt_encoder.cuh"
+#include "opus_packet.h"
 
 #ifndef CB_HD
 #if defined(__CUDACC__)
@@ -308,23 +309,108 @@ CB_TABLE int32_t kBwThreshStereoVoice[8] = {11000, 1000, 14000, 1000, 21000, 200
 CB_TABLE int32_t kBwThreshStereoMusic[8] = {12000, 1000, 18000, 2000, 21000, 2000, 30000, 2000};
 
 template <class TM>
-CB_DEV void skip_phases(TM tm) {
-    for (int i = 0; i < kEncPhases; i++) tm.phase();
+CB_DEV void skip_phases(TM tm, int nsub = 1) {
+    for (int i = 0; i < nsub * kEncPhases; i++) tm.phase();
+}
+
+// What a 40 / 60 ms frame leaves for its 20 ms sub-frames (opus_encoder.c:1362-1438): the settings the outer call forces on the
+// inner calls, and what it restores afterwards.
+struct LongFrameCtx {
+    int nb_frames, bytes_per_frame;
+    int bak_mode, bak_bandwidth, bak_channels;
+};
+enum { kLongFrame = -1000 };   // internal: "outer decisions committed, now code the sub-frames"
+
+// opus_repacketizer_cat + opus_repacketizer_out_range_impl (repacketizer.c:49-227) for nb (2 or 3) single-frame packets of
+// one configuration: src[i] / len[i] are whole sub-packets (TOC + payload, possibly CBR-padded code 3).  Writes the merged
+// packet to `data` (<= maxlen), padded to maxlen when `pad`.  Returns its length or a negative error.
+CB_DEV int repacketize_frames(uint8_t *data, int maxlen, const uint8_t *const *src, const int *plen, int nb, int pad) {
+    const uint8_t *frames[3];
+    int len[3];
+    uint8_t toc = 0;
+    for (int i = 0; i < nb; i++) {
+        if (plen[i] < 1) return OPUS_INVALID_PACKET_;
+        uint8_t t;
+        int16_t size[48];
+        int offset;
+        const int cnt = pkt_parse(src[i], plen[i], 0, &t, size, &offset, nullptr);
+        if (cnt != 1) return cnt < 0 ? cnt : OPUS_INVALID_PACKET_;
+        if (i == 0) toc = t;
+        else if ((toc & 0xFC) != (t & 0xFC)) return OPUS_INVALID_PACKET_;
+        frames[i] = src[i] + offset;
+        len[i] = size[0];
+    }
+    int tot_size = 0;
+    uint8_t *ptr = data;
+    if (nb == 2) {
+        if (len[1] == len[0]) {
+            tot_size = 2 * len[0] + 1;
+            if (tot_size > maxlen) return OPUS_BUFFER_TOO_SMALL_;
+            *ptr++ = (uint8_t)((toc & 0xFC) | 0x1);
+        } else {
+            tot_size = len[0] + len[1] + 2 + (len[0] >= 252);
+            if (tot_size > maxlen) return OPUS_BUFFER_TOO_SMALL_;
+            *ptr++ = (uint8_t)((toc & 0xFC) | 0x2);
+            if (len[0] < 252) *ptr++ = (uint8_t)len[0];
+            else { ptr[0] = (uint8_t)(252 + (len[0] & 3)); ptr[1] = (uint8_t)((len[0] - ptr[0]) >> 2); ptr += 2; }
+        }
+    }
+    if (nb > 2 || (pad && tot_size < maxlen)) {
+        ptr = data;
+        tot_size = 0;
+        int vbr = 0;
+        for (int i = 1; i < nb; i++)
+            if (len[i] != len[0]) { vbr = 1; break; }
+        if (vbr) {
+            tot_size += 2;
+            for (int i = 0; i < nb - 1; i++) tot_size += 1 + (len[i] >= 252) + len[i];
+            tot_size += len[nb - 1];
+            if (tot_size > maxlen) return OPUS_BUFFER_TOO_SMALL_;
+            *ptr++ = (uint8_t)((toc & 0xFC) | 0x3);
+            *ptr++ = (uint8_t)(nb | 0x80);
+        } else {
+            tot_size += nb * len[0] + 2;
+            if (tot_size > maxlen) return OPUS_BUFFER_TOO_SMALL_;
+            *ptr++ = (uint8_t)((toc & 0xFC) | 0x3);
+            *ptr++ = (uint8_t)nb;
+        }
+        const int pad_amount = pad ? maxlen - tot_size : 0;
+        if (pad_amount != 0) {
+            data[1] |= 0x40;
+            const int nb_255s = (pad_amount - 1) / 255;
+            for (int i = 0; i < nb_255s; i++) *ptr++ = 255;
+            *ptr++ = (uint8_t)(pad_amount - 255 * nb_255s - 1);
+            tot_size += pad_amount;
+        }
+        if (vbr)
+            for (int i = 0; i < nb - 1; i++) {
+                if (len[i] < 252) *ptr++ = (uint8_t)len[i];
+                else { ptr[0] = (uint8_t)(252 + (len[i] & 3)); ptr[1] = (uint8_t)((len[i] - ptr[0]) >> 2); ptr += 2; }
+            }
+    }
+    for (int i = 0; i < nb; i++) {
+        for (int k = 0; k < len[i]; k++) ptr[k] = frames[i][k];
+        ptr += len[i];
+    }
+    if (pad)
+        while (ptr < data + maxlen) *ptr++ = 0;
+    return tot_size;
 }
 
 // opus_encode_native (opus_encoder.c:938-2005), MODE_CELT_ONLY path.  pcm: frame_size x channels int16; out: >= out_data_bytes.
 // st: head of the state (maybe a shared-memory copy), gst: the full block in HBM (delay buffer and sample histories).
 // Returns (uniformly on all lanes) the packet length or a negative error code.
 template <class TM>
-CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &S, EncGlobal &G, const int16_t *pcm, int frame_size, uint8_t *out,
-                             int out_data_bytes) {
+CB_DEV int opus_encode_one(TM tm, CbEncState *st, CbEncState *gst, EncShared &S, EncGlobal &G, const int16_t *pcm, int frame_size, uint8_t *out,
+                           int out_data_bytes, LongFrameCtx &lc) {
     const bool L0 = tm.lane() == 0;
     const int Fs = st->Fs, channels = st->channels;
+    const int nsub = frame_size > Fs / 50 ? (frame_size > Fs / 25 ? 3 : 2) : 1;   // phase barriers this frame owes its block
     int max_data_bytes = imin(1276, out_data_bytes);
     // frame_size has been through frame_size_select() on the host (opus_encode, opus_encoder.c:2007-2025)
     if ((!st->variable_duration && 400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs && 25 * frame_size != Fs &&
          50 * frame_size != 3 * Fs) || 400 * frame_size < Fs || max_data_bytes <= 0)
-        { skip_phases(tm); return OPUS_BAD_ARG_; }
+        { skip_phases(tm, nsub); return OPUS_BAD_ARG_; }
     const int delay_compensation = st->application == kAppLowdelay ? 0 : st->delay_compensation;
     const int lsb_depth = imin(16, st->lsb_depth);
     const int total_buffer = delay_compensation;
@@ -384,7 +470,7 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
         }
         if (!st->use_vbr) ret = max_data_bytes;
         tm.sync();
-        skip_phases(tm);
+        skip_phases(tm, nsub);
         return ret;
     }
     equiv_rate = bitrate_bps - (40 * stream_channels + 20) * (Fs / frame_size - 50);
@@ -407,10 +493,9 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     if (mode != CB_MODE_CELT_ONLY && frame_size < Fs / 100) mode = CB_MODE_CELT_ONLY;
     if (max_data_bytes < (frame_rate > 50 ? 12000 : 8000) * frame_size / (Fs * 8)) mode = CB_MODE_CELT_ONLY;
-    if (mode != CB_MODE_CELT_ONLY) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }                 // SILK / hybrid: not in this engine
-    if (st->prev_mode > 0 && st->prev_mode != CB_MODE_CELT_ONLY) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }
-    if (st->application == kAppVoip) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }               // hp_cutoff (SILK biquad) path
-    if (frame_size > Fs / 50) { skip_phases(tm); return OPUS_UNIMPLEMENTED_; }                      // 40/60 ms repacketised frames
+    if (mode != CB_MODE_CELT_ONLY) { skip_phases(tm, nsub); return OPUS_UNIMPLEMENTED_; }                 // SILK / hybrid: not in this engine
+    if (st->prev_mode > 0 && st->prev_mode != CB_MODE_CELT_ONLY) { skip_phases(tm, nsub); return OPUS_UNIMPLEMENTED_; }
+    if (st->application == kAppVoip) { skip_phases(tm, nsub); return OPUS_UNIMPLEMENTED_; }               // hp_cutoff (SILK biquad) path
     // bandwidth (opus_encoder.c:1229-1292)
     int bandwidth;
     {
@@ -440,6 +525,35 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     if (bandwidth == 1102) bandwidth = 1103;   // CELT has no mediumband
     const int curr_bandwidth = bandwidth;
     const int bytes_target = imin(max_data_bytes, bitrate_bps * frame_size / (Fs * 8)) - 1;
+
+    if (frame_size > Fs / 50) {
+        // 40 / 60 ms in CELT-only mode: the decisions above stand for the whole frame, the audio is coded as 2 or 3 20 ms frames
+        // with mode / bandwidth / channels forced, then merged by the repacketizer (opus_encoder.c:1362-1438)
+        tm.sync();
+        if (L0) {
+            st->rangeFinal = 0;
+            st->voice_ratio = -1;
+            st->bitrate_bps = bitrate_bps;
+            st->stream_channels = stream_channels;
+            st->mode = mode;
+            st->bandwidth = bandwidth;
+            if (want_width) { st->width_XX = sw.XX; st->width_XY = sw.XY; st->width_YY = sw.YY; st->width_smoothed = sw.smoothed; st->width_max_follower = sw.max_follower; }
+        }
+        lc.nb_frames = nsub;
+        lc.bytes_per_frame = imin(1276, (out_data_bytes - 3) / nsub);
+        lc.bak_mode = st->user_forced_mode;
+        lc.bak_bandwidth = st->user_bandwidth;
+        lc.bak_channels = st->force_channels;
+        tm.sync();
+        if (L0) {
+            st->user_forced_mode = mode;
+            st->user_bandwidth = bandwidth;
+            st->force_channels = stream_channels;
+            st->prev_channels = stream_channels;
+        }
+        tm.sync();
+        return kLongFrame;
+    }
 
     // ---- commit point: from here on the frame is coded ----
     int16_t *pcm_buf = S.u.pcm_buf;
@@ -537,6 +651,54 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     tm.sync();
     return ret;
+}
+
+
+// opus_encode_native for any frame size (2.5-60 ms).  pcm: frame_size x channels int16 at the API rate; out: >= out_data_bytes.
+// One call site of the frame coder: the outer pass of a 40/60 ms frame only commits its decisions, the sub-frames follow and the
+// repacketizer merges them.  (A separate out-of-line copy for long frames measured no faster and 150 KB bigger.)
+template <class TM>
+CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &S, EncGlobal &G, const int16_t *pcm, int frame_size, uint8_t *out,
+                             int out_data_bytes) {
+    LongFrameCtx lc;
+    lc.nb_frames = 0;
+    int sub_len[3] = {0, 0, 0};
+    int i = -1;
+    int failed = 0;
+    const int Fs = st->Fs, channels = st->channels;
+    for (;;) {
+        const int16_t *p = i < 0 ? pcm : pcm + (size_t)i * channels * (Fs / 50);
+        const int fs = i < 0 ? frame_size : Fs / 50;
+        uint8_t *o = i < 0 ? out : G.tmp_data + i * lc.bytes_per_frame;
+        const int ob = i < 0 ? out_data_bytes : lc.bytes_per_frame;
+        int r;
+        if (i >= 0 && (failed || ob < 1)) { skip_phases(tm); r = OPUS_INTERNAL_ERROR_; }
+        else r = opus_encode_one(tm, st, gst, S, G, p, fs, o, ob, lc);
+        if (i < 0) {
+            if (r != kLongFrame) return r;
+            i = 0;
+            continue;
+        }
+        if (r < 0) failed = 1;
+        sub_len[i] = r;
+        if (++i == lc.nb_frames) break;
+    }
+    int ret = OPUS_INTERNAL_ERROR_;
+    tm.sync();
+    if (tm.lane() == 0) {
+        if (!failed) {
+            const int repacketize_len = st->use_vbr ? out_data_bytes : imin(3 * st->bitrate_bps / (3 * 8 * 50 / lc.nb_frames), out_data_bytes);
+            const uint8_t *src[3] = {G.tmp_data, G.tmp_data + lc.bytes_per_frame, G.tmp_data + 2 * lc.bytes_per_frame};
+            ret = repacketize_frames(out, repacketize_len, src, sub_len, lc.nb_frames, !st->use_vbr);
+            if (ret < 0) ret = OPUS_INTERNAL_ERROR_;
+        }
+        st->user_forced_mode = lc.bak_mode;
+        st->user_bandwidth = lc.bak_bandwidth;
+        st->force_channels = lc.bak_channels;
+        S.v.ret = ret;
+    }
+    tm.sync();
+    return S.v.ret;
 }
 
 }  // namespace cb

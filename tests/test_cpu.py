@@ -214,6 +214,29 @@ def test_hostsim_encoder_other_api_rates():
                 assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (Fs, ch, ms, br, app)
 
 
+@needs_ref
+def test_hostsim_encoder_long_frames():
+    """40 / 60 ms frames through the repacketizer path, VBR and padded CBR, with and without a tight max_data_bytes."""
+    hs = _hostsim()
+    n = 0
+    for Fs in (48000, 16000):
+        for ch in (1, 2):
+            for ms in (40, 60):
+                for maxb in (1276, 400):
+                    br, vbr, cvbr = ((24000, 1, 1), (64000, 0, 0), (128000, 1, 0), (510000, 1, 0))[n % 4]
+                    fs = Fs * ms // 1000
+                    x = O.test_signal(Fs, ch, 170 + n, ("music", "tone", "clicks", "noise")[n % 4])
+                    n += 1
+                    d, o, l, r = O.encode_stream(x, fs, br, ch, Fs=Fs, vbr=vbr, cvbr=cvbr, complexity=10, max_bytes=maxb)
+                    F = x.shape[0] // fs
+                    out = np.zeros((F, 1276), dtype=np.uint8)
+                    lens = np.zeros(F, dtype=np.int32)
+                    rng = np.zeros(F, dtype=np.uint32)
+                    cfg = np.array([O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, br, vbr, cvbr, 10, maxb, 0, 0], dtype=np.int32)
+                    hs.hostsim_encode_stream(O.ptr(np.ascontiguousarray(x)), F, fs, ch, Fs, O.ptr(cfg), O.ptr(out), 1276, O.ptr(lens), O.ptr(rng))
+                    assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (Fs, ch, ms, br, maxb)
+
+
 def test_encoder_host_api_ctl_and_padding():
     """Host-side half of the encoder C ABI: sizes, init argument checks, ctl set/get round trips and range checks
     (opus-fix/tests/test_opus_api.c encoder section), opus_packet_pad / unpad against the reference's."""

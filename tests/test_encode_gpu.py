@@ -248,3 +248,37 @@ def test_encode_other_api_rates(Fs):
                 assert np.array_equal(rl, l[s_]), ("len", Fs, ch, ms, br, s_)
                 for f in range(F):
                     assert np.array_equal(rd[f, :rl[f]], d[s_, f, :rl[f]]), ("bytes", Fs, ch, ms, br, s_, f)
+
+
+@pytest.mark.parametrize("ms", [40, 60])
+def test_encode_long_frames_repacketized(ms):
+    """40 / 60 ms frames: coded as 2 / 3 forced-configuration 20 ms frames and merged by the
+    repacketizer into code 1 / 2 / 3 packets, CBR ones padded (opus_encoder.c:1362-1438, repacketizer.c:102-227)."""
+    cb = _cb()
+    k = 0
+    for Fs, ch, br, vbr, cvbr, maxb in ((48000, 2, 96000, 1, 0, 1276), (48000, 2, 64000, 0, 0, 1276), (48000, 1, 32000, 1, 1, 1276),
+                                        (48000, 2, 510000, 1, 0, 1276), (48000, 2, 128000, 1, 0, 400), (16000, 2, 48000, 0, 0, 1276)):
+        fs = Fs * ms // 1000
+        pcms = [O.test_signal(Fs * 2, ch, 800 + k + i, kind) for i, kind in enumerate(("music", "tone", "clicks"))]
+        k += 3
+        F = pcms[0].shape[0] // fs
+        enc = cb.EncoderBatch(len(pcms), Fs, ch, bitrate=br, vbr=vbr, cvbr=cvbr, complexity=10)
+        d, l = enc.encode_span(np.concatenate([p[:F * fs] for p in pcms]), F, fs, max_data_bytes=maxb)
+        fr = enc.final_ranges()
+        enc.close()
+        d = d.reshape(len(pcms), F, maxb)
+        l = l.reshape(len(pcms), F)
+        for s_, x in enumerate(pcms):
+            rd, ro, rl, rr = O.encode_stream(x, fs, br, ch, Fs=Fs, vbr=vbr, cvbr=cvbr, complexity=10, max_bytes=maxb)
+            assert np.array_equal(rl, l[s_]), ("len", ms, Fs, ch, br, s_)
+            for f in range(F):
+                assert np.array_equal(rd[ro[f]:ro[f] + rl[f]], d[s_, f, :rl[f]]), ("bytes", ms, Fs, ch, br, s_, f)
+            assert int(rr[-1]) == int(fr[s_])
+        # and our decoder takes the multi-frame packets back (codes 1-3)
+        dec = cb.DecoderBatch(1, Fs, ch)
+        offs = np.arange(F, dtype=np.int64) * maxb
+        out, rets = dec.decode_span(d[0].reshape(-1), offs, l[0], F, fs)
+        dec.close()
+        assert (rets == fs).all()
+        rp, _, _ = O.decode_stream(d[0].reshape(-1), offs, l[0], fs, ch, Fs=Fs)
+        assert np.array_equal(rp, out)
