@@ -69,6 +69,7 @@ struct EncShared {
         } pf;
         int tin[2 * (kMaxFrame + kOverlap)];          // transient_analysis: staged input (int32), rewritten in place as int16
         int fft[kMaxFrame];                            // MDCT: one channel's FFT buffer (all short blocks at once)
+        uint8_t subpackets[3 * 1276];                  // 40/60 ms frames: the coded 20 ms sub-packets, staged for the repacketizer
         struct {                                       // normalised spectrum and what works on it
             int16_t X[2 * kMaxFrame];
             union {
@@ -91,7 +92,6 @@ struct EncGlobal {
     int in[2 * (kMaxFrame + kOverlap)];              // pre-emphasised input + overlap history, per channel
     int pre[2 * (kCombMaxPeriod + kMaxFrame)];       // pre-filter history + new samples, per channel
     int freq[2 * kMaxFrame];                          // MDCT output
-    uint8_t tmp_data[3 * 1276];                       // 40/60 ms frames: the 20 ms sub-packets before repacketisation
 };
 
 // Encoder-side compute_allocation hooks (rate.c:346-364,391-411)

@@ -669,7 +669,8 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     for (;;) {
         const int16_t *p = i < 0 ? pcm : pcm + (size_t)i * channels * (Fs / 50);
         const int fs = i < 0 ? frame_size : Fs / 50;
-        uint8_t *o = i < 0 ? out : G.tmp_data + i * lc.bytes_per_frame;
+        // sub-packets are coded into the TAIL of the caller's slot (nb * bytes_per_frame <= out_data_bytes - 3 by construction)
+        uint8_t *o = i < 0 ? out : out + out_data_bytes - (lc.nb_frames - i) * lc.bytes_per_frame;
         const int ob = i < 0 ? out_data_bytes : lc.bytes_per_frame;
         int r;
         if (i >= 0 && (failed || ob < 1)) { skip_phases(tm); r = OPUS_INTERNAL_ERROR_; }
@@ -685,10 +686,17 @@ CB_DEV int opus_encode_frame(TM tm, CbEncState *st, CbEncState *gst, EncShared &
     }
     int ret = OPUS_INTERNAL_ERROR_;
     tm.sync();
+    // the merged packet is assembled at the front of the same slot: stage the sub-packets in shared memory first
+    uint8_t *stg = S.u.subpackets;
+    {
+        const uint8_t *tail = out + out_data_bytes - lc.nb_frames * lc.bytes_per_frame;
+        CB_TEAM_FOR(k, lc.nb_frames * lc.bytes_per_frame, tm) stg[k] = tail[k];
+    }
+    tm.sync();
     if (tm.lane() == 0) {
         if (!failed) {
             const int repacketize_len = st->use_vbr ? out_data_bytes : imin(3 * st->bitrate_bps / (3 * 8 * 50 / lc.nb_frames), out_data_bytes);
-            const uint8_t *src[3] = {G.tmp_data, G.tmp_data + lc.bytes_per_frame, G.tmp_data + 2 * lc.bytes_per_frame};
+            const uint8_t *src[3] = {stg, stg + lc.bytes_per_frame, stg + 2 * lc.bytes_per_frame};
             ret = repacketize_frames(out, repacketize_len, src, sub_len, lc.nb_frames, !st->use_vbr);
             if (ret < 0) ret = OPUS_INTERNAL_ERROR_;
         }
