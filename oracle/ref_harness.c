@@ -78,6 +78,30 @@ int ref_encode_stream(const int16_t *pcm, int F, int frame_size, int channels, i
     return rc;
 }
 
+/* Encode F frames with a ctl script: before frame f the K (request, value) pairs script[(f*K+k)*2 .. +2) are applied through
+ * opus_encoder_ctl (request 0 = nothing, request OPUS_RESET_STATE takes no value) — the shape of the reference's own encoder fuzz
+ * loop (opus-fix/tests/test_opus_encode.c:236-330), restricted to integer-valued requests. */
+int ref_encode_stream_script(const int16_t *pcm, int F, int frame_size, int channels, int Fs, const ref_enc_cfg *cfg,
+                             const int32_t *script, int K, uint8_t *out, int stride, int32_t *lens, uint32_t *ranges)
+{
+    OpusEncoder *e = make_encoder(Fs, channels, cfg);
+    int f, k;
+    if (!e) return OPUS_ALLOC_FAIL;
+    for (f = 0; f < F; f++) {
+        for (k = 0; k < K; k++) {
+            int req = script[(f * K + k) * 2], val = script[(f * K + k) * 2 + 1];
+            if (req == 0) continue;
+            if (req == OPUS_RESET_STATE) opus_encoder_ctl(e, OPUS_RESET_STATE);
+            else opus_encoder_ctl(e, req, val);
+        }
+        lens[f] = opus_encode(e, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * stride,
+                              cfg->max_bytes < stride ? cfg->max_bytes : stride);
+        if (ranges) opus_encoder_ctl(e, OPUS_GET_FINAL_RANGE(&ranges[f]));
+    }
+    opus_encoder_destroy(e);
+    return 0;
+}
+
 /* Decode F packets of one stream (packed layout).  rets[f] = opus_decode return value. */
 int ref_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F,
                       int frame_size, int channels, int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets)

@@ -93,4 +93,31 @@ int hostsim_encode_stream(const int16_t *pcm, int F, int frame_size, int channel
     free(st);
     return rc;
 }
+// Same with a ctl script (see oracle/ref_harness.c ref_encode_stream_script): K (request, value) pairs before every frame.
+int hostsim_encode_stream_script(const int16_t *pcm, int F, int frame_size, int channels, int Fs, const int *cfg, const int32_t *script, int K,
+                                 uint8_t *out, int stride, int32_t *lens, uint32_t *ranges) {
+    CbEncState *st = (CbEncState *)calloc(1, sizeof(CbEncState));
+    cb::EncShared *S = (cb::EncShared *)calloc(1, sizeof(cb::EncShared));
+    cb::EncGlobal *G = (cb::EncGlobal *)calloc(1, sizeof(cb::EncGlobal));
+    if (cb::enc_state_init(st, Fs, channels, cfg[0]) != 0) return -1;
+    int dummy = 0;
+    cb::enc_ctl(st, 4002, cfg[1], &dummy);
+    cb::enc_ctl(st, 4006, cfg[2], &dummy);
+    cb::enc_ctl(st, 4020, cfg[3], &dummy);
+    cb::enc_ctl(st, 4010, cfg[4], &dummy);
+    cb::SoloTeam tm;
+    for (int f = 0; f < F; f++) {
+        for (int k = 0; k < K; k++) {
+            const int req = script[(f * K + k) * 2], val = script[(f * K + k) * 2 + 1];
+            if (req != 0) cb::enc_ctl(st, req, val, &dummy);
+        }
+        lens[f] = cb::opus_encode_frame(tm, st, st, *S, *G, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * stride,
+                                        cfg[5] < stride ? cfg[5] : stride);
+        if (ranges) ranges[f] = st->rangeFinal;
+    }
+    free(G);
+    free(S);
+    free(st);
+    return 0;
+}
 }

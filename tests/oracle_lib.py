@@ -47,6 +47,8 @@ def ref():
         lib.ref_decode_streams_mt.restype = C.c_double
         lib.ref_decode_streams_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_encode_stream_script.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RefEncCfg), C.c_void_p, C.c_int,
+                                                 C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.ref_encode_streams_mt.restype = C.c_double
         lib.ref_encode_streams_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                               C.POINTER(RefEncCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -136,3 +138,53 @@ def decode_stream(data, offs, lens, frame_size, channels, Fs=48000):
                             ptr(np.ascontiguousarray(lens, dtype=np.int32)), F, frame_size, channels, Fs,
                             ptr(pcm), ptr(ranges), ptr(rets))
     return pcm, ranges, rets
+
+
+def ctl_script(seed, F, channels, K=2, allow_mode=False):
+    """Random encoder ctl changes, K slots before every frame: int32 [F, K, 2] of (request, value); request 0 = nothing.
+    The shape of the reference's own encoder fuzz loop (opus-fix/tests/test_opus_encode.c:236-330)."""
+    rs = np.random.RandomState(seed)
+    script = np.zeros((F, K, 2), dtype=np.int32)
+    for f in range(F):
+        for k in range(K):
+            if rs.rand() >= 0.25:
+                continue
+            c = rs.randint(12)
+            if c == 0:
+                script[f, k] = (4002, int(rs.choice([6000, 12000, 24000, 32000, 48000, 64000, 96000, 128000, 256000, 510000, -1000, -1])))
+            elif c == 1:
+                script[f, k] = (4006, rs.randint(2))
+            elif c == 2:
+                script[f, k] = (4020, rs.randint(2))
+            elif c == 3:
+                script[f, k] = (4010, rs.randint(11))
+            elif c == 4:
+                script[f, k] = (4022, int(rs.choice([1, 2, -1000])) if channels == 2 else -1000)
+            elif c == 5:
+                script[f, k] = (4008, int(rs.choice([-1000, 1101, 1102, 1103, 1104, 1105])))
+            elif c == 6:
+                script[f, k] = (4004, int(rs.choice([1101, 1102, 1103, 1104, 1105])))
+            elif c == 7:
+                script[f, k] = (4014, rs.randint(0, 30))
+            elif c == 8:
+                script[f, k] = (4036, rs.randint(8, 25))
+            elif c == 9:
+                script[f, k] = (4042, rs.randint(2))
+            elif c == 10:
+                script[f, k] = (4024, int(rs.choice([-1000, 3001, 3002])))
+            elif rs.rand() < 0.2:
+                script[f, k] = (4028, 0)
+    return script
+
+
+def encode_stream_script(pcm, frame_size, channels, script, Fs=48000, application=OPUS_APPLICATION_RESTRICTED_LOWDELAY, stride=1276):
+    """Reference encode with a ctl script.  Returns (packets [F, stride], lens, ranges)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    F, K = script.shape[0], script.shape[1]
+    out = np.zeros((F, stride), dtype=np.uint8)
+    lens = np.zeros(F, dtype=np.int32)
+    ranges = np.zeros(F, dtype=np.uint32)
+    cfg = RefEncCfg(application, 64000, 1, 1, 10, stride, 0, 0)
+    ref().ref_encode_stream_script(ptr(pcm), F, frame_size, channels, Fs, C.byref(cfg), ptr(np.ascontiguousarray(script)), K, ptr(out), stride,
+                                   ptr(lens), ptr(ranges))
+    return out, lens, ranges

@@ -32,6 +32,8 @@ def _hostsim():
                                          C.c_void_p, C.c_void_p]
     hs.hostsim_encode_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_void_p]
+    hs.hostsim_encode_stream_script.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_void_p]
     return hs
 
 
@@ -235,6 +237,31 @@ def test_hostsim_encoder_long_frames():
                     cfg = np.array([O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, br, vbr, cvbr, 10, maxb, 0, 0], dtype=np.int32)
                     hs.hostsim_encode_stream(O.ptr(np.ascontiguousarray(x)), F, fs, ch, Fs, O.ptr(cfg), O.ptr(out), 1276, O.ptr(lens), O.ptr(rng))
                     assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (Fs, ch, ms, br, maxb)
+
+
+@needs_ref
+def test_hostsim_encoder_ctl_fuzz_vs_oracle():
+    """Random ctl changes between frames (bitrate incl. AUTO/MAX, VBR / CVBR, complexity, forced channels, bandwidth caps, loss %,
+    LSB depth, prediction, signal type, RESET_STATE) — the reference's own fuzz shape (tests/test_opus_encode.c:236-330), every
+    frame size incl. 40 / 60 ms.  Exercises the hysteresis paths (stereo <-> mono, bandwidth steps, CBR <-> VBR)."""
+    hs = _hostsim()
+    for seed in range(36):
+        ch = 1 + seed % 2
+        fs = (120, 240, 480, 960, 1920, 2880)[seed % 6]
+        F = 100 if fs <= 960 else 30
+        x = O.test_signal(fs * F, ch, seed, ("music", "tone", "clicks", "noise")[seed % 4])
+        script = O.ctl_script(seed, F, ch)
+        rd, rl, rr = O.encode_stream_script(x, fs, ch, script)
+        out = np.zeros((F, 1276), dtype=np.uint8)
+        lens = np.zeros(F, dtype=np.int32)
+        rng = np.zeros(F, dtype=np.uint32)
+        cfg = np.array([O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, 64000, 1, 1, 10, 1276, 0, 0], dtype=np.int32)
+        hs.hostsim_encode_stream_script(O.ptr(np.ascontiguousarray(x)), F, fs, ch, 48000, O.ptr(cfg), O.ptr(np.ascontiguousarray(script)), 2,
+                                        O.ptr(out), 1276, O.ptr(lens), O.ptr(rng))
+        assert np.array_equal(rl, lens), (seed, int(np.nonzero(rl != lens)[0][0]))
+        assert np.array_equal(rr, rng), seed
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], out[f, :rl[f]]), (seed, f)
 
 
 def test_encoder_host_api_ctl_and_padding():

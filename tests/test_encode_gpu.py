@@ -282,3 +282,36 @@ def test_encode_long_frames_repacketized(ms):
         assert (rets == fs).all()
         rp, _, _ = O.decode_stream(d[0].reshape(-1), offs, l[0], fs, ch, Fs=Fs)
         assert np.array_equal(rp, out)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 6, 11])
+def test_scalar_api_ctl_fuzz(seed):
+    """opus_encoder_ctl between opus_encode calls (state round-trips host <-> HBM every frame): random setting changes, the
+    reference's own fuzz shape (tests/test_opus_encode.c:236-330)."""
+    cb = _cb()
+    L = cb.lib()
+    ch = 1 + seed % 2
+    fs = (120, 240, 480, 960, 1920, 2880)[seed % 6]
+    F = 50 if fs <= 960 else 20
+    x = O.test_signal(fs * F, ch, seed, ("music", "tone", "clicks", "noise")[seed % 4])
+    script = O.ctl_script(seed, F, ch)
+    rd, rl, rr = O.encode_stream_script(x, fs, ch, script)
+    err = C.c_int(0)
+    h = C.c_void_p(L.opus_encoder_create(48000, ch, cb.OPUS_APPLICATION_RESTRICTED_LOWDELAY, C.byref(err)))
+    for req, v in ((4002, 64000), (4006, 1), (4020, 1), (4010, 10)):
+        assert L.opus_encoder_ctl(h, req, C.c_int32(v)) == 0
+    out = np.zeros(1276, dtype=np.uint8)
+    v = C.c_uint32(0)
+    for f in range(F):
+        for k in range(script.shape[1]):
+            req, val = int(script[f, k, 0]), int(script[f, k, 1])
+            if req == 4028:
+                L.opus_encoder_ctl(h, req)
+            elif req:
+                L.opus_encoder_ctl(h, req, C.c_int32(val))
+        n = L.opus_encode(h, O.ptr(x[f * fs:(f + 1) * fs]), fs, O.ptr(out), 1276)
+        assert n == rl[f], (seed, f, n, int(rl[f]))
+        assert np.array_equal(out[:n], rd[f, :n]), (seed, f)
+        L.opus_encoder_ctl(h, cb.OPUS_GET_FINAL_RANGE_REQUEST, C.byref(v))
+        assert v.value == int(rr[f]), (seed, f)
+    L.opus_encoder_destroy(h)
