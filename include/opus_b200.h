@@ -99,8 +99,8 @@ void opus_decoder_destroy(OpusDecoder *st);                                     
 
 /* ---- encoder: opus-fix/include/opus.h:171-328, src/opus_encoder.c:150-252,482-510,2007-2507 ----
  * Scope: frames are coded in MODE_CELT_ONLY (OPUS_APPLICATION_RESTRICTED_LOWDELAY, or
- * OPUS_APPLICATION_AUDIO when the reference's own mode decision / OPUS_SET_FORCE_MODE picks CELT), 8-48 kHz, 2.5-20 ms.
- * A frame the reference would code with SILK/hybrid, OPUS_APPLICATION_VOIP and 40/60 ms frames return
+ * OPUS_APPLICATION_AUDIO when the reference's own mode decision / OPUS_SET_FORCE_MODE picks CELT), 8-48 kHz, 2.5-60 ms.
+ * A frame the reference would code with SILK/hybrid and OPUS_APPLICATION_VOIP return
  * OPUS_UNIMPLEMENTED and leave the state untouched. */
 int opus_encoder_get_size(int channels);                                                        /* opus_encoder.c:150 */
 OpusEncoder *opus_encoder_create(opus_int32 Fs, int channels, int application, int *error);     /* opus_encoder.c:482 */
