@@ -48,28 +48,32 @@ CB_DEV_NOINLINE void haar1(int16_t *X, int N0, int stride) {
         }
 }
 
-// deinterleave_hadamard / interleave_hadamard (bands.c:532-579) through the thread scratch.
-CB_DEV_NOINLINE void deinterleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+// deinterleave_hadamard / interleave_hadamard (bands.c:532-579) through the thread scratch (never aliases X).
+CB_DEV_NOINLINE void deinterleave_hadamard(int16_t *__restrict__ X, int16_t *__restrict__ tmp, int N0, int stride, int hadamard) {
     const int N = N0 * stride;
     const uint8_t *ordery = kOrdery + stride - 2;
     CB_NOUNROLL for (int i = 0; i < stride; i++) {
         const int row = hadamard ? ordery[i] : i;
-        CB_NOUNROLL for (int j = 0; j < N0; j++) tmp[row * N0 + j] = X[j * stride + i];
+        int16_t *d = tmp + row * N0;
+        const int16_t *x = X + i;
+        CB_NOUNROLL for (int j = 0; j < N0; j++) d[j] = x[j * stride];
     }
     CB_NOUNROLL for (int p = 0; p < N; p++) X[p] = tmp[p];
 }
-CB_DEV_NOINLINE void interleave_hadamard(int16_t *X, int16_t *tmp, int N0, int stride, int hadamard) {
+CB_DEV_NOINLINE void interleave_hadamard(int16_t *__restrict__ X, int16_t *__restrict__ tmp, int N0, int stride, int hadamard) {
     const int N = N0 * stride;
     const uint8_t *ordery = kOrdery + stride - 2;
     CB_NOUNROLL for (int i = 0; i < stride; i++) {
         const int row = hadamard ? ordery[i] : i;
-        CB_NOUNROLL for (int j = 0; j < N0; j++) tmp[j * stride + i] = X[row * N0 + j];
+        int16_t *d = tmp + i;
+        const int16_t *x = X + row * N0;
+        CB_NOUNROLL for (int j = 0; j < N0; j++) d[j * stride] = x[j];
     }
     CB_NOUNROLL for (int p = 0; p < N; p++) X[p] = tmp[p];
 }
 
 // stereo_merge (bands.c:375-424)
-CB_DEV_NOINLINE void stereo_merge(int16_t *X, int16_t *Y, int mid, int N) {
+CB_DEV_NOINLINE void stereo_merge(int16_t *__restrict__ X, int16_t *__restrict__ Y, int mid, int N) {
     int xp = 0, side = 0;
     CB_NOUNROLL for (int j = 0; j < N; j++) {
         xp = mac16_16(xp, Y[j], X[j]);
@@ -227,10 +231,12 @@ CB_DEV unsigned partition_leaf(BandCtx &ctx, int16_t *X, int N, int b, int B, co
                 }
                 cm = cm_mask;
             } else {
+                int16_t *__restrict__ d = X;
+                const int16_t *__restrict__ src = lowband;
                 CB_NOUNROLL for (int j = 0; j < N; j++) {
                     sd = lcg_rand(sd);
                     int t = (sd & 0x8000) ? 4 : -4;   // QCONST16(1.0f/256, 10)
-                    X[j] = (int16_t)(lowband[j] + t);
+                    d[j] = (int16_t)(src[j] + t);
                 }
                 cm = (unsigned)fill;
             }
@@ -338,7 +344,11 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     if (tf_change > 0) recombine = tf_change;
     if (ctx.dry) lowband = nullptr;
     if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
-        CB_NOUNROLL for (int j = 0; j < N; j++) lowband_scratch[j] = lowband[j];
+        {
+            int16_t *__restrict__ d = lowband_scratch;
+            const int16_t *__restrict__ src = lowband;
+            CB_NOUNROLL for (int j = 0; j < N; j++) d[j] = src[j];
+        }
         lowband = lowband_scratch;
     }
     CB_NOUNROLL for (int k = 0; k < recombine; k++) {
@@ -379,10 +389,26 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     B <<= recombine;
     if (lowband_out) {
         const int n = s16(celt_sqrt(shl32(N0, 22)));
-        CB_NOUNROLL for (int j = 0; j < N0; j++) lowband_out[j] = (int16_t)mul16_16_q15(n, X[j]);
+        int16_t *__restrict__ d = lowband_out;
+        const int16_t *__restrict__ src = X;
+        CB_NOUNROLL for (int j = 0; j < N0; j++) d[j] = (int16_t)mul16_16_q15(n, src[j]);
     }
     cm &= (1u << B) - 1;
     return cm;
+}
+
+// Copy a finished band from the working copy (16-byte aligned) to the IR spectrum: band offsets are multiples of M = 1 << LM
+// int16 and widths multiples of M, the frame's spectrum is 16-byte aligned.
+CB_DEV void store_band(int16_t *g, const int16_t *x, int N, int LM) {
+    if (LM == 3) {
+        CB_NOUNROLL for (int j = 0; j < N; j += 8) *reinterpret_cast<int4 *>(g + j) = *reinterpret_cast<const int4 *>(x + j);
+    } else if (LM == 2) {
+        CB_NOUNROLL for (int j = 0; j < N; j += 4) *reinterpret_cast<int2 *>(g + j) = *reinterpret_cast<const int2 *>(x + j);
+    } else if (LM == 1) {
+        CB_NOUNROLL for (int j = 0; j < N; j += 2) *reinterpret_cast<int *>(g + j) = *reinterpret_cast<const int *>(x + j);
+    } else {
+        CB_NOUNROLL for (int j = 0; j < N; j++) g[j] = x[j];
+    }
 }
 
 // quant_all_bands, decoder (bands.c:1337-1502) with quant_band_stereo (bands.c:1176-1335) folded into the
@@ -390,13 +416,13 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
 CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, uint8_t *collapse_masks, const int *pulses,
                                 int shortBlocks, int spread, int dual_stereo, int intensity, const int *tf_res, int total_bits,
                                 int balance, EcDec &ec_io, int LM, int codedBands, unsigned *seed, int16_t *norm, int16_t *tmp,
-                                bool dry) {
+                                int16_t *xw, int16_t *lbs, bool dry) {
     const int M = 1 << LM;
     const int B = shortBlocks ? M : 1;
     const int C = Y_ != nullptr ? 2 : 1;
     const int norm_offset = M * kEBands[start];
     int16_t *norm2 = norm + M * kEBands[kNbEBands - 1] - norm_offset;
-    int16_t *lowband_scratch = X_ + M * kEBands[kNbEBands - 1];
+    int16_t *lowband_scratch = lbs;
     int lowband_offset = 0;
     int update_lowband = 1;
     BandCtx ctx;
@@ -407,8 +433,10 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
     CB_NOUNROLL for (int i = start; i < end; i++) {
         ctx.i = i;
         const int last = (i == end - 1);
-        int16_t *X = X_ + M * kEBands[i];
-        int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;
+        // The band is decoded in the thread's working copy and stored to the IR once, with the widest stores its alignment
+        // allows: byte-granular read-modify-write of the IR made stage A's L1->L2 write path its busiest unit (profiles/).
+        int16_t *X = xw;
+        int16_t *Y = Y_ != nullptr ? xw + 176 : nullptr;
         const int N = M * kEBands[i + 1] - M * kEBands[i];
         const int tell = (int)ctx.ec.tell_frac();
         if (i != start) balance -= tell;
@@ -549,6 +577,10 @@ CB_DEV void quant_all_bands_dec(int start, int end, int16_t *X_, int16_t *Y_, ui
         }
         if (!dry && (mode == kStereo || mode == kStereoN2) && s.inv)
             CB_NOUNROLL for (int j = 0; j < N; j++) Y[j] = (int16_t)(-Y[j]);
+        if (!dry) {
+            store_band(X_ + M * kEBands[i], X, N, LM);
+            if (Y != nullptr) store_band(Y_ + M * kEBands[i], Y, N, LM);
+        }
         if (npass > 0 && mode != kDual) x_cm = y_cm = cm_acc;
         collapse_masks[i * C + 0] = (uint8_t)x_cm;
         collapse_masks[i * C + C - 1] = (uint8_t)y_cm;

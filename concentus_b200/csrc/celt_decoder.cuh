@@ -15,10 +15,6 @@
 #include "celt_mdct.cuh"
 #include "opus_state.h"
 
-#if !defined(__CUDACC__)
-struct int4 { int x, y, z, w; };   // host simulation stand-in for the CUDA vector type
-#include <cstdint>
-#endif
 
 namespace cb {
 
@@ -26,10 +22,12 @@ namespace cb {
 // Stage A
 // ---------------------------------------------------------------------------------------------------
 
-// Per-thread scratch of stage A, in global memory, contiguous per thread.
+// Per-thread working set of stage A: a local (stack) object of the parse thread.
 struct ParseScratch {
     int16_t norm[2 * 8 * 78];   // folding source
-    int16_t tmp[176];           // pulse vector / hadamard staging
+    alignas(16) int16_t tmp[176];           // pulse vector / hadamard staging
+    alignas(16) int16_t xw[2 * 176];        // the band being decoded, X | Y: worked on here, copied to the IR once per band
+    alignas(16) int16_t lbs[176];           // lowband_scratch
 };
 
 // Parse one received CELT frame (payload of `len` >= 2 bytes).  X: C*N int16 for this frame.  *seed is the
@@ -112,7 +110,7 @@ CB_DEV void celt_parse_frame(const uint8_t *data, int len, int LM, int C, int en
     unsigned sd = *seed;
     quant_all_bands_dec(start, end, X, C == 2 ? X + N : nullptr, ir.collapse, pulses, shortBlocks, spread_decision, dual_stereo,
                         intensity, tf_res, len * (8 << kBitRes) - anti_collapse_rsv, balance, dec, LM, codedBands, &sd, ps.norm,
-                        ps.tmp, dry);
+                        ps.tmp, ps.xw, ps.lbs, dry);
     int anti_collapse_on = 0;
     if (anti_collapse_rsv > 0) anti_collapse_on = (int)dec.bits(1);
     decode_energy_finalise(start, end, fine_quant, fine_priority, len * 8 - dec.tell(), dec, C, ir.eoff);

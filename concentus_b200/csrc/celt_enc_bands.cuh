@@ -282,6 +282,33 @@ CB_DEV bool pvq_better(const PvqBest &a, const PvqBest &b) {
     return l > r || (l == r && a.id < b.id);
 }
 
+// Position the sequential scan of vq.c:265-294 selects, given every lane's own best (sentinel num < 0, den = 0 on lanes without
+// a position).  SoloTeam: the lane's best is the answer.
+CB_DEV int pvq_pick(SoloTeam, const PvqBest &best, int) { return best.id; }
+#if defined(__CUDACC__)
+// WarpTeam: a float estimate of num/den picks a provisional winner with one redux.max; its (num, den) are then compared
+// EXACTLY (the reference's cross-multiplication) on every lane.  No lane strictly better: the winner is the lowest id among the
+// exact ties (one redux.min).  Otherwise (the estimate mis-ordered two near-equal ratios) the exact shuffle tree decides.
+CB_DEV int pvq_pick(WarpTeam tm, PvqBest best, int levels) {
+    const unsigned full = 0xffffffffu;
+    const unsigned key = best.den > 0 ? __float_as_uint(__fdividef((float)best.num, (float)best.den)) + 1u : 0u;
+    const unsigned kmax = __reduce_max_sync(full, key);
+    const int m = __ffs((int)__ballot_sync(full, key == kmax)) - 1;
+    const int num_m = __shfl_sync(full, best.num, m), den_m = __shfl_sync(full, best.den, m);
+    const int l = mul16_16(den_m, best.num), r = mul16_16(best.den, num_m);
+    if (__ballot_sync(full, l > r) == 0u)
+        return (int)__reduce_min_sync(full, l == r && best.den > 0 ? (unsigned)best.id : 0x7fffffffu);
+    CB_NOUNROLL for (int lv = 0; lv < levels; lv++) {
+        PvqBest o;
+        o.num = tm.shfl_xor(best.num, 1 << lv);
+        o.den = tm.shfl_xor(best.den, 1 << lv);
+        o.id = tm.shfl_xor(best.id, 1 << lv);
+        if (pvq_better(o, best)) best = o;
+    }
+    return tm.bcast(best.id, 0);
+}
+#endif
+
 // alg_quant (vq.c:161-325), no resynthesis.  The greedy search is the encoder's hottest loop (profiles/): every lane scans its
 // share of the N positions in increasing order with the reference's strict '>' test (first maximum wins), then a shuffle tree
 // takes the best of the lanes with ties going to the lower index — the same element the sequential scan selects, because with
@@ -332,14 +359,7 @@ CB_DEV_NOINLINE void alg_quant_small(TM tm, int16_t *X, int N, int K, EcEnc &enc
             best.den = s16(yy + yj);
             best.num = s16(mul16_16_q15(Rxy, Rxy));
         }
-        CB_NOUNROLL for (int l = 0; l < levels; l++) {
-            PvqBest o;
-            o.num = tm.shfl_xor(best.num, 1 << l);
-            o.den = tm.shfl_xor(best.den, 1 << l);
-            o.id = tm.shfl_xor(best.id, 1 << l);
-            if (pvq_better(o, best)) best = o;
-        }
-        const int best_id = tm.bcast(best.id, 0);
+        const int best_id = pvq_pick(tm, best, levels);
         xy = wadd(xy, tm.bcast(xj, best_id));
         yy = s16(yy + tm.bcast(yj, best_id));
         if (j == best_id) {
@@ -427,14 +447,7 @@ CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int 
                 best.id = j;
             }
         }
-        CB_NOUNROLL for (int l = 0; l < levels; l++) {
-            PvqBest o;
-            o.num = tm.shfl_xor(best.num, 1 << l);
-            o.den = tm.shfl_xor(best.den, 1 << l);
-            o.id = tm.shfl_xor(best.id, 1 << l);
-            if (pvq_better(o, best)) best = o;
-        }
-        const int best_id = tm.bcast(best.id, 0);
+        const int best_id = pvq_pick(tm, best, levels);
         xy = wadd(xy, X[best_id]);
         yy = s16(yy + y[best_id]);
         tm.sync();

@@ -5,7 +5,7 @@
 // extract_collapse_mask, alg_unquant, renormalise_vector).
 //
 // Stage A code: scalar, executed by the one thread that owns the frame; vectors are int16 arrays in
-// that thread's private scratch (global memory, contiguous per thread, L1-resident lines).
+// that thread's local memory (ParseScratch).
 // renormalise_vector is also used by stage B (anti-collapse) and is therefore team-templated.
 #pragma once
 #include "celt_ec.cuh"
@@ -129,7 +129,7 @@ CB_DEV void unit_gain(int E, int gain, int &g, int &k) {
 
 // alg_unquant (vq.c:329-346) = decode_pulses + normalise_residual + exp_rotation + extract_collapse_mask.
 // `iy` is scratch for >= N int16.
-CB_DEV unsigned alg_unquant(int16_t *X, int N, int K, int spread, int B, EcDec &dec, int gain, int16_t *iy) {
+CB_DEV unsigned alg_unquant(int16_t *__restrict__ X, int N, int K, int spread, int B, EcDec &dec, int gain, int16_t *__restrict__ iy) {
     unsigned idx = dec.uint_(pvq_v(N, K));
     int Ryy = pvq_decode_index(N, K, idx, iy);
     int g, k;
@@ -144,11 +144,12 @@ CB_DEV unsigned alg_unquant(int16_t *X, int N, int K, int spread, int B, EcDec &
         int i = 0;
         CB_NOUNROLL for (int blk = 0; blk < B; blk++) {
             int any = 0;
-            CB_NOUNROLL for (int j = 0; j < N0; j++, i++) {
-                int v = iy[i];
+            CB_NOUNROLL for (int j = 0; j < N0; j++) {
+                int v = iy[i + j];
                 any |= v;
-                X[i] = (int16_t)pshr32(mul16_16(g, v), k + 1);
+                X[i + j] = (int16_t)pshr32(mul16_16(g, v), k + 1);
             }
+            i += N0;
             mask |= (unsigned)(any != 0) << blk;
         }
         CB_NOUNROLL for (; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);

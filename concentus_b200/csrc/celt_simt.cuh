@@ -36,6 +36,8 @@
 #define CB_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
 #define CB_MATH static inline
 #define CB_NOUNROLL
+struct int4 { int x, y, z, w; };   // host simulation stand-ins for the CUDA vector types
+struct int2 { int x, y; };
 #endif
 
 namespace cb {

@@ -70,13 +70,16 @@ struct IrView {
 // launch for the very first packet of a stream).
 __global__ void __launch_bounds__(CB_PARSE_THREADS, CB_PARSE_MINBLOCKS)
 parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, const int64_t *offs, const int32_t *lens, int n, int F,
-             int f0, int f1, int call_f0, int R, int cap, int decode_fec, IrView ir, ParseScratch *scratch) {
+             int f0, int f1, int call_f0, int R, int cap, int decode_fec, IrView ir) {
     const int runs = (f1 - f0 + R - 1) / R;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * runs) return;
     const int s = t / runs, r = t - s * runs;
     const CbDecState *st = pool + slots[s];
-    ParseScratch &ps = scratch[t];
+    // Thread-local working set (5.6 KB of local memory: lane-interleaved, write-back in L1).  As per-thread rows of a global
+    // array the same data made every 2-byte store a 32-byte write-through to L2: 251 GB of L1->L2 writes per 2.4 GB of output,
+    // the L1->crossbar request path 52 % busy (profiles/r1_dec_v4_parse_kernel); local: parse 186 -> 114 ms per chunk.
+    ParseScratch ps;
     const int first = f0 + r * R;
     const int last = first + R < f1 ? first + R : f1;
     opus_parse_run(st, data, offs + (size_t)s * F, lens + (size_t)s * F, call_f0, first, last, cap, decode_fec, ir.kmax, ir.xstride,
@@ -239,7 +242,7 @@ struct Ctx {
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
     DevBuf d_slots, d_data, d_offs, d_lens, d_pcm[2], d_rets, d_stage;
-    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_scratch, d_plc;
+    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_plc;
     size_t ir_budget = (size_t)16 << 30;  // bytes of IR + staging per chunk buffer (env CB200_IR_MB)
     int run_len = 3;                      // packets per stage-A thread (env CB200_RUN)
     PinBuf h_stage, h_slots, h_misc;
@@ -493,9 +496,7 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs) {
             !g.d_range[b].reserve(slots * sizeof(CbSigRange)))
             return false;
     }
-    const size_t threads = (size_t)n * ((pl.Fc + pl.R - 1) / pl.R);
-    if (!g.d_plc.reserve((size_t)n * sizeof(PlcScratch))) return false;   // concealment scratch, one per stream (lost frames only)
-    return g.d_scratch.reserve(threads * sizeof(ParseScratch));
+    return g.d_plc.reserve((size_t)n * sizeof(PlcScratch));   // concealment scratch, one per stream (lost frames only)
 }
 
 IrView ir_view(const Plan &pl, int b) {
@@ -523,7 +524,7 @@ void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_d
     if (c >= 2) cudaStreamWaitEvent(g.parse_stream, g.ev_synth[b], 0);
     timing_begin(0, g.parse_stream);
     parse_kernel<<<(unsigned)((threads + CB_PARSE_THREADS - 1) / CB_PARSE_THREADS), CB_PARSE_THREADS, 0, g.parse_stream>>>(
-        g.pool, d_slots, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v, (ParseScratch *)g.d_scratch.p);
+        g.pool, d_slots, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v);
     timing_end(g.parse_stream);
     cudaEventRecord(g.ev_parse[b], g.parse_stream);
     // stage B(c): after A(c); its staging buffer b must have been drained by C(c-2)

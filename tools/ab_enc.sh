@@ -1,0 +1,7 @@
+#!/bin/bash
+# Dev tool: A/B the encoder kernel over library variants in build_variants/ (run on the GPU box via gpurun).
+# usage: tools/ab_enc.sh variant...     ("cur" = the in-tree library)
+for v in "$@"; do
+  if [ "$v" = cur ]; then lib=/root/repo/concentus_b200/libconcentus_b200.so; else lib=/root/repo/build_variants/$v.so; fi
+  echo "$v: $(CB200_LIB=$lib python tools/enc_bench.py 4096 50 2>&1 | grep -E 'rep 2|parity' | tr '\n' ' ')"
+done
