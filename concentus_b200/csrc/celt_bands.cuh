@@ -202,9 +202,23 @@ CB_DEV unsigned quant_band_n1(BandCtx &ctx, int16_t *X, int16_t *Y, int16_t *low
     return 1;
 }
 
-// One leaf of the partition tree (bands.c:989-1036): PVQ decode, or fill when no pulse was affordable.
-CB_DEV unsigned partition_leaf(BandCtx &ctx, int16_t *X, int N, int b, int B, const int16_t *lowband, int LM, int gain, int fill) {
-    unsigned cm = 0;
+// A leaf of the partition tree, recorded by the walker and executed afterwards.  The symbol walk (range decoder, bit
+// accounting) diverges between the lanes of a warp — every lane parses another frame — but none of it depends on spectrum
+// values: a leaf's PVQ index is read during the walk, while its pulse vector (cwrsi), normalisation, rotation, or its fold /
+// noise fill run in quant_band's leaf loop, which all lanes of the warp enter together (profiles/r1_dec_v5: cwrsi and the
+// rotation ran with 5 of 32 lanes when executed from inside the walk).
+struct LeafRec {
+    int16_t *X;
+    const int16_t *lowband;   // fold source (kind kLeafFold)
+    unsigned idx;             // PVQ codeword (kind kLeafPvq)
+    int16_t N, K, B, gain, fill;
+    uint8_t kind, shift;      // shift: position of this leaf's collapse bits in the band's mask
+};
+enum { kLeafPvq, kLeafZero, kLeafNoise, kLeafFold, kMaxLeaves = 16 };   // <= 2^(maxLM+1) leaves per quant_band
+
+// One leaf of the partition tree (bands.c:989-1036), walk half: pulse count, bit accounting, the PVQ index.
+CB_DEV void partition_leaf(BandCtx &ctx, LeafRec *leaves, int &nleaves, int16_t *X, int N, int b, int B, const int16_t *lowband, int LM,
+                           int gain, int fill, int shift) {
     int q = bits2pulses(ctx.i, LM, b);
     int curr_bits = pulses2bits(ctx.i, LM, q);
     ctx.remaining_bits -= curr_bits;
@@ -214,56 +228,76 @@ CB_DEV unsigned partition_leaf(BandCtx &ctx, int16_t *X, int N, int b, int B, co
         curr_bits = pulses2bits(ctx.i, LM, q);
         ctx.remaining_bits -= curr_bits;
     }
+    unsigned idx = 0;
+    int K = 0, kind;
     if (q != 0) {
-        if (ctx.dry) { const int K = get_pulses(q); (void)ctx.ec.uint_(pvq_v(N, K)); return 0; }
-        cm = alg_unquant(X, N, get_pulses(q), ctx.spread, B, ctx.ec, gain, ctx.tmp);
-    } else if (!ctx.dry) {
-        const unsigned cm_mask = (1u << B) - 1;
-        fill &= (int)cm_mask;
-        if (!fill) {
-            CB_NOUNROLL for (int j = 0; j < N; j++) X[j] = 0;
-        } else {
-            unsigned sd = ctx.seed;
-            if (lowband == nullptr) {
-                CB_NOUNROLL for (int j = 0; j < N; j++) {
-                    sd = lcg_rand(sd);
-                    X[j] = (int16_t)((int)sd >> 20);
-                }
-                cm = cm_mask;
-            } else {
-                int16_t *__restrict__ d = X;
-                const int16_t *__restrict__ src = lowband;
-                CB_NOUNROLL for (int j = 0; j < N; j++) {
-                    sd = lcg_rand(sd);
-                    int t = (sd & 0x8000) ? 4 : -4;   // QCONST16(1.0f/256, 10)
-                    d[j] = (int16_t)(src[j] + t);
-                }
-                cm = (unsigned)fill;
-            }
-            ctx.seed = sd;
-            renormalise_vector(SoloTeam{}, X, N, gain);
-        }
+        K = get_pulses(q);
+        idx = ctx.ec.uint_(pvq_v(N, K));
+        kind = kLeafPvq;
+    } else {
+        fill &= (1 << B) - 1;
+        kind = !fill ? kLeafZero : lowband == nullptr ? kLeafNoise : kLeafFold;
     }
-    return cm;
+    if (ctx.dry) return;
+    LeafRec &r = leaves[nleaves++];
+    r.X = X; r.lowband = lowband; r.idx = idx;
+    r.N = (int16_t)N; r.K = (int16_t)K; r.B = (int16_t)B; r.gain = (int16_t)gain; r.fill = (int16_t)fill;
+    r.kind = (uint8_t)kind; r.shift = (uint8_t)shift;
+}
+
+// Execute half (vq.c:329-346 alg_unquant after the index is known; bands.c:1005-1036 for the fills): returns the leaf's
+// collapse mask at its position in the band's mask.
+CB_DEV unsigned run_leaf(const LeafRec &r, int spread, unsigned &seed) {
+    int16_t *X = r.X;
+    const int N = r.N, B = r.B, gain = r.gain;
+    unsigned cm;
+    if (r.kind == kLeafPvq) {
+        cm = alg_unquant_idx(X, N, r.K, spread, B, r.idx, gain);
+    } else if (r.kind == kLeafZero) {
+        CB_NOUNROLL for (int j = 0; j < N; j++) X[j] = 0;
+        cm = 0;
+    } else {
+        unsigned sd = seed;
+        if (r.kind == kLeafNoise) {
+            CB_NOUNROLL for (int j = 0; j < N; j++) {
+                sd = lcg_rand(sd);
+                X[j] = (int16_t)((int)sd >> 20);
+            }
+            cm = (1u << B) - 1;
+        } else {
+            int16_t *__restrict__ d = X;
+            const int16_t *__restrict__ src = r.lowband;
+            CB_NOUNROLL for (int j = 0; j < N; j++) {
+                sd = lcg_rand(sd);
+                int t = (sd & 0x8000) ? 4 : -4;   // QCONST16(1.0f/256, 10)
+                d[j] = (int16_t)(src[j] + t);
+            }
+            cm = (unsigned)r.fill;
+        }
+        seed = sd;
+        renormalise_vector(SoloTeam{}, X, N, gain);
+    }
+    return cm << r.shift;
 }
 
 // quant_partition (bands.c:864-1040) as an explicit walker.  A frame holds the arguments of one call and,
-// once it has split, what the reference keeps in locals across its two recursive calls.
+// once it has split, what the reference keeps in locals across its two recursive calls.  The collapse mask of a split is
+// cm(mid) | cm(side) << (B0 >> 1) (bands.c:975-985), so a leaf's bits land at the sum of its side-branch shifts.
 struct PartFrame {
     int16_t *X, *lowband;
-    int N, b, B, LM, gain, fill;
+    int N, b, B, LM, gain, fill, shift;
     // after a split:
     int16_t *Y, *lowband2;
-    int B0, mbits, sbits, itheta, rebalance0, gmid, gside, cm, mid_first;
+    int B0, mbits, sbits, itheta, rebalance0, gmid, gside, mid_first;
     int stage;   // 0 = entered, 1 = first child returned, 2 = second child returned
 };
 
-CB_DEV unsigned quant_partition(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int gain, int fill) {
+CB_DEV void quant_partition(BandCtx &ctx, LeafRec *leaves, int &nleaves, int16_t *X, int N, int b, int B, int16_t *lowband, int LM, int gain,
+                            int fill) {
     PartFrame st[5];
     int sp = 0;
     st[0].X = X; st[0].lowband = lowband; st[0].N = N; st[0].b = b; st[0].B = B; st[0].LM = LM; st[0].gain = gain;
-    st[0].fill = fill; st[0].stage = 0;
-    unsigned ret = 0;
+    st[0].fill = fill; st[0].shift = 0; st[0].stage = 0;
     while (sp >= 0) {
         PartFrame &f = st[sp];
         if (f.stage == 0) {
@@ -299,36 +333,31 @@ CB_DEV unsigned quant_partition(BandCtx &ctx, int16_t *X, int N, int b, int B, i
                 f.mid_first = mbits >= sbits;
                 PartFrame &c = st[sp + 1];
                 c.N = n; c.B = Bn; c.LM = lm; c.stage = 0;
-                if (f.mid_first) { c.X = f.X; c.lowband = f.lowband; c.b = mbits; c.gain = f.gmid; c.fill = fl; }
-                else { c.X = f.Y; c.lowband = f.lowband2; c.b = sbits; c.gain = f.gside; c.fill = fl >> Bn; }
+                if (f.mid_first) { c.X = f.X; c.lowband = f.lowband; c.b = mbits; c.gain = f.gmid; c.fill = fl; c.shift = f.shift; }
+                else { c.X = f.Y; c.lowband = f.lowband2; c.b = sbits; c.gain = f.gside; c.fill = fl >> Bn; c.shift = f.shift + (B0 >> 1); }
                 sp++;
             } else {
-                ret = partition_leaf(ctx, f.X, f.N, f.b, f.B, f.lowband, f.LM, f.gain, f.fill);
+                partition_leaf(ctx, leaves, nleaves, f.X, f.N, f.b, f.B, f.lowband, f.LM, f.gain, f.fill, f.shift);
                 sp--;
             }
         } else if (f.stage == 1) {
             PartFrame &c = st[sp + 1];
             c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
             if (f.mid_first) {
-                f.cm = (int)ret;
                 int rebalance = f.mbits - (f.rebalance0 - ctx.remaining_bits);
                 if (rebalance > 3 << kBitRes && f.itheta != 0) f.sbits += rebalance - (3 << kBitRes);
-                c.X = f.Y; c.lowband = f.lowband2; c.b = f.sbits; c.gain = f.gside; c.fill = f.fill >> f.B;
+                c.X = f.Y; c.lowband = f.lowband2; c.b = f.sbits; c.gain = f.gside; c.fill = f.fill >> f.B; c.shift = f.shift + (f.B0 >> 1);
             } else {
-                f.cm = (int)(ret << (f.B0 >> 1));
                 int rebalance = f.sbits - (f.rebalance0 - ctx.remaining_bits);
                 if (rebalance > 3 << kBitRes && f.itheta != 16384) f.mbits += rebalance - (3 << kBitRes);
-                c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gmid; c.fill = f.fill;
+                c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gmid; c.fill = f.fill; c.shift = f.shift;
             }
             f.stage = 2;
             sp++;
         } else {
-            if (f.mid_first) ret = (unsigned)f.cm | (ret << (f.B0 >> 1));
-            else ret = (unsigned)f.cm | ret;
             sp--;
         }
     }
-    return ret;
 }
 
 // quant_band (bands.c:1044-1170)
@@ -369,8 +398,16 @@ CB_DEV unsigned quant_band(BandCtx &ctx, int16_t *X, int N, int b, int B, int16_
     N_B0 = N_B;
     if (B0 > 1 && lowband) deinterleave_hadamard(lowband, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);
 
-    cm = quant_partition(ctx, X, N, b, B, lowband, LM, gain, fill);
+    LeafRec leaves[kMaxLeaves];
+    int nleaves = 0;
+    quant_partition(ctx, leaves, nleaves, X, N, b, B, lowband, LM, gain, fill);
     if (ctx.dry) return 0;
+    // the leaf loop: every lane of the warp that decodes this band arrives here together
+    {
+        unsigned sd = ctx.seed;
+        CB_NOUNROLL for (int l = 0; l < nleaves; l++) cm |= run_leaf(leaves[l], ctx.spread, sd);
+        ctx.seed = sd;
+    }
 
     // resynthesis (decoder): undo the reorganisation
     if (B0 > 1) interleave_hadamard(X, ctx.tmp, N_B >> recombine, B0 << recombine, longBlocks);

@@ -127,32 +127,30 @@ CB_DEV void unit_gain(int E, int gain, int &g, int &k) {
     g = s16(mul16_16_p15(celt_rsqrt_norm(t), gain));
 }
 
-// alg_unquant (vq.c:329-346) = decode_pulses + normalise_residual + exp_rotation + extract_collapse_mask.
-// `iy` is scratch for >= N int16.
-CB_DEV unsigned alg_unquant(int16_t *__restrict__ X, int N, int K, int spread, int B, EcDec &dec, int gain, int16_t *__restrict__ iy) {
-    unsigned idx = dec.uint_(pvq_v(N, K));
-    int Ryy = pvq_decode_index(N, K, idx, iy);
+// alg_unquant (vq.c:329-346) once the codeword is known = cwrsi + normalise_residual + exp_rotation + extract_collapse_mask.
+// The pulse vector is decoded straight into X and scaled in place.
+CB_DEV unsigned alg_unquant_idx(int16_t *X, int N, int K, int spread, int B, unsigned idx, int gain) {
+    int Ryy = pvq_decode_index(N, K, idx, X);
     int g, k;
     unit_gain(Ryy, gain, g, k);
     // normalise_residual (vq.c:117-136) fused with extract_collapse_mask (vq.c:139-157)
     unsigned mask = 0;
     if (B <= 1) {
-        CB_NOUNROLL for (int i = 0; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);
+        CB_NOUNROLL for (int i = 0; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, X[i]), k + 1);
         mask = 1;
     } else {
         const int N0 = (int)udiv((unsigned)N, (unsigned)B);
         int i = 0;
         CB_NOUNROLL for (int blk = 0; blk < B; blk++) {
             int any = 0;
-            CB_NOUNROLL for (int j = 0; j < N0; j++) {
-                int v = iy[i + j];
+            CB_NOUNROLL for (int j = 0; j < N0; j++, i++) {
+                int v = X[i];
                 any |= v;
-                X[i + j] = (int16_t)pshr32(mul16_16(g, v), k + 1);
+                X[i] = (int16_t)pshr32(mul16_16(g, v), k + 1);
             }
-            i += N0;
             mask |= (unsigned)(any != 0) << blk;
         }
-        CB_NOUNROLL for (; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, iy[i]), k + 1);
+        CB_NOUNROLL for (; i < N; i++) X[i] = (int16_t)pshr32(mul16_16(g, X[i]), k + 1);
     }
     exp_rotation_dec(X, N, B, K, spread);
     return mask;
