@@ -211,6 +211,10 @@ CB_MATH int bitexact_log2tan(int isin, int icos) {
 
 // celt_lcg_rand (celt/bands.c:63-66)
 CB_DEV unsigned lcg_rand(unsigned seed) { return 1664525u * seed + 1013904223u; }
+// k steps of the generator at once, k <= 22 (the widest band at LM 0): x -> kLcgMul[k] * x + kLcgAdd[k]  (mod 2^32)
+CB_TABLE uint32_t kLcgMul[23] = {1u, 1664525u, 389569705u, 2940799637u, 158984081u, 2862450781u, 3211393721u, 1851289957u, 3934847009u, 2184914861u, 246739401u, 1948736821u, 2941245873u, 4195587069u, 4088025561u, 980655621u, 2001863745u, 657792333u, 65284841u, 1282409429u, 3808694225u, 2968195997u, 2417331449u};
+CB_TABLE uint32_t kLcgAdd[23] = {0u, 1013904223u, 1196435762u, 3519870697u, 2868466484u, 1649599747u, 2670642822u, 1476291629u, 2748932008u, 2180890343u, 2498801434u, 3421909937u, 3167820124u, 2636375307u, 3801544430u, 28987765u, 2210837584u, 3039689583u, 1338634754u, 1649346937u, 2768872580u, 2254235155u, 2326606934u};
+CB_DEV unsigned lcg_jump(unsigned seed, int k) { return kLcgMul[k] * seed + kLcgAdd[k]; }
 
 // celt_udiv / celt_sudiv are plain divisions in this build (celt/entcode.h:131-160).
 CB_DEV unsigned udiv(unsigned n, unsigned d) { return n / d; }

@@ -665,11 +665,12 @@ CB_DEV void anti_collapse(TM tm, int16_t *X_, const uint8_t *collapse_masks, int
             const unsigned mask = collapse_masks[i * C + c];
             CB_NOUNROLL for (int k = 0; k < 1 << LM; k++) {
                 if (!(mask & (1u << k))) {
-                    // every lane steps the generator so the seed stays team-uniform; lane j%W stores slot j
-                    CB_NOUNROLL for (int j = 0; j < N0; j++) {
-                        seed = lcg_rand(seed);
-                        if ((j % TM::W) == tm.lane()) X[(j << LM) + k] = (int16_t)((seed & 0x8000) ? r : -r);
+                    // sample j takes the generator's (j+1)-th step: an affine jump per lane instead of N0 steps on every lane
+                    CB_TEAM_FOR(j, N0, tm) {
+                        const unsigned sj = lcg_jump(seed, j + 1);
+                        X[(j << LM) + k] = (int16_t)((sj & 0x8000) ? r : -r);
                     }
+                    seed = lcg_jump(seed, N0);
                     renormalize = 1;
                 }
             }

@@ -245,6 +245,22 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
 template <class TM>
 CB_DEV void history_shift(TM tm, int *mem, int N, int count = -1) {
     if (count < 0) count = kDecBuf - N + kOverlap / 2;
+    if (((count | N) & 3) == 0) {
+        // 16-byte vectors, two per lane and step (the history is 16-byte aligned in the state; N is a multiple of 120)
+        int4 *m4 = reinterpret_cast<int4 *>(mem);
+        const int nv = count >> 2, sh = N >> 2;
+        CB_NOUNROLL for (int base = 0; base < nv; base += 2 * TM::W) {
+            const int i0 = base + tm.lane(), i1 = i0 + TM::W;
+            int4 a = {0, 0, 0, 0}, b = {0, 0, 0, 0};
+            if (i0 < nv) a = m4[i0 + sh];
+            if (i1 < nv) b = m4[i1 + sh];
+            tm.sync();
+            if (i0 < nv) m4[i0] = a;
+            if (i1 < nv) m4[i1] = b;
+        }
+        tm.sync();
+        return;
+    }
     CB_NOUNROLL for (int base = 0; base < count; base += TM::W) {
         int i = base + tm.lane();
         int v = 0;
@@ -406,6 +422,14 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
         int *dst = sig[c];
         CB_TEAM_FOR(j, N, tm) dst[j] = src[j];
     }
+            for (int u = 0; u < 4; u++) { const int j = base + u * TM::W + tm.lane(); if (j < nv) v[u] = src[j]; }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+            for (int u = 0; u < 4; u++) { const int j = base + u * TM::W + tm.lane(); if (j < nv) dst[j] = v[u]; }
+        }
+    }
+#endif
     tm.sync();
     if (ir.flags & CB_IR_OVERRUN) return OPUS_INTERNAL_ERROR_;
     return N / st->downsample;
