@@ -422,14 +422,6 @@ CB_DEV int celt_synth_frame(TM tm, CbDecState *st, SynthScratch &S, const CbFram
         int *dst = sig[c];
         CB_TEAM_FOR(j, N, tm) dst[j] = src[j];
     }
-            for (int u = 0; u < 4; u++) { const int j = base + u * TM::W + tm.lane(); if (j < nv) v[u] = src[j]; }
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-            for (int u = 0; u < 4; u++) { const int j = base + u * TM::W + tm.lane(); if (j < nv) dst[j] = v[u]; }
-        }
-    }
-#endif
     tm.sync();
     if (ir.flags & CB_IR_OVERRUN) return OPUS_INTERNAL_ERROR_;
     return N / st->downsample;
