@@ -59,10 +59,10 @@ struct EncWarpSmem {
 };
 
 // One warp per stream, frames 0..F-1 in order.  PCM of frame (s,f): pcm[(s*F+f)*frame_size*channels]; packet slot:
-// data[(s*F+f)*stride], at most max_bytes are written; rets[s*F+f] = packet length or error.
+// data[(s*F+f)*stride], at most max_bytes are written; rets[s*F+f] = packet length or error.  One launch codes frames [f0, f1).
 __global__ void __launch_bounds__(CB_ENC_WPB * 32, CB_ENC_MINBLOCKS)
 encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const int16_t *pcm, uint8_t *data, int *rets, int n, int F,
-                   int frame_size, int max_bytes, int stride) {
+                   int f0, int f1, int frame_size, int max_bytes, int stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_ENC_WPB + warp;
@@ -70,7 +70,7 @@ encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const
 #if defined(CB_PHASE_SYNC)
         {
             WarpTeam idle{lane};
-            for (int f = 0; f < F * kEncPhases; f++) idle.phase();   // keep the block's phase barriers balanced
+            for (int f = 0; f < (f1 - f0) * kEncPhases; f++) idle.phase();   // keep the block's phase barriers balanced
         }
 #endif
         return;
@@ -83,7 +83,7 @@ encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const
     EncGlobal &G = scratch[s];
     const int channels = st->channels;
     WarpTeam tm{lane};
-    for (int f = 0; f < F; f++) {
+    for (int f = f0; f < f1; f++) {
         const size_t k = (size_t)s * F + f;
         const int r = opus_encode_frame(tm, st, gst, W.S, G, pcm + k * frame_size * channels, frame_size, data + k * stride, max_bytes);
         if (lane == 0) rets[k] = r;
@@ -142,8 +142,10 @@ struct PinBuf {
 struct EncCtx {
     std::mutex mu;
     bool tried = false, ok = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    enum { kMaxSub = 8 };
+    cudaEvent_t ev_in[kMaxSub] = {}, ev_done[kMaxSub] = {}, ev_prev = nullptr;
     CbEncState *pool = nullptr;
     int pool_cap = 0;
     std::vector<SlotInfo> reg;
@@ -164,8 +166,14 @@ bool ctx_init_locked() {
     if (dev < 0) return false;
     if (cudaSetDevice(dev) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     cudaEventCreate(&e.ev0);
     cudaEventCreate(&e.ev1);
+    for (int i = 0; i < EncCtx::kMaxSub; i++) {
+        cudaEventCreateWithFlags(&e.ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e.ev_done[i], cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&e.ev_prev, cudaEventDisableTiming);
     if (!e.h_stage.reserve(sizeof(CbEncState) * kStageStates) || !e.d_stage.reserve(sizeof(CbEncState) * kStageStates)) return false;
     cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CB_ENC_WPB * sizeof(EncWarpSmem)));
 #ifndef CB_ENC_CARVEOUT
@@ -317,12 +325,16 @@ int check_span(OpusEncoder **st, int n) {
     return OPUS_OK;
 }
 
+void launch_frames(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int f0, int f1, int frame_size,
+                   int max_bytes, int stride) {
+    encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, CB_ENC_WPB * sizeof(EncWarpSmem), e.stream>>>(
+        e.pool, d_slots, (EncGlobal *)e.d_scratch.p, d_pcm, d_data, d_rets, n, F, f0, f1, frame_size, max_bytes, stride);
+    e.launches++;
+}
 void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int frame_size, int max_bytes, int stride) {
     cudaEventRecord(e.ev0, e.stream);
-    encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, CB_ENC_WPB * sizeof(EncWarpSmem), e.stream>>>(e.pool, d_slots, (EncGlobal *)e.d_scratch.p, d_pcm, d_data,
-                                                                                           d_rets, n, F, frame_size, max_bytes, stride);
+    launch_frames(d_slots, d_pcm, d_data, d_rets, n, F, 0, F, frame_size, max_bytes, stride);
     cudaEventRecord(e.ev1, e.stream);
-    e.launches++;
 }
 
 int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, int frame_size, uint8_t *data, int max_bytes, int stride,
@@ -341,12 +353,41 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
         !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n))
         return OPUS_ALLOC_FAIL;
     cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
-    cudaMemcpyAsync(e.d_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, e.stream);
-    launch_span((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, frame_size, max_bytes, stride);
-    cudaMemcpyAsync(data, e.d_data.p, NF * stride, cudaMemcpyDeviceToHost, e.stream);
+    // Large spans are cut into up to kMaxSub sub-spans of frames: the PCM of sub-span k+1 goes up and the packets of sub-span
+    // k-1 come down on the copy stream while sub-span k is coded (the state stays resident between the launches).
+    int nsub = 1;
+    if (pcm_bytes >= ((size_t)32 << 20)) nsub = F / 8 < 1 ? 1 : (F / 8 > 5 ? 5 : F / 8);
+    const size_t row_pcm = (size_t)frame_size * channels * sizeof(int16_t);   // one frame of one stream
+    if (nsub == 1) {
+        cudaMemcpyAsync(e.d_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, e.stream);
+        launch_span((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, frame_size, max_bytes, stride);
+        cudaMemcpyAsync(data, e.d_data.p, NF * stride, cudaMemcpyDeviceToHost, e.stream);
+    } else {
+        cudaEventRecord(e.ev_prev, e.stream);                 // earlier work on the device buffers (previous call) is done
+        cudaStreamWaitEvent(e.copy_stream, e.ev_prev, 0);
+        const int per = (F + nsub - 1) / nsub;
+        for (int k = 0; k < nsub; k++) {
+            const int f0 = k * per, f1 = hmin(F, f0 + per);
+            cudaMemcpy2DAsync((char *)e.d_pcm.p + f0 * row_pcm, F * row_pcm, (const char *)pcm + f0 * row_pcm, F * row_pcm, (f1 - f0) * row_pcm,
+                              (size_t)n, cudaMemcpyHostToDevice, e.copy_stream);
+            cudaEventRecord(e.ev_in[k], e.copy_stream);
+        }
+        cudaEventRecord(e.ev0, e.stream);
+        for (int k = 0; k < nsub; k++) {
+            const int f0 = k * per, f1 = hmin(F, f0 + per);
+            cudaStreamWaitEvent(e.stream, e.ev_in[k], 0);
+            launch_frames((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, f0, f1, frame_size,
+                          max_bytes, stride);
+            cudaEventRecord(e.ev_done[k], e.stream);
+            cudaStreamWaitEvent(e.copy_stream, e.ev_done[k], 0);
+            cudaMemcpy2DAsync(data + (size_t)f0 * stride, (size_t)F * stride, (const uint8_t *)e.d_data.p + (size_t)f0 * stride, (size_t)F * stride,
+                              (size_t)(f1 - f0) * stride, (size_t)n, cudaMemcpyDeviceToHost, e.copy_stream);
+        }
+        cudaEventRecord(e.ev1, e.stream);
+    }
     cudaMemcpyAsync(ret, e.d_rets.p, sizeof(int) * NF, cudaMemcpyDeviceToHost, e.stream);
     mark_device_newer_locked(st, n);
-    if (cudaStreamSynchronize(e.stream) != cudaSuccess) {
+    if (cudaStreamSynchronize(e.stream) != cudaSuccess || cudaStreamSynchronize(e.copy_stream) != cudaSuccess) {
         fprintf(stderr, "concentus_b200: CUDA failure in encode span: %s\n", cudaGetErrorString(cudaGetLastError()));
         return OPUS_INTERNAL_ERROR;
     }

@@ -101,6 +101,28 @@ def test_encode_many_streams_one_launch():
             assert np.array_equal(rd[f, :rl[f]], d[s, f, :rl[f]]), ("bytes", sigs[s], f)
 
 
+def test_encode_pipelined_host_span():
+    """A host-buffer span big enough (>= 32 MB of PCM) to be cut into sub-spans whose PCM upload / packet download overlap the
+    coding of their neighbours: 320 streams x 30 frames in ONE call, 40 distinct signals; every stream against the oracle."""
+    cb = _cb()
+    ch, fs, F, n = 2, 960, 30, 320
+    kinds = ("music", "tone", "clicks", "noise")
+    base = [O.test_signal(fs * F, ch, 4000 + i, kinds[i % 4]) for i in range(40)]
+    refs = [_ref_encode(b, fs, 96000, ch, 1, 0, 10) for b in base]
+    enc = cb.EncoderBatch(n, 48000, ch, bitrate=96000, vbr=1, cvbr=0, complexity=10)
+    d, l = enc.encode_span(np.concatenate([base[s % 40] for s in range(n)]), F, fs)
+    fr = enc.final_ranges()
+    enc.close()
+    d = d.reshape(n, F, 1276)
+    l = l.reshape(n, F)
+    for s in range(n):
+        rd, rl, rr = refs[s % 40]
+        assert np.array_equal(rl, l[s]), ("len", s)
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], d[s, f, :rl[f]]), ("bytes", s, f)
+        assert int(rr[-1]) == int(fr[s]), ("final range", s)
+
+
 def test_scalar_api_and_state_copy():
     """opus_encode one frame at a time, a memcpy'd state block continues identically (tests/test_opus_encode.c:198,214),
     OPUS_RESET_STATE restarts the stream, ctl argument checks (tests/test_opus_api.c)."""
