@@ -269,6 +269,35 @@ def bench_encode(args, L, cb, torch, dev, local, world, dist, rank, cores, peaks
                 "kernel": "encode_span_kernel", "kernel_ms_per_launch": kms, "algorithmic_bytes_per_launch": algo,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "note": "integer-issue / latency bound (one warp per stream, frames serial within a stream); limiter evidence under profiles/"}
+    # parity at the bench's full size (untimed): fresh encoders, the same call, sampled streams against the oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        import oracle_lib as O
+        encp = cb.EncoderBatch(S, FS, CH, bitrate=ENC_BITRATE, vbr=1, cvbr=0, complexity=10)
+        rc = L.opus_encode_span_device(encp.handles, S, F, C.c_void_p(d_pcm.data_ptr()), FRAME, C.c_void_p(d_data.data_ptr()), stride,
+                                       C.c_void_p(d_ret.data_ptr()))
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        L.opus_b200_enc_synchronize()
+        pick = sorted(set(np.linspace(0, S - 1, 8).astype(int).tolist()))
+        sel = torch.tensor(pick, device=dev)
+        got_d = d_data.view(S, F, stride)[sel].cpu().numpy()
+        got_l = d_ret.view(S, F)[sel].cpu().numpy()
+        src = d_pcm[sel].cpu().numpy()
+        fr = encp.final_ranges()
+        bad = []
+        for k, sidx in enumerate(pick):
+            rd, ro, rl, rr = O.encode_stream(src[k], FRAME, ENC_BITRATE, CH, vbr=1, cvbr=0, complexity=10, max_bytes=1276)
+            rd = rd.reshape(F, 1276)
+            ok = np.array_equal(rl, got_l[k]) and all(np.array_equal(rd[f, :rl[f]], got_d[k, f, :rl[f]]) for f in range(F)) \
+                and int(rr[-1]) == int(fr[sidx])
+            if not ok:
+                bad.append(int(sidx))
+        encp.close()
+        parity = {"streams_checked": len(pick), "frames_each": int(F), "mismatching_streams": bad,
+                  "against": "oracle/_ref (unmodified opus-fix), fresh state, packets byte-for-byte + final range"}
+        assert not bad, "encode parity failed at bench size: streams %s" % bad
+
     # e2e: pinned host PCM in, host packets out, one opus_encode_span call per second of audio
     e2e = None
     if not args.no_e2e:
@@ -315,7 +344,7 @@ def bench_encode(args, L, cb, torch, dev, local, world, dist, rank, cores, peaks
     torch.cuda.empty_cache()
     return {"metric": "CELT encode audio-sec per sec (x realtime), 48k stereo", "value": value, "unit": "x realtime", "ms_per_step": ms / args.steps,
             "mean_packet_bytes": mean_len, "config": encode_workload_config(args, world), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity}
 
 
 def F_chunk(seconds):
@@ -346,6 +375,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-encode", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed full-size parity pass against the oracle")
     ap.add_argument("--enc-seconds", type=int, default=6, help="audio seconds per stream per encode step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -452,6 +482,30 @@ def main():
                 "note": "integer-issue / latency bound path (SURVEY.md 8d): the HBM fraction is reported as the contract asks; the "
                         "limiter evidence (issue utilisation, divergence, stall reasons) is under profiles/"}
 
+    # ---------------- parity at the bench's full size (untimed): fresh decoders, the same device-resident call, sampled streams
+    # compared over their whole length with the oracle (unmodified opus-fix) ----------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        import oracle_lib as O
+        decp = cb.DecoderBatch(S, FS, CH)
+        rc = L.opus_decode_span_device(decp.handles, S, F, C.c_void_p(d_blob.data_ptr()), C.c_void_p(d_offs.data_ptr()),
+                                       C.c_void_p(d_lens.data_ptr()), C.c_void_p(d_pcm.data_ptr()), FRAME, C.c_void_p(d_ret.data_ptr()))
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        L.opus_b200_synchronize()
+        pick = sorted(set(np.linspace(0, S - 1, 8).astype(int).tolist()))
+        rows = d_pcm.view(S, F * FRAME * CH)[torch.tensor(pick, device=dev)].cpu().numpy()
+        fr = decp.final_ranges()
+        bad = []
+        for k, sidx in enumerate(pick):
+            rp, rr, rret = O.decode_stream(blob, offs.reshape(S, F)[sidx], lens.reshape(S, F)[sidx], FRAME, CH)
+            if not (np.array_equal(rp.reshape(-1), rows[k]) and int(rr[-1]) == int(fr[sidx]) and (rret == FRAME).all()):
+                bad.append(int(sidx))
+        decp.close()
+        parity = {"streams_checked": len(pick), "packets_each": int(F), "mismatching_streams": bad,
+                  "against": "oracle/_ref (unmodified opus-fix), fresh state, PCM sample-for-sample + final range"}
+        assert not bad, "decode parity failed at bench size: streams %s" % bad
+
     # ---------------- e2e: host buffers through opus_decode_span (H2D + kernel + D2H per chunk call) ----------------
     e2e = None
     if not args.no_e2e:
@@ -515,7 +569,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "encode": encode}
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "encode": encode}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -56,6 +56,10 @@ struct SoloTeam {
 };
 
 #if defined(__CUDACC__)
+#if defined(CB_PHASE_PROF)
+static __device__ long long g_phase_cycles[64], g_phase_wait[64], g_phase_last;
+static __device__ int g_phase_idx;
+#endif
 struct WarpTeam {
     static constexpr int W = 32;
     int lane_;
@@ -85,6 +89,21 @@ struct WarpTeam {
     // sub-block groups of CB_PHASE_GROUP warps on named barriers 1..15 (A/B knob: less waiting, more code positions in flight)
     CB_MEM void phase() const {
         asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / CB_PHASE_GROUP), "r"(CB_PHASE_GROUP * 32) : "memory");
+    }
+#elif defined(CB_PHASE_SYNC) && defined(CB_PHASE_PROF)
+    // dev build: thread 0 of block 0 accumulates the cycles between consecutive phase boundaries per boundary ordinal
+    // (tools/enc_phase_prof.py); arrival time is taken before the barrier, so a slot is this stream's own latency
+    CB_MEM void phase() const {
+        const bool rec = blockIdx.x == 0 && threadIdx.x == 0;
+        const long long now = clock64();
+        const int k = g_phase_idx % 30;   // kEncPhases
+        if (rec) g_phase_cycles[k] += now - g_phase_last;
+        __syncthreads();
+        if (rec) {
+            g_phase_last = clock64();
+            g_phase_wait[k] += g_phase_last - now;
+            g_phase_idx++;
+        }
     }
 #elif defined(CB_PHASE_SYNC)
     CB_MEM void phase() const { __syncthreads(); }

@@ -402,6 +402,22 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
 extern "C" {
 
 long long opus_b200_enc_kernel_launches(void) { return e.launches; }
+#if defined(CB_PHASE_PROF)
+// dev build only: cycles per phase slot of stream 0 (own work, then barrier wait); reset != 0 clears the counters
+int opus_b200_enc_phase_prof(long long *cycles, long long *wait, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(cycles, cb::g_phase_cycles, sizeof(long long) * 64);
+    cudaMemcpyFromSymbol(wait, cb::g_phase_wait, sizeof(long long) * 64);
+    if (reset) {
+        long long z[64] = {0};
+        int zi = 0;
+        cudaMemcpyToSymbol(cb::g_phase_cycles, z, sizeof(z));
+        cudaMemcpyToSymbol(cb::g_phase_wait, z, sizeof(z));
+        cudaMemcpyToSymbol(cb::g_phase_idx, &zi, sizeof(zi));
+    }
+    return 0;
+}
+#endif
 void *opus_b200_enc_stream(void) {
     std::lock_guard<std::mutex> lk(e.mu);
     if (!ctx_init_locked()) return nullptr;

@@ -196,3 +196,75 @@ def test_scalar_api_null_packet_and_fec_flag():
             r = L.opus_decode(C.c_void_p(h), O.ptr(pkt), int(l[f]), O.ptr(out), 960, 0)
         assert r == 960 and np.array_equal(out, rp[f * 960:(f + 1) * 960]), f
     L.opus_decoder_destroy(C.c_void_p(h))
+
+
+_MULTICHUNK = r'''
+import ctypes as C, sys, os
+import numpy as np
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import oracle_lib as O
+import concentus_b200 as cb
+import torch
+L = cb.lib()
+assert L.opus_b200_init(0) == 0
+fs, ch, nsec = 960, 2, 4
+kinds = ("music", "tone", "clicks", "noise")
+datas, offs_all, lens_all, base = [], [], [], 0
+n = 12
+for s in range(n):
+    x = O.test_signal(48000 * nsec, ch, 900 + s, kinds[s % 4])
+    d, o, l, _ = O.encode_stream(x, fs, (64000, 96000, 160000)[s % 3], ch, vbr=1, cvbr=0)
+    d, o = O.pack(d, o, l)
+    l = l.copy()
+    rs = np.random.RandomState(s)
+    if s % 3 == 1:
+        l[rs.rand(len(l)) < 0.15] = 0          # random loss: concealment state and the fold seed cross chunk boundaries
+    if s % 3 == 2:
+        for f in range(15, len(l), 37):
+            l[f:f + 7] = 0                       # bursts past the noise-PLC threshold
+    datas.append(d); offs_all.append(o + base); lens_all.append(l); base += len(d)
+data = np.concatenate(datas); offs = np.stack(offs_all); lens = np.stack(lens_all)
+F = lens.shape[1]
+ref = [O.decode_stream(data, offs[s], lens[s], fs, ch) for s in range(n)]
+
+def check(pcm, rets, fr, tag):
+    pcm = pcm.reshape(n, F, -1); rets = rets.reshape(n, F)
+    for s in range(n):
+        rp, rr, rret = ref[s]
+        assert np.array_equal(rret, rets[s]), (tag, "ret", s)
+        bad = np.nonzero((rp.reshape(F, -1) != pcm[s]).any(axis=1))[0]
+        assert bad.size == 0, (tag, "pcm", s, "first bad frame", int(bad[0]))
+        assert int(rr[-1]) == int(fr[s]), (tag, "final range", s)
+
+# host-buffer path, ONE call over all F packets: the library cuts it into chunks (CB200_IR_HOST_MB is tiny here)
+dec = cb.DecoderBatch(n, 48000, ch)
+p, r = dec.decode_span(data, offs.reshape(-1), lens.reshape(-1), F, fs)
+check(p, r, dec.final_ranges(), "host")
+dec.close()
+# device-resident path
+dev = torch.device("cuda", 0)
+d_blob = torch.from_numpy(data).to(dev); d_offs = torch.from_numpy(offs.reshape(-1).astype(np.int64)).to(dev)
+d_lens = torch.from_numpy(lens.reshape(-1).astype(np.int32)).to(dev)
+d_pcm = torch.zeros((n * F * fs * ch,), dtype=torch.int16, device=dev); d_ret = torch.zeros((n * F,), dtype=torch.int32, device=dev)
+dec = cb.DecoderBatch(n, 48000, ch)
+rc = L.opus_decode_span_device(dec.handles, n, F, C.c_void_p(d_blob.data_ptr()), C.c_void_p(d_offs.data_ptr()), C.c_void_p(d_lens.data_ptr()),
+                               C.c_void_p(d_pcm.data_ptr()), fs, C.c_void_p(d_ret.data_ptr()))
+assert rc == 0, rc
+torch.cuda.synchronize(); L.opus_b200_synchronize()
+check(d_pcm.cpu().numpy(), d_ret.cpu().numpy(), dec.final_ranges(), "device")
+dec.close()
+print("chunks-ok", F)
+'''
+
+
+def test_decode_multichunk_pipeline():
+    """The time-chunked, double-buffered three-stage pipeline the bench runs on (DESIGN.md §3): forced here with a 2 MB IR budget
+    so that 200 packets x 12 streams take ~14 chunks, with random and burst packet loss so that the fold seed, the loss streak
+    and the concealment state all cross chunk boundaries.  Host-buffer and device-resident entry points, vs the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CB200_IR_MB="2", CB200_IR_HOST_MB="2")
+    out = subprocess.run([sys.executable, "-c", _MULTICHUNK], capture_output=True, text=True, cwd=root, env=env, timeout=600)
+    assert out.returncode == 0 and "chunks-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
