@@ -41,7 +41,7 @@ EXPORTS = [
     "opus_decode_span_device", "opus_decoder_sync", "opus_b200_init", "opus_b200_synchronize", "opus_b200_stream",
     "opus_b200_kernel_launches", "opus_b200_last_kernel_ms", "opus_b200_stage_times", "opus_b200_device_index",
     "opus_encoder_get_size", "opus_encoder_create", "opus_encoder_init", "opus_encode", "opus_encoder_ctl", "opus_encoder_destroy",
-    "opus_packet_pad", "opus_packet_unpad", "opus_encode_batch", "opus_encode_span", "opus_encode_span_device", "opus_encoder_sync",
+    "opus_packet_pad", "opus_packet_unpad", "opus_encode_batch", "opus_encode_span", "opus_encode_span_device", "opus_encode_span_ranges", "opus_encoder_sync",
     "opus_b200_enc_synchronize", "opus_b200_enc_stream", "opus_b200_enc_kernel_launches", "opus_b200_enc_last_kernel_ms",
 ]
 
@@ -91,6 +91,7 @@ def lib():
         L.opus_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
         L.opus_encode_span.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p]
         L.opus_encode_span_device.argtypes = L.opus_encode_span.argtypes
+        L.opus_encode_span_ranges.argtypes = L.opus_encode_span.argtypes + [C.c_void_p]
         L.opus_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_void_p, C.c_int]
         L.opus_encoder_sync.argtypes = [C.c_void_p, C.c_int]
         L.opus_packet_pad.argtypes = [C.c_void_p, C.c_int32, C.c_int32]

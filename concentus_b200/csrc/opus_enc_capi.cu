@@ -61,8 +61,8 @@ struct EncWarpSmem {
 // One warp per stream, frames 0..F-1 in order.  PCM of frame (s,f): pcm[(s*F+f)*frame_size*channels]; packet slot:
 // data[(s*F+f)*stride], at most max_bytes are written; rets[s*F+f] = packet length or error.  One launch codes frames [f0, f1).
 __global__ void __launch_bounds__(CB_ENC_WPB * 32, CB_ENC_MINBLOCKS)
-encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const int16_t *pcm, uint8_t *data, int *rets, int n, int F,
-                   int f0, int f1, int frame_size, int max_bytes, int stride) {
+encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const int16_t *pcm, uint8_t *data, int *rets, unsigned *ranges,
+                   int n, int F, int f0, int f1, int frame_size, int max_bytes, int stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_ENC_WPB + warp;
@@ -86,7 +86,10 @@ encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const
     for (int f = f0; f < f1; f++) {
         const size_t k = (size_t)s * F + f;
         const int r = opus_encode_frame(tm, st, gst, W.S, G, pcm + k * frame_size * channels, frame_size, data + k * stride, max_bytes);
-        if (lane == 0) rets[k] = r;
+        if (lane == 0) {
+            rets[k] = r;
+            if (ranges) ranges[k] = st->rangeFinal;   // OPUS_GET_FINAL_RANGE after this frame (what opus_demo stores per packet)
+        }
         __syncwarp();
     }
     for (int i = lane; i < CB_ENC_HEAD_BYTES / 4; i += 32) reinterpret_cast<int *>(gst)[i] = W.head[i];
@@ -150,7 +153,7 @@ struct EncCtx {
     int pool_cap = 0;
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
-    DevBuf d_slots, d_pcm, d_data, d_rets, d_stage, d_scratch;
+    DevBuf d_slots, d_pcm, d_data, d_rets, d_ranges, d_stage, d_scratch;
     PinBuf h_stage, h_slots;
     long long launches = 0;
     float last_ms = 0.f;
@@ -326,19 +329,20 @@ int check_span(OpusEncoder **st, int n) {
 }
 
 void launch_frames(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int f0, int f1, int frame_size,
-                   int max_bytes, int stride) {
+                   int max_bytes, int stride, unsigned *d_ranges = nullptr) {
     encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, CB_ENC_WPB * sizeof(EncWarpSmem), e.stream>>>(
-        e.pool, d_slots, (EncGlobal *)e.d_scratch.p, d_pcm, d_data, d_rets, n, F, f0, f1, frame_size, max_bytes, stride);
+        e.pool, d_slots, (EncGlobal *)e.d_scratch.p, d_pcm, d_data, d_rets, d_ranges, n, F, f0, f1, frame_size, max_bytes, stride);
     e.launches++;
 }
-void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int frame_size, int max_bytes, int stride) {
+void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int frame_size, int max_bytes, int stride,
+                 unsigned *d_ranges = nullptr) {
     cudaEventRecord(e.ev0, e.stream);
-    launch_frames(d_slots, d_pcm, d_data, d_rets, n, F, 0, F, frame_size, max_bytes, stride);
+    launch_frames(d_slots, d_pcm, d_data, d_rets, n, F, 0, F, frame_size, max_bytes, stride, d_ranges);
     cudaEventRecord(e.ev1, e.stream);
 }
 
 int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, int frame_size, uint8_t *data, int max_bytes, int stride,
-                            int *ret, bool keep_resident) {
+                            int *ret, bool keep_resident, uint32_t *ranges = nullptr) {
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
     int rc = check_span(st, n);
     if (rc != OPUS_OK) return rc;
@@ -350,8 +354,10 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
     const size_t NF = (size_t)n * F;
     const size_t pcm_bytes = NF * frame_size * channels * sizeof(int16_t);
     if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_pcm.reserve(pcm_bytes) || !e.d_data.reserve(NF * stride) ||
-        !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n))
+        !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n) ||
+        (ranges && !e.d_ranges.reserve(sizeof(uint32_t) * NF)))
         return OPUS_ALLOC_FAIL;
+    unsigned *d_ranges = ranges ? (unsigned *)e.d_ranges.p : nullptr;
     cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
     // Large spans are cut into up to kMaxSub sub-spans of frames: the PCM of sub-span k+1 goes up and the packets of sub-span
     // k-1 come down on the copy stream while sub-span k is coded (the state stays resident between the launches).
@@ -360,7 +366,8 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
     const size_t row_pcm = (size_t)frame_size * channels * sizeof(int16_t);   // one frame of one stream
     if (nsub == 1) {
         cudaMemcpyAsync(e.d_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, e.stream);
-        launch_span((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, frame_size, max_bytes, stride);
+        launch_span((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, frame_size, max_bytes, stride,
+                    d_ranges);
         cudaMemcpyAsync(data, e.d_data.p, NF * stride, cudaMemcpyDeviceToHost, e.stream);
     } else {
         cudaEventRecord(e.ev_prev, e.stream);                 // earlier work on the device buffers (previous call) is done
@@ -377,7 +384,7 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
             const int f0 = k * per, f1 = hmin(F, f0 + per);
             cudaStreamWaitEvent(e.stream, e.ev_in[k], 0);
             launch_frames((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, f0, f1, frame_size,
-                          max_bytes, stride);
+                          max_bytes, stride, d_ranges);
             cudaEventRecord(e.ev_done[k], e.stream);
             cudaStreamWaitEvent(e.copy_stream, e.ev_done[k], 0);
             cudaMemcpy2DAsync(data + (size_t)f0 * stride, (size_t)F * stride, (const uint8_t *)e.d_data.p + (size_t)f0 * stride, (size_t)F * stride,
@@ -386,6 +393,7 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
         cudaEventRecord(e.ev1, e.stream);
     }
     cudaMemcpyAsync(ret, e.d_rets.p, sizeof(int) * NF, cudaMemcpyDeviceToHost, e.stream);
+    if (ranges) cudaMemcpyAsync(ranges, d_ranges, sizeof(uint32_t) * NF, cudaMemcpyDeviceToHost, e.stream);
     mark_device_newer_locked(st, n);
     if (cudaStreamSynchronize(e.stream) != cudaSuccess || cudaStreamSynchronize(e.copy_stream) != cudaSuccess) {
         fprintf(stderr, "concentus_b200: CUDA failure in encode span: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -537,6 +545,13 @@ int opus_encode_span(OpusEncoder **st, int n, int F, const opus_int16 *pcm, int 
     if (!st || n <= 0 || F <= 0 || frame_size <= 0 || max_data_bytes <= 0 || !pcm || !data || !ret) return OPUS_BAD_ARG;
     std::lock_guard<std::mutex> lk(e.mu);
     return encode_span_host_locked(st, n, F, pcm, frame_size, data, hmin(max_data_bytes, 1276), max_data_bytes, ret, true);
+}
+
+int opus_encode_span_ranges(OpusEncoder **st, int n, int F, const opus_int16 *pcm, int frame_size, unsigned char *data,
+                            opus_int32 max_data_bytes, opus_int32 *ret, opus_uint32 *final_range) {
+    if (!st || n <= 0 || F <= 0 || frame_size <= 0 || max_data_bytes <= 0 || !pcm || !data || !ret || !final_range) return OPUS_BAD_ARG;
+    std::lock_guard<std::mutex> lk(e.mu);
+    return encode_span_host_locked(st, n, F, pcm, frame_size, data, hmin(max_data_bytes, 1276), max_data_bytes, ret, true, final_range);
 }
 
 int opus_encode_batch(OpusEncoder **st, const opus_int16 *const *pcm, int frame_size, unsigned char *const *data, opus_int32 max_data_bytes,

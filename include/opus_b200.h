@@ -159,6 +159,10 @@ int opus_encode_span(OpusEncoder **st, int n, int F, const opus_int16 *pcm, int 
                      opus_int32 max_data_bytes, opus_int32 *ret);
 int opus_encode_span_device(OpusEncoder **st, int n, int F, const opus_int16 *d_pcm, int frame_size, unsigned char *d_data,
                             opus_int32 max_data_bytes, opus_int32 *d_ret);
+/* opus_encode_span that also reports OPUS_GET_FINAL_RANGE after every frame: final_range[s*F+f] — what opus_demo stores next to
+ * each packet in its .bit container (src/opus_demo.c:748-760) and checks against its decoder (:806-816). */
+int opus_encode_span_ranges(OpusEncoder **st, int n, int F, const opus_int16 *pcm, int frame_size, unsigned char *data,
+                            opus_int32 max_data_bytes, opus_int32 *ret, opus_uint32 *final_range);
 int opus_encoder_sync(OpusEncoder **st, int n);
 
 /* ---- runtime ---- */

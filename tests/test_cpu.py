@@ -5,6 +5,7 @@ import ctypes as C
 import glob
 import os
 import re
+import struct
 import subprocess
 import sys
 import zlib
@@ -452,3 +453,59 @@ def test_stream_sharding_world_size_2_gloo():
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 4099      # contiguous, disjoint, complete
     assert res[0][0] + res[1][0] == 4099 and abs(res[0][0] - res[1][0]) <= 1
     assert ms == 11.0
+
+
+# ---- the .bit container: pinned on files written by the reference's own opus_demo -----------------------
+
+def _opus_demo():
+    exe = os.path.join(ROOT, "oracle", "_ref", "opus_demo")
+    O.ref()   # builds oracle/_ref (library and opus_demo) when the reference sources are present
+    assert os.path.exists(exe), "oracle/_ref/opus_demo missing: run `make -C oracle` where /root/reference exists"
+    return exe
+
+
+@pytest.mark.parametrize("ch,fs,br", [(2, 960, 64000), (1, 480, 48000), (2, 120, 128000)])
+def test_bit_container_reads_what_opus_demo_writes(tmp_path, ch, fs, br):
+    """opus_demo -e (src/opus_demo.c:748-760) writes the file; our reader must return exactly the packets and final ranges the
+    oracle's encoder produces for the same input, and our writer must reproduce the file byte for byte."""
+    from concentus_b200 import bitfile
+    pcm = O.test_signal(48000, ch, 77 + ch, "music")
+    raw = tmp_path / "in.raw"
+    pcm.astype("<i2").tofile(raw)
+    bit = tmp_path / "ref.bit"
+    ms = {120: "2.5", 240: "5", 480: "10", 960: "20"}[fs]
+    r = subprocess.run([_opus_demo(), "-e", "restricted-lowdelay", "48000", str(ch), str(br), "-framesize", ms, str(raw), str(bit)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    data, offs, lens, ranges = bitfile.read_bit(str(bit))
+    # opus_demo codes one extra all-zero frame when the input ends on a frame boundary (src/opus_demo.c:672-690)
+    x = np.concatenate([pcm, np.zeros((fs, ch), dtype=np.int16)])
+    rd, ro, rl, rr = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=0, complexity=10, max_bytes=1500)
+    F = len(rl)
+    assert len(lens) == F and np.array_equal(lens, rl)
+    assert np.array_equal(ranges, rr)
+    for f in range(F):
+        assert np.array_equal(data[offs[f]:offs[f] + lens[f]], rd[ro[f]:ro[f] + rl[f]]), f
+    out = tmp_path / "ours.bit"
+    bitfile.write_bit(str(out), data, offs, lens, ranges)
+    assert open(out, "rb").read() == open(bit, "rb").read()
+
+
+def test_bit_container_edge_cases(tmp_path):
+    from concentus_b200 import bitfile
+    empty = tmp_path / "empty.bit"
+    empty.write_bytes(b"")
+    d, o, l, r = bitfile.read_bit(str(empty))
+    assert len(l) == 0 and len(o) == 0 and len(r) == 0
+    # a lost packet (length 0) and a truncated tail: the reader stops where opus_demo would (short read, :665-670)
+    pk = bytes([0xFC, 1, 2, 3])
+    good = struct.pack(">II", 4, 0x12345678) + pk + struct.pack(">II", 0, 0) + struct.pack(">II", 4, 7) + pk
+    f = tmp_path / "trunc.bit"
+    f.write_bytes(good + struct.pack(">II", 100, 1) + b"\x01\x02")
+    d, o, l, r = bitfile.read_bit(str(f))
+    assert l.tolist() == [4, 0, 4] and r.tolist() == [0x12345678, 0, 7]
+    assert bytes(d[o[2]:o[2] + 4]) == pk
+    # an absurd length field ends the stream as well (opus_demo: "Invalid payload length")
+    g = tmp_path / "bad.bit"
+    g.write_bytes(good + struct.pack(">II", 1 << 20, 1))
+    assert bitfile.read_bit(str(g))[2].tolist() == [4, 0, 4]
