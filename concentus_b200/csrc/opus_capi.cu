@@ -69,21 +69,26 @@ struct IrView {
 // packet before it; inside the run the seed chains naturally.  No decoder state is written here (st->rng is read once per
 // launch for the very first packet of a stream).
 __global__ void __launch_bounds__(CB_PARSE_THREADS, CB_PARSE_MINBLOCKS)
-parse_kernel(const CbDecState *pool, const int *slots, const uint8_t *data, const int64_t *offs, const int32_t *lens, int n, int F,
+parse_kernel(const CbCallCtx *call_ctx, const uint8_t *data, const int64_t *offs, const int32_t *lens, int n, int F,
              int f0, int f1, int call_f0, int R, int cap, int decode_fec, IrView ir) {
     const int runs = (f1 - f0 + R - 1) / R;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * runs) return;
     const int s = t / runs, r = t - s * runs;
-    const CbDecState *st = pool + slots[s];
     // Thread-local working set (5.6 KB of local memory: lane-interleaved, write-back in L1).  As per-thread rows of a global
     // array the same data made every 2-byte store a 32-byte write-through to L2: 251 GB of L1->L2 writes per 2.4 GB of output,
     // the L1->crossbar request path 52 % busy (profiles/r1_dec_v4_parse_kernel); local: parse 186 -> 114 ms per chunk.
     ParseScratch ps;
     const int first = f0 + r * R;
     const int last = first + R < f1 ? first + R : f1;
-    opus_parse_run(st, data, offs + (size_t)s * F, lens + (size_t)s * F, call_f0, first, last, cap, decode_fec, ir.kmax, ir.xstride,
+    opus_parse_run(call_ctx[s], data, offs + (size_t)s * F, lens + (size_t)s * F, call_f0, first, last, cap, decode_fec, ir.kmax, ir.xstride,
                    ir.pk + (size_t)s * ir.Fc, ir.fr + (size_t)s * ir.Fc * ir.kmax, ir.X + (size_t)s * ir.Fc * ir.xstride, f0, ps);
+}
+
+// Snapshot of what stage A needs of every stream's state, taken once per call before any stage runs (see CbCallCtx).
+__global__ void call_ctx_kernel(const CbDecState *pool, const int *slots, CbCallCtx *out, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) call_ctx_from_state(out[s], pool + slots[s]);
 }
 
 // Stage B — synthesis, one warp per stream, packets f0..f1 in order.  PCM row of packet (s,f) starts at
@@ -242,7 +247,7 @@ struct Ctx {
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
     DevBuf d_slots, d_data, d_offs, d_lens, d_pcm[2], d_rets, d_stage;
-    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_plc;
+    DevBuf d_irpk[2], d_irfr[2], d_irx[2], d_sig[2], d_range[2], d_plc, d_callctx;
     size_t ir_budget = (size_t)16 << 30;  // bytes of IR + staging per chunk buffer (env CB200_IR_MB)
     // Host-buffer calls copy each chunk's PCM out while the next chunk decodes; the last chunk's copy overlaps nothing, so
     // they run on smaller chunks (measured: e2e 108 K -> 126 K x realtime; the device-resident path keeps the large ones)
@@ -506,6 +511,7 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs, bool host_io) {
             !g.d_range[b].reserve(slots * sizeof(CbSigRange)))
             return false;
     }
+    if (!g.d_callctx.reserve((size_t)n * sizeof(CbCallCtx))) return false;
     return g.d_plc.reserve((size_t)n * sizeof(PlcScratch));   // concealment scratch, one per stream (lost frames only)
 }
 
@@ -534,7 +540,7 @@ void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_d
     if (c >= 2) cudaStreamWaitEvent(g.parse_stream, g.ev_synth[b], 0);
     timing_begin(0, g.parse_stream);
     parse_kernel<<<(unsigned)((threads + CB_PARSE_THREADS - 1) / CB_PARSE_THREADS), CB_PARSE_THREADS, 0, g.parse_stream>>>(
-        g.pool, d_slots, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v);
+        (const CbCallCtx *)g.d_callctx.p, d_data, d_offs, d_lens, pl.n, pl.F, f0, f1, 0, pl.R, pl.cap, pl.fec, v);
     timing_end(g.parse_stream);
     cudaEventRecord(g.ev_parse[b], g.parse_stream);
     // stage B(c): after A(c); its staging buffer b must have been drained by C(c-2)
@@ -773,6 +779,8 @@ int opus_decode_span_device(OpusDecoder **st, int n, int F, const unsigned char 
     if (!plan_call(pl, n, F, frame_size, 0, st[0]->st.Fs, false)) return OPUS_ALLOC_FAIL;
     cudaMemcpyAsync(g.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, g.stream);
     cudaEventRecord(g.ev0, g.stream);
+    call_ctx_kernel<<<(n + 127) / 128, 128, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (CbCallCtx *)g.d_callctx.p, n);
+    g.launches++;
     cudaEventRecord(g.ev_call, g.stream);
     for (int c = 0; c < pl.nchunks; c++)
         enqueue_chunk(pl, c, (const int *)g.d_slots.p, d_data, d_offs, d_len, d_pcm, F, 0, d_ret);
@@ -813,6 +821,8 @@ static int decode_span_host_locked(OpusDecoder **st, int n, int F, const unsigne
     cudaMemcpyAsync(g.d_offs.p, offs, sizeof(int64_t) * NF, cudaMemcpyHostToDevice, g.stream);
     cudaMemcpyAsync(g.d_lens.p, len, sizeof(int32_t) * NF, cudaMemcpyHostToDevice, g.stream);
     cudaEventRecord(g.ev0, g.stream);
+    call_ctx_kernel<<<(n + 127) / 128, 128, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (CbCallCtx *)g.d_callctx.p, n);
+    g.launches++;
     cudaEventRecord(g.ev_call, g.stream);
     for (int c = 0; c < nchunks; c++) {
         const int b = c & 1;

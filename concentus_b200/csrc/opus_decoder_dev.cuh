@@ -171,15 +171,29 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     }
 }
 
+// What stage A reads of a stream's state: the context at the START OF THE CALL.  It is a snapshot (taken on the call's stream
+// before any stage runs) and not the live state, because a call is pipelined over chunks: stage A of chunk c+1 runs while stage B
+// of chunk c is already advancing rng / loss_count / frame_size in the state.  (Found by tools/parity_sweep.py: a loss run that
+// covers the start of a call through its whole first chunk made a second-chunk run fall back to a half-updated state.)
+struct CbCallCtx {
+    uint32_t rng;
+    int32_t loss_count, frame_size, bandwidth, prev_mode, channels, Fs;
+};
+CB_DEV void call_ctx_from_state(CbCallCtx &c, const CbDecState *st) {
+    c.rng = st->rng; c.loss_count = st->loss_count; c.frame_size = st->frame_size; c.bandwidth = st->bandwidth;
+    c.prev_mode = st->prev_mode; c.channels = st->channels; c.Fs = st->Fs;
+}
+
 // One stage-A work item: packets [first, last) of one stream (a "run").  st = the stream's state as it was when the launch
 // began (stage B of this launch has not run yet), call_f0 = first packet of the call, f0 = first packet of the chunk whose IR
 // arrays pk_s / fr_s / X_s (already offset to this stream) are being filled: packet f goes to slot f - f0.
 // Two phases around ONE call site of the (large) packet parser.  Seeking: f walks BACK from first-1 to the nearest packet
 // that holds a received frame (it fixes seed, loss streak, frame size and bandwidth: SeedTrack), dry-parsing into the run's
 // first IR slot as scratch; then f walks FORWARD — dry over the lost / rejected packets up to the run, for real over the run.
-CB_DEV void opus_parse_run(const CbDecState *st, const uint8_t *data, const int64_t *offs_s, const int32_t *lens_s, int call_f0, int first,
+CB_DEV void opus_parse_run(const CbCallCtx &st0, const uint8_t *data, const int64_t *offs_s, const int32_t *lens_s, int call_f0, int first,
                            int last, int cap, int decode_fec, int kmax, int xstride, CbPacketIR *pk_s, CbFrameIR *fr_s, int16_t *X_s, int f0,
                            ParseScratch &ps) {
+    const CbCallCtx *st = &st0;
     const int Fs = st->Fs;
     const size_t slot0 = (size_t)(first - f0);
     SeedTrack tr;

@@ -15,8 +15,9 @@ int hostsim_dec_state_size(void) { return (int)sizeof(CbDecState); }
 
 // Decode F packets of one stream (packed layout).  cap = pcm capacity per packet (samples per channel).
 // Stage A (parse -> IR), stage B (synth) and stage C (de-emphasis) per packet, exactly the hand-offs the kernels use.
-int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F, int cap, int channels,
-                          int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets) {
+// bounds (nb entries, ascending, last = F) are the ends of the emulated calls; nullptr = calls of 16 packets.
+int hostsim_decode_stream_calls(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F, int cap, int channels,
+                                int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets, const int *bounds, int nb) {
     // Emulates the kernels' schedule: the call is cut into chunks of Fc packets; for a chunk, stage A runs first for every run
     // of R packets from the state as it stood when the chunk began (each run reconstructing its own context), then stages B
     // and C consume the chunk in order.  (The kernels use the state at CALL start for all chunks and walk back across chunk
@@ -34,10 +35,19 @@ int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_
     std::vector<int16_t> X((size_t)Fc * xstride);
     std::vector<int> sig((size_t)cap * (48000 / Fs) * 2 + 16);
     cb::SoloTeam tm;
-    for (int f0 = 0; f0 < F; f0 += Fc) {
-        const int f1 = f0 + Fc < F ? f0 + Fc : F;
+    int bi = 0;
+    for (int f0 = 0; f0 < F;) {
+        int f1 = f0 + Fc < F ? f0 + Fc : F;
+        if (bounds) f1 = bi < nb ? bounds[bi++] : F;
+        if ((size_t)(f1 - f0) > pk.size()) {
+            pk.resize(f1 - f0);
+            fr.resize((size_t)(f1 - f0) * kmax);
+            X.resize((size_t)(f1 - f0) * xstride);
+        }
+        cb::CbCallCtx c0;
+        cb::call_ctx_from_state(c0, st);
         for (int first = f0; first < f1; first += R)   // stage A, run by run, any order
-            cb::opus_parse_run(st, data, offs, lens, f0, first, first + R < f1 ? first + R : f1, cap, 0, kmax, xstride, pk.data(), fr.data(),
+            cb::opus_parse_run(c0, data, offs, lens, f0, first, first + R < f1 ? first + R : f1, cap, 0, kmax, xstride, pk.data(), fr.data(),
                                X.data(), f0, *ps);
         for (int f = f0; f < f1; f++) {                // stages B and C
             const int slot = f - f0;
@@ -48,12 +58,17 @@ int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_
             if (rets) rets[f] = r;
             if (ranges) ranges[f] = st->rangeFinal;
         }
+        f0 = f1;
     }
     free(plc);
     free(ps);
     free(S);
     free(st);
     return 0;
+}
+int hostsim_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F, int cap, int channels,
+                          int Fs, int16_t *pcm, uint32_t *ranges, int32_t *rets) {
+    return hostsim_decode_stream_calls(data, offs, lens, F, cap, channels, Fs, pcm, ranges, rets, nullptr, 0);
 }
 }
 

@@ -241,6 +241,24 @@ dec = cb.DecoderBatch(n, 48000, ch)
 p, r = dec.decode_span(data, offs.reshape(-1), lens.reshape(-1), F, fs)
 check(p, r, dec.final_ranges(), "host")
 dec.close()
+# two host calls, the second one starting inside a loss run that covers more than its whole first chunk: the runs of its
+# second chunk have nothing received to walk back to and take their context from the call-start snapshot while stage B of the
+# first chunk is already advancing the live state (the race tools/parity_sweep.py found)
+lens2 = lens.copy()
+cut = 101
+for s in range(n):
+    lens2[s, cut - (s % 3):cut + 14 + 5 * (s % 4)] = 0
+ref2 = [O.decode_stream(data, offs[s], lens2[s], fs, ch) for s in range(n)]
+dec = cb.DecoderBatch(n, 48000, ch)
+pa, ra = dec.decode_span(data, offs[:, :cut].reshape(-1), lens2[:, :cut].reshape(-1), cut, fs)
+pb, rb = dec.decode_span(data, offs[:, cut:].reshape(-1), lens2[:, cut:].reshape(-1), F - cut, fs)
+fr2 = dec.final_ranges()
+dec.close()
+p2 = np.concatenate([pa.reshape(n, cut, -1), pb.reshape(n, F - cut, -1)], axis=1)
+r2 = np.concatenate([ra.reshape(n, cut), rb.reshape(n, F - cut)], axis=1)
+ref_keep, ref = ref, ref2
+check(p2, r2, fr2, "two calls, loss across the boundary")
+ref = ref_keep
 # device-resident path
 dev = torch.device("cuda", 0)
 d_blob = torch.from_numpy(data).to(dev); d_offs = torch.from_numpy(offs.reshape(-1).astype(np.int64)).to(dev)

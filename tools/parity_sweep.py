@@ -1,0 +1,114 @@
+"""Randomised parity sweep on the GPU (beyond the fixed grid of tests/): batches of streams with per-stream random bitrate,
+CBR/VBR/CVBR, complexity and signal, for random (channels, frame size); the CUDA encoder against the oracle byte-for-byte, then
+the CUDA decoder on the oracle's packets with a random loss pattern against the oracle sample-for-sample.  Prints one line per
+batch and a summary; exit code 1 on any mismatch.
+
+usage: python tools/parity_sweep.py [batches=24] [streams_per_batch=48] [seed=1]       (SWEEP_ONLY=51,123 runs just those batches)
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("SWEEP_PKG"):
+    sys.path.insert(0, os.environ["SWEEP_PKG"])   # A/B against an older package + library
+import oracle_lib as O
+
+RATES = [24000, 32000, 40000, 48000, 64000, 80000, 96000, 128000, 160000, 192000, 256000, 320000, 510000]
+KINDS = ("music", "tone", "clicks", "noise")
+
+
+def draw_batch(rs, NS):
+    """All random parameters of one batch, drawn before any work, so that a batch can be reproduced alone."""
+    ch = int(rs.choice([1, 2]))
+    fs = int(rs.choice([120, 240, 480, 960]))
+    nsec = 2 if fs >= 480 else 1
+    F = 48000 * nsec // fs
+    cfgs = [(int(rs.choice(RATES)), [(0, 0), (1, 0), (1, 1)][rs.randint(3)], int(rs.randint(11)), KINDS[rs.randint(4)], int(rs.randint(1 << 30)))
+            for _ in range(NS)]
+    cut = int(rs.randint(1, F))                       # two spans: state crosses a launch boundary at a random frame
+    loss = np.zeros((NS, F), dtype=np.int8)           # 0 = received, 1 = lost (NULL packet), 2 = cut to the TOC byte
+    for i in range(NS):
+        mode = rs.randint(4)
+        if mode == 1:
+            loss[i][rs.rand(F) < 0.1] = 1
+        elif mode == 2:
+            s0 = int(rs.randint(1, max(2, F - 12)))
+            loss[i][s0:s0 + int(rs.randint(1, 12))] = 1
+        elif mode == 3:
+            loss[i][rs.rand(F) < 0.05] = 2
+    return ch, fs, F, cfgs, cut, loss
+
+
+def main():
+    import concentus_b200 as cb
+    NB = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    NS = int(sys.argv[2]) if len(sys.argv) > 2 else 48
+    SEED = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    ONLY = [int(x) for x in os.environ.get("SWEEP_ONLY", "").split(",") if x]
+    L = cb.lib()
+    assert L.opus_b200_init(0) == 0
+    rs = np.random.RandomState(SEED)
+    bad_total, t0 = 0, time.time()
+    for b in range(NB):
+        ch, fs, F, cfgs, cut, loss = draw_batch(rs, NS)
+        if ONLY and b not in ONLY:
+            continue
+        pcms = [O.test_signal(F * fs, ch, sd, kind) for (_, _, _, kind, sd) in cfgs]
+        enc = cb.EncoderBatch(NS, 48000, ch)
+        for i, (br, (vbr, cvbr), cx, _, _) in enumerate(cfgs):
+            hp = C.c_void_p(enc.handles[i])
+            for req, v in ((cb.OPUS_SET_BITRATE_REQUEST, br), (cb.OPUS_SET_VBR_REQUEST, vbr), (cb.OPUS_SET_VBR_CONSTRAINT_REQUEST, cvbr),
+                           (cb.OPUS_SET_COMPLEXITY_REQUEST, cx)):
+                assert L.opus_encoder_ctl(hp, req, C.c_int32(v)) == 0
+        x = np.stack([p.reshape(F, fs * ch) for p in pcms])
+        d1, l1 = enc.encode_span(x[:, :cut].reshape(-1, ch), cut, fs)
+        d2, l2 = enc.encode_span(x[:, cut:].reshape(-1, ch), F - cut, fs)
+        efr = enc.final_ranges()
+        enc.close()
+        d = np.concatenate([d1.reshape(NS, cut, 1276), d2.reshape(NS, F - cut, 1276)], axis=1)
+        l = np.concatenate([l1.reshape(NS, cut), l2.reshape(NS, F - cut)], axis=1)
+        refs = [O.encode_stream(pcms[i], fs, cfgs[i][0], ch, vbr=cfgs[i][1][0], cvbr=cfgs[i][1][1], complexity=cfgs[i][2], max_bytes=1276)
+                for i in range(NS)]
+        bad_e = []
+        for i, (rd, ro, rl, rr) in enumerate(refs):
+            rd = rd.reshape(F, 1276)
+            ok = np.array_equal(rl, l[i]) and all(np.array_equal(rd[f, :rl[f]], d[i, f, :rl[f]]) for f in range(F)) and int(rr[-1]) == int(efr[i])
+            if not ok:
+                bad_e.append((i, cfgs[i]))
+        # decode the oracle's packets with the per-stream loss pattern
+        lens = np.stack([r[2] for r in refs]).copy()
+        lens[loss == 1] = 0
+        lens[loss == 2] = 1
+        blob = np.concatenate([r[0] for r in refs])
+        offs = (np.arange(NS * F, dtype=np.int64) * 1276).reshape(NS, F)
+        dec = cb.DecoderBatch(NS, 48000, ch)
+        p1, r1 = dec.decode_span(blob, offs[:, :cut].reshape(-1), lens[:, :cut].reshape(-1), cut, fs)
+        p2, r2 = dec.decode_span(blob, offs[:, cut:].reshape(-1), lens[:, cut:].reshape(-1), F - cut, fs)
+        dfr = dec.final_ranges()
+        dec.close()
+        pcm = np.concatenate([p1.reshape(NS, cut, fs * ch), p2.reshape(NS, F - cut, fs * ch)], axis=1)
+        rets = np.concatenate([r1.reshape(NS, cut), r2.reshape(NS, F - cut)], axis=1)
+        bad_d = []
+        for i in range(NS):
+            rp, rr, rret = O.decode_stream(blob, offs[i], lens[i], fs, ch)
+            ok = np.array_equal(rret, rets[i]) and np.array_equal(rp.reshape(F, -1), pcm[i]) and int(rr[-1]) == int(dfr[i])
+            if not ok:
+                fb = np.nonzero((rp.reshape(F, -1) != pcm[i]).any(axis=1))[0]
+                bad_d.append((i, cfgs[i], "first bad frame", int(fb[0]) if fb.size else -1, "rets equal", bool(np.array_equal(rret, rets[i])),
+                              "range equal", int(rr[-1]) == int(dfr[i]), "lost", np.nonzero(loss[i])[0][:12].tolist(),
+                              "loss kinds", sorted(set(loss[i].tolist()))))
+        bad_total += len(bad_e) + len(bad_d)
+        print("batch %2d: ch=%d frame=%4d F=%3d cut=%3d  encode bad %d  decode bad %d %s" % (b, ch, fs, F, cut, len(bad_e), len(bad_d),
+                                                                                          (bad_e + bad_d)[:2] if (bad_e or bad_d) else ""), flush=True)
+    print("parity sweep: %d batches x %d streams, seed %d: %d mismatching streams, %.0f s" % (NB, NS, SEED, bad_total, time.time() - t0))
+    sys.exit(1 if bad_total else 0)
+
+
+if __name__ == "__main__":
+    main()
