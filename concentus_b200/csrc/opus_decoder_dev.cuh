@@ -298,7 +298,11 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, PlcScratch 
     bool any = false;
     int result;
     if (pk.ret < 0) {
+        // rejected packet: the state stays untouched; its PCM row is zero-filled so that batch / span calls never hand stale
+        // buffer contents back (libopus leaves the caller's buffer unspecified on error)
         result = pk.ret;
+        CB_TEAM_FOR(i, cap * st->channels, tm) pcm[i] = 0;
+        tm.sync();
     } else if (pk.lost) {
         // conceal `cap` samples, frame by frame
         CbFrameIR lostir;

@@ -286,3 +286,36 @@ def test_decode_multichunk_pipeline():
     env = dict(os.environ, CB200_IR_MB="2", CB200_IR_HOST_MB="2")
     out = subprocess.run([sys.executable, "-c", _MULTICHUNK], capture_output=True, text=True, cwd=root, env=env, timeout=600)
     assert out.returncode == 0 and "chunks-ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_rejected_packet_leaves_zero_pcm_and_untouched_state():
+    """A packet the decoder rejects inside a span (a code-3 TOC with no count byte: OPUS_INVALID_PACKET, opus.c:228) must not
+    touch the stream's state (the following packets decode as in the reference, which skips it the same way) and must not hand
+    back stale buffer contents: its PCM row is zeros.  Found by tools/parity_sweep.py (wide mode)."""
+    cb = _cb()
+    ch, fs = 2, 960
+    x = O.test_signal(48000, ch, 77, "music")
+    d, o, l, _ = O.encode_stream(x, fs, 64000, ch, vbr=1, cvbr=0)
+    d, o = O.pack(d, o, l)
+    F = len(l)
+    dec = cb.DecoderBatch(1, 48000, ch)
+    dec.decode_span(d, o, l, F, fs)                 # fills the library's PCM staging with non-zero audio
+    dec.close()
+    d2 = d.copy()
+    l2 = l.copy()
+    for f in (7, 20):
+        d2[o[f]] = 0xFF                              # CELT fullband stereo, code 3
+        l2[f] = 1
+    rp, rr, rret = O.decode_stream(d2, o, l2, fs, ch)
+    assert rret[7] == -4 and rret[20] == -4
+    dec = cb.DecoderBatch(1, 48000, ch)
+    p, r = dec.decode_span(d2, o, l2, F, fs)
+    fr = dec.final_ranges()
+    dec.close()
+    assert np.array_equal(r, rret)
+    p = p.reshape(F, -1)
+    assert not p[7].any() and not p[20].any()
+    ok = np.ones(F, dtype=bool)
+    ok[[7, 20]] = False
+    assert np.array_equal(p[ok], rp.reshape(F, -1)[ok])
+    assert int(fr[0]) == int(rr[-1])

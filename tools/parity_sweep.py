@@ -3,7 +3,9 @@ CBR/VBR/CVBR, complexity and signal, for random (channels, frame size); the CUDA
 the CUDA decoder on the oracle's packets with a random loss pattern against the oracle sample-for-sample.  Prints one line per
 batch and a summary; exit code 1 on any mismatch.
 
-usage: python tools/parity_sweep.py [batches=24] [streams_per_batch=48] [seed=1]       (SWEEP_ONLY=51,123 runs just those batches)
+usage: python tools/parity_sweep.py [batches=24] [streams_per_batch=48] [seed=1] [wide]     (SWEEP_ONLY=51,123 runs just those batches)
+`wide` also draws the encoder's API rate (8-48 kHz), 40 / 60 ms frames (repacketized multi-frame packets), and a decoder whose
+rate and channel count differ from the stream's.
 """
 import ctypes as C
 import os
@@ -23,12 +25,21 @@ RATES = [24000, 32000, 40000, 48000, 64000, 80000, 96000, 128000, 160000, 192000
 KINDS = ("music", "tone", "clicks", "noise")
 
 
-def draw_batch(rs, NS):
+def draw_batch(rs, NS, wide=False):
     """All random parameters of one batch, drawn before any work, so that a batch can be reproduced alone."""
     ch = int(rs.choice([1, 2]))
     fs = int(rs.choice([120, 240, 480, 960]))
     nsec = 2 if fs >= 480 else 1
     F = 48000 * nsec // fs
+    if wide:
+        Fs = int(rs.choice([8000, 12000, 16000, 24000, 48000]))
+        ms10 = int(rs.choice([25, 50, 100, 200, 400, 600]))            # frame duration in 0.1 ms
+        fs = Fs * ms10 // 10000
+        F = int(Fs * (2 if ms10 >= 100 else 1)) // fs
+        dFs = int(rs.choice([8000, 12000, 16000, 24000, 48000]))
+        dch = int(rs.choice([1, 2]))
+    else:
+        Fs, dFs, dch = 48000, 48000, ch
     cfgs = [(int(rs.choice(RATES)), [(0, 0), (1, 0), (1, 1)][rs.randint(3)], int(rs.randint(11)), KINDS[rs.randint(4)], int(rs.randint(1 << 30)))
             for _ in range(NS)]
     cut = int(rs.randint(1, F))                       # two spans: state crosses a launch boundary at a random frame
@@ -42,7 +53,7 @@ def draw_batch(rs, NS):
             loss[i][s0:s0 + int(rs.randint(1, 12))] = 1
         elif mode == 3:
             loss[i][rs.rand(F) < 0.05] = 2
-    return ch, fs, F, cfgs, cut, loss
+    return ch, fs, F, cfgs, cut, loss, Fs, dFs, dch
 
 
 def main():
@@ -50,17 +61,19 @@ def main():
     NB = int(sys.argv[1]) if len(sys.argv) > 1 else 24
     NS = int(sys.argv[2]) if len(sys.argv) > 2 else 48
     SEED = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    WIDE = len(sys.argv) > 4 and sys.argv[4] == "wide"
     ONLY = [int(x) for x in os.environ.get("SWEEP_ONLY", "").split(",") if x]
     L = cb.lib()
     assert L.opus_b200_init(0) == 0
     rs = np.random.RandomState(SEED)
     bad_total, t0 = 0, time.time()
     for b in range(NB):
-        ch, fs, F, cfgs, cut, loss = draw_batch(rs, NS)
+        ch, fs, F, cfgs, cut, loss, Fs, dFs, dch = draw_batch(rs, NS, WIDE)
+        dfs = fs * dFs // Fs                           # samples per packet at the decoder's rate
         if ONLY and b not in ONLY:
             continue
         pcms = [O.test_signal(F * fs, ch, sd, kind) for (_, _, _, kind, sd) in cfgs]
-        enc = cb.EncoderBatch(NS, 48000, ch)
+        enc = cb.EncoderBatch(NS, Fs, ch)
         for i, (br, (vbr, cvbr), cx, _, _) in enumerate(cfgs):
             hp = C.c_void_p(enc.handles[i])
             for req, v in ((cb.OPUS_SET_BITRATE_REQUEST, br), (cb.OPUS_SET_VBR_REQUEST, vbr), (cb.OPUS_SET_VBR_CONSTRAINT_REQUEST, cvbr),
@@ -73,7 +86,7 @@ def main():
         enc.close()
         d = np.concatenate([d1.reshape(NS, cut, 1276), d2.reshape(NS, F - cut, 1276)], axis=1)
         l = np.concatenate([l1.reshape(NS, cut), l2.reshape(NS, F - cut)], axis=1)
-        refs = [O.encode_stream(pcms[i], fs, cfgs[i][0], ch, vbr=cfgs[i][1][0], cvbr=cfgs[i][1][1], complexity=cfgs[i][2], max_bytes=1276)
+        refs = [O.encode_stream(pcms[i], fs, cfgs[i][0], ch, Fs=Fs, vbr=cfgs[i][1][0], cvbr=cfgs[i][1][1], complexity=cfgs[i][2], max_bytes=1276)
                 for i in range(NS)]
         bad_e = []
         for i, (rd, ro, rl, rr) in enumerate(refs):
@@ -87,16 +100,16 @@ def main():
         lens[loss == 2] = 1
         blob = np.concatenate([r[0] for r in refs])
         offs = (np.arange(NS * F, dtype=np.int64) * 1276).reshape(NS, F)
-        dec = cb.DecoderBatch(NS, 48000, ch)
-        p1, r1 = dec.decode_span(blob, offs[:, :cut].reshape(-1), lens[:, :cut].reshape(-1), cut, fs)
-        p2, r2 = dec.decode_span(blob, offs[:, cut:].reshape(-1), lens[:, cut:].reshape(-1), F - cut, fs)
+        dec = cb.DecoderBatch(NS, dFs, dch)
+        p1, r1 = dec.decode_span(blob, offs[:, :cut].reshape(-1), lens[:, :cut].reshape(-1), cut, dfs)
+        p2, r2 = dec.decode_span(blob, offs[:, cut:].reshape(-1), lens[:, cut:].reshape(-1), F - cut, dfs)
         dfr = dec.final_ranges()
         dec.close()
-        pcm = np.concatenate([p1.reshape(NS, cut, fs * ch), p2.reshape(NS, F - cut, fs * ch)], axis=1)
+        pcm = np.concatenate([p1.reshape(NS, cut, dfs * dch), p2.reshape(NS, F - cut, dfs * dch)], axis=1)
         rets = np.concatenate([r1.reshape(NS, cut), r2.reshape(NS, F - cut)], axis=1)
         bad_d = []
         for i in range(NS):
-            rp, rr, rret = O.decode_stream(blob, offs[i], lens[i], fs, ch)
+            rp, rr, rret = O.decode_stream(blob, offs[i], lens[i], dfs, dch, Fs=dFs)
             ok = np.array_equal(rret, rets[i]) and np.array_equal(rp.reshape(F, -1), pcm[i]) and int(rr[-1]) == int(dfr[i])
             if not ok:
                 fb = np.nonzero((rp.reshape(F, -1) != pcm[i]).any(axis=1))[0]
@@ -104,7 +117,7 @@ def main():
                               "range equal", int(rr[-1]) == int(dfr[i]), "lost", np.nonzero(loss[i])[0][:12].tolist(),
                               "loss kinds", sorted(set(loss[i].tolist()))))
         bad_total += len(bad_e) + len(bad_d)
-        print("batch %2d: ch=%d frame=%4d F=%3d cut=%3d  encode bad %d  decode bad %d %s" % (b, ch, fs, F, cut, len(bad_e), len(bad_d),
+        print("batch %2d: ch=%d Fs=%5d frame=%4d F=%3d cut=%3d dec=%5d/%d  encode bad %d  decode bad %d %s" % (b, ch, Fs, fs, F, cut, dFs, dch, len(bad_e), len(bad_d),
                                                                                           (bad_e + bad_d)[:2] if (bad_e or bad_d) else ""), flush=True)
     print("parity sweep: %d batches x %d streams, seed %d: %d mismatching streams, %.0f s" % (NB, NS, SEED, bad_total, time.time() - t0))
     sys.exit(1 if bad_total else 0)
