@@ -38,8 +38,12 @@ def draw_batch(rs, NS, wide=False):
         F = int(Fs * (2 if ms10 >= 100 else 1)) // fs
         dFs = int(rs.choice([8000, 12000, 16000, 24000, 48000]))
         dch = int(rs.choice([1, 2]))
+        maxb = int(rs.choice([1276, 1276, 500, 200]))                   # max_data_bytes of the batch
+        extra = [(int(rs.choice([0, 0, 1, 2])) if ch == 2 else 0,       # OPUS_SET_FORCE_CHANNELS (0 = auto)
+                  int(rs.choice([0, 0, 0, 1101, 1102, 1103, 1104, 1105])))   # OPUS_SET_BANDWIDTH (0 = auto)
+                 for _ in range(NS)]
     else:
-        Fs, dFs, dch = 48000, 48000, ch
+        Fs, dFs, dch, maxb, extra = 48000, 48000, ch, 1276, [(0, 0)] * NS
     cfgs = [(int(rs.choice(RATES)), [(0, 0), (1, 0), (1, 1)][rs.randint(3)], int(rs.randint(11)), KINDS[rs.randint(4)], int(rs.randint(1 << 30)))
             for _ in range(NS)]
     cut = int(rs.randint(1, F))                       # two spans: state crosses a launch boundary at a random frame
@@ -53,7 +57,20 @@ def draw_batch(rs, NS, wide=False):
             loss[i][s0:s0 + int(rs.randint(1, 12))] = 1
         elif mode == 3:
             loss[i][rs.rand(F) < 0.05] = 2
-    return ch, fs, F, cfgs, cut, loss, Fs, dFs, dch
+    return ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra
+
+
+def ref_encode(pcm, fs, br, ch, Fs, vbr, cvbr, cx, maxb, force_channels, bandwidth):
+    """The oracle's encoder with the full settings struct -> (data [F*1276], offs, lens, ranges)."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    F = pcm.shape[0] // fs
+    out = np.zeros(F * 1276, dtype=np.uint8)
+    lens = np.zeros(F, dtype=np.int32)
+    ranges = np.zeros(F, dtype=np.uint32)
+    cfg = O.RefEncCfg(O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, br, vbr, cvbr, cx, maxb, force_channels, bandwidth)
+    rc = O.ref().ref_encode_stream(O.ptr(pcm), F, fs, ch, Fs, C.byref(cfg), O.ptr(out), 1276, O.ptr(lens), O.ptr(ranges))
+    assert rc == 0, rc
+    return out, np.arange(F, dtype=np.int64) * 1276, lens, ranges
 
 
 def main():
@@ -68,7 +85,7 @@ def main():
     rs = np.random.RandomState(SEED)
     bad_total, t0 = 0, time.time()
     for b in range(NB):
-        ch, fs, F, cfgs, cut, loss, Fs, dFs, dch = draw_batch(rs, NS, WIDE)
+        ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra = draw_batch(rs, NS, WIDE)
         dfs = fs * dFs // Fs                           # samples per packet at the decoder's rate
         if ONLY and b not in ONLY:
             continue
@@ -79,15 +96,18 @@ def main():
             for req, v in ((cb.OPUS_SET_BITRATE_REQUEST, br), (cb.OPUS_SET_VBR_REQUEST, vbr), (cb.OPUS_SET_VBR_CONSTRAINT_REQUEST, cvbr),
                            (cb.OPUS_SET_COMPLEXITY_REQUEST, cx)):
                 assert L.opus_encoder_ctl(hp, req, C.c_int32(v)) == 0
+            if extra[i][0]:
+                assert L.opus_encoder_ctl(hp, cb.OPUS_SET_FORCE_CHANNELS_REQUEST, C.c_int32(extra[i][0])) == 0
+            if extra[i][1]:
+                assert L.opus_encoder_ctl(hp, cb.OPUS_SET_BANDWIDTH_REQUEST, C.c_int32(extra[i][1])) == 0
         x = np.stack([p.reshape(F, fs * ch) for p in pcms])
-        d1, l1 = enc.encode_span(x[:, :cut].reshape(-1, ch), cut, fs)
-        d2, l2 = enc.encode_span(x[:, cut:].reshape(-1, ch), F - cut, fs)
+        d1, l1 = enc.encode_span(x[:, :cut].reshape(-1, ch), cut, fs, max_data_bytes=maxb)
+        d2, l2 = enc.encode_span(x[:, cut:].reshape(-1, ch), F - cut, fs, max_data_bytes=maxb)
         efr = enc.final_ranges()
         enc.close()
-        d = np.concatenate([d1.reshape(NS, cut, 1276), d2.reshape(NS, F - cut, 1276)], axis=1)
+        d = np.concatenate([d1.reshape(NS, cut, maxb), d2.reshape(NS, F - cut, maxb)], axis=1)
         l = np.concatenate([l1.reshape(NS, cut), l2.reshape(NS, F - cut)], axis=1)
-        refs = [O.encode_stream(pcms[i], fs, cfgs[i][0], ch, Fs=Fs, vbr=cfgs[i][1][0], cvbr=cfgs[i][1][1], complexity=cfgs[i][2], max_bytes=1276)
-                for i in range(NS)]
+        refs = [ref_encode(pcms[i], fs, cfgs[i][0], ch, Fs, cfgs[i][1][0], cfgs[i][1][1], cfgs[i][2], maxb, extra[i][0], extra[i][1]) for i in range(NS)]
         bad_e = []
         for i, (rd, ro, rl, rr) in enumerate(refs):
             rd = rd.reshape(F, 1276)
