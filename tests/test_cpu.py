@@ -509,3 +509,30 @@ def test_bit_container_edge_cases(tmp_path):
     g = tmp_path / "bad.bit"
     g.write_bytes(good + struct.pack(">II", 1 << 20, 1))
     assert bitfile.read_bit(str(g))[2].tolist() == [4, 0, 4]
+
+
+def test_hostsim_call_boundaries_with_loss_runs():
+    """The decoder headers under explicit call boundaries (hostsim_decode_stream_calls): stage A of a call starts from the
+    call-start snapshot (CbCallCtx) and tracks seed / loss streak through lost packets; calls that begin inside a burst, right
+    after one, and with TOC-only packets."""
+    hs = _hostsim()
+    hs.hostsim_decode_stream_calls.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_void_p, C.c_int]
+    for k, (ch, fs, br, cuts) in enumerate(((2, 480, 96000, [83, 200]), (2, 240, 40000, [50, 51, 120, 200]), (1, 960, 64000, [7, 30, 31, 100]))):
+        x = O.test_signal(fs * cuts[-1], ch, 600 + k, ("music", "clicks", "tone")[k])
+        d, o, l, _ = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=0)
+        d, o = O.pack(d, o, l)
+        l = l.copy()
+        F = len(l)
+        c0 = cuts[0]
+        l[c0 - (k % 2):c0 + 11] = 0          # a burst that starts at / just before the first boundary and outlasts pitch-based PLC
+        l[c0 + 30] = 1                        # TOC-only
+        rp, rr, rret = O.decode_stream(d, o, l, fs, ch)
+        pcm = np.zeros((F * fs, ch), dtype=np.int16)
+        rng = np.zeros(F, dtype=np.uint32)
+        ret = np.zeros(F, dtype=np.int32)
+        b = np.array(cuts, dtype=np.int32)
+        hs.hostsim_decode_stream_calls(O.ptr(d), O.ptr(np.ascontiguousarray(o, dtype=np.int64)), O.ptr(np.ascontiguousarray(l, dtype=np.int32)),
+                                       F, fs, ch, 48000, O.ptr(pcm), O.ptr(rng), O.ptr(ret), O.ptr(b), len(cuts))
+        assert np.array_equal(ret, rret) and np.array_equal(rng, rr), (ch, fs)
+        bad = np.nonzero((rp.reshape(F, -1) != pcm.reshape(F, -1)).any(axis=1))[0]
+        assert bad.size == 0, (ch, fs, int(bad[0]))
