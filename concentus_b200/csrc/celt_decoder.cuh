@@ -203,7 +203,7 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
             m = mul16_32_q15(kPreemphCoef0, t);
             if (j == next) {
                 int v = sig2word16(t);
-                if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+                if (gain >= 0) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
                 y[k * CC] = (int16_t)v;
                 k++;
                 next += downsample;
@@ -224,7 +224,7 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
                     int t = wadd(xs[u], m);
                     m = mul16_32_q15(kPreemphCoef0, t);
                     int v = sig2word16(t);
-                    if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+                    if (gain >= 0) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
                     y[(j + u) * CC] = (int16_t)v;
                 }
             }
@@ -233,7 +233,7 @@ CB_DEV int deemphasis_channel(const int *x, int n, int16_t *y, int CC, int downs
             int t = wadd(x[j], m);
             m = mul16_32_q15(kPreemphCoef0, t);
             int v = sig2word16(t);
-            if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+            if (gain >= 0) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
             y[j * CC] = (int16_t)v;
         }
     }

@@ -130,7 +130,7 @@ __device__ __forceinline__ int deemph_pair_stereo(const int *x, int n, int16_t *
             int t = wadd(xs[u], m);
             m = mul16_32_q15(kPreemphCoef0, t);
             int v = sig2word16(t);
-            if (gain) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
+            if (gain >= 0) { int g = mul16_32_p16(v, gain); v = g > 32767 ? 32767 : (g < -32767 ? -32767 : g); }
             if (u & 1) w[u >> 1] |= (unsigned)(v & 0xffff) << 16;
             else w[u >> 1] = (unsigned)(v & 0xffff);
         }
@@ -158,7 +158,7 @@ deemph_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n
     const int channels = st->channels;
     if (c >= channels) return;
     const int ds = st->downsample;
-    const int gain = st->decode_gain ? celt_exp2(s16(mul16_16_p15(21771, st->decode_gain))) : 0;   // QCONST16(6.48814081e-4f, 25)
+    const int gain = st->decode_gain ? celt_exp2(s16(mul16_16_p15(21771, st->decode_gain))) : -1;   // QCONST16(6.48814081e-4f, 25); -1 = no gain stage (a very negative gain gives 0 = silence, opus_decoder.c:700-711)
     const unsigned pairmask = 3u << ((threadIdx.x & 31) & ~1);
     const bool paired = channels == 2 && ds == 1;
     int m = st->preemph_memD[c];

@@ -355,7 +355,7 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, PlcScratch 
 CB_DEV void opus_deemph_packet(CbDecState *st, int c, const int *sigbase, const CbSigRange &rg, int16_t *pcm, int cap) {
     if (rg.end <= rg.begin) return;
     const int ds = st->downsample, CC = st->channels;
-    const int gain = st->decode_gain ? celt_exp2(s16(mul16_16_p15(21771, st->decode_gain))) : 0;   // QCONST16(6.48814081e-4f, 25)
+    const int gain = st->decode_gain ? celt_exp2(s16(mul16_16_p15(21771, st->decode_gain))) : -1;   // QCONST16(6.48814081e-4f, 25); -1 = no gain stage (a very negative gain gives 0 = silence, opus_decoder.c:700-711)
     const int *x = sigbase + c * (cap * ds) + rg.begin;
     int16_t *y = pcm + (rg.begin / ds) * CC + c;
     st->preemph_memD[c] = deemphasis_channel(x, rg.end - rg.begin, y, CC, ds, st->preemph_memD[c], gain);

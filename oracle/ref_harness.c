@@ -119,6 +119,28 @@ int ref_decode_stream(const uint8_t *data, const int64_t *offs, const int32_t *l
     return 0;
 }
 
+/* The same with OPUS_SET_GAIN(gain_q8) applied before the first packet and OPUS_SET_GAIN(gain2_q8) before packet `switch_at`
+ * (src/opus_decoder.c:836-846; applied in opus_decode_native :700-711). */
+int ref_decode_stream_gain(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F,
+                           int frame_size, int channels, int Fs, int gain_q8, int gain2_q8, int switch_at,
+                           int16_t *pcm, uint32_t *ranges, int32_t *rets)
+{
+    int err = 0, f;
+    OpusDecoder *d = opus_decoder_create(Fs, channels, &err);
+    if (!d) return err;
+    opus_decoder_ctl(d, OPUS_SET_GAIN(gain_q8));
+    for (f = 0; f < F; f++) {
+        const uint8_t *p = lens[f] > 0 ? data + offs[f] : NULL;
+        int n;
+        if (f == switch_at) opus_decoder_ctl(d, OPUS_SET_GAIN(gain2_q8));
+        n = opus_decode(d, p, lens[f], pcm + (size_t)f * frame_size * channels, frame_size, 0);
+        if (rets) rets[f] = n;
+        if (ranges) opus_decoder_ctl(d, OPUS_GET_FINAL_RANGE(&ranges[f]));
+    }
+    opus_decoder_destroy(d);
+    return 0;
+}
+
 /* ---- one-stream-per-thread pool (BASELINE.md §3 "Driver") ------------------------------------------ */
 typedef struct {
     int kind; /* 0 = decode, 1 = encode */

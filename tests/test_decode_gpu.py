@@ -319,3 +319,44 @@ def test_rejected_packet_leaves_zero_pcm_and_untouched_state():
     ok[[7, 20]] = False
     assert np.array_equal(p[ok], rp.reshape(F, -1)[ok])
     assert int(fr[0]) == int(rr[-1])
+
+
+def test_decoder_gain_ctl():
+    """OPUS_SET_GAIN (src/opus_decoder.c:836-846, applied per sample in opus_decode_native :700-711; here inside stage C):
+    positive and negative Q8 gains incl. ones that saturate, changed in the middle of the stream between two span calls, mono
+    and stereo, 48 and 16 kHz output, with lost packets (the gain also scales concealed audio)."""
+    cb = _cb()
+    L = cb.lib()
+    R = O.ref()
+    cases = [(2, 960, 48000, 768, -1500), (1, 480, 48000, -3000, 2500), (2, 960, 16000, 5000, 300), (2, 240, 48000, 32767, -32768)]
+    for k, (ch, fs, dFs, g1, g2) in enumerate(cases):
+        x = O.test_signal(48000, ch, 50 + k, ("music", "noise", "tone", "clicks")[k])
+        d, o, l, _ = O.encode_stream(x, fs, 64000, ch, vbr=1, cvbr=0)
+        d, o = O.pack(d, o, l)
+        l = l.copy()
+        l[11::13] = 0
+        F = len(l)
+        cut = F // 2
+        dfs = fs * dFs // 48000
+        rp = np.zeros((F * dfs, ch), dtype=np.int16)
+        rr = np.zeros(F, dtype=np.uint32)
+        rret = np.zeros(F, dtype=np.int32)
+        R.ref_decode_stream_gain(O.ptr(d), O.ptr(np.ascontiguousarray(o, dtype=np.int64)), O.ptr(np.ascontiguousarray(l, dtype=np.int32)), F, dfs, ch, dFs,
+                                 g1, g2, cut, O.ptr(rp), O.ptr(rr), O.ptr(rret))
+        dec = cb.DecoderBatch(1, dFs, ch)
+        h = C.c_void_p(dec.handles[0])
+        assert L.opus_decoder_ctl(h, cb.OPUS_SET_GAIN_REQUEST, C.c_int32(g1)) == 0
+        p1, r1 = dec.decode_span(d, o[:cut], l[:cut], cut, dfs)
+        assert L.opus_decoder_ctl(h, cb.OPUS_SET_GAIN_REQUEST, C.c_int32(g2)) == 0
+        got = C.c_int32(0)
+        assert L.opus_decoder_ctl(h, 4045, C.byref(got)) == 0 and got.value == g2      # OPUS_GET_GAIN
+        p2, r2 = dec.decode_span(d, o[cut:], l[cut:], F - cut, dfs)
+        dec.close()
+        assert np.array_equal(np.concatenate([r1, r2]), rret), (ch, fs, dFs)
+        got_pcm = np.concatenate([p1, p2]).reshape(F, -1)
+        bad = np.nonzero((rp.reshape(F, -1) != got_pcm).any(axis=1))[0]
+        assert bad.size == 0, (ch, fs, dFs, g1, g2, "first bad frame", int(bad[0]))
+    # out-of-range gains are rejected like the reference (opus_decoder.c:839)
+    dec = cb.DecoderBatch(1, 48000, 2)
+    assert L.opus_decoder_ctl(C.c_void_p(dec.handles[0]), cb.OPUS_SET_GAIN_REQUEST, C.c_int32(40000)) == -1
+    dec.close()
