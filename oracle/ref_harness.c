@@ -141,6 +141,30 @@ int ref_decode_stream_gain(const uint8_t *data, const int64_t *offs, const int32
     return 0;
 }
 
+/* Decode with the getters read after every packet and OPUS_RESET_STATE issued before packet `reset_at` (-1 = never):
+ * info[f*4 + {0,1,2,3}] = OPUS_GET_PITCH, OPUS_GET_LAST_PACKET_DURATION, OPUS_GET_BANDWIDTH, OPUS_GET_SAMPLE_RATE. */
+int ref_decode_stream_info(const uint8_t *data, const int64_t *offs, const int32_t *lens, int F,
+                           int frame_size, int channels, int Fs, int reset_at, int16_t *pcm, uint32_t *ranges,
+                           int32_t *rets, int32_t *info)
+{
+    int err = 0, f;
+    OpusDecoder *d = opus_decoder_create(Fs, channels, &err);
+    if (!d) return err;
+    for (f = 0; f < F; f++) {
+        const uint8_t *p = lens[f] > 0 ? data + offs[f] : NULL;
+        opus_int32 v = 0;
+        if (f == reset_at) opus_decoder_ctl(d, OPUS_RESET_STATE);
+        rets[f] = opus_decode(d, p, lens[f], pcm + (size_t)f * frame_size * channels, frame_size, 0);
+        opus_decoder_ctl(d, OPUS_GET_FINAL_RANGE(&ranges[f]));
+        opus_decoder_ctl(d, OPUS_GET_PITCH(&v)); info[f * 4 + 0] = v;
+        opus_decoder_ctl(d, OPUS_GET_LAST_PACKET_DURATION(&v)); info[f * 4 + 1] = v;
+        opus_decoder_ctl(d, OPUS_GET_BANDWIDTH(&v)); info[f * 4 + 2] = v;
+        opus_decoder_ctl(d, OPUS_GET_SAMPLE_RATE(&v)); info[f * 4 + 3] = v;
+    }
+    opus_decoder_destroy(d);
+    return 0;
+}
+
 /* ---- one-stream-per-thread pool (BASELINE.md §3 "Driver") ------------------------------------------ */
 typedef struct {
     int kind; /* 0 = decode, 1 = encode */

@@ -360,3 +360,47 @@ def test_decoder_gain_ctl():
     dec = cb.DecoderBatch(1, 48000, 2)
     assert L.opus_decoder_ctl(C.c_void_p(dec.handles[0]), cb.OPUS_SET_GAIN_REQUEST, C.c_int32(40000)) == -1
     dec.close()
+
+
+def test_decoder_getters_and_reset_per_packet():
+    """opus_decoder_ctl getters after every packet of the scalar API — OPUS_GET_PITCH (celt_decoder.c:1208, the post-filter
+    period), OPUS_GET_LAST_PACKET_DURATION, OPUS_GET_BANDWIDTH, OPUS_GET_SAMPLE_RATE, OPUS_GET_FINAL_RANGE — and
+    OPUS_RESET_STATE in the middle of a stream (src/opus_decoder.c:812-822), with lost packets; vs the reference."""
+    cb = _cb()
+    L = cb.lib()
+    R = O.ref()
+    for k, (ch, fs, dFs, kind, br) in enumerate(((2, 960, 48000, "tone", 64000), (1, 480, 24000, "music", 48000), (2, 240, 48000, "clicks", 128000))):
+        x = O.test_signal(48000, ch, 90 + k, kind)
+        d, o, l, _ = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=0)
+        d, o = O.pack(d, o, l)
+        l = l.copy()
+        l[6::11] = 0
+        F = min(len(l), 60)
+        reset_at = 23
+        dfs = fs * dFs // 48000
+        rp = np.zeros((F * dfs, ch), dtype=np.int16)
+        rr = np.zeros(F, dtype=np.uint32)
+        rret = np.zeros(F, dtype=np.int32)
+        info = np.zeros((F, 4), dtype=np.int32)
+        R.ref_decode_stream_info(O.ptr(d), O.ptr(np.ascontiguousarray(o, dtype=np.int64)), O.ptr(np.ascontiguousarray(l, dtype=np.int32)), F, dfs, ch, dFs,
+                                 reset_at, O.ptr(rp), O.ptr(rr), O.ptr(rret), O.ptr(info))
+        err = C.c_int(0)
+        L.opus_decoder_create.restype = C.c_void_p
+        h = C.c_void_p(L.opus_decoder_create(dFs, ch, C.byref(err)))
+        out = np.zeros((dfs, ch), dtype=np.int16)
+        v = C.c_int32(0)
+        u = C.c_uint32(0)
+        for f in range(F):
+            if f == reset_at:
+                assert L.opus_decoder_ctl(h, cb.OPUS_RESET_STATE) == 0
+            p = O.ptr(d[o[f]:]) if l[f] > 0 else None
+            n = L.opus_decode(h, p, int(l[f]), O.ptr(out), dfs, 0)
+            assert n == rret[f], (k, f, n, int(rret[f]))
+            assert np.array_equal(out[:max(n, 0)], rp[f * dfs:f * dfs + max(n, 0)]), (k, f)
+            L.opus_decoder_ctl(h, cb.OPUS_GET_FINAL_RANGE_REQUEST, C.byref(u))
+            assert u.value == int(rr[f]), (k, f, "final range")
+            for j, req in enumerate((cb.OPUS_GET_PITCH_REQUEST, cb.OPUS_GET_LAST_PACKET_DURATION_REQUEST, cb.OPUS_GET_BANDWIDTH_REQUEST,
+                                     cb.OPUS_GET_SAMPLE_RATE_REQUEST)):
+                assert L.opus_decoder_ctl(h, req, C.byref(v)) == 0
+                assert v.value == int(info[f, j]), (k, f, ("pitch", "last_packet_duration", "bandwidth", "sample_rate")[j], v.value, int(info[f, j]))
+        L.opus_decoder_destroy(h)
