@@ -75,8 +75,19 @@ struct SeedTrack {
     int channels;     // decoder output channels (constant)
 };
 
-// One concealment frame of `audiosize` samples (API rate): what celt_decode_lost does to (rng, loss_count).
+// One concealment frame of `audiosize` samples (API rate): what celt_decode_lost does to (rng, loss_count).  More than 20 ms
+// (the frame size a SILK / hybrid TOC can set) is concealed in 20 ms pieces (opus_decoder.c:257-268).
+CB_DEV bool track_lost_chunk(SeedTrack &tr, int audiosize, int Fs);
 CB_DEV bool track_lost_frame(SeedTrack &tr, int audiosize, int Fs) {
+    const int F20 = Fs / 50;
+    do {
+        const int a = imin(audiosize, F20);
+        if (!track_lost_chunk(tr, a, Fs)) return false;
+        audiosize -= a;
+    } while (audiosize > 0);
+    return true;
+}
+CB_DEV bool track_lost_chunk(SeedTrack &tr, int audiosize, int Fs) {
     const int N = audiosize * (48000 / Fs);
     int LM;
     for (LM = 0; LM <= kMaxLM; LM++)
@@ -128,7 +139,14 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     uint8_t toc;
     const int count = pkt_parse(data, len, 0, &toc, size, &offset, nullptr);
     if (count < 0) { pk.ret = count; return; }
-    if (packet_mode != CB_MODE_CELT_ONLY) { pk.ret = OPUS_UNIMPLEMENTED_; return; }   // scope edge: no SILK / hybrid
+    // scope edge: no SILK / hybrid decoding.  A SILK / hybrid TOC whose frames are all empty (<= 1 byte) is still ours: every
+    // frame is concealed from the CELT state (opus_decoder.c:246-252) — the "PLC frames" an encoder emits when max_data_bytes
+    // leaves no room for a frame (opus_encoder.c:1240-1270) look like that.
+    if (packet_mode != CB_MODE_CELT_ONLY) {
+        bool all_empty = !decode_fec;
+        for (int i = 0; i < count; i++) all_empty &= size[i] <= 1;
+        if (!all_empty) { pk.ret = OPUS_UNIMPLEMENTED_; return; }
+    }
     if (decode_fec) { pk.ret = 0; pk.lost = 1; track_lost_packet(tr, cap, Fs); return; }   // CELT carries no in-band FEC (opus_decoder.c:655-657)
     if (count * packet_frame_size > cap) { pk.ret = OPUS_BUFFER_TOO_SMALL_; return; }
     if (count > kmax) { pk.ret = OPUS_BUFFER_TOO_SMALL_; return; }   // cannot happen when kmax = cap / (Fs/400)
@@ -144,7 +162,7 @@ CB_DEV void opus_parse_packet(const uint8_t *data, int len, int cap, int Fs, int
     const int end = bandwidth_to_endband(pk.bandwidth);
     const int N = packet_frame_size * (48000 / Fs);   // CELT frame length at 48 kHz
     int LM = 0;
-    while ((kShortMdct << LM) != N && LM < kMaxLM) LM++;
+    while ((kShortMdct << LM) != N && LM < kMaxLM) LM++;   // (a 40 / 60 ms SILK-TOC frame has no LM: its frames are all concealed)
     const uint8_t *p = data + offset;
     int xoff = 0;
     int nb_samples = 0;
@@ -265,7 +283,24 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, PlcScratch &
             tm.sync();
             return audiosize;
         }
-        // audiosize > 20 ms cannot happen: it is clamped to st->frame_size and CELT frames are <= 20 ms
+        // more than 20 ms (st->frame_size set by a SILK / hybrid TOC whose frames are all empty): concealed in 20 ms pieces,
+        // each one a complete opus_decode_frame(NULL) call of the reference (opus_decoder.c:257-268)
+        if (audiosize > F20) {
+            int done = 0;
+            bool any = false;
+            while (done < audiosize) {
+                const int chunk = imin(audiosize - done, F20);
+                int *sig2[2] = {sig[0] + done * st->downsample, sig[1] + done * st->downsample};
+                const int r = celt_decode_lost_frame(tm, st, S, P, sig2, chunk, bandwidth_to_endband(st->bandwidth));
+                if (tm.lane() == 0) { st->rangeFinal = 0; st->prev_mode = mode; st->prev_redundancy = 0; }
+                tm.sync();
+                if (r < 0) { *staged = any; return r; }
+                any = true;
+                done += chunk;
+            }
+            *staged = true;
+            return audiosize;
+        }
         if (audiosize < F20) {
             if (audiosize > F10) audiosize = F10;
             else if (mode != CB_MODE_SILK_ONLY && audiosize > F5 && audiosize < F10) audiosize = F5;
@@ -348,6 +383,13 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, PlcScratch 
         }
     }
     if (tm.lane() == 0) { range->begin = any ? sb : 0; range->end = any ? se : 0; }
+    // a packet shorter than the row's capacity: the rest of the row is zero-filled, so batch / span calls hand back
+    // deterministic buffers (stage C writes [0, result) only)
+    if (result >= 0 && result < cap) {
+        const int CC = st->channels;
+        CB_TEAM_FOR(i, (cap - result) * CC, tm) pcm[result * CC + i] = 0;
+        tm.sync();
+    }
     return result;
 }
 

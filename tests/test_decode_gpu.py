@@ -404,3 +404,38 @@ def test_decoder_getters_and_reset_per_packet():
                 assert L.opus_decoder_ctl(h, req, C.byref(v)) == 0
                 assert v.value == int(info[f, j]), (k, f, ("pitch", "last_packet_duration", "bandwidth", "sample_rate")[j], v.value, int(info[f, j]))
         L.opus_decoder_destroy(h)
+
+
+def test_plc_packets_with_non_celt_toc_and_oversized_capacity():
+    """(1) When max_data_bytes leaves no room for a frame the encoder emits "PLC frames": a TOC-only packet whose TOC says SILK
+    for 40 / 60 ms frames (opus_encoder.c:1240-1270), CBR-padded to a code-3 packet with an empty frame.  The decoder conceals
+    them from the CELT state, 40 / 60 ms in 20 ms pieces (opus_decoder.c:246-268) — not OPUS_UNIMPLEMENTED.  (2) A PCM
+    capacity larger than the packet's duration: received packets return their own duration (the rest of the row reads zero),
+    lost packets are concealed over the whole capacity.  Found by tools/parity_sweep.py (wide mode)."""
+    cb = _cb()
+    for k, (Fs, ch, ms, vbr, maxb, capmul) in enumerate(((48000, 2, 60, 0, 3, 1), (12000, 2, 60, 1, 3, 1), (16000, 1, 40, 0, 8, 1),
+                                                         (48000, 2, 20, 1, 1276, 3), (48000, 1, 10, 1, 1276, 2), (24000, 2, 5, 0, 1276, 3))):
+        fs = Fs * ms // 1000
+        x = O.test_signal(Fs * 2, ch, 30 + k, ("music", "tone", "clicks")[k % 3])
+        F = x.shape[0] // fs
+        normal = O.encode_stream(x, fs, 64000, ch, Fs=Fs, vbr=vbr, cvbr=0, complexity=5, max_bytes=1276)
+        tiny = O.encode_stream(x, fs, 64000, ch, Fs=Fs, vbr=vbr, cvbr=0, complexity=5, max_bytes=maxb)
+        # a stream that alternates between real packets and what the starved encoder produced for the same frames
+        data = np.concatenate([normal[0], tiny[0]])
+        use_tiny = (np.arange(F) % 5) >= 3
+        offs = np.where(use_tiny, tiny[1] + len(normal[0]), normal[1])
+        lens = np.where(use_tiny, tiny[2], normal[2]).astype(np.int32)
+        lens[7::11] = 0
+        cap = fs * capmul
+        rp, rr, rret = O.decode_stream(data, offs, lens, cap, ch, Fs=Fs)
+        assert (rret > 0).all(), (k, rret[:12])
+        dec = cb.DecoderBatch(1, Fs, ch)
+        p1, r1 = dec.decode_span(data, offs[:F // 2], lens[:F // 2], F // 2, cap)
+        p2, r2 = dec.decode_span(data, offs[F // 2:], lens[F // 2:], F - F // 2, cap)
+        fr = dec.final_ranges()
+        dec.close()
+        assert np.array_equal(np.concatenate([r1, r2]), rret), (k, Fs, ms, maxb)
+        got = np.concatenate([p1, p2]).reshape(F, -1)
+        bad = np.nonzero((rp.reshape(F, -1) != got).any(axis=1))[0]
+        assert bad.size == 0, (k, Fs, ms, maxb, capmul, "first bad row", int(bad[0]))
+        assert int(fr[0]) == int(rr[-1])

@@ -38,12 +38,13 @@ def draw_batch(rs, NS, wide=False):
         F = int(Fs * (2 if ms10 >= 100 else 1)) // fs
         dFs = int(rs.choice([8000, 12000, 16000, 24000, 48000]))
         dch = int(rs.choice([1, 2]))
-        maxb = int(rs.choice([1276, 1276, 500, 200]))                   # max_data_bytes of the batch
+        maxb = int(rs.choice([1276, 1276, 500, 200, 40, 8, 3]))         # max_data_bytes of the batch
+        capmul = float(rs.choice([1, 1, 1, 2, 3, 0.5]))                 # decoder PCM capacity per packet / packet duration
         extra = [(int(rs.choice([0, 0, 1, 2])) if ch == 2 else 0,       # OPUS_SET_FORCE_CHANNELS (0 = auto)
                   int(rs.choice([0, 0, 0, 1101, 1102, 1103, 1104, 1105])))   # OPUS_SET_BANDWIDTH (0 = auto)
                  for _ in range(NS)]
     else:
-        Fs, dFs, dch, maxb, extra = 48000, 48000, ch, 1276, [(0, 0)] * NS
+        Fs, dFs, dch, maxb, extra, capmul = 48000, 48000, ch, 1276, [(0, 0)] * NS, 1
     cfgs = [(int(rs.choice(RATES)), [(0, 0), (1, 0), (1, 1)][rs.randint(3)], int(rs.randint(11)), KINDS[rs.randint(4)], int(rs.randint(1 << 30)))
             for _ in range(NS)]
     cut = int(rs.randint(1, F))                       # two spans: state crosses a launch boundary at a random frame
@@ -57,7 +58,7 @@ def draw_batch(rs, NS, wide=False):
             loss[i][s0:s0 + int(rs.randint(1, 12))] = 1
         elif mode == 3:
             loss[i][rs.rand(F) < 0.05] = 2
-    return ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra
+    return ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra, capmul
 
 
 def ref_encode(pcm, fs, br, ch, Fs, vbr, cvbr, cx, maxb, force_channels, bandwidth):
@@ -85,8 +86,10 @@ def main():
     rs = np.random.RandomState(SEED)
     bad_total, t0 = 0, time.time()
     for b in range(NB):
-        ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra = draw_batch(rs, NS, WIDE)
-        dfs = fs * dFs // Fs                           # samples per packet at the decoder's rate
+        ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra, capmul = draw_batch(rs, NS, WIDE)
+        dfs = int(fs * dFs // Fs * capmul)             # PCM capacity per packet at the decoder's rate
+        if dfs * 25 > dFs * 3:                         # opus_decode conceals at most 120 ms
+            dfs = fs * dFs // Fs
         if ONLY and b not in ONLY:
             continue
         pcms = [O.test_signal(F * fs, ch, sd, kind) for (_, _, _, kind, sd) in cfgs]
@@ -111,7 +114,7 @@ def main():
         bad_e = []
         for i, (rd, ro, rl, rr) in enumerate(refs):
             rd = rd.reshape(F, 1276)
-            ok = np.array_equal(rl, l[i]) and all(np.array_equal(rd[f, :rl[f]], d[i, f, :rl[f]]) for f in range(F)) and int(rr[-1]) == int(efr[i])
+            ok = np.array_equal(rl, l[i]) and all(np.array_equal(rd[f, :max(rl[f], 0)], d[i, f, :max(rl[f], 0)]) for f in range(F)) and int(rr[-1]) == int(efr[i])
             if not ok:
                 bad_e.append((i, cfgs[i]))
         # decode the oracle's packets with the per-stream loss pattern
@@ -130,14 +133,20 @@ def main():
         bad_d = []
         for i in range(NS):
             rp, rr, rret = O.decode_stream(blob, offs[i], lens[i], dfs, dch, Fs=dFs)
-            ok = np.array_equal(rret, rets[i]) and np.array_equal(rp.reshape(F, -1), pcm[i]) and int(rr[-1]) == int(dfr[i])
+            rp = rp.reshape(F, dfs * dch)
+            # what a caller may read: the first ret samples of every row; the rest of a row is compared too (the library
+            # zero-fills it, the reference leaves the caller's zero-initialised buffer alone)
+            head_ok = all(np.array_equal(rp[f, :max(int(rret[f]), 0) * dch], pcm[i, f, :max(int(rret[f]), 0) * dch]) for f in range(F))
+            ok = np.array_equal(rret, rets[i]) and head_ok and np.array_equal(rp, pcm[i]) and int(rr[-1]) == int(dfr[i])
             if not ok:
-                fb = np.nonzero((rp.reshape(F, -1) != pcm[i]).any(axis=1))[0]
-                bad_d.append((i, cfgs[i], "first bad frame", int(fb[0]) if fb.size else -1, "rets equal", bool(np.array_equal(rret, rets[i])),
-                              "range equal", int(rr[-1]) == int(dfr[i]), "lost", np.nonzero(loss[i])[0][:12].tolist(),
-                              "loss kinds", sorted(set(loss[i].tolist()))))
+                fb = np.nonzero((rp != pcm[i]).any(axis=1))[0]
+                fr_ = np.nonzero(rret != rets[i])[0]
+                bad_d.append((i, cfgs[i], "rets equal", bool(np.array_equal(rret, rets[i])),
+                              ("first ret diff", int(fr_[0]), int(rret[fr_[0]]), int(rets[i][fr_[0]]), "len", int(lens[i][fr_[0]])) if fr_.size else "",
+                              "decoded samples equal", bool(head_ok), "first bad row", int(fb[0]) if fb.size else -1,
+                              "range equal", int(rr[-1]) == int(dfr[i]), "lost", np.nonzero(loss[i])[0][:8].tolist()))
         bad_total += len(bad_e) + len(bad_d)
-        print("batch %2d: ch=%d Fs=%5d frame=%4d F=%3d cut=%3d dec=%5d/%d  encode bad %d  decode bad %d %s" % (b, ch, Fs, fs, F, cut, dFs, dch, len(bad_e), len(bad_d),
+        print("batch %2d: ch=%d Fs=%5d frame=%4d maxb=%4d F=%3d cut=%3d dec=%5d/%d cap=%4d  encode bad %d  decode bad %d %s" % (b, ch, Fs, fs, maxb, F, cut, dFs, dch, dfs, len(bad_e), len(bad_d),
                                                                                           (bad_e + bad_d)[:2] if (bad_e or bad_d) else ""), flush=True)
     print("parity sweep: %d batches x %d streams, seed %d: %d mismatching streams, %.0f s" % (NB, NS, SEED, bad_total, time.time() - t0))
     sys.exit(1 if bad_total else 0)
