@@ -260,6 +260,32 @@ struct CbSigRange {
     int32_t begin, end;
 };
 
+// Concealment of one lost frame of frame_size samples, out of line (rare path; keeps the synthesis loop's registers free).  More
+// than 20 ms — st->frame_size set by a SILK / hybrid TOC whose frames are all empty — goes in 20 ms pieces, each one a complete
+// opus_decode_frame(NULL) call of the reference (opus_decoder.c:257-268).  Returns < 0 when the first piece failed.
+template <class TM>
+CB_DEV_NOINLINE int conceal_frame(TM tm, CbDecState *st, SynthScratch &S, PlcScratch &P, int *const *sig, int frame_size, int F20, int mode) {
+    int done = 0, r = 0;
+    do {
+        const int chunk = imin(frame_size - done, F20);
+        int *sig2[2] = {sig[0] + done * st->downsample, sig[1] + done * st->downsample};
+        r = celt_decode_lost_frame(tm, st, S, P, sig2, chunk, bandwidth_to_endband(st->bandwidth));
+        if (r < 0) break;
+        done += chunk;
+        if (done < frame_size) {   // what the reference's inner call leaves behind before the next piece
+            if (tm.lane() == 0) { st->rangeFinal = 0; st->prev_mode = mode; st->prev_redundancy = 0; }
+            tm.sync();
+        }
+    } while (done < frame_size);
+    return done > 0 ? done : r;
+}
+// Zero-fill n samples of a PCM row (rejected packets, row tails), out of line for the same reason.
+template <class TM>
+CB_DEV_NOINLINE void zero_pcm(TM tm, int16_t *p, int n) {
+    CB_TEAM_FOR(i, n, tm) p[i] = 0;
+    tm.sync();
+}
+
 // opus_decode_frame remainder for one frame (opus_decoder.c:246-252,265-272,452-596).  sig[c] points at this frame's
 // position in the packet's staging area; *staged is set when the frame left signal there.
 template <class TM>
@@ -283,24 +309,8 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, PlcScratch &
             tm.sync();
             return audiosize;
         }
-        // more than 20 ms (st->frame_size set by a SILK / hybrid TOC whose frames are all empty): concealed in 20 ms pieces,
-        // each one a complete opus_decode_frame(NULL) call of the reference (opus_decoder.c:257-268)
-        if (audiosize > F20) {
-            int done = 0;
-            bool any = false;
-            while (done < audiosize) {
-                const int chunk = imin(audiosize - done, F20);
-                int *sig2[2] = {sig[0] + done * st->downsample, sig[1] + done * st->downsample};
-                const int r = celt_decode_lost_frame(tm, st, S, P, sig2, chunk, bandwidth_to_endband(st->bandwidth));
-                if (tm.lane() == 0) { st->rangeFinal = 0; st->prev_mode = mode; st->prev_redundancy = 0; }
-                tm.sync();
-                if (r < 0) { *staged = any; return r; }
-                any = true;
-                done += chunk;
-            }
-            *staged = true;
-            return audiosize;
-        }
+        // more than 20 ms (st->frame_size set by a SILK / hybrid TOC whose frames are all empty) is concealed in 20 ms pieces
+        // below, each one a complete opus_decode_frame(NULL) call of the reference (opus_decoder.c:257-268)
         if (audiosize < F20) {
             if (audiosize > F10) audiosize = F10;
             else if (mode != CB_MODE_SILK_ONLY && audiosize > F5 && audiosize < F10) audiosize = F5;
@@ -309,9 +319,13 @@ CB_DEV int opus_synth_frame(TM tm, CbDecState *st, SynthScratch &S, PlcScratch &
     if (audiosize > frame_size) return OPUS_BAD_ARG_;
     frame_size = audiosize;
     int celt_ret;
-    if (lost) celt_ret = celt_decode_lost_frame(tm, st, S, P, sig, imin(F20, frame_size), bandwidth_to_endband(st->bandwidth));
-    else celt_ret = celt_synth_frame(tm, st, S, ir, X, sig);
-    *staged = !(lost && celt_ret < 0);
+    if (lost) {
+        celt_ret = conceal_frame(tm, st, S, P, sig, frame_size, F20, mode);
+        *staged = celt_ret >= 0;
+    } else {
+        celt_ret = celt_synth_frame(tm, st, S, ir, X, sig);
+        *staged = true;
+    }
     // decode gain (opus_decoder.c:567-577) is applied by stage C when it writes the PCM
     if (tm.lane() == 0) {
         st->rangeFinal = (lost || ir.len <= 1) ? 0 : ir.rng_final;
@@ -336,8 +350,7 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, PlcScratch 
         // rejected packet: the state stays untouched; its PCM row is zero-filled so that batch / span calls never hand stale
         // buffer contents back (libopus leaves the caller's buffer unspecified on error)
         result = pk.ret;
-        CB_TEAM_FOR(i, cap * st->channels, tm) pcm[i] = 0;
-        tm.sync();
+        zero_pcm(tm, pcm, cap * st->channels);
     } else if (pk.lost) {
         // conceal `cap` samples, frame by frame
         CbFrameIR lostir;
@@ -385,11 +398,7 @@ CB_DEV int opus_synth_packet(TM tm, CbDecState *st, SynthScratch &S, PlcScratch 
     if (tm.lane() == 0) { range->begin = any ? sb : 0; range->end = any ? se : 0; }
     // a packet shorter than the row's capacity: the rest of the row is zero-filled, so batch / span calls hand back
     // deterministic buffers (stage C writes [0, result) only)
-    if (result >= 0 && result < cap) {
-        const int CC = st->channels;
-        CB_TEAM_FOR(i, (cap - result) * CC, tm) pcm[result * CC + i] = 0;
-        tm.sync();
-    }
+    if (result >= 0 && result < cap) zero_pcm(tm, pcm + result * st->channels, (cap - result) * st->channels);
     return result;
 }
 
