@@ -536,3 +536,21 @@ def test_hostsim_call_boundaries_with_loss_runs():
         assert np.array_equal(ret, rret) and np.array_equal(rng, rr), (ch, fs)
         bad = np.nonzero((rp.reshape(F, -1) != pcm.reshape(F, -1)).any(axis=1))[0]
         assert bad.size == 0, (ch, fs, int(bad[0]))
+
+
+def test_hostsim_random_wide_sweep():
+    """A small slice of tools/hostsim_sweep.py in the CPU suite: random batches in wide mode (API rates, 40 / 60 ms frames,
+    starved max_data_bytes, forced channels / bandwidth, decoder rate / channels / PCM capacity differing from the stream's,
+    random / burst / TOC-only loss, a call boundary at a random packet) through the kernel headers with 1-lane teams."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import hostsim_sweep as HS
+    import parity_sweep as PS
+    rs = np.random.RandomState(2024)
+    bad = []
+    for b in range(10):
+        ch, fs, F, cfgs, cut, loss, Fs, dFs, dch, maxb, extra, capmul = PS.draw_batch(rs, 6, True)
+        for i in range(6):
+            r = HS.one_stream((b, i, ch, fs, F, cfgs[i], cut, loss[i], Fs, dFs, dch, maxb, extra[i], capmul))
+            if not (r[2] and r[3]):
+                bad.append(r)
+    assert not bad, bad[:3]
