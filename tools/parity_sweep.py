@@ -21,6 +21,7 @@ if os.environ.get("SWEEP_PKG"):
     sys.path.insert(0, os.environ["SWEEP_PKG"])   # A/B against an older package + library
 import oracle_lib as O
 
+DURATION_MULT = int(os.environ.get("SWEEP_DURATION_MULT", "1"))   # streams of 1-2 s by default; x N for long-horizon state
 RATES = [24000, 32000, 40000, 48000, 64000, 80000, 96000, 128000, 160000, 192000, 256000, 320000, 510000]
 KINDS = ("music", "tone", "clicks", "noise")
 
@@ -30,12 +31,12 @@ def draw_batch(rs, NS, wide=False):
     ch = int(rs.choice([1, 2]))
     fs = int(rs.choice([120, 240, 480, 960]))
     nsec = 2 if fs >= 480 else 1
-    F = 48000 * nsec // fs
+    F = 48000 * nsec * DURATION_MULT // fs
     if wide:
         Fs = int(rs.choice([8000, 12000, 16000, 24000, 48000]))
         ms10 = int(rs.choice([25, 50, 100, 200, 400, 600]))            # frame duration in 0.1 ms
         fs = Fs * ms10 // 10000
-        F = int(Fs * (2 if ms10 >= 100 else 1)) // fs
+        F = int(Fs * (2 if ms10 >= 100 else 1)) * DURATION_MULT // fs
         dFs = int(rs.choice([8000, 12000, 16000, 24000, 48000]))
         dch = int(rs.choice([1, 2]))
         maxb = int(rs.choice([1276, 1276, 500, 200, 40, 8, 3]))         # max_data_bytes of the batch
