@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/opus_b200.h"
@@ -170,7 +171,11 @@ deemph_kernel(CbDecState *pool, const int *slots, IrView ir, int16_t *pcm, int n
         const int *x = ir.sig + slot * ir.sigstride + c * (cap * ds) + rg.begin;
         const int cnt = rg.end - rg.begin;
         int16_t *y0 = out + (rg.begin / ds) * channels;
-        if (paired && (cnt & 7) == 0 && ((((uintptr_t)x) | ((uintptr_t)y0)) & 15) == 0)
+        // the two lanes of a stereo pair must take the same path (the paired one shuffles): x of channel 1 is offset by cap*ds
+        // ints, so its alignment can differ from channel 0's — combine the per-lane predicates over the pair
+        bool vec_ok = paired && (cnt & 7) == 0 && ((((uintptr_t)x) | ((uintptr_t)y0)) & 15) == 0;
+        if (paired) vec_ok = __all_sync(pairmask, vec_ok);
+        if (vec_ok)
             m = deemph_pair_stereo(x, cnt, y0, c, m, gain, pairmask);
         else
             m = deemphasis_channel(x, cnt, y0 + c, channels, ds, m, gain);
@@ -365,6 +370,13 @@ int make_resident_locked(OpusDecoder **st, int n, int *h_slots) {
         if (!d || d->magic != kDecMagic) return OPUS_BAD_ARG;
         if (!resident(d)) need_new++;
     }
+    // the same state twice in one batch would race two warps on it
+    if (n > 1) {
+        std::unordered_set<const void *> seen;
+        seen.reserve((size_t)n * 2);
+        for (int i = 0; i < n; i++)
+            if (!seen.insert(st[i]).second) return OPUS_BAD_ARG;
+    }
     int in_use = g.pool_cap - (int)g.free_slots.size();
     if (!pool_reserve_locked(in_use + need_new)) return OPUS_ALLOC_FAIL;
     std::vector<int> up_idx;
@@ -385,12 +397,6 @@ int make_resident_locked(OpusDecoder **st, int n, int *h_slots) {
         }
         h_slots[i] = d->slot;
     }
-    // duplicates in one batch would race on one state
-    // (cheap check only for small n; large batches are the caller's responsibility)
-    if (n <= 64)
-        for (int i = 0; i < n; i++)
-            for (int j = i + 1; j < n; j++)
-                if (st[i] == st[j]) return OPUS_BAD_ARG;
     CbDecState *hs = (CbDecState *)g.h_stage.p;
     int *hsl = (int *)g.h_slots.p;   // caller reserved >= n ints... use a separate region at the tail
     (void)hsl;
@@ -666,6 +672,10 @@ int opus_decoder_get_size(int channels) {
 int opus_decoder_init(OpusDecoder *st, opus_int32 Fs, int channels) {
     if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2))
         return OPUS_BAD_ARG;
+    {   // re-initialising a live block in place (the reference's tests do): give its pool slot back first
+        std::lock_guard<std::mutex> lk(g.mu);
+        if (g.ok && st->magic == kDecMagic && st->slot >= 0 && st->slot < g.pool_cap && g.reg[st->slot].owner == st) release_slot_locked(st);
+    }
     memset(st, 0, sizeof(OpusDecoder));
     st->magic = kDecMagic;
     st->slot = -1;
@@ -770,6 +780,11 @@ int opus_decode_span_device(OpusDecoder **st, int n, int F, const unsigned char 
     if (!st || n <= 0 || F <= 0 || frame_size <= 0) return OPUS_BAD_ARG;
     std::lock_guard<std::mutex> lk(g.mu);
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    // the IR / staging geometry of a call is sized from one (Fs, channels): every stream must share it
+    for (int i = 0; i < n; i++) {
+        if (!st[i] || st[i]->magic != kDecMagic) return OPUS_BAD_ARG;
+        if (st[i]->st.channels != st[0]->st.channels || st[i]->st.Fs != st[0]->st.Fs) return OPUS_BAD_ARG;
+    }
     if (!g.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
     int *hsl = (int *)g.h_slots.p;
     int rc = make_resident_locked(st, n, hsl);
@@ -796,10 +811,12 @@ static int decode_span_host_locked(OpusDecoder **st, int n, int F, const unsigne
                                    const int64_t *offs, const opus_int32 *len, opus_int16 *pcm, int frame_size,
                                    int decode_fec, int *ret, bool keep_resident) {
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    if (!st[0] || st[0]->magic != kDecMagic) return OPUS_BAD_ARG;
     const int channels = st[0]->st.channels;
     for (int i = 0; i < n; i++) {
         if (!st[i] || st[i]->magic != kDecMagic) return OPUS_BAD_ARG;
-        if (st[i]->st.channels != channels) return OPUS_BAD_ARG;
+        // the IR / staging geometry of a call is sized from one (Fs, channels): every stream must share it
+        if (st[i]->st.channels != channels || st[i]->st.Fs != st[0]->st.Fs) return OPUS_BAD_ARG;
     }
     if (!g.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
     int *hsl = (int *)g.h_slots.p;
@@ -857,7 +874,7 @@ int opus_decode_span(OpusDecoder **st, int n, int F, const unsigned char *data, 
     int64_t bytes = 0;
     const size_t NF = (size_t)n * F;
     for (size_t i = 0; i < NF; i++) {
-        if (len[i] < 0) return OPUS_BAD_ARG;
+        if (len[i] < 0 || offs[i] < 0) return OPUS_BAD_ARG;
         int64_t e = offs[i] + len[i];
         if (len[i] > 0 && e > bytes) bytes = e;
     }
@@ -874,11 +891,13 @@ int opus_decode_batch(OpusDecoder **st, const unsigned char *const *data, const 
     }
     std::lock_guard<std::mutex> lk(g.mu);
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
-    // group by channel count (the span kernel wants a uniform PCM row size)
-    for (int pass = 1; pass <= 2; pass++) {
+    // group by (Fs, channel count): the span kernels want a uniform PCM row size and one IR geometry per call
+    static const int kRates[5] = {48000, 24000, 16000, 12000, 8000};
+    for (int grp = 0; grp < 10; grp++) {
+        const int pass = 1 + (grp & 1), rate = kRates[grp >> 1];
         std::vector<int> idx;
         for (int i = 0; i < n; i++)
-            if (st[i] && st[i]->magic == kDecMagic && st[i]->st.channels == pass) idx.push_back(i);
+            if (st[i] && st[i]->magic == kDecMagic && st[i]->st.channels == pass && st[i]->st.Fs == rate) idx.push_back(i);
         if (idx.empty()) continue;
         const int m = (int)idx.size();
         std::vector<OpusDecoder *> sts(m);

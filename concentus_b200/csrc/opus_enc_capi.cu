@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/opus_b200.h"
@@ -234,10 +235,12 @@ int make_resident_locked(OpusEncoder **st, int n, int *h_slots) {
         if (!d || d->magic != kEncMagic) return OPUS_BAD_ARG;
         if (!resident(d)) need_new++;
     }
-    if (n <= 64)
+    if (n > 1) {   // the same state twice in one batch would race two warps on it
+        std::unordered_set<const void *> seen;
+        seen.reserve((size_t)n * 2);
         for (int i = 0; i < n; i++)
-            for (int j = i + 1; j < n; j++)
-                if (st[i] == st[j]) return OPUS_BAD_ARG;
+            if (!seen.insert(st[i]).second) return OPUS_BAD_ARG;
+    }
     const int in_use = e.pool_cap - (int)e.free_slots.size();
     if (!pool_reserve_locked(in_use + need_new)) return OPUS_ALLOC_FAIL;
     std::vector<int> up_idx;
@@ -319,11 +322,16 @@ int sync_states_locked(OpusEncoder **st, int n, bool release) {
     return OPUS_OK;
 }
 
-// Common checks of a span call; all streams must share Fs / channels.
-int check_span(OpusEncoder **st, int n) {
+// Common checks of a span call; all streams must share Fs / channels, and frame_size must be the size every stream actually
+// codes: opus_encode runs frame_size_select (opus_encoder.c:807-826,2007-2025) first, so a stream whose
+// OPUS_SET_EXPERT_FRAME_DURATION selects another size, or a size that is no Opus frame, is an argument error here (the kernel
+// would otherwise walk PCM rows of the wrong length).  The ctl-visible configuration never changes on the device, so a stale host
+// block still holds it.
+int check_span(OpusEncoder **st, int n, int frame_size) {
     for (int i = 0; i < n; i++) {
         if (!st[i] || st[i]->magic != kEncMagic) return OPUS_BAD_ARG;
         if (st[i]->st.channels != st[0]->st.channels || st[i]->st.Fs != st[0]->st.Fs) return OPUS_BAD_ARG;
+        if (frame_size_select(frame_size, st[i]->st.variable_duration, st[i]->st.Fs) != frame_size) return OPUS_BAD_ARG;
     }
     return OPUS_OK;
 }
@@ -344,7 +352,7 @@ void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int 
 int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, int frame_size, uint8_t *data, int max_bytes, int stride,
                             int *ret, bool keep_resident, uint32_t *ranges = nullptr) {
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
-    int rc = check_span(st, n);
+    int rc = check_span(st, n, frame_size);
     if (rc != OPUS_OK) return rc;
     const int channels = st[0]->st.channels;
     if (!e.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
@@ -452,6 +460,10 @@ int opus_encoder_init(OpusEncoder *st, opus_int32 Fs, int channels, int applicat
     if ((Fs != 48000 && Fs != 24000 && Fs != 16000 && Fs != 12000 && Fs != 8000) || (channels != 1 && channels != 2) ||
         (application != OPUS_APPLICATION_VOIP && application != OPUS_APPLICATION_AUDIO && application != OPUS_APPLICATION_RESTRICTED_LOWDELAY))
         return OPUS_BAD_ARG;
+    {   // re-initialising a live block in place: give its pool slot back first
+        std::lock_guard<std::mutex> lk(e.mu);
+        if (e.ok && st->magic == kEncMagic && st->slot >= 0 && st->slot < e.pool_cap && e.reg[st->slot].owner == st) release_slot_locked(st);
+    }
     memset(st, 0, sizeof(OpusEncoder));
     st->magic = kEncMagic;
     st->slot = -1;
@@ -526,7 +538,7 @@ int opus_encode_span_device(OpusEncoder **st, int n, int F, const opus_int16 *d_
     if (!st || n <= 0 || F <= 0 || frame_size <= 0 || max_data_bytes <= 0) return OPUS_BAD_ARG;
     std::lock_guard<std::mutex> lk(e.mu);
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
-    int rc = check_span(st, n);
+    int rc = check_span(st, n, frame_size);
     if (rc != OPUS_OK) return rc;
     if (!e.h_slots.reserve(sizeof(int) * (size_t)n)) return OPUS_ALLOC_FAIL;
     int *hsl = (int *)e.h_slots.p;

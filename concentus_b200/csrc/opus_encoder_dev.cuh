@@ -408,7 +408,7 @@ CB_DEV int opus_encode_one(TM tm, CbEncState *st, CbEncState *gst, EncShared &S,
     const int nsub = frame_size > Fs / 50 ? (frame_size > Fs / 25 ? 3 : 2) : 1;   // phase barriers this frame owes its block
     int max_data_bytes = imin(1276, out_data_bytes);
     // frame_size has been through frame_size_select() on the host (opus_encode, opus_encoder.c:2007-2025)
-    if ((!st->variable_duration && 400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs && 25 * frame_size != Fs &&
+    if ((400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs && 25 * frame_size != Fs &&
          50 * frame_size != 3 * Fs) || 400 * frame_size < Fs || max_data_bytes <= 0)
         { skip_phases(tm, nsub); return OPUS_BAD_ARG_; }
     const int delay_compensation = st->application == kAppLowdelay ? 0 : st->delay_compensation;

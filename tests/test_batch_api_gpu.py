@@ -94,3 +94,116 @@ def test_encode_batch_mixed_channels_and_settings():
                 assert v.value == int(refs[i][3][f]), (i, f)
     for h in hs:
         L.opus_encoder_destroy(C.c_void_p(h))
+
+
+def test_decode_batch_mixed_sample_rates():
+    """Decoders of different API rates (and channel counts) in ONE opus_decode_batch call: the call groups them by (Fs, channels);
+    a span call given mixed rates is an argument error (its staging geometry is per call)."""
+    cb = _cb()
+    L = cb.lib()
+    F = 20
+    x = O.test_signal(960 * F, 2, 77, "music")
+    d, o, l, _ = O.encode_stream(x, 960, 64000, 2, vbr=1, cvbr=0)
+    d, o = O.pack(d, o, l)
+    cfgs = [(48000, 2), (8000, 2), (16000, 1), (24000, 2), (48000, 1), (12000, 1)]
+    n = len(cfgs)
+    refs = [O.decode_stream(d, o, l, 960 * Fs // 48000, ch, Fs=Fs) for Fs, ch in cfgs]
+    L.opus_decoder_create.restype = C.c_void_p
+    err = C.c_int(0)
+    hs = (C.c_void_p * n)(*[L.opus_decoder_create(Fs, ch, C.byref(err)) for Fs, ch in cfgs])
+    cap = 960                                                 # one capacity for all: 20 ms at 48 kHz, more than enough below
+    outs = [np.zeros((cap, ch), dtype=np.int16) for _, ch in cfgs]
+    pcm_ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in outs])
+    rets = np.zeros(n, dtype=np.int32)
+    for f in range(F):
+        pk = np.ascontiguousarray(d[o[f]:o[f] + l[f]])
+        data_ptrs = (C.c_void_p * n)(*[pk.ctypes.data] * n)
+        lens = np.full(n, int(l[f]), dtype=np.int32)
+        assert L.opus_decode_batch(hs, data_ptrs, O.ptr(lens), pcm_ptrs, cap, 0, O.ptr(rets), n) == 0
+        for i, (Fs, ch) in enumerate(cfgs):
+            fs_i = 960 * Fs // 48000
+            rp, rr, rret = refs[i]
+            assert rets[i] == fs_i == rret[f], (i, f, int(rets[i]))
+            assert np.array_equal(outs[i][:fs_i], rp[f * fs_i:(f + 1) * fs_i]), (i, f)
+    # span entry points: mixed rates -> OPUS_BAD_ARG, nothing launched
+    two = (C.c_void_p * 2)(hs[0], hs[1])
+    offs = np.zeros(2, dtype=np.int64)
+    lens = np.full(2, int(l[0]), dtype=np.int32)
+    blob = np.ascontiguousarray(d[:int(l[0])])
+    pcm = np.zeros((2 * 960, 2), dtype=np.int16)
+    r2 = np.zeros(2, dtype=np.int32)
+    assert L.opus_decode_span(two, 2, 1, O.ptr(blob), O.ptr(offs), O.ptr(lens), O.ptr(pcm), 960, O.ptr(r2)) == cb.OPUS_BAD_ARG
+    offs[1] = -4
+    two = (C.c_void_p * 2)(hs[0], hs[4])
+    assert L.opus_decode_span(two, 1, 2, O.ptr(blob), O.ptr(offs), O.ptr(lens), O.ptr(pcm), 960, O.ptr(r2)) == cb.OPUS_BAD_ARG   # negative offset
+    for h in hs:
+        L.opus_decoder_destroy(C.c_void_p(h))
+
+
+@pytest.mark.parametrize("cap", [961, 1001, 964])
+def test_decode_odd_capacity_stereo(cap):
+    """PCM capacities that are not a multiple of 8 (channel 1's staging row is then not 16-byte aligned): both lanes of a
+    stereo pair must take the same de-emphasis path."""
+    cb = _cb()
+    n, F = 6, 12
+    datas, offs, lens, refs = [], [], [], []
+    base = 0
+    for s in range(n):
+        x = O.test_signal(960 * F, 2, 900 + s, ["music", "tone", "clicks"][s % 3])
+        d, o, l, _ = O.encode_stream(x, 960, 96000, 2, vbr=1, cvbr=0)
+        d, o = O.pack(d, o, l)
+        refs.append(O.decode_stream(d, o, l, 960, 2))
+        datas.append(d); offs.append(o + base); lens.append(l); base += len(d)
+    data, offs, lens = np.concatenate(datas), np.concatenate(offs), np.concatenate(lens)
+    dec = cb.DecoderBatch(n, 48000, 2)
+    pcm, rets = dec.decode_span(data, offs, lens, F, cap)
+    dec.close()
+    assert (rets == 960).all()
+    pcm = pcm.reshape(n, F, cap, 2)
+    for s in range(n):
+        rp = refs[s][0].reshape(F, 960, 2)
+        assert np.array_equal(pcm[s, :, :960], rp), s
+        assert not pcm[s, :, 960:].any()
+
+
+def test_duplicate_state_in_large_batch_is_rejected():
+    cb = _cb()
+    L = cb.lib()
+    n = 200
+    dec = cb.DecoderBatch(n, 48000, 2)
+    hs = (C.c_void_p * n)(*dec.handles)
+    hs[150] = hs[3]
+    offs = np.zeros(n, dtype=np.int64)
+    lens = np.zeros(n, dtype=np.int32)
+    pcm = np.zeros((n * 120, 2), dtype=np.int16)
+    r = np.zeros(n, dtype=np.int32)
+    assert L.opus_decode_span(hs, n, 1, None, O.ptr(offs), O.ptr(lens), O.ptr(pcm), 120, O.ptr(r)) == cb.OPUS_BAD_ARG
+    dec.close()
+    enc = cb.EncoderBatch(n, 48000, 2, bitrate=64000)
+    hs = (C.c_void_p * n)(*enc.handles)
+    hs[199] = hs[0]
+    x = np.zeros((n * 120, 2), dtype=np.int16)
+    out = np.zeros((n, 100), dtype=np.uint8)
+    assert L.opus_encode_span(hs, n, 1, O.ptr(x), 120, O.ptr(out), 100, O.ptr(r)) == cb.OPUS_BAD_ARG
+    enc.close()
+
+
+def test_encode_span_rejects_sizes_the_stream_would_not_code():
+    """opus_encode runs frame_size_select first (opus_encoder.c:807-826); the span calls take the size actually coded."""
+    cb = _cb()
+    L = cb.lib()
+    n = 3
+    enc = cb.EncoderBatch(n, 48000, 2, bitrate=64000)
+    x = np.zeros((n * 5000, 2), dtype=np.int16)
+    out = np.zeros((n, 1276), dtype=np.uint8)
+    r = np.zeros(n, dtype=np.int32)
+    for bad in (900, 1000, 1500, 5000, 100):
+        assert L.opus_encode_span(enc.handles, n, 1, O.ptr(x), bad, O.ptr(out), 1276, O.ptr(r)) == cb.OPUS_BAD_ARG, bad
+    # OPUS_SET_EXPERT_FRAME_DURATION(10 ms) on one stream: a 20 ms span is not what that stream codes
+    assert L.opus_encoder_ctl(C.c_void_p(enc.handles[1]), 4040, C.c_int32(5003)) == 0
+    assert L.opus_encode_span(enc.handles, n, 1, O.ptr(x), 960, O.ptr(out), 1276, O.ptr(r)) == cb.OPUS_BAD_ARG
+    assert L.opus_encode_span(enc.handles, n, 1, O.ptr(x), 480, O.ptr(out), 1276, O.ptr(r)) == cb.OPUS_BAD_ARG   # the others code 480 only if asked to
+    assert L.opus_encoder_ctl(C.c_void_p(enc.handles[1]), 4040, C.c_int32(5000)) == 0
+    assert L.opus_encode_span(enc.handles, n, 1, O.ptr(x), 960, O.ptr(out), 1276, O.ptr(r)) == 0
+    assert (r > 0).all()
+    enc.close()
