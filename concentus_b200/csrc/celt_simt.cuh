@@ -120,6 +120,11 @@ struct WarpTeam {
         return (int)(inc - (unsigned)v);
     }
 };
+// A warp team whose phase() is a no-op: kernels of the frame-synchronous encoder pipeline (celt_enc_pipe.cuh) are small enough
+// for the instruction cache, and their warps must not meet at block barriers.
+struct FreeWarpTeam : WarpTeam {
+    CB_MEM void phase() const {}
+};
 #endif
 
 }  // namespace cb

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/opus_b200.h"
+#include "enc_pipe_host.h"
 #include "opus_encoder_dev.cuh"
 
 using namespace cb;
@@ -59,11 +60,13 @@ struct EncWarpSmem {
     int head[CB_ENC_HEAD_BYTES / 4];
 };
 
+// The one-kernel path: takes every stream the frame-synchronous pipeline (opus_enc_pipe.cu) does not (OPUS_APPLICATION_AUDIO,
+// 40 / 60 ms frames, "PLC frame" budgets) — and everything when CB200_ENC_PIPE=0.
 // One warp per stream, frames 0..F-1 in order.  PCM of frame (s,f): pcm[(s*F+f)*frame_size*channels]; packet slot:
 // data[(s*F+f)*stride], at most max_bytes are written; rets[s*F+f] = packet length or error.  One launch codes frames [f0, f1).
 __global__ void __launch_bounds__(CB_ENC_WPB * 32, CB_ENC_MINBLOCKS)
-encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const int16_t *pcm, uint8_t *data, int *rets, unsigned *ranges,
-                   int n, int F, int f0, int f1, int frame_size, int max_bytes, int stride) {
+encode_span_kernel(CbEncState *pool, const int *slots, const int *sidx, EncGlobal *scratch, const int16_t *pcm, uint8_t *data, int *rets,
+                   unsigned *ranges, int n, int F, int f0, int f1, int frame_size, int max_bytes, int stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_ENC_WPB + warp;
@@ -84,8 +87,9 @@ encode_span_kernel(CbEncState *pool, const int *slots, EncGlobal *scratch, const
     EncGlobal &G = scratch[s];
     const int channels = st->channels;
     WarpTeam tm{lane};
+    const int srow = sidx ? sidx[s] : s;   // the stream's row of PCM / packets / rets (a launch may cover a subset of a call's streams)
     for (int f = f0; f < f1; f++) {
-        const size_t k = (size_t)s * F + f;
+        const size_t k = (size_t)srow * F + f;
         const int r = opus_encode_frame(tm, st, gst, W.S, G, pcm + k * frame_size * channels, frame_size, data + k * stride, max_bytes);
         if (lane == 0) {
             rets[k] = r;
@@ -154,8 +158,13 @@ struct EncCtx {
     int pool_cap = 0;
     std::vector<SlotInfo> reg;
     std::vector<int> free_slots;
-    DevBuf d_slots, d_pcm, d_data, d_rets, d_ranges, d_stage, d_scratch;
-    PinBuf h_stage, h_slots;
+    DevBuf d_slots, d_pcm, d_data, d_rets, d_ranges, d_stage, d_scratch, d_split;
+    PinBuf h_stage, h_slots, h_split[4];
+    cudaStream_t legacy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_legacy = nullptr;
+    int use_pipe = 1;
+    unsigned split_seq = 0;
+    long long pipe_streams = 0, legacy_streams = 0;
     long long launches = 0;
     float last_ms = 0.f;
     double total_ms = 0;
@@ -178,6 +187,10 @@ bool ctx_init_locked() {
         cudaEventCreateWithFlags(&e.ev_done[i], cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&e.ev_prev, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&e.legacy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e.ev_legacy, cudaEventDisableTiming);
+    if (const char *v = getenv("CB200_ENC_PIPE")) e.use_pipe = atoi(v);
     if (!e.h_stage.reserve(sizeof(CbEncState) * kStageStates) || !e.d_stage.reserve(sizeof(CbEncState) * kStageStates)) return false;
     cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CB_ENC_WPB * sizeof(EncWarpSmem)));
 #ifndef CB_ENC_CARVEOUT
@@ -336,17 +349,65 @@ int check_span(OpusEncoder **st, int n, int frame_size) {
     return OPUS_OK;
 }
 
-void launch_frames(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int f0, int f1, int frame_size,
-                   int max_bytes, int stride, unsigned *d_ranges = nullptr) {
-    encode_span_kernel<<<(n + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, CB_ENC_WPB * sizeof(EncWarpSmem), e.stream>>>(
-        e.pool, d_slots, (EncGlobal *)e.d_scratch.p, d_pcm, d_data, d_rets, d_ranges, n, F, f0, f1, frame_size, max_bytes, stride);
-    e.launches++;
+// How a call's streams are divided between the two encoder paths (device arrays in e.d_split).
+struct SpanSplit {
+    int n_pipe = 0, n_legacy = 0;
+    const int *d_pslots = nullptr, *d_psidx = nullptr, *d_lslots = nullptr, *d_lsidx = nullptr;
+};
+
+// Decide per stream (host side, ctl-visible configuration only) and upload the two index lists.
+bool split_span(OpusEncoder **st, const int *h_slots, int n, int frame_size, int max_bytes, SpanSplit &sp) {
+    PinBuf &hb = e.h_split[e.split_seq++ & 3];   // a small ring: an earlier call's upload may still be in flight
+    if (!hb.reserve(sizeof(int) * 4 * (size_t)n) || !e.d_split.reserve(sizeof(int) * 4 * (size_t)n)) return false;
+    int *h = (int *)hb.p;
+    int *pslots = h, *psidx = h + n, *lslots = h + 2 * n, *lsidx = h + 3 * n;
+    for (int i = 0; i < n; i++) {
+        if (e.use_pipe && enc_pipe_takes(&st[i]->st, frame_size, max_bytes)) { pslots[sp.n_pipe] = h_slots[i]; psidx[sp.n_pipe++] = i; }
+        else { lslots[sp.n_legacy] = h_slots[i]; lsidx[sp.n_legacy++] = i; }
+    }
+    cudaMemcpyAsync(e.d_split.p, h, sizeof(int) * 4 * (size_t)n, cudaMemcpyHostToDevice, e.stream);
+    const int *d = (const int *)e.d_split.p;
+    sp.d_pslots = d; sp.d_psidx = d + n; sp.d_lslots = d + 2 * n; sp.d_lsidx = d + 3 * n;
+    e.pipe_streams += sp.n_pipe;
+    e.legacy_streams += sp.n_legacy;
+    return true;
 }
-void launch_span(const int *d_slots, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int n, int F, int frame_size, int max_bytes, int stride,
-                 unsigned *d_ranges = nullptr) {
+
+int launch_frames(const SpanSplit &sp, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int F, int f0, int f1, int frame_size, int channels, int Fs,
+                  int max_bytes, int stride, unsigned *d_ranges = nullptr) {
+    if (sp.n_legacy > 0) {
+        // the one-kernel path runs beside the pipeline on its own stream
+        if (!e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)sp.n_legacy)) return OPUS_ALLOC_FAIL;
+        cudaStream_t ls = sp.n_pipe > 0 ? e.legacy_stream : e.stream;
+        if (sp.n_pipe > 0) {
+            cudaEventRecord(e.ev_fork, e.stream);
+            cudaStreamWaitEvent(ls, e.ev_fork, 0);
+        }
+        encode_span_kernel<<<(sp.n_legacy + CB_ENC_WPB - 1) / CB_ENC_WPB, CB_ENC_WPB * 32, CB_ENC_WPB * sizeof(EncWarpSmem), ls>>>(
+            e.pool, sp.d_lslots, sp.d_lsidx, (EncGlobal *)e.d_scratch.p, d_pcm, d_data, d_rets, d_ranges, sp.n_legacy, F, f0, f1, frame_size, max_bytes,
+            stride);
+        e.launches++;
+        if (sp.n_pipe > 0) cudaEventRecord(e.ev_legacy, ls);
+    }
+    if (sp.n_pipe > 0) {
+        EncPipeCall c;
+        c.pool = e.pool; c.d_slots = sp.d_pslots; c.d_sidx = sp.d_psidx; c.n = sp.n_pipe;
+        c.F = F; c.f0 = f0; c.f1 = f1; c.frame_size = frame_size; c.channels = channels; c.Fs = Fs;
+        c.max_bytes = max_bytes; c.stride = stride;
+        c.d_pcm = d_pcm; c.d_data = d_data; c.d_rets = d_rets; c.d_ranges = d_ranges;
+        const int r = enc_pipe_enqueue(c, e.stream);
+        if (r < 0) return r;
+        e.launches += r;
+        if (sp.n_legacy > 0) cudaStreamWaitEvent(e.stream, e.ev_legacy, 0);
+    }
+    return OPUS_OK;
+}
+int launch_span(const SpanSplit &sp, const int16_t *d_pcm, uint8_t *d_data, int *d_rets, int F, int frame_size, int channels, int Fs, int max_bytes,
+                int stride, unsigned *d_ranges = nullptr) {
     cudaEventRecord(e.ev0, e.stream);
-    launch_frames(d_slots, d_pcm, d_data, d_rets, n, F, 0, F, frame_size, max_bytes, stride, d_ranges);
+    const int rc = launch_frames(sp, d_pcm, d_data, d_rets, F, 0, F, frame_size, channels, Fs, max_bytes, stride, d_ranges);
     cudaEventRecord(e.ev1, e.stream);
+    return rc;
 }
 
 int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, int frame_size, uint8_t *data, int max_bytes, int stride,
@@ -361,12 +422,13 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
     if (rc != OPUS_OK) return rc;
     const size_t NF = (size_t)n * F;
     const size_t pcm_bytes = NF * frame_size * channels * sizeof(int16_t);
-    if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_pcm.reserve(pcm_bytes) || !e.d_data.reserve(NF * stride) ||
-        !e.d_rets.reserve(sizeof(int) * NF) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n) ||
+    if (!e.d_pcm.reserve(pcm_bytes) || !e.d_data.reserve(NF * stride) || !e.d_rets.reserve(sizeof(int) * NF) ||
         (ranges && !e.d_ranges.reserve(sizeof(uint32_t) * NF)))
         return OPUS_ALLOC_FAIL;
     unsigned *d_ranges = ranges ? (unsigned *)e.d_ranges.p : nullptr;
-    cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
+    SpanSplit sp;
+    if (!split_span(st, hsl, n, frame_size, max_bytes, sp)) return OPUS_ALLOC_FAIL;
+    const int Fs = st[0]->st.Fs;
     // Large spans are cut into up to kMaxSub sub-spans of frames: the PCM of sub-span k+1 goes up and the packets of sub-span
     // k-1 come down on the copy stream while sub-span k is coded (the state stays resident between the launches).
     int nsub = 1;
@@ -374,8 +436,8 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
     const size_t row_pcm = (size_t)frame_size * channels * sizeof(int16_t);   // one frame of one stream
     if (nsub == 1) {
         cudaMemcpyAsync(e.d_pcm.p, pcm, pcm_bytes, cudaMemcpyHostToDevice, e.stream);
-        launch_span((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, frame_size, max_bytes, stride,
-                    d_ranges);
+        rc = launch_span(sp, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, F, frame_size, channels, Fs, max_bytes, stride, d_ranges);
+        if (rc != OPUS_OK) return rc;
         cudaMemcpyAsync(data, e.d_data.p, NF * stride, cudaMemcpyDeviceToHost, e.stream);
     } else {
         cudaEventRecord(e.ev_prev, e.stream);                 // earlier work on the device buffers (previous call) is done
@@ -391,8 +453,9 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
         for (int k = 0; k < nsub; k++) {
             const int f0 = k * per, f1 = hmin(F, f0 + per);
             cudaStreamWaitEvent(e.stream, e.ev_in[k], 0);
-            launch_frames((const int *)e.d_slots.p, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, n, F, f0, f1, frame_size,
-                          max_bytes, stride, d_ranges);
+            rc = launch_frames(sp, (const int16_t *)e.d_pcm.p, (uint8_t *)e.d_data.p, (int *)e.d_rets.p, F, f0, f1, frame_size, channels, Fs, max_bytes,
+                               stride, d_ranges);
+            if (rc != OPUS_OK) return rc;
             cudaEventRecord(e.ev_done[k], e.stream);
             cudaStreamWaitEvent(e.copy_stream, e.ev_done[k], 0);
             cudaMemcpy2DAsync(data + (size_t)f0 * stride, (size_t)F * stride, (const uint8_t *)e.d_data.p + (size_t)f0 * stride, (size_t)F * stride,
@@ -418,6 +481,19 @@ int encode_span_host_locked(OpusEncoder **st, int n, int F, const int16_t *pcm, 
 extern "C" {
 
 long long opus_b200_enc_kernel_launches(void) { return e.launches; }
+// streams x calls coded by the frame-synchronous pipeline / by the one-kernel path since start (tests check which path ran)
+void opus_b200_enc_path_counts(long long *pipe, long long *legacy) {
+    if (pipe) *pipe = e.pipe_streams;
+    if (legacy) *legacy = e.legacy_streams;
+}
+// 1 (default): streams the pipeline takes go through it; 0: everything through the one-kernel path.  Returns the previous setting.
+int opus_b200_enc_set_pipeline(int on) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
+    const int prev = e.use_pipe;
+    e.use_pipe = on != 0;
+    return prev;
+}
 #if defined(CB_PHASE_PROF)
 // dev build only: cycles per phase slot of stream 0 (own work, then barrier wait); reset != 0 clears the counters
 int opus_b200_enc_phase_prof(long long *cycles, long long *wait, int reset) {
@@ -544,9 +620,10 @@ int opus_encode_span_device(OpusEncoder **st, int n, int F, const opus_int16 *d_
     int *hsl = (int *)e.h_slots.p;
     rc = make_resident_locked(st, n, hsl);
     if (rc != OPUS_OK) return rc;
-    if (!e.d_slots.reserve(sizeof(int) * (size_t)n) || !e.d_scratch.reserve(sizeof(EncGlobal) * (size_t)n)) return OPUS_ALLOC_FAIL;
-    cudaMemcpyAsync(e.d_slots.p, hsl, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, e.stream);
-    launch_span((const int *)e.d_slots.p, d_pcm, d_data, d_ret, n, F, frame_size, hmin(max_data_bytes, 1276), max_data_bytes);
+    SpanSplit sp;
+    if (!split_span(st, hsl, n, frame_size, hmin(max_data_bytes, 1276), sp)) return OPUS_ALLOC_FAIL;
+    rc = launch_span(sp, d_pcm, d_data, d_ret, F, frame_size, st[0]->st.channels, st[0]->st.Fs, hmin(max_data_bytes, 1276), max_data_bytes);
+    if (rc != OPUS_OK) return rc;
     mark_device_newer_locked(st, n);
     if (cudaGetLastError() != cudaSuccess) return OPUS_INTERNAL_ERROR;
     return OPUS_OK;

@@ -1,0 +1,315 @@
+// opus_enc_pipe.cu — kernels and host orchestration of the frame-synchronous encoder pipeline (celt_enc_pipe.cuh has the design
+// and the per-stage device functions; enc_pipe_host.h is the interface opus_enc_capi.cu calls).
+//
+// A launch's streams are cut into G groups; each group advances frame by frame through K1..K5 on its own CUDA stream, with the
+// front end (P0 / FE1 / FE2) of the NEXT chunk of frames running on a side stream.  Kernels of different groups overlap, so the
+// thread-per-stream stages (a few hundred warps, latency bound) of one group hide behind the warp-per-stream stages of another.
+#define CB_SMALL_CODE 1
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "celt_enc_pipe.cuh"
+#include "enc_pipe_host.h"
+
+using namespace cb;
+
+#ifndef CB_PIPE_WPB
+#define CB_PIPE_WPB 4          // warps per block of the warp-per-item kernels
+#endif
+
+namespace {
+
+struct PipeBufs {              // device views of one group's buffers
+    int16_t *D;                // [n][Fc][fsz*CC]
+    int *P[2];                 // [n][CC][pstride], double-buffered over chunks
+    EncPlan *plans[2];         // [n][Fc]
+    FeFrame *fe[2];            // [n][Fc]
+    int *m0;                   // [n][2] pre-emphasis memory entering the chunk
+    EncPipeCtx *ctx;           // [n]
+    EncPipeBuf *buf;           // [n]
+};
+
+// ---- P0: the Opus layer of a chunk, one thread per stream ------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+pipe_prepass_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, const int16_t *pcm, int fbase, int nfr, int16_t *D,
+                    EncPlan *plans, int *m0) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    CbEncState *st = pool + slots[t];
+    const size_t row = (size_t)g.fsz * g.CC;
+    m0[2 * t] = st->preemph_memE[0];
+    m0[2 * t + 1] = st->preemph_memE[1];
+    for (int fi = 0; fi < nfr; fi++) {
+        const int16_t *src = pcm + ((size_t)sidx[t] * g.F + fbase + fi) * row;
+        int16_t *dst = D + ((size_t)t * g.Fc + fi) * row;
+        EncPlan pl;
+        pipe_plan_frame(st, src, g.fsz, g.max_bytes, dst, pl);
+        plans[(size_t)t * g.Fc + fi] = pl;
+        if (pl.code)
+            for (int c = 0; c < g.CC; c++) st->preemph_memE[c] = pipe_preemph_mem_after(g, dst, c);
+    }
+}
+
+// ---- FE1: pre-emphasis + maxima, one warp per (stream, frame); the warp of frame 0 also installs the 1024-sample history ----
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_fe1_kernel(const CbEncState *pool, const int *slots, PipeGeom g, int nfr, const int16_t *D, const EncPlan *plans, const int *m0, int *P,
+                const int *Pprev, int prev_nfr, FeFrame *fe) {
+    const int w = blockIdx.x * CB_PIPE_WPB + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= g.n * nfr) return;
+    const int s = w / nfr, fi = w - s * nfr;
+    FreeWarpTeam tm{{lane}};
+    int *Prow = P + (size_t)s * g.CC * g.pstride;
+    if (fi == 0) {
+        for (int c = 0; c < g.CC; c++) {
+            int *h = Prow + c * g.pstride;
+            if (Pprev) {
+                const int *src = Pprev + ((size_t)s * g.CC + c) * g.pstride + prev_nfr * g.N;
+                for (int i = lane; i < kPipeHist; i += 32) h[i] = src[i];
+            } else {
+                const int *src = pool[slots[s]].prefilter_mem + c * kCombMaxPeriod;
+                for (int i = lane; i < kPipeHist; i += 32) h[i] = src[i];
+            }
+        }
+    }
+    const EncPlan &pl = plans[(size_t)s * g.Fc + fi];
+    if (!pl.code) return;
+    const size_t row = (size_t)g.fsz * g.CC;
+    const int16_t *d = D + ((size_t)s * g.Fc + fi) * row;
+    int mi[2];
+    for (int c = 0; c < g.CC; c++) mi[c] = fi == 0 ? m0[2 * s + c] : pipe_preemph_mem_after(g, d - row, c);
+    pipe_preemph_frame(tm, g, pl, d, Prow, fi, mi, fe[(size_t)s * g.Fc + fi]);
+}
+
+// ---- FE2: pitch analysis, one warp per (stream, frame) ---------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_fe2_kernel(PipeGeom g, int nfr, const EncPlan *plans, const int *P, FeFrame *fe) {
+    __shared__ PitchScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * CB_PIPE_WPB + wib;
+    if (w >= g.n * nfr) return;
+    const int s = w / nfr, fi = w - s * nfr;
+    FreeWarpTeam tm{{lane}};
+    const int *Prow = P + (size_t)s * g.CC * g.pstride;
+    pipe_pitch_frame(tm, g, plans[(size_t)s * g.Fc + fi], Prow + fi * g.N, Prow + g.pstride + fi * g.N, sm[wib], fe[(size_t)s * g.Fc + fi]);
+}
+
+// ---- K1 ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, const FeFrame *fe,
+                 EncPipeCtx *ctx, uint8_t *data) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    uint8_t *out = data + ((size_t)sidx[t] * g.F + f) * g.stride;
+    pipe_head(pool + slots[t], g, plans[(size_t)t * g.Fc + fi], fe[(size_t)t * g.Fc + fi], ctx[t], out);
+}
+
+// ---- K2: one warp per (stream, channel) ---------------------------------------------------------------------------------------
+struct CombScratch { int tin[kMaxFrame + kOverlap]; int sc[4]; };
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_comb_kernel(CbEncState *pool, const int *slots, PipeGeom g, int fi, const int *P, EncPipeCtx *ctx, EncPipeBuf *buf) {
+    __shared__ CombScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * CB_PIPE_WPB + wib;
+    if (w >= g.n * g.CC) return;
+    const int s = w / g.CC, c = w - s * g.CC;
+    FreeWarpTeam tm{{lane}};
+    const int *pre = P + ((size_t)s * g.CC + c) * g.pstride + fi * g.N;
+    pipe_comb_channel(tm, pool + slots[s], g, ctx[s], pre, buf[s].in + c * (g.N + kOverlap), c, sm[wib].tin, sm[wib].sc);
+}
+
+// ---- K3: one warp per stream ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, EncPipeBuf *buf) {
+    __shared__ __align__(16) TransformScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    if (s >= g.n) return;
+    FreeWarpTeam tm{{lane}};
+    pipe_transform(tm, pool + slots[s], g, ctx[s], buf[s], sm[wib]);
+}
+
+// ---- K4 ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    pipe_decide(pool + slots[t], g, ctx[t]);
+}
+
+// ---- K5: one warp per stream ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_bands_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
+                  EncPipeBuf *buf, uint8_t *data, int *rets, unsigned *ranges) {
+    __shared__ __align__(16) BandScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    if (s >= g.n) return;
+    FreeWarpTeam tm{{lane}};
+    CbEncState *st = pool + slots[s];
+    const size_t k = (size_t)sidx[s] * g.F + f;
+    const int r = pipe_bands(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], buf[s], sm[wib], data + k * g.stride);
+    if (lane == 0) {
+        rets[k] = r;
+        if (ranges) ranges[k] = st->rangeFinal;
+    }
+}
+
+// ---- end of the span: the last 1024 pre-emphasised samples go back into the state -------------------------------------------------
+__global__ void pipe_epilogue_kernel(CbEncState *pool, const int *slots, PipeGeom g, const int *P, int last_nfr) {
+    const int s = blockIdx.x;
+    if (s >= g.n) return;
+    CbEncState *st = pool + slots[s];
+    for (int c = 0; c < g.CC; c++) {
+        const int *src = P + ((size_t)s * g.CC + c) * g.pstride + last_nfr * g.N;
+        for (int i = threadIdx.x; i < kCombMaxPeriod; i += blockDim.x) st->prefilter_mem[c * kCombMaxPeriod + i] = src[i];
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    bool reserve(size_t n) {
+        if (n <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) return false;
+        cap = want;
+        return true;
+    }
+};
+
+enum { kMaxGroups = 8 };
+struct Group {
+    cudaStream_t main = nullptr, side = nullptr;
+    cudaEvent_t ev_fe[2] = {nullptr, nullptr}, ev_steps[2] = {nullptr, nullptr}, ev_done = nullptr;
+    DevBuf D, P[2], plans[2], fe[2], m0, ctx, buf;
+};
+struct PipeCtx {
+    bool init = false;
+    int groups = 2;
+    int chunk = 16;
+    Group g[kMaxGroups];
+    cudaEvent_t ev_fork = nullptr;
+} pc;
+
+bool pipe_init() {
+    if (pc.init) return true;
+    if (const char *e = getenv("CB200_ENC_GROUPS")) pc.groups = atoi(e);
+    if (pc.groups < 1) pc.groups = 1;
+    if (pc.groups > kMaxGroups) pc.groups = kMaxGroups;
+    if (const char *e = getenv("CB200_ENC_CHUNK")) pc.chunk = atoi(e);
+    if (pc.chunk < 1) pc.chunk = 1;
+    for (int i = 0; i < kMaxGroups; i++) {
+        Group &G = pc.g[i];
+        if (cudaStreamCreateWithFlags(&G.main, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int b = 0; b < 2; b++) {
+            cudaEventCreateWithFlags(&G.ev_fe[b], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&G.ev_steps[b], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&G.ev_done, cudaEventDisableTiming);
+    }
+    cudaEventCreateWithFlags(&pc.ev_fork, cudaEventDisableTiming);
+    pc.init = cudaGetLastError() == cudaSuccess;
+    return pc.init;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// one group: streams [k0, k0+n) of the pipeline's list
+int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
+    g.n = n;
+    const int nframes = c.f1 - c.f0;
+    const int Fc = g.Fc;
+    const size_t row = (size_t)g.fsz * g.CC;
+    if (!G.D.reserve((size_t)n * Fc * row * sizeof(int16_t)) || !G.m0.reserve((size_t)n * 2 * sizeof(int)) ||
+        !G.ctx.reserve((size_t)n * sizeof(EncPipeCtx)) || !G.buf.reserve((size_t)n * sizeof(EncPipeBuf)))
+        return -7;
+    for (int b = 0; b < 2; b++)
+        if (!G.P[b].reserve((size_t)n * g.CC * g.pstride * sizeof(int)) || !G.plans[b].reserve((size_t)n * Fc * sizeof(EncPlan)) ||
+            !G.fe[b].reserve((size_t)n * Fc * sizeof(FeFrame)))
+            return -7;
+    const int *slots = c.d_slots + k0, *sidx = c.d_sidx + k0;
+    int launches = 0;
+    const int nchunks = cdiv(nframes, Fc);
+    const int tpb = 64;
+    int prev_nfr = 0;
+    for (int k = 0; k < nchunks; k++) {
+        const int b = k & 1;
+        const int fbase = c.f0 + k * Fc;
+        const int nfr = nframes - k * Fc < Fc ? nframes - k * Fc : Fc;
+        // ---- front end of chunk k on the side stream (buffers b are free once the frame steps of chunk k-2 are done) ----
+        if (k >= 2) cudaStreamWaitEvent(G.side, G.ev_steps[b], 0);
+        pipe_prepass_kernel<<<cdiv(n, tpb), tpb, 0, G.side>>>(c.pool, slots, sidx, g, c.d_pcm, fbase, nfr, (int16_t *)G.D.p, (EncPlan *)G.plans[b].p,
+                                                              (int *)G.m0.p);
+        pipe_fe1_kernel<<<cdiv(n * nfr, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.side>>>(c.pool, slots, g, nfr, (const int16_t *)G.D.p,
+                                                                                    (const EncPlan *)G.plans[b].p, (const int *)G.m0.p, (int *)G.P[b].p,
+                                                                                    k > 0 ? (const int *)G.P[b ^ 1].p : nullptr, prev_nfr,
+                                                                                    (FeFrame *)G.fe[b].p);
+        pipe_fe2_kernel<<<cdiv(n * nfr, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.side>>>(g, nfr, (const EncPlan *)G.plans[b].p, (const int *)G.P[b].p,
+                                                                                    (FeFrame *)G.fe[b].p);
+        cudaEventRecord(G.ev_fe[b], G.side);
+        launches += 3;
+        // ---- frame steps of chunk k on the main stream ----
+        cudaStreamWaitEvent(G.main, G.ev_fe[b], 0);
+        for (int fi = 0; fi < nfr; fi++) {
+            const int f = fbase + fi;
+            pipe_head_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (const FeFrame *)G.fe[b].p,
+                                                               (EncPipeCtx *)G.ctx.p, c.d_data);
+            pipe_comb_kernel<<<cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, fi, (const int *)G.P[b].p, (EncPipeCtx *)G.ctx.p,
+                                                                                          (EncPipeBuf *)G.buf.p);
+            pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
+            pipe_decide_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p);
+            pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
+                                                                                    (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets, c.d_ranges);
+            launches += 5;
+        }
+        cudaEventRecord(G.ev_steps[b], G.main);
+        prev_nfr = nfr;
+    }
+    pipe_epilogue_kernel<<<n, 128, 0, G.main>>>(c.pool, slots, g, (const int *)G.P[(nchunks - 1) & 1].p, prev_nfr);
+    launches++;
+    return launches;
+}
+
+}  // namespace
+
+int enc_pipe_takes(const CbEncState *st, int frame_size, int out_data_bytes) { return enc_pipe_eligible(st, frame_size, out_data_bytes); }
+
+int enc_pipe_enqueue(const EncPipeCall &c, cudaStream_t stream) {
+    if (!pipe_init()) return -3;
+    if (c.n <= 0 || c.f1 <= c.f0) return 0;
+    PipeGeom g;
+    g.n = c.n; g.CC = c.channels; g.Fs = c.Fs; g.upsample = 48000 / c.Fs; g.fsz = c.frame_size; g.N = c.frame_size * g.upsample;
+    for (g.LM = 0; g.LM <= kMaxLM; g.LM++)
+        if ((kShortMdct << g.LM) == g.N) break;
+    if (g.LM > kMaxLM) return -1;
+    g.F = c.F;
+    const int nframes = c.f1 - c.f0;
+    g.Fc = nframes < pc.chunk ? nframes : pc.chunk;
+    g.max_bytes = c.max_bytes; g.stride = c.stride;
+    g.pstride = kPipeHist + g.Fc * g.N;
+    // groups: enough streams each to fill the warp-per-stream kernels
+    int G = pc.groups;
+    while (G > 1 && c.n / G < 256) G--;
+    cudaEventRecord(pc.ev_fork, stream);
+    int launches = 0;
+    const int per = (c.n + G - 1) / G;
+    for (int i = 0; i < G; i++) {
+        const int k0 = i * per, n = c.n - k0 < per ? c.n - k0 : per;
+        if (n <= 0) break;
+        Group &Gr = pc.g[i];
+        cudaStreamWaitEvent(Gr.main, pc.ev_fork, 0);
+        cudaStreamWaitEvent(Gr.side, pc.ev_fork, 0);
+        const int r = enqueue_group(Gr, c, k0, n, g);
+        if (r < 0) return r;
+        launches += r;
+        cudaEventRecord(Gr.ev_done, Gr.main);
+        cudaStreamWaitEvent(stream, Gr.ev_done, 0);
+    }
+    if (cudaGetLastError() != cudaSuccess) return -3;
+    return launches;
+}

@@ -241,28 +241,11 @@ CB_DEV_NOINLINE void dc_reject_channel(const int16_t *in, int16_t *out, int32_t 
 struct StereoWidth {
     int XX, XY, YY, smoothed, max_follower, width;
 };
-// compute_stereo_width (opus_encoder.c:861-936); the new memory is returned in `w` (committed by the caller)
-template <class TM>
-CB_DEV void compute_stereo_width_team(TM tm, const int16_t *pcm, int frame_size, int Fs, const CbEncState *st, StereoWidth &w) {
+// compute_stereo_width (opus_encoder.c:861-936), second half: the smoothed memories and the width from the frame's three sums.
+// The new memory is returned in `w` (committed by the caller).
+CB_DEV_NOINLINE void stereo_width_finish(int xx, int xy, int yy, int frame_size, int Fs, const CbEncState *st, StereoWidth &w) {
     const int frame_rate = Fs / frame_size;
     const int short_alpha = s16(32767 - 25 * 32767 / imax(50, frame_rate));
-    int xx = 0, xy = 0, yy = 0;
-    CB_TEAM_FOR(g, (frame_size - 3 + 3) / 4, tm) {
-        const int i = 4 * g;
-        if (i < frame_size - 3) {
-            int pxx = 0, pxy = 0, pyy = 0;
-            CB_NOUNROLL for (int k = 0; k < 4; k++) {
-                const int x = pcm[2 * (i + k)], y = pcm[2 * (i + k) + 1];
-                pxx += mul16_16(x, x) >> 2;
-                pxy += mul16_16(x, y) >> 2;
-                pyy += mul16_16(y, y) >> 2;
-            }
-            xx = wadd(xx, pxx >> 10);
-            xy = wadd(xy, pxy >> 10);
-            yy = wadd(yy, pyy >> 10);
-        }
-    }
-    xx = tm.sum(xx); xy = tm.sum(xy); yy = tm.sum(yy);
     w.XX = wadd(st->width_XX, mul16_32_q15(short_alpha, wsub(xx, st->width_XX)));
     w.XY = wadd(st->width_XY, mul16_32_q15(short_alpha, wsub(xy, st->width_XY)));
     w.YY = wadd(st->width_YY, mul16_32_q15(short_alpha, wsub(yy, st->width_YY)));
@@ -280,6 +263,28 @@ CB_DEV void compute_stereo_width_team(TM tm, const int16_t *pcm, int frame_size,
         w.max_follower = s16(imax(w.max_follower - 655 / frame_rate, w.smoothed));
     }
     w.width = s16(imin(32767, 20 * w.max_follower));
+}
+// first half: the three correlation sums over the frame (groups of four samples, opus_encoder.c:880-903)
+template <class TM>
+CB_DEV void compute_stereo_width_team(TM tm, const int16_t *pcm, int frame_size, int Fs, const CbEncState *st, StereoWidth &w) {
+    int xx = 0, xy = 0, yy = 0;
+    CB_TEAM_FOR(g, (frame_size - 3 + 3) / 4, tm) {
+        const int i = 4 * g;
+        if (i < frame_size - 3) {
+            int pxx = 0, pxy = 0, pyy = 0;
+            CB_NOUNROLL for (int k = 0; k < 4; k++) {
+                const int x = pcm[2 * (i + k)], y = pcm[2 * (i + k) + 1];
+                pxx += mul16_16(x, x) >> 2;
+                pxy += mul16_16(x, y) >> 2;
+                pyy += mul16_16(y, y) >> 2;
+            }
+            xx = wadd(xx, pxx >> 10);
+            xy = wadd(xy, pxy >> 10);
+            yy = wadd(yy, pyy >> 10);
+        }
+    }
+    xx = tm.sum(xx); xy = tm.sum(xy); yy = tm.sum(yy);
+    stereo_width_finish(xx, xy, yy, frame_size, Fs, st, w);
 }
 
 // stereo_fade (opus_encoder.c:411-441), in place

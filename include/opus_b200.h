@@ -180,6 +180,12 @@ int opus_b200_enc_synchronize(void);
 void *opus_b200_enc_stream(void);          /* the cudaStream_t the encoder launches on */
 long long opus_b200_enc_kernel_launches(void);
 float opus_b200_enc_last_kernel_ms(void);  /* device time of the last encode span (CUDA events on the encoder stream) */
+/* The encoder has two device paths: the frame-synchronous kernel pipeline (OPUS_APPLICATION_RESTRICTED_LOWDELAY streams, frames
+ * up to 20 ms) and a one-kernel path for everything else; both are bit-exact with the reference.  set_pipeline(0) sends every
+ * stream through the one-kernel path (A/B measurements, tests); returns the previous setting.  path_counts: streams x calls
+ * each path has coded so far. */
+int opus_b200_enc_set_pipeline(int on);
+void opus_b200_enc_path_counts(long long *pipeline, long long *one_kernel);
 
 #ifdef __cplusplus
 }

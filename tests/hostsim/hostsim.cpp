@@ -136,3 +136,85 @@ int hostsim_encode_stream_script(const int16_t *pcm, int F, int frame_size, int 
     return 0;
 }
 }
+
+// ---- encoder, frame-synchronous pipeline (celt_enc_pipe.cuh): the same slices the pipeline kernels run, 1-lane teams ----------
+#include "../../concentus_b200/csrc/celt_enc_pipe.cuh"
+
+extern "C" {
+
+// Encode F frames of one stream through the pipeline stages in chunks of Fc frames.  Returns -100 when the stream is not one
+// the pipeline takes (the library then uses the one-kernel path), else 0.  Same cfg / outputs as hostsim_encode_stream.
+int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int channels, int Fs, const int *cfg, uint8_t *out, int stride,
+                               int32_t *lens, uint32_t *ranges, int Fc) {
+    CbEncState *st = (CbEncState *)calloc(1, sizeof(CbEncState));
+    if (cb::enc_state_init(st, Fs, channels, cfg[0]) != 0) return -1;
+    int dummy = 0;
+    cb::enc_ctl(st, 4002, cfg[1], &dummy);
+    cb::enc_ctl(st, 4006, cfg[2], &dummy);
+    cb::enc_ctl(st, 4020, cfg[3], &dummy);
+    cb::enc_ctl(st, 4010, cfg[4], &dummy);
+    if (cfg[6]) cb::enc_ctl(st, 4022, cfg[6], &dummy);
+    if (cfg[7]) cb::enc_ctl(st, 4008, cfg[7], &dummy);
+    const int out_bytes = cfg[5] < stride ? cfg[5] : stride;
+    if (!cb::enc_pipe_eligible(st, frame_size, out_bytes)) { free(st); return -100; }
+    cb::PipeGeom g;
+    g.n = 1; g.CC = channels; g.Fs = Fs; g.upsample = 48000 / Fs; g.fsz = frame_size; g.N = frame_size * g.upsample;
+    for (g.LM = 0; g.LM <= 3; g.LM++) if ((120 << g.LM) == g.N) break;
+    g.F = F; g.Fc = Fc; g.max_bytes = out_bytes < 1276 ? out_bytes : 1276; g.stride = stride;
+    g.pstride = cb::kPipeHist + Fc * g.N;
+    const int row = frame_size * channels;
+    std::vector<int16_t> D((size_t)Fc * row);
+    std::vector<int> P((size_t)channels * g.pstride);
+    std::vector<cb::EncPlan> plans(Fc);
+    std::vector<cb::FeFrame> fe(Fc);
+    cb::EncPipeCtx *X = (cb::EncPipeCtx *)calloc(1, sizeof(cb::EncPipeCtx));
+    cb::EncPipeBuf *B = (cb::EncPipeBuf *)calloc(1, sizeof(cb::EncPipeBuf));
+    cb::PitchScratch *ps = (cb::PitchScratch *)calloc(1, sizeof(cb::PitchScratch));
+    cb::TransformScratch *ts = (cb::TransformScratch *)calloc(1, sizeof(cb::TransformScratch));
+    cb::BandScratch *bs = (cb::BandScratch *)calloc(1, sizeof(cb::BandScratch));
+    std::vector<int> tin(960 + 120);
+    int sc[4];
+    cb::SoloTeam tm;
+    for (int c = 0; c < channels; c++)
+        for (int i = 0; i < cb::kPipeHist; i++) P[(size_t)c * g.pstride + i] = st->prefilter_mem[c * cb::kPipeHist + i];
+    int rc = 0;
+    for (int f0 = 0; f0 < F; f0 += Fc) {
+        const int nfr = F - f0 < Fc ? F - f0 : Fc;
+        // P0: the Opus layer of the chunk
+        int m0[2] = {st->preemph_memE[0], st->preemph_memE[1]};
+        for (int fi = 0; fi < nfr; fi++) {
+            cb::pipe_plan_frame(st, pcm + (size_t)(f0 + fi) * row, frame_size, out_bytes, D.data() + (size_t)fi * row, plans[fi]);
+            if (plans[fi].code)
+                for (int c = 0; c < channels; c++) st->preemph_memE[c] = cb::pipe_preemph_mem_after(g, D.data() + (size_t)fi * row, c);
+        }
+        // FE1 / FE2, frame-parallel on the device
+        for (int fi = 0; fi < nfr; fi++) {
+            if (!plans[fi].code) continue;
+            int mi[2];
+            for (int c = 0; c < channels; c++) mi[c] = fi == 0 ? m0[c] : cb::pipe_preemph_mem_after(g, D.data() + (size_t)(fi - 1) * row, c);
+            cb::pipe_preemph_frame(tm, g, plans[fi], D.data() + (size_t)fi * row, P.data(), fi, mi, fe[fi]);
+        }
+        for (int fi = nfr - 1; fi >= 0; fi--)   // any order
+            cb::pipe_pitch_frame(tm, g, plans[fi], P.data() + fi * g.N, P.data() + g.pstride + fi * g.N, *ps, fe[fi]);
+        // frame steps
+        for (int fi = 0; fi < nfr; fi++) {
+            uint8_t *o = out + (size_t)(f0 + fi) * stride;
+            cb::pipe_head(st, g, plans[fi], fe[fi], *X, o);
+            for (int c = 0; c < channels; c++)
+                cb::pipe_comb_channel(tm, st, g, *X, P.data() + (size_t)c * g.pstride + fi * g.N, B->in + c * (g.N + cb::kOverlap), c, tin.data(), sc);
+            cb::pipe_transform(tm, st, g, *X, *B, *ts);
+            cb::pipe_decide(st, g, *X);
+            const int r = cb::pipe_bands(tm, st, g, plans[fi], *X, *B, *bs, o);
+            lens[f0 + fi] = r;
+            if (r < 0) rc = r;
+            if (ranges) ranges[f0 + fi] = st->rangeFinal;
+        }
+        // the chunk's tail of P is the next chunk's history
+        for (int c = 0; c < channels; c++)
+            for (int i = 0; i < cb::kPipeHist; i++) P[(size_t)c * g.pstride + i] = P[(size_t)c * g.pstride + nfr * g.N + i];
+        if (rc < 0) break;
+    }
+    free(bs); free(ts); free(ps); free(B); free(X); free(st);
+    return rc;
+}
+}

@@ -33,6 +33,8 @@ def _hostsim():
                                          C.c_void_p, C.c_void_p]
     hs.hostsim_encode_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                          C.c_void_p]
+    hs.hostsim_encode_stream_pipe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_int]
     hs.hostsim_encode_stream_script.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                 C.c_int, C.c_void_p, C.c_void_p]
     return hs
@@ -174,6 +176,61 @@ def test_hostsim_encoder_vs_oracle_mini_sweep():
         d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx)
         out, lens, rng = _hostsim_encode(hs, x, fs, br, ch, vbr, cvbr, cx)
         assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), cases[i]
+
+
+def _hostsim_encode_pipe(hs, pcm, fs, br, ch, vbr, cvbr, cx, Fs=48000, max_bytes=1276, Fc=4):
+    """The frame-synchronous encoder pipeline (celt_enc_pipe.cuh) on the CPU: its stages in the kernels' order, chunks of Fc frames."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    F = pcm.shape[0] // fs
+    out = np.zeros((F, 1276), dtype=np.uint8)
+    lens = np.zeros(F, dtype=np.int32)
+    rng = np.zeros(F, dtype=np.uint32)
+    cfg = np.array([O.OPUS_APPLICATION_RESTRICTED_LOWDELAY, br, vbr, cvbr, cx, max_bytes, 0, 0], dtype=np.int32)
+    rc = hs.hostsim_encode_stream_pipe(O.ptr(pcm), F, fs, ch, Fs, O.ptr(cfg), O.ptr(out), 1276, O.ptr(lens), O.ptr(rng), Fc)
+    return rc, out, lens, rng
+
+
+@needs_ref
+def test_hostsim_encoder_pipeline_vs_oracle_mini_sweep():
+    """The pipeline's slicing of the frame (prepass / front end / head / comb / transform / decide / bands) against the oracle:
+    frame size x channels x bitrate x CBR/VBR/CVBR x complexity x signal kind, chunk lengths that do and do not divide the span."""
+    hs = _hostsim()
+    rs = np.random.RandomState(12)
+    cases = [(k, ch, fs, br, m, cx) for k in ("music", "tone", "clicks", "noise") for ch in (1, 2) for fs in (120, 240, 480, 960)
+             for br in (32000, 48000, 64000, 96000, 128000, 192000, 256000, 510000) for m in ((0, 0), (1, 0), (1, 1)) for cx in (0, 5, 10)]
+    for n, i in enumerate(rs.permutation(len(cases))[:150]):
+        kind, ch, fs, br, (vbr, cvbr), cx = cases[i]
+        x = O.test_signal(24000, ch, 500 + int(i), kind)
+        d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx, max_bytes=1276)
+        rc, out, lens, rng = _hostsim_encode_pipe(hs, x, fs, br, ch, vbr, cvbr, cx, Fc=(1, 3, 4, 7, 16)[n % 5])
+        assert rc == 0, (cases[i], rc)
+        assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), cases[i]
+
+
+@needs_ref
+def test_hostsim_encoder_pipeline_long_and_api_rates():
+    hs = _hostsim()
+    x = O.test_signal(48000 * 21, 2, 5, "music")
+    d, o, l, r = O.encode_stream(x, 960, 96000, 2, vbr=1, cvbr=1, complexity=10, max_bytes=1276)
+    rc, out, lens, rng = _hostsim_encode_pipe(hs, x, 960, 96000, 2, 1, 1, 10, Fc=16)
+    assert rc == 0 and _same_packets(d, o, l, out, lens) and np.array_equal(r, rng)
+    n = 0
+    for Fs in (8000, 12000, 16000, 24000):
+        for ch in (1, 2):
+            for ms in (2.5, 5, 10, 20):
+                br, vbr, cvbr = ((24000, 1, 1), (64000, 0, 0), (128000, 1, 0))[n % 3]
+                fs = int(Fs * ms / 1000)
+                x = O.test_signal(Fs // 2, ch, 70 + n, ("music", "tone", "clicks", "noise")[n % 4])
+                n += 1
+                d, o, l, r = O.encode_stream(x, fs, br, ch, Fs=Fs, vbr=vbr, cvbr=cvbr, complexity=10, max_bytes=1276)
+                rc, out, lens, rng = _hostsim_encode_pipe(hs, x, fs, br, ch, vbr, cvbr, 10, Fs=Fs, Fc=5)
+                assert rc == 0 and _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (Fs, ch, ms, br)
+    # low-rate stereo (narrowing, stereo -> mono decision) and a tight byte budget
+    for (ch, fs, br, maxb) in ((2, 960, 24000, 1276), (2, 120, 32000, 1276), (2, 480, 36000, 1276), (2, 960, 96000, 120), (1, 240, 510000, 300)):
+        x = O.test_signal(48000, ch, 9, "music")
+        d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=1, cvbr=0, complexity=10, max_bytes=maxb)
+        rc, out, lens, rng = _hostsim_encode_pipe(hs, x, fs, br, ch, 1, 0, 10, max_bytes=maxb, Fc=6)
+        assert rc == 0 and _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), (ch, fs, br, maxb)
 
 
 @needs_ref

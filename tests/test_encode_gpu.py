@@ -53,25 +53,44 @@ def _check_group(signals, ch, fs, br, vbr, cvbr, cx, nsec=1, spans=2):
 SIGS = [("music", 11), ("tone", 12), ("clicks", 13), ("noise", 14)]
 
 
+@pytest.fixture(params=["pipeline", "one_kernel"])
+def enc_path(request):
+    """The encoder's two device paths (include/opus_b200.h): the frame-synchronous kernel pipeline and the one-kernel path."""
+    cb = _cb()
+    L = cb.lib()
+    prev = L.opus_b200_enc_set_pipeline(1 if request.param == "pipeline" else 0)
+    assert prev >= 0
+    p0, l0 = C.c_longlong(0), C.c_longlong(0)
+    L.opus_b200_enc_path_counts(C.byref(p0), C.byref(l0))
+    yield request.param
+    p1, l1 = C.c_longlong(0), C.c_longlong(0)
+    L.opus_b200_enc_path_counts(C.byref(p1), C.byref(l1))
+    L.opus_b200_enc_set_pipeline(1)
+    if request.param == "pipeline":
+        assert p1.value > p0.value, "the pipeline did not take the streams of this test"
+    else:
+        assert p1.value == p0.value and l1.value > l0.value
+
+
 @pytest.mark.parametrize("fs", [120, 240, 480, 960])
 @pytest.mark.parametrize("ch", [1, 2])
-def test_encode_frame_sizes_vbr(fs, ch):
+def test_encode_frame_sizes_vbr(fs, ch, enc_path):
     _check_group(SIGS, ch, fs, 96000, 1, 0, 10)
 
 
 @pytest.mark.parametrize("br", [32000, 48000, 64000, 128000, 192000, 256000, 510000])
-def test_encode_bitrates_cbr_stereo(br):
+def test_encode_bitrates_cbr_stereo(br, enc_path):
     _check_group(SIGS, 2, 960, br, 0, 0, 10)
 
 
 @pytest.mark.parametrize("br", [32000, 64000, 256000])
 @pytest.mark.parametrize("fs", [120, 480])
-def test_encode_cvbr_mono(br, fs):
+def test_encode_cvbr_mono(br, fs, enc_path):
     _check_group(SIGS, 1, fs, br, 1, 1, 10)
 
 
 @pytest.mark.parametrize("cx", [0, 2, 4, 5, 8])
-def test_encode_complexities(cx):
+def test_encode_complexities(cx, enc_path):
     _check_group(SIGS, 2, 960, 64000, 1, 1, cx)
     _check_group(SIGS[:2], 2, 240, 128000, 1, 0, cx)
 
@@ -244,7 +263,7 @@ def test_mixed_settings_in_one_launch():
 
 
 @pytest.mark.parametrize("Fs", [8000, 12000, 16000, 24000])
-def test_encode_other_api_rates(Fs):
+def test_encode_other_api_rates(Fs, enc_path):
     """API rates below 48 kHz: zero-stuffing pre-emphasis (celt_encoder.c:490-533), MDCT bound
     (:451-460), bandwidth capped at the input's Nyquist rate; both applications, every frame size."""
     cb = _cb()
@@ -337,3 +356,59 @@ def test_scalar_api_ctl_fuzz(seed):
         L.opus_encoder_ctl(h, cb.OPUS_GET_FINAL_RANGE_REQUEST, C.byref(v))
         assert v.value == int(rr[f]), (seed, f)
     L.opus_encoder_destroy(h)
+
+
+def test_pipeline_groups_chunks_and_mixed_paths():
+    """The frame-synchronous pipeline at a size that uses several stream groups (>= 512 streams) and several chunks of frames
+    (front end of chunk k+1 overlapping the frame steps of chunk k, buffers reused from chunk k+2 on), in the same launch as
+    streams only the one-kernel path takes (OPUS_APPLICATION_AUDIO forced to CELT); two calls, state carried across."""
+    cb = _cb()
+    L = cb.lib()
+    ch, fs, F, n = 2, 960, 44, 640
+    kinds = ("music", "tone", "clicks", "noise")
+    nb = 16
+    base = [O.test_signal(fs * F, ch, 7000 + i, kinds[i % 4]) for i in range(nb)]
+    apps = [cb.OPUS_APPLICATION_AUDIO if (s % 7) == 3 else cb.OPUS_APPLICATION_RESTRICTED_LOWDELAY for s in range(n)]
+    refs = {}
+    for b in range(nb):
+        for app in (cb.OPUS_APPLICATION_AUDIO, cb.OPUS_APPLICATION_RESTRICTED_LOWDELAY):
+            d, o, l, r = O.encode_stream(base[b], fs, 96000, ch, vbr=1, cvbr=(b % 2), complexity=10, application=app, max_bytes=1276)
+            refs[(b, app)] = (d.reshape(-1, 1276), l, r)
+    err = C.c_int(0)
+    hs = []
+    for s in range(n):
+        h = L.opus_encoder_create(48000, ch, apps[s], C.byref(err))
+        for req, val in ((cb.OPUS_SET_BITRATE_REQUEST, 96000), (cb.OPUS_SET_VBR_REQUEST, 1), (cb.OPUS_SET_VBR_CONSTRAINT_REQUEST, (s % nb) % 2),
+                         (cb.OPUS_SET_COMPLEXITY_REQUEST, 10)):
+            assert L.opus_encoder_ctl(C.c_void_p(h), req, C.c_int32(val)) == 0
+        if apps[s] == cb.OPUS_APPLICATION_AUDIO:
+            assert L.opus_encoder_ctl(C.c_void_p(h), cb.OPUS_SET_FORCE_MODE_REQUEST, C.c_int32(1002)) == 0
+        hs.append(h)
+    hs = (C.c_void_p * n)(*hs)
+    p0, l0 = C.c_longlong(0), C.c_longlong(0)
+    L.opus_b200_enc_path_counts(C.byref(p0), C.byref(l0))
+    allp = np.stack([base[s % nb].reshape(F, fs * ch) for s in range(n)])
+    data = np.zeros((n, F, 1276), dtype=np.uint8)
+    lens = np.zeros((n, F), dtype=np.int32)
+    for a, b in ((0, 37), (37, 44)):
+        x = np.ascontiguousarray(allp[:, a:b]).reshape(-1)
+        d = np.zeros((n * (b - a), 1276), dtype=np.uint8)
+        l = np.zeros(n * (b - a), dtype=np.int32)
+        assert L.opus_encode_span(hs, n, b - a, O.ptr(x), fs, O.ptr(d), 1276, O.ptr(l)) == 0
+        data[:, a:b] = d.reshape(n, b - a, 1276)
+        lens[:, a:b] = l.reshape(n, b - a)
+    p1, l1 = C.c_longlong(0), C.c_longlong(0)
+    L.opus_b200_enc_path_counts(C.byref(p1), C.byref(l1))
+    n_audio = sum(1 for a in apps if a == cb.OPUS_APPLICATION_AUDIO)
+    assert p1.value - p0.value == 2 * (n - n_audio) and l1.value - l0.value == 2 * n_audio
+    v = C.c_uint32(0)
+    for s in range(n):
+        rd, rl, rr = refs[(s % nb, apps[s])]
+        assert np.array_equal(rl, lens[s]), ("len", s, int(np.nonzero(rl != lens[s])[0][0]))
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], data[s, f, :rl[f]]), ("bytes", s, f)
+        if s % 41 == 0:
+            L.opus_encoder_ctl(C.c_void_p(hs[s]), cb.OPUS_GET_FINAL_RANGE_REQUEST, C.byref(v))
+            assert v.value == int(rr[-1]), s
+    for h in hs:
+        L.opus_encoder_destroy(C.c_void_p(h))

@@ -17,6 +17,8 @@ br = int(sys.argv[3]) if len(sys.argv) > 3 else 96000
 fs, ch = 960, 2
 L = cb.lib()
 assert L.opus_b200_init(0) == 0
+if os.environ.get("ENC_PATH") == "one_kernel":
+    L.opus_b200_enc_set_pipeline(0)
 uniq = min(n, 64)
 base = [O.test_signal(fs * F, ch, 500 + i, ("music", "tone", "clicks", "music")[i % 4]) for i in range(uniq)]
 pcm = np.concatenate([base[i % uniq] for i in range(n)])
