@@ -191,6 +191,9 @@ CB_DEV_NOINLINE void deinterleave_hadamard_team(TM tm, int16_t *X, int16_t *tmp,
     tm.sync();
 }
 
+#if defined(CB_WALK_DEBUG)
+static int g_dbg_tell[3][32]; static unsigned g_dbg_rng[3][32]; static int g_dbg_which = 1; static int g_dbg_log = 0;
+#endif
 // One residue class of exp_rotation1 (vq.c:43-67): the pairs (i, i+stride) with i = r (mod stride) form an independent chain.
 // Each sweep carries the element it shares with the next pair in a register: one load and one store per step.
 CB_DEV void exp_rotation1_chain(int16_t *X, int len, int stride, int c, int s, int r) {
@@ -316,8 +319,9 @@ CB_DEV int pvq_pick(FreeWarpTeam tm, PvqBest best, int levels) { return pvq_pick
 // Ryy > 0 and Rxy >= 0 the cross-multiplied comparison is a strict weak order on the ratios.
 // alg_quant for N <= team width: position j lives in lane j's registers (|X|, y, iy, sign), nothing touches shared memory
 // until the pulse vector is handed to the indexer.  Same arithmetic and tie-breaking as the general version below.
+// (the search only: the pulse vector is left in ps.iy)
 template <class TM>
-CB_DEV_NOINLINE void alg_quant_small(TM tm, int16_t *X, int N, int K, EcEnc &enc, PvqScratch &ps) {
+CB_DEV_NOINLINE void alg_quant_small_core(TM tm, int16_t *X, int N, int K, PvqScratch &ps) {
     const int j = tm.lane();
     const bool active = j < N;
     int xj = active ? (int)X[j] : 0;
@@ -373,18 +377,13 @@ CB_DEV_NOINLINE void alg_quant_small(TM tm, int16_t *X, int N, int K, EcEnc &enc
         ps.iy[j] = (int16_t)(sgn < 0 ? -iyj : iyj);
     }
     tm.sync();
-    enc.uint_(pvq_encode_index(tm, N, K, ps.iy), pvq_v(N, K));
 }
 
+// the general search (any N), pulse vector left in ps.iy
 template <class TM>
-CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
+CB_DEV_NOINLINE void alg_quant_core(TM tm, int16_t *X, int N, int K, PvqScratch &ps) {
     int16_t *y = ps.y, *iy = ps.iy;
     int8_t *signx = ps.sign;
-    exp_rotation_enc(tm, X, N, B, K, spread);
-    if (TM::W > 1 && N <= TM::W) {
-        alg_quant_small(tm, X, N, K, enc, ps);
-        return;
-    }
     CB_TEAM_FOR(j, N, tm) {
         const int x = X[j];
         if (x > 0) signx[j] = 1;
@@ -463,7 +462,18 @@ CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int 
         if (signx[j] < 0) iy[j] = (int16_t)(-iy[j]);
     }
     tm.sync();
-    enc.uint_(pvq_encode_index(tm, N, K, iy), pvq_v(N, K));
+}
+
+// alg_quant (vq.c:161-325): spreading rotation, search, codeword
+template <class TM>
+CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
+    exp_rotation_enc(tm, X, N, B, K, spread);
+    if (TM::W > 1 && N <= TM::W) alg_quant_small_core(tm, X, N, K, ps);
+    else alg_quant_core(tm, X, N, K, ps);
+#if defined(CB_WALK_DEBUG)
+    { unsigned idx = pvq_encode_index(tm, N, K, ps.iy); if (g_dbg_log) printf("   [%s] leaf N=%d K=%d B=%d idx=%u\n", g_dbg_which == 0 ? "ref" : "slow", N, K, B, idx); }
+#endif
+    enc.uint_(pvq_encode_index(tm, N, K, ps.iy), pvq_v(N, K));
 }
 
 template <class TM>
@@ -661,6 +671,9 @@ CB_DEV void quant_all_bands_enc(TM tm, int start, int end, int16_t *X_, int16_t 
         tm.phase();   // one per band, kNbEBands per frame (balanced below): co-resident streams walk the band loop together
 #endif
         ctx.i = i;
+#if defined(CB_WALK_DEBUG)
+        g_dbg_tell[0][i] = (int)ctx.ec.tell_frac(); g_dbg_rng[0][i] = ctx.ec.rng;
+#endif
         int16_t *X = X_ + M * kEBands[i];
         int16_t *Y = Y_ != nullptr ? Y_ + M * kEBands[i] : nullptr;
         const int N = M * kEBands[i + 1] - M * kEBands[i];

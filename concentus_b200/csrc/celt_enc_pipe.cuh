@@ -23,10 +23,16 @@
 //                                               and the X-only statistics of spreading / stereo / trim analysis
 //     K4  decide       thread / stream          tf Viterbi, coarse energy (two-pass), tf / spread / dynalloc / trim symbols, VBR,
 //                                               compute_allocation, fine energy
-//     K5  bands        warp / stream            quant_all_bands + finalise + packet tail
+//     K5  bands        the band loop, cut into a data-parallel part and a scalar chain (celt_enc_bandpipe.cuh):
+//         K5a prep     warp / stream            stereo angles, mid / side vectors, reordering, split-angle trees
+//         K5b chain-S  thread / stream          the loop on a budget-only range coder -> list of leaves (position, N, K)
+//         K5c leaves   warp / stream            rotation + PVQ search + codeword index of every listed leaf
+//         K5d chain-X  thread / stream          the loop with the real coder and indices, finalise, packet tail
+//         (pipe_bands, the loop as one warp-per-stream stage, is kept: hostsim / A-B)
 //
 // Every stage is a function template over the team type so tests/hostsim can run the very same slices with 1-lane teams.
 #pragma once
+#include "celt_enc_bandpipe.cuh"
 #include "opus_encoder_dev.cuh"
 
 namespace cb {
@@ -1062,6 +1068,78 @@ CB_DEV int pipe_bands(TM tm, CbEncState *st, const PipeGeom &g, const EncPlan &p
     tm.sync();
     if (tm.lane() == 0) V.ret = pipe_finish(st, g, pl, X, out);
     tm.sync();
+    return V.ret;
+}
+
+// ---- K5a..K5d: the band loop as prep / chain-S / leaves / chain-X (celt_enc_bandpipe.cuh) ------------------------------------------
+struct PrepScratch {
+    int16_t Xall[kXallStride];
+    int16_t tmp[176];
+    int seg[16];
+};
+template <class TM>
+CB_DEV void pipe_band_prep(TM tm, const CbEncState *st, const PipeGeom &g, const EncPipeCtx &X, const EncPipeBuf &B, BandPrep &P, int16_t *XallG,
+                           PrepScratch &S) {
+    if (!X.code) return;
+    const int C = X.cfg.C, N = g.N;
+    CB_TEAM_FOR(i, N, tm) S.Xall[i] = B.X[i];
+    if (C == 2) CB_TEAM_FOR(i, N, tm) S.Xall[kMaxFrame + i] = B.X[N + i];
+    tm.sync();
+    band_prep_team(tm, S.Xall, X.bandE, X.tf_res, X.cfg.end, C, g.LM, X.v.shortBlocks, X.v.dual_stereo, st->intensity, P, S.tmp, S.seg);
+    tm.sync();
+    CB_NOUNROLL for (int v = 0; v < 3; v++) {
+        if (v > 0 && C == 1) break;
+        CB_TEAM_FOR(i, N, tm) XallG[v * kMaxFrame + i] = S.Xall[v * kMaxFrame + i];
+    }
+}
+CB_DEV_NOINLINE void pipe_band_spec(const CbEncState *st, const PipeGeom &g, const EncPipeCtx &X, const BandPrep &P, LeafList &L) {
+    if (!X.code) { L.count = 0; return; }
+    const EncVars &V = X.v;
+    SpecPolicy p;
+    p.ec.from(V.ec);
+    p.list = &L;
+    p.cur_band = -1;
+    L.count = 0;
+    L.overflow = 0;
+    band_walk(p, P, X.cfg.end, X.cfg.C, X.pulses, V.shortBlocks, st->spread_decision, V.dual_stereo, st->intensity, X.tf_res,
+              V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, g.LM, V.codedBands);
+}
+struct LeafScratch {
+    int16_t V[176];
+    PvqScratch pvq;
+};
+template <class TM>
+CB_DEV void pipe_leaves(TM tm, const CbEncState *st, const EncPipeCtx &X, LeafList &L, const int16_t *XallG, LeafScratch &S) {
+    if (!X.code) return;
+    const int spread = st->spread_decision;
+    const int cnt = L.count;
+    CB_NOUNROLL for (int k = 0; k < cnt; k++) {
+        const LeafTask t = L.task[k];
+        CB_TEAM_FOR(j, t.N, tm) S.V[j] = XallG[t.off + j];
+        tm.sync();
+        const unsigned idx = leaf_quant_team(tm, S.V, t.N, t.K, spread, t.B, S.pvq);
+        if (tm.lane() == 0) L.index[k] = idx;
+        tm.sync();
+    }
+}
+CB_DEV_NOINLINE int pipe_band_exact_finish(CbEncState *st, const PipeGeom &g, const EncPlan &pl, EncPipeCtx &X, const BandPrep &P, const LeafList &L,
+                                           int16_t *XallG, uint8_t *out, int *misses) {
+    if (!X.code) return X.v.ret;
+    EncVars &V = X.v;
+    PvqScratch ps;
+    ExactPolicy p;
+    p.ec = V.ec;
+    p.list = &L;
+    p.Xall = XallG;
+    p.prep = &P;
+    p.ps = &ps;
+    p.cursor = 0;
+    p.misses = 0;
+    band_walk(p, P, X.cfg.end, X.cfg.C, X.pulses, V.shortBlocks, st->spread_decision, V.dual_stereo, st->intensity, X.tf_res,
+              V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, g.LM, V.codedBands);
+    V.ec = p.ec;
+    if (misses) *misses += p.misses;
+    V.ret = pipe_finish(st, g, pl, X, out);
     return V.ret;
 }
 

@@ -25,3 +25,5 @@ struct EncPipeCall {
 int enc_pipe_enqueue(const EncPipeCall &c, cudaStream_t stream);
 // 1 when the stream may go through the pipeline (host-side test on its ctl-visible configuration)
 int enc_pipe_takes(const CbEncState *st, int frame_size, int out_data_bytes);
+// statistics of the split band loop: leaves chain-X searched itself (its budget differed from chain-S's) / leaves listed
+void enc_pipe_stats(long long *misses, long long *leaves);

@@ -492,7 +492,7 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs, bool host_io) {
     pl.n = n; pl.F = F; pl.cap = cap; pl.fec = fec;
     int k = cap / (Fs / 400);
     pl.kmax = k < 1 ? 1 : (k > 48 ? 48 : k);
-    pl.xstride = cap * (48000 / Fs) * 2;
+    pl.xstride = (cap * (48000 / Fs) * 2 + 7) & ~7;   // stage A stores bands with up to 16-byte vectors (store_band): every packet's spectrum must start 16-byte aligned
     pl.sigstride = cap * (48000 / Fs) * 2;
     pl.R = g.run_len;
     const size_t per_packet = sizeof(CbPacketIR) + (size_t)pl.kmax * sizeof(CbFrameIR) + (size_t)pl.xstride * sizeof(int16_t) +

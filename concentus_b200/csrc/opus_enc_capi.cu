@@ -486,6 +486,12 @@ void opus_b200_enc_path_counts(long long *pipe, long long *legacy) {
     if (pipe) *pipe = e.pipe_streams;
     if (legacy) *legacy = e.legacy_streams;
 }
+// split band loop statistics (opus_enc_pipe.cu): leaves the exact chain searched itself / leaves the speculative chain listed
+void opus_b200_enc_band_stats(long long *misses, long long *leaves) {
+    std::lock_guard<std::mutex> lk(e.mu);
+    if (e.ok) cudaDeviceSynchronize();
+    enc_pipe_stats(misses, leaves);
+}
 // 1 (default): streams the pipeline takes go through it; 0: everything through the one-kernel path.  Returns the previous setting.
 int opus_b200_enc_set_pipeline(int on) {
     std::lock_guard<std::mutex> lk(e.mu);

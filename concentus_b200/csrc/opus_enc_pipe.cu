@@ -157,6 +157,47 @@ pipe_bands_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
     }
 }
 
+// ---- K5a..K5d: the band loop as prep / chain-S / leaves / chain-X (celt_enc_bandpipe.cuh) ----------------------------------------
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_prep_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, const EncPipeBuf *buf, BandPrep *prep, int16_t *xall) {
+    __shared__ __align__(16) PrepScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    if (s >= g.n) return;
+    FreeWarpTeam tm{{lane}};
+    pipe_band_prep(tm, pool + slots[s], g, ctx[s], buf[s], prep[s], xall + (size_t)s * kXallStride, sm[wib]);
+}
+__global__ void __launch_bounds__(64)
+pipe_spec_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, const BandPrep *prep, LeafList *leaves) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    pipe_band_spec(pool + slots[t], g, ctx[t], prep[t], leaves[t]);
+}
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+pipe_leaves_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, LeafList *leaves, const int16_t *xall) {
+    __shared__ __align__(16) LeafScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    if (s >= g.n) return;
+    FreeWarpTeam tm{{lane}};
+    pipe_leaves(tm, pool + slots[s], ctx[s], leaves[s], xall + (size_t)s * kXallStride, sm[wib]);
+}
+__global__ void __launch_bounds__(64)
+pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
+                  const BandPrep *prep, const LeafList *leaves, int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, int *misses) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.n) return;
+    CbEncState *st = pool + slots[t];
+    const size_t k = (size_t)sidx[t] * g.F + f;
+    int miss = 0;
+    const int r = pipe_band_exact_finish(st, g, plans[(size_t)t * g.Fc + fi], ctx[t], prep[t], leaves[t], xall + (size_t)t * kXallStride, data + k * g.stride,
+                                         &miss);
+    rets[k] = r;
+    if (ranges) ranges[k] = st->rangeFinal;
+    if (miss) atomicAdd(misses, miss);
+    atomicAdd(misses + 1, leaves[t].count);
+}
+
 // ---- end of the span: the last 1024 pre-emphasised samples go back into the state -------------------------------------------------
 __global__ void pipe_epilogue_kernel(CbEncState *pool, const int *slots, PipeGeom g, const int *P, int last_nfr) {
     const int s = blockIdx.x;
@@ -185,14 +226,16 @@ enum { kMaxGroups = 8 };
 struct Group {
     cudaStream_t main = nullptr, side = nullptr;
     cudaEvent_t ev_fe[2] = {nullptr, nullptr}, ev_steps[2] = {nullptr, nullptr}, ev_done = nullptr;
-    DevBuf D, P[2], plans[2], fe[2], m0, ctx, buf;
+    DevBuf D, P[2], plans[2], fe[2], m0, ctx, buf, prep, leaves, xall;
 };
 struct PipeCtx {
     bool init = false;
     int groups = 2;
     int chunk = 16;
+    int split_bands = 1;        // 1: the band loop as prep / chain-S / leaves / chain-X; 0: one warp-per-stream stage (A/B)
     Group g[kMaxGroups];
     cudaEvent_t ev_fork = nullptr;
+    int *d_stats = nullptr;     // [0] leaves chain-X had to search itself, [1] leaves listed by chain-S
 } pc;
 
 bool pipe_init() {
@@ -202,6 +245,9 @@ bool pipe_init() {
     if (pc.groups > kMaxGroups) pc.groups = kMaxGroups;
     if (const char *e = getenv("CB200_ENC_CHUNK")) pc.chunk = atoi(e);
     if (pc.chunk < 1) pc.chunk = 1;
+    if (const char *e = getenv("CB200_ENC_SPLIT_BANDS")) pc.split_bands = atoi(e);
+    if (cudaMalloc(&pc.d_stats, 2 * sizeof(int)) != cudaSuccess) return false;
+    cudaMemset(pc.d_stats, 0, 2 * sizeof(int));
     for (int i = 0; i < kMaxGroups; i++) {
         Group &G = pc.g[i];
         if (cudaStreamCreateWithFlags(&G.main, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -226,7 +272,9 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
     const int Fc = g.Fc;
     const size_t row = (size_t)g.fsz * g.CC;
     if (!G.D.reserve((size_t)n * Fc * row * sizeof(int16_t)) || !G.m0.reserve((size_t)n * 2 * sizeof(int)) ||
-        !G.ctx.reserve((size_t)n * sizeof(EncPipeCtx)) || !G.buf.reserve((size_t)n * sizeof(EncPipeBuf)))
+        !G.ctx.reserve((size_t)n * sizeof(EncPipeCtx)) || !G.buf.reserve((size_t)n * sizeof(EncPipeBuf)) ||
+        !G.prep.reserve((size_t)n * sizeof(BandPrep)) || !G.leaves.reserve((size_t)n * sizeof(LeafList)) ||
+        !G.xall.reserve((size_t)n * kXallStride * sizeof(int16_t)))
         return -7;
     for (int b = 0; b < 2; b++)
         if (!G.P[b].reserve((size_t)n * g.CC * g.pstride * sizeof(int)) || !G.plans[b].reserve((size_t)n * Fc * sizeof(EncPlan)) ||
@@ -263,9 +311,23 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                                                                                           (EncPipeBuf *)G.buf.p);
             pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
             pipe_decide_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p);
-            pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
-                                                                                    (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets, c.d_ranges);
-            launches += 5;
+            if (!pc.split_bands) {
+                pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
+                                                                                        (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets,
+                                                                                        c.d_ranges);
+                launches += 5;
+            } else {
+                pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
+                                                                                       (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
+                pipe_spec_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p,
+                                                                   (LeafList *)G.leaves.p);
+                pipe_leaves_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p, (LeafList *)G.leaves.p,
+                                                                                         (const int16_t *)G.xall.p);
+                pipe_exact_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p,
+                                                                    (const BandPrep *)G.prep.p, (const LeafList *)G.leaves.p, (int16_t *)G.xall.p, c.d_data,
+                                                                    c.d_rets, c.d_ranges, pc.d_stats);
+                launches += 8;
+            }
         }
         cudaEventRecord(G.ev_steps[b], G.main);
         prev_nfr = nfr;
@@ -276,6 +338,14 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
 }
 
 }  // namespace
+
+// leaves the exact chain had to search itself / leaves listed by the speculative chain, since start (reads after a device sync)
+void enc_pipe_stats(long long *misses, long long *leaves) {
+    int h[2] = {0, 0};
+    if (pc.init) cudaMemcpy(h, pc.d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+    if (misses) *misses = h[0];
+    if (leaves) *leaves = h[1];
+}
 
 int enc_pipe_takes(const CbEncState *st, int frame_size, int out_data_bytes) { return enc_pipe_eligible(st, frame_size, out_data_bytes); }
 

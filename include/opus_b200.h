@@ -186,6 +186,9 @@ float opus_b200_enc_last_kernel_ms(void);  /* device time of the last encode spa
  * each path has coded so far. */
 int opus_b200_enc_set_pipeline(int on);
 void opus_b200_enc_path_counts(long long *pipeline, long long *one_kernel);
+/* The pipeline's band loop runs a budget-only chain first, searches every leaf it lists in parallel, then the exact chain;
+ * a leaf whose pulse count the exact chain finds different is searched there.  Counters since start (synchronises). */
+void opus_b200_enc_band_stats(long long *searched_by_exact_chain, long long *leaves_listed);
 
 #ifdef __cplusplus
 }

@@ -140,7 +140,18 @@ int hostsim_encode_stream_script(const int16_t *pcm, int F, int frame_size, int 
 // ---- encoder, frame-synchronous pipeline (celt_enc_pipe.cuh): the same slices the pipeline kernels run, 1-lane teams ----------
 #include "../../concentus_b200/csrc/celt_enc_pipe.cuh"
 
+static int g_band_mode = 1;          // 0: the band loop as one stage (pipe_bands); 1: prep / chain-S / leaves / chain-X
+static long long g_leaves = 0, g_misses = 0, g_frames = 0;
+
 extern "C" {
+
+void hostsim_set_band_mode(int m) { g_band_mode = m; }
+void hostsim_band_stats(long long *leaves, long long *misses, long long *frames, int reset) {
+    if (leaves) *leaves = g_leaves;
+    if (misses) *misses = g_misses;
+    if (frames) *frames = g_frames;
+    if (reset) g_leaves = g_misses = g_frames = 0;
+}
 
 // Encode F frames of one stream through the pipeline stages in chunks of Fc frames.  Returns -100 when the stream is not one
 // the pipeline takes (the library then uses the one-kernel path), else 0.  Same cfg / outputs as hostsim_encode_stream.
@@ -172,6 +183,11 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
     cb::PitchScratch *ps = (cb::PitchScratch *)calloc(1, sizeof(cb::PitchScratch));
     cb::TransformScratch *ts = (cb::TransformScratch *)calloc(1, sizeof(cb::TransformScratch));
     cb::BandScratch *bs = (cb::BandScratch *)calloc(1, sizeof(cb::BandScratch));
+    cb::PrepScratch *prs = (cb::PrepScratch *)calloc(1, sizeof(cb::PrepScratch));
+    cb::LeafScratch *lfs = (cb::LeafScratch *)calloc(1, sizeof(cb::LeafScratch));
+    cb::BandPrep *bp = (cb::BandPrep *)calloc(1, sizeof(cb::BandPrep));
+    cb::LeafList *ll = (cb::LeafList *)calloc(1, sizeof(cb::LeafList));
+    std::vector<int16_t> xall(cb::kXallStride);
     std::vector<int> tin(960 + 120);
     int sc[4];
     cb::SoloTeam tm;
@@ -204,7 +220,17 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
                 cb::pipe_comb_channel(tm, st, g, *X, P.data() + (size_t)c * g.pstride + fi * g.N, B->in + c * (g.N + cb::kOverlap), c, tin.data(), sc);
             cb::pipe_transform(tm, st, g, *X, *B, *ts);
             cb::pipe_decide(st, g, *X);
-            const int r = cb::pipe_bands(tm, st, g, plans[fi], *X, *B, *bs, o);
+            int r;
+            if (g_band_mode == 0) {
+                r = cb::pipe_bands(tm, st, g, plans[fi], *X, *B, *bs, o);
+            } else {
+                cb::pipe_band_prep(tm, st, g, *X, *B, *bp, xall.data(), *prs);
+                cb::pipe_band_spec(st, g, *X, *bp, *ll);
+                cb::pipe_leaves(tm, st, *X, *ll, xall.data(), *lfs);
+                int miss = 0;
+                r = cb::pipe_band_exact_finish(st, g, plans[fi], *X, *bp, *ll, xall.data(), o, &miss);
+                g_leaves += ll->count; g_misses += miss; g_frames++;
+            }
             lens[f0 + fi] = r;
             if (r < 0) rc = r;
             if (ranges) ranges[f0 + fi] = st->rangeFinal;
@@ -214,6 +240,7 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
             for (int i = 0; i < cb::kPipeHist; i++) P[(size_t)c * g.pstride + i] = P[(size_t)c * g.pstride + nfr * g.N + i];
         if (rc < 0) break;
     }
+    free(ll); free(bp); free(lfs); free(prs);
     free(bs); free(ts); free(ps); free(B); free(X); free(st);
     return rc;
 }

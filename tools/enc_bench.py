@@ -45,3 +45,10 @@ for s in list(range(0, n, max(1, n // 16)))[:16]:
     ok = np.array_equal(rl, l[s]) and all(np.array_equal(rd[f, :rl[f]], d[s, f, :rl[f]]) for f in range(F))
     bad += not ok
 print("parity spot-check: %d bad of 16" % bad)
+import ctypes as C
+m, lv = C.c_longlong(0), C.c_longlong(0)
+try:
+    L.opus_b200_enc_band_stats(C.byref(m), C.byref(lv))
+    print("split band loop: %d leaves listed, %d searched by the exact chain (%.2f %%)" % (lv.value, m.value, 100.0 * m.value / max(1, lv.value)))
+except Exception as ex:
+    print("no band stats:", ex)
