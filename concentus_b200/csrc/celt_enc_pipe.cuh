@@ -114,16 +114,25 @@ struct EncPipeBuf {
 // Eligibility (host side, enc_pipe_eligible): OPUS_APPLICATION_RESTRICTED_LOWDELAY, frame <= 20 ms, not a "PLC frame" budget.
 // Returns the plan; when plan.code the frame's PCM has been DC-rejected (and narrowed) into `D`.
 // ---------------------------------------------------------------------------------------------------------------------------
-CB_DEV_NOINLINE void pipe_plan_frame(CbEncState *st, const int16_t *pcm, int frame_size, int out_data_bytes, int16_t *D, EncPlan &pl) {
+// What the decisions of a frame leave for its sample pass and its commit
+struct PlanPre {
+    int code, ret;
+    int want_width, fade, g1, g2, dc_shift;
+    int bitrate_bps, equiv_rate, stream_channels, mode, bandwidth, curr_bandwidth, max_data_bytes, bytes_target, lsb_depth, stereoWidth_Q14;
+};
+
+// (1) the decisions: scalars only, nothing is written
+CB_DEV_NOINLINE void pipe_plan_pre(const CbEncState *st, int frame_size, int out_data_bytes, PlanPre &pp) {
     const int Fs = st->Fs, channels = st->channels;
-    pl.code = 0;
+    pp.code = 0;
+    pp.want_width = 0; pp.fade = 0;
     int max_data_bytes = imin(1276, out_data_bytes);
     if ((400 * frame_size != Fs && 200 * frame_size != Fs && 100 * frame_size != Fs && 50 * frame_size != Fs) || max_data_bytes <= 0 ||
         st->application != kAppLowdelay) {
-        pl.ret = OPUS_INTERNAL_ERROR_;   // not a frame for this pipeline: the host's eligibility test keeps these out
+        pp.ret = OPUS_INTERNAL_ERROR_;   // not a frame for this pipeline: the host's eligibility test keeps these out
         return;
     }
-    const int lsb_depth = imin(16, st->lsb_depth);
+    pp.lsb_depth = imin(16, st->lsb_depth);
     int bitrate_bps;
     if (st->user_bitrate_bps == kOpusAuto) bitrate_bps = 60 * Fs / frame_size + Fs * channels;
     else if (st->user_bitrate_bps == kBitrateMax) bitrate_bps = max_data_bytes * 8 * Fs / frame_size;
@@ -152,28 +161,9 @@ CB_DEV_NOINLINE void pipe_plan_frame(CbEncState *st, const int16_t *pcm, int fra
         stream_channels = channels;
     }
     const bool tiny = max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * frame_rate < 300 || bitrate_bps < 2400));
-    if (tiny) { pl.ret = OPUS_INTERNAL_ERROR_; return; }
-    StereoWidth sw;
-    sw.width = 0;
-    const bool want_width = channels == 2 && st->force_channels != 1;
-    if (want_width) {
-        int xx = 0, xy = 0, yy = 0;
-        CB_NOUNROLL for (int i = 0; i < frame_size - 3; i += 4) {
-            int pxx = 0, pxy = 0, pyy = 0;
-            CB_NOUNROLL for (int k = 0; k < 4; k++) {
-                const int x = pcm[2 * (i + k)], y = pcm[2 * (i + k) + 1];
-                pxx += mul16_16(x, x) >> 2;
-                pxy += mul16_16(x, y) >> 2;
-                pyy += mul16_16(y, y) >> 2;
-            }
-            xx = wadd(xx, pxx >> 10);
-            xy = wadd(xy, pxy >> 10);
-            yy = wadd(yy, pyy >> 10);
-        }
-        stereo_width_finish(xx, xy, yy, frame_size, Fs, st, sw);
-    }
+    if (tiny) { pp.ret = OPUS_INTERNAL_ERROR_; return; }
+    pp.want_width = channels == 2 && st->force_channels != 1;
     equiv_rate = bitrate_bps - (40 * stream_channels + 20) * (Fs / frame_size - 50);
-    const int mode = CB_MODE_CELT_ONLY;
     int bandwidth;
     {
         const int32_t *voice_t, *music_t;
@@ -199,45 +189,37 @@ CB_DEV_NOINLINE void pipe_plan_frame(CbEncState *st, const int16_t *pcm, int fra
     if (Fs <= 12000 && bandwidth > 1102) bandwidth = 1102;
     if (Fs <= 8000 && bandwidth > 1101) bandwidth = 1101;
     if (bandwidth == 1102) bandwidth = 1103;
-    const int curr_bandwidth = bandwidth;
-    const int bytes_target = imin(max_data_bytes, bitrate_bps * frame_size / (Fs * 8)) - 1;
+    pp.bytes_target = imin(max_data_bytes, bitrate_bps * frame_size / (Fs * 8)) - 1;
+    pp.dc_shift = celt_ilog2(Fs / (3 * 3));
+    pp.stereoWidth_Q14 = imin(1 << 14, 2 * imax(0, equiv_rate - 30000));
+    if (channels == 2 && (st->hybrid_stereo_width_Q14 < (1 << 14) || pp.stereoWidth_Q14 < (1 << 14))) {
+        int g1 = st->hybrid_stereo_width_Q14, g2 = pp.stereoWidth_Q14;
+        pp.g1 = g1 == 16384 ? 32767 : shl16(g1, 1);
+        pp.g2 = g2 == 16384 ? 32767 : shl16(g2, 1);
+        pp.fade = 1;
+    }
+    pp.bitrate_bps = bitrate_bps; pp.equiv_rate = equiv_rate; pp.stream_channels = stream_channels; pp.mode = CB_MODE_CELT_ONLY;
+    pp.bandwidth = bandwidth; pp.curr_bandwidth = bandwidth; pp.max_data_bytes = max_data_bytes;
+    pp.code = 1;
+    pp.ret = 0;
+}
 
-    // ---- commit point ----
-    {
-        const int shift = celt_ilog2(Fs / (3 * 3));
-        if (channels == 2) {   // the two channels' recurrences interleaved: independent chains
-            int a0 = st->hp_mem[0], a1 = st->hp_mem[1], b0 = st->hp_mem[2], b1 = st->hp_mem[3];
-            CB_NOUNROLL for (int i = 0; i < frame_size; i++) {
-                const int xa = shl32(pcm[2 * i], 15), xb = shl32(pcm[2 * i + 1], 15);
-                const int ta = wsub(xa, a0), tb = wsub(xb, b0);
-                a0 = wadd(a0, pshr32(ta, shift));
-                b0 = wadd(b0, pshr32(tb, shift));
-                const int ya = wsub(ta, a1), yb = wsub(tb, b1);
-                a1 = wadd(a1, pshr32(ya, shift));
-                b1 = wadd(b1, pshr32(yb, shift));
-                int va = pshr32(ya, 15), vb = pshr32(yb, 15);
-                va = va > 32767 ? 32767 : (va < -32767 ? -32767 : va);
-                vb = vb > 32767 ? 32767 : (vb < -32767 ? -32767 : vb);
-                D[2 * i] = (int16_t)va;
-                D[2 * i + 1] = (int16_t)vb;
-            }
-            st->hp_mem[0] = a0; st->hp_mem[1] = a1; st->hp_mem[2] = b0; st->hp_mem[3] = b1;
-        } else {
-            dc_reject_channel(pcm, D, st->hp_mem, frame_size, 1, 0, shift);
-        }
+// (3) the commit, after the frame's samples have been processed (xx / xy / yy: compute_stereo_width's sums when pp.want_width)
+CB_DEV_NOINLINE void pipe_plan_post(CbEncState *st, const PlanPre &pp, int frame_size, int xx, int xy, int yy, EncPlan &pl) {
+    pl.code = pp.code;
+    pl.ret = pp.ret;
+    if (!pp.code) return;
+    const int channels = st->channels;
+    if (pp.want_width) {
+        StereoWidth sw;
+        stereo_width_finish(xx, xy, yy, frame_size, st->Fs, st, sw);
+        st->width_XX = sw.XX; st->width_XY = sw.XY; st->width_YY = sw.YY; st->width_smoothed = sw.smoothed; st->width_max_follower = sw.max_follower;
     }
-    const int stereoWidth_Q14 = imin(1 << 14, 2 * imax(0, equiv_rate - 30000));
-    if (channels == 2 && (st->hybrid_stereo_width_Q14 < (1 << 14) || stereoWidth_Q14 < (1 << 14))) {
-        int g1 = st->hybrid_stereo_width_Q14, g2 = stereoWidth_Q14;
-        g1 = g1 == 16384 ? 32767 : shl16(g1, 1);
-        g2 = g2 == 16384 ? 32767 : shl16(g2, 1);
-        stereo_fade_team(SoloTeam{}, D, g1, g2, frame_size, Fs);
-        st->hybrid_stereo_width_Q14 = stereoWidth_Q14;
-    }
-    pl.cfg.C = stream_channels;
-    pl.cfg.end = curr_bandwidth == 1101 ? 13 : curr_bandwidth <= 1103 ? 17 : curr_bandwidth == 1104 ? 19 : 21;
+    if (pp.fade) st->hybrid_stereo_width_Q14 = pp.stereoWidth_Q14;
+    pl.cfg.C = pp.stream_channels;
+    pl.cfg.end = pp.curr_bandwidth == 1101 ? 13 : pp.curr_bandwidth <= 1103 ? 17 : pp.curr_bandwidth == 1104 ? 19 : 21;
     pl.cfg.complexity = st->complexity;
-    pl.cfg.lsb_depth = lsb_depth;
+    pl.cfg.lsb_depth = pp.lsb_depth;
     pl.cfg.loss_rate = st->packet_loss_perc;
     pl.cfg.variable_duration = st->variable_duration;
     const int celt_pred = st->prediction_disabled ? 0 : 2;
@@ -247,29 +229,85 @@ CB_DEV_NOINLINE void pipe_plan_frame(CbEncState *st, const int16_t *pcm, int fra
     if (st->use_vbr) {
         pl.cfg.vbr = 1;
         pl.cfg.constrained_vbr = st->vbr_constraint;
-        pl.cfg.bitrate = imin(bitrate_bps, 260000 * channels);
-        nb_compr_bytes = max_data_bytes - 1;
+        pl.cfg.bitrate = imin(pp.bitrate_bps, 260000 * channels);
+        nb_compr_bytes = pp.max_data_bytes - 1;
     } else {
         pl.cfg.vbr = 0;
         pl.cfg.constrained_vbr = st->vbr_constraint;
         pl.cfg.bitrate = kBitrateMax;
-        nb_compr_bytes = bytes_target;
+        nb_compr_bytes = pp.bytes_target;
     }
-    nb_compr_bytes = imin(max_data_bytes - 1, nb_compr_bytes);
+    nb_compr_bytes = imin(pp.max_data_bytes - 1, nb_compr_bytes);
     st->voice_ratio = -1;
-    st->bitrate_bps = bitrate_bps;
-    st->stream_channels = stream_channels;
-    st->mode = mode;
-    st->bandwidth = bandwidth;
-    if (want_width) { st->width_XX = sw.XX; st->width_XY = sw.XY; st->width_YY = sw.YY; st->width_smoothed = sw.smoothed; st->width_max_follower = sw.max_follower; }
-    st->prev_mode = mode;
-    st->prev_channels = stream_channels;
+    st->bitrate_bps = pp.bitrate_bps;
+    st->stream_channels = pp.stream_channels;
+    st->mode = pp.mode;
+    st->bandwidth = pp.bandwidth;
+    st->prev_mode = pp.mode;
+    st->prev_channels = pp.stream_channels;
     st->prev_framesize = frame_size;
     st->first = 0;
-    pl.code = 1;
-    pl.ret = 0;
-    pl.mode = mode; pl.curr_bandwidth = curr_bandwidth; pl.stream_channels = stream_channels;
-    pl.max_data_bytes = max_data_bytes; pl.nb_compr_bytes = nb_compr_bytes; pl.use_vbr = st->use_vbr;
+    pl.mode = pp.mode; pl.curr_bandwidth = pp.curr_bandwidth; pl.stream_channels = pp.stream_channels;
+    pl.max_data_bytes = pp.max_data_bytes; pl.nb_compr_bytes = nb_compr_bytes; pl.use_vbr = st->use_vbr;
+}
+
+// (2) one sample of dc_reject (opus_encoder.c:362-385) for one channel; m0 / m1: the channel's two filter memories
+CB_DEV int dc_reject_step(int x16, int &m0, int &m1, int shift) {
+    const int x = shl32(x16, 15);
+    const int tmp = wsub(x, m0);
+    m0 = wadd(m0, pshr32(tmp, shift));
+    const int y = wsub(tmp, m1);
+    m1 = wadd(m1, pshr32(y, shift));
+    int v = pshr32(y, 15);
+    return v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
+}
+// the stereo_fade gain at sample i (opus_encoder.c:411-441)
+CB_DEV int stereo_fade_gain(int i, int g1, int g2, int Fs) {
+    const int inc = 48000 / Fs;
+    const int overlap = kOverlap / inc;
+    g1 = s16(32767 - g1);
+    g2 = s16(32767 - g2);
+    if (i >= overlap) return g2;
+    const int w = s16(mul16_16_q15(kWindow120[i * inc], kWindow120[i * inc]));
+    return s16(mac16_16(mul16_16(w, g2), 32767 - w, g1) >> 15);
+}
+
+// The three steps for one frame by one thread (tests/hostsim; the prepass kernel spreads step 2 over a lane per channel).
+CB_DEV_NOINLINE void pipe_plan_frame(CbEncState *st, const int16_t *pcm, int frame_size, int out_data_bytes, int16_t *D, EncPlan &pl) {
+    PlanPre pp;
+    pipe_plan_pre(st, frame_size, out_data_bytes, pp);
+    int xx = 0, xy = 0, yy = 0;
+    if (pp.code) {
+        const int channels = st->channels, Fs = st->Fs;
+        if (pp.want_width) {
+            CB_NOUNROLL for (int i = 0; i < frame_size - 3; i += 4) {
+                int pxx = 0, pxy = 0, pyy = 0;
+                CB_NOUNROLL for (int k = 0; k < 4; k++) {
+                    const int x = pcm[2 * (i + k)], y = pcm[2 * (i + k) + 1];
+                    pxx += mul16_16(x, x) >> 2;
+                    pxy += mul16_16(x, y) >> 2;
+                    pyy += mul16_16(y, y) >> 2;
+                }
+                xx = wadd(xx, pxx >> 10);
+                xy = wadd(xy, pxy >> 10);
+                yy = wadd(yy, pyy >> 10);
+            }
+        }
+        CB_NOUNROLL for (int c = 0; c < channels; c++) {
+            int m0 = st->hp_mem[2 * c], m1 = st->hp_mem[2 * c + 1];
+            CB_NOUNROLL for (int i = 0; i < frame_size; i++) D[channels * i + c] = (int16_t)dc_reject_step(pcm[channels * i + c], m0, m1, pp.dc_shift);
+            st->hp_mem[2 * c] = m0; st->hp_mem[2 * c + 1] = m1;
+        }
+        if (pp.fade)
+            CB_NOUNROLL for (int i = 0; i < frame_size; i++) {
+                const int gq = stereo_fade_gain(i, pp.g1, pp.g2, Fs);
+                int diff = s16(((int)D[i * 2] - (int)D[i * 2 + 1]) >> 1);
+                diff = mul16_16_q15(gq, diff);
+                D[i * 2] = (int16_t)(D[i * 2] - diff);
+                D[i * 2 + 1] = (int16_t)(D[i * 2 + 1] + diff);
+            }
+    }
+    pipe_plan_post(st, pp, frame_size, xx, xy, yy, pl);
 }
 
 // Host-side test: may this stream go through the pipeline for a span of `frame_size` frames with `out_data_bytes` per packet?

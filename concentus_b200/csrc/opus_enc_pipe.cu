@@ -32,24 +32,155 @@ struct PipeBufs {              // device views of one group's buffers
     EncPipeBuf *buf;           // [n]
 };
 
-// ---- P0: the Opus layer of a chunk, one thread per stream ------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+// ---- staging for the thread-per-stream kernels ------------------------------------------------------------------------------------
+// A scalar stage walks a few KB of per-stream data with dependent accesses; from global memory every one of them costs an L2 round
+// trip (the first version of K4 ran 21 cycles per instruction).  So a block takes 32 streams: all its 128 threads copy the streams'
+// structs into shared memory (coalesced, several loads in flight), warp 0 runs the stage — one lane per stream — on the copies, and
+// the block writes back what the stage changed.  Struct strides are chosen against bank conflicts: an odd number of words, or
+// 2 * odd where the struct holds an 8-byte pointer.
+enum { kScalarT = 32, kScalarThreads = 128 };
+constexpr int odd_stride(int words) { return words | 1; }
+constexpr int even_odd_stride(int words) { return ((words + 1) / 2 % 2 == 1) ? (words + 1) / 2 * 2 : (words + 1) / 2 * 2 + 2; }
+constexpr int kHeadWords = CB_ENC_HEAD_BYTES / 4, kHeadStride = odd_stride(kHeadWords);
+constexpr int kCtxWords = (int)((sizeof(EncPipeCtx) + 3) / 4), kCtxStride = even_odd_stride(kCtxWords);
+constexpr int kPrepWords = (int)((sizeof(BandPrep) + 3) / 4), kPrepStride = odd_stride(kPrepWords);
+constexpr int kLeafWords = (int)((sizeof(LeafList) + 3) / 4), kLeafStride = odd_stride(kLeafWords);
+constexpr int kHeadCtxWords = (int)(offsetof(EncPipeCtx, spread_sum) / 4);   // what K1 produces
+constexpr int kLeafTaskWords = (int)(offsetof(LeafList, index) / 4);   // what chain-S produces
+static_assert(sizeof(EncPipeCtx) % 8 == 0 && sizeof(BandPrep) % 4 == 0 && sizeof(LeafList) % 4 == 0, "struct sizes");
+
+__device__ __forceinline__ void stage_copy_in(int *sm, int stride, int words, int *const *ptrs, int nvalid) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < nvalid; k += kScalarThreads / 32) {
+        const int *src = ptrs[k];
+        int *dst = sm + k * stride;
+#pragma unroll 4
+        for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    }
+}
+__device__ __forceinline__ void stage_copy_out(const int *sm, int stride, int words, int *const *ptrs, int nvalid) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < nvalid; k += kScalarThreads / 32) {
+        int *dst = ptrs[k];
+        const int *src = sm + k * stride;
+#pragma unroll 4
+        for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    }
+}
+
+// ---- P0: the Opus layer of a chunk --------------------------------------------------------------------------------------------
+// A block takes 32 streams.  The sample pass (compute_stereo_width sums, dc_reject, stereo_fade: all order dependent along time,
+// independent across streams and — but for the pointwise fade — channels) runs with one lane per (stream, channel) on tiles of
+// kPreTile samples that the whole block moves between global and shared memory with coalesced 32-bit accesses; a thread walking
+// its own row in global memory cost 32 transactions per load (first version: 1 ms per frame step).
+enum { kPreTile = 64, kPreRow = kPreTile * 2 + 2 };   // int16 per stream row of a tile: an odd number of words
+__global__ void __launch_bounds__(128)
 pipe_prepass_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, const int16_t *pcm, int fbase, int nfr, int16_t *D,
-                    EncPlan *plans, int *m0) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n) return;
-    CbEncState *st = pool + slots[t];
-    const size_t row = (size_t)g.fsz * g.CC;
-    m0[2 * t] = st->preemph_memE[0];
-    m0[2 * t + 1] = st->preemph_memE[1];
+                    EncPlan *plans, int *m0out) {
+    __shared__ __align__(16) int16_t tile[32][kPreRow];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * 32;
+    const int nvalid = g.n - t0 < 32 ? g.n - t0 : 32;
+    const int CC = g.CC, fsz = g.fsz;
+    const size_t row = (size_t)fsz * CC;
+    // worker threads: tid < 64, stream ws = tid >> 1, channel wc = tid & 1
+    const int ws = tid >> 1, wc = tid & 1;
+    const bool worker = tid < 64;
+    const bool live = worker && ws < nvalid && wc < CC;
+    CbEncState *st = worker && ws < nvalid ? pool + slots[t0 + ws] : nullptr;
+    int hm0 = 0, hm1 = 0, last_v = 0, any_coded = 0;
+    if (live) {
+        hm0 = st->hp_mem[2 * wc];
+        hm1 = st->hp_mem[2 * wc + 1];
+        m0out[2 * (t0 + ws) + wc] = st->preemph_memE[wc];
+    } else if (worker && ws < nvalid) {
+        m0out[2 * (t0 + ws) + wc] = 0;
+    }
     for (int fi = 0; fi < nfr; fi++) {
-        const int16_t *src = pcm + ((size_t)sidx[t] * g.F + fbase + fi) * row;
-        int16_t *dst = D + ((size_t)t * g.Fc + fi) * row;
-        EncPlan pl;
-        pipe_plan_frame(st, src, g.fsz, g.max_bytes, dst, pl);
-        plans[(size_t)t * g.Fc + fi] = pl;
-        if (pl.code)
-            for (int c = 0; c < g.CC; c++) st->preemph_memE[c] = pipe_preemph_mem_after(g, dst, c);
+        // ---- decisions: the channel-0 lane of every stream, shared with its partner ----
+        PlanPre pp;
+        pp.code = 0; pp.ret = 0; pp.want_width = 0; pp.fade = 0; pp.g1 = 0; pp.g2 = 0; pp.dc_shift = 0;
+        if (worker && ws < nvalid && wc == 0) pipe_plan_pre(st, fsz, g.max_bytes, pp);
+        int code = pp.code, want_width = pp.want_width, fade = pp.fade, fg1 = pp.g1, fg2 = pp.g2, dshift = pp.dc_shift;
+        if (worker) {
+            code = __shfl_sync(0xffffffffu, code, lane & ~1);
+            want_width = __shfl_sync(0xffffffffu, want_width, lane & ~1);
+            fade = __shfl_sync(0xffffffffu, fade, lane & ~1);
+            fg1 = __shfl_sync(0xffffffffu, fg1, lane & ~1);
+            fg2 = __shfl_sync(0xffffffffu, fg2, lane & ~1);
+            dshift = __shfl_sync(0xffffffffu, dshift, lane & ~1);
+        }
+        int acc_a = 0, acc_b = 0;      // channel 0: xx, xy; channel 1: yy
+        int part_a = 0, part_b = 0;
+        for (int pos = 0; pos < fsz; pos += kPreTile) {
+            const int nt = fsz - pos < kPreTile ? fsz - pos : kPreTile;
+            const int words = nt * CC / 2;   // fsz * CC is even for every Opus frame size
+            // ---- tile in: warp w moves streams w, w+4, ... ----
+            for (int k = warp; k < nvalid; k += 4) {
+                const int *src = reinterpret_cast<const int *>(pcm + ((size_t)sidx[t0 + k] * g.F + fbase + fi) * row + (size_t)pos * CC);
+                int *dst = reinterpret_cast<int *>(&tile[k][0]);
+                for (int w = lane; w < words; w += 32) dst[w] = src[w];
+            }
+            __syncthreads();
+            // ---- the samples, one lane per (stream, channel) ----
+            if (worker) {
+                for (int i = 0; i < nt; i++) {
+                    const int x = live ? (int)tile[ws][CC * i + wc] : 0;
+                    const int xo = __shfl_xor_sync(0xffffffffu, x, 1);
+                    int v = 0;
+                    if (live && code) {
+                        if (want_width) {
+                            const int gi = pos + i;
+                            if ((gi & ~3) < fsz - 3) {
+                                if (wc == 0) { part_a += mul16_16(x, x) >> 2; part_b += mul16_16(x, xo) >> 2; }
+                                else part_a += mul16_16(x, x) >> 2;
+                                if ((gi & 3) == 3) {
+                                    acc_a = wadd(acc_a, part_a >> 10);
+                                    acc_b = wadd(acc_b, part_b >> 10);
+                                    part_a = part_b = 0;
+                                }
+                            }
+                        }
+                        v = dc_reject_step(x, hm0, hm1, dshift);
+                    }
+                    const int vo = __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (live && code) {
+                        if (fade) {
+                            const int gq = stereo_fade_gain(pos + i, fg1, fg2, g.Fs);
+                            const int l = wc == 0 ? v : vo, r = wc == 0 ? vo : v;
+                            int diff = s16((l - r) >> 1);
+                            diff = mul16_16_q15(gq, diff);
+                            v = wc == 0 ? (int)(int16_t)(l - diff) : (int)(int16_t)(r + diff);
+                        }
+                        tile[ws][CC * i + wc] = (int16_t)v;
+                        last_v = v;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- tile out ----
+            for (int k = warp; k < nvalid; k += 4) {
+                int *dst = reinterpret_cast<int *>(D + ((size_t)(t0 + k) * g.Fc + fi) * row + (size_t)pos * CC);
+                const int *src = reinterpret_cast<const int *>(&tile[k][0]);
+                for (int w = lane; w < words; w += 32) dst[w] = src[w];
+            }
+            __syncthreads();
+        }
+        // ---- commit ----
+        if (worker) {
+            const int yy = __shfl_xor_sync(0xffffffffu, acc_a, 1);
+            if (ws < nvalid && wc == 0) {
+                EncPlan pl;
+                pipe_plan_post(st, pp, fsz, acc_a, acc_b, yy, pl);
+                plans[(size_t)(t0 + ws) * g.Fc + fi] = pl;
+            }
+            if (code) any_coded = 1;
+        }
+    }
+    if (live && any_coded) {
+        st->hp_mem[2 * wc] = hm0;
+        st->hp_mem[2 * wc + 1] = hm1;
+        st->preemph_memE[wc] = g.upsample == 1 ? mul16_16(kPreemphCoef0, last_v) >> 3 : 0;
     }
 }
 
@@ -97,13 +228,27 @@ pipe_fe2_kernel(PipeGeom g, int nfr, const EncPlan *plans, const int *P, FeFrame
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kScalarThreads)
 pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, const FeFrame *fe,
                  EncPipeCtx *ctx, uint8_t *data) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n) return;
-    uint8_t *out = data + ((size_t)sidx[t] * g.F + f) * g.stride;
-    pipe_head(pool + slots[t], g, plans[(size_t)t * g.Fc + fi], fe[(size_t)t * g.Fc + fi], ctx[t], out);
+    extern __shared__ __align__(16) int sm[];
+    __shared__ int *p_head[kScalarT], *p_ctx[kScalarT];
+    int *sm_head = sm, *sm_ctx = sm + kScalarT * kHeadStride + (kScalarT * kHeadStride & 1);
+    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
+    if (tid < nvalid) { p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]); p_ctx[tid] = reinterpret_cast<int *>(ctx + t0 + tid); }
+    __syncthreads();
+    stage_copy_in(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    __syncthreads();
+    if (tid < nvalid) {
+        const int t = t0 + tid;
+        uint8_t *out = data + ((size_t)sidx[t] * g.F + f) * g.stride;
+        pipe_head(reinterpret_cast<CbEncState *>(sm_head + tid * kHeadStride), g, plans[(size_t)t * g.Fc + fi], fe[(size_t)t * g.Fc + fi],
+                  *reinterpret_cast<EncPipeCtx *>(sm_ctx + tid * kCtxStride), out);
+    }
+    __syncthreads();
+    stage_copy_out(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_out(sm_ctx, kCtxStride, kHeadCtxWords, p_ctx, nvalid);   // K1 writes the leading scalars of the context only
 }
 
 // ---- K2: one warp per (stream, channel) ---------------------------------------------------------------------------------------
@@ -132,11 +277,23 @@ pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kScalarThreads)
 pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n) return;
-    pipe_decide(pool + slots[t], g, ctx[t]);
+    extern __shared__ __align__(16) int sm[];
+    __shared__ int *p_head[kScalarT], *p_ctx[kScalarT];
+    int *sm_head = sm, *sm_ctx = sm + kScalarT * kHeadStride + (kScalarT * kHeadStride & 1);
+    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
+    if (tid < nvalid) { p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]); p_ctx[tid] = reinterpret_cast<int *>(ctx + t0 + tid); }
+    __syncthreads();
+    stage_copy_in(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_in(sm_ctx, kCtxStride, kCtxWords, p_ctx, nvalid);
+    __syncthreads();
+    if (tid < nvalid)
+        pipe_decide(reinterpret_cast<CbEncState *>(sm_head + tid * kHeadStride), g, *reinterpret_cast<EncPipeCtx *>(sm_ctx + tid * kCtxStride));
+    __syncthreads();
+    stage_copy_out(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_out(sm_ctx, kCtxStride, kCtxWords, p_ctx, nvalid);
 }
 
 // ---- K5: one warp per stream ------------------------------------------------------------------------------------------------
@@ -167,11 +324,22 @@ pipe_prep_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const Enc
     FreeWarpTeam tm{{lane}};
     pipe_band_prep(tm, pool + slots[s], g, ctx[s], buf[s], prep[s], xall + (size_t)s * kXallStride, sm[wib]);
 }
-__global__ void __launch_bounds__(64)
-pipe_spec_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, const BandPrep *prep, LeafList *leaves) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n) return;
-    pipe_band_spec(pool + slots[t], g, ctx[t], prep[t], leaves[t]);
+__global__ void __launch_bounds__(kScalarThreads)
+pipe_spec_kernel(const CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, BandPrep *prep, LeafList *leaves) {
+    extern __shared__ __align__(16) int sm[];
+    __shared__ int *p_prep[kScalarT], *p_leaf[kScalarT];
+    int *sm_prep = sm, *sm_leaf = sm + kScalarT * kPrepStride;
+    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
+    if (tid < nvalid) { p_prep[tid] = reinterpret_cast<int *>(prep + t0 + tid); p_leaf[tid] = reinterpret_cast<int *>(leaves + t0 + tid); }
+    __syncthreads();
+    stage_copy_in(sm_prep, kPrepStride, kPrepWords, p_prep, nvalid);
+    __syncthreads();
+    if (tid < nvalid)
+        pipe_band_spec(pool + slots[t0 + tid], g, ctx[t0 + tid], *reinterpret_cast<const BandPrep *>(sm_prep + tid * kPrepStride),
+                       *reinterpret_cast<LeafList *>(sm_leaf + tid * kLeafStride));
+    __syncthreads();
+    stage_copy_out(sm_leaf, kLeafStride, kLeafTaskWords, p_leaf, nvalid);
 }
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32)
 pipe_leaves_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, LeafList *leaves, const int16_t *xall) {
@@ -182,20 +350,39 @@ pipe_leaves_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const E
     FreeWarpTeam tm{{lane}};
     pipe_leaves(tm, pool + slots[s], ctx[s], leaves[s], xall + (size_t)s * kXallStride, sm[wib]);
 }
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kScalarThreads)
 pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
-                  const BandPrep *prep, const LeafList *leaves, int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, int *misses) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.n) return;
-    CbEncState *st = pool + slots[t];
-    const size_t k = (size_t)sidx[t] * g.F + f;
-    int miss = 0;
-    const int r = pipe_band_exact_finish(st, g, plans[(size_t)t * g.Fc + fi], ctx[t], prep[t], leaves[t], xall + (size_t)t * kXallStride, data + k * g.stride,
-                                         &miss);
-    rets[k] = r;
-    if (ranges) ranges[k] = st->rangeFinal;
-    if (miss) atomicAdd(misses, miss);
-    atomicAdd(misses + 1, leaves[t].count);
+                  BandPrep *prep, LeafList *leaves, int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, int *misses) {
+    extern __shared__ __align__(16) int sm[];
+    __shared__ int *p_head[kScalarT], *p_prep[kScalarT], *p_leaf[kScalarT];
+    int *sm_head = sm, *sm_prep = sm_head + kScalarT * kHeadStride, *sm_leaf = sm_prep + kScalarT * kPrepStride;
+    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
+    if (tid < nvalid) {
+        p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]);
+        p_prep[tid] = reinterpret_cast<int *>(prep + t0 + tid);
+        p_leaf[tid] = reinterpret_cast<int *>(leaves + t0 + tid);
+    }
+    __syncthreads();
+    stage_copy_in(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_in(sm_prep, kPrepStride, kPrepWords, p_prep, nvalid);
+    stage_copy_in(sm_leaf, kLeafStride, kLeafWords, p_leaf, nvalid);
+    __syncthreads();
+    if (tid < nvalid) {
+        const int t = t0 + tid;
+        CbEncState *st = reinterpret_cast<CbEncState *>(sm_head + tid * kHeadStride);
+        const LeafList &L = *reinterpret_cast<const LeafList *>(sm_leaf + tid * kLeafStride);
+        const size_t k = (size_t)sidx[t] * g.F + f;
+        int miss = 0;
+        const int r = pipe_band_exact_finish(st, g, plans[(size_t)t * g.Fc + fi], ctx[t], *reinterpret_cast<const BandPrep *>(sm_prep + tid * kPrepStride), L,
+                                             xall + (size_t)t * kXallStride, data + k * g.stride, &miss);
+        rets[k] = r;
+        if (ranges) ranges[k] = st->rangeFinal;
+        if (miss) atomicAdd(misses, miss);
+        atomicAdd(misses + 1, L.count);
+    }
+    __syncthreads();
+    stage_copy_out(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
 }
 
 // ---- end of the span: the last 1024 pre-emphasised samples go back into the state -------------------------------------------------
@@ -208,6 +395,10 @@ __global__ void pipe_epilogue_kernel(CbEncState *pool, const int *slots, PipeGeo
         for (int i = threadIdx.x; i < kCombMaxPeriod; i += blockDim.x) st->prefilter_mem[c * kCombMaxPeriod + i] = src[i];
     }
 }
+
+constexpr int kSmemHeadCtx = (kScalarT * kHeadStride + 1 + kScalarT * kCtxStride) * 4;
+constexpr int kSmemSpec = (kScalarT * kPrepStride + kScalarT * kLeafStride) * 4;
+constexpr int kSmemExact = (kScalarT * kHeadStride + kScalarT * kPrepStride + kScalarT * kLeafStride) * 4;
 
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
@@ -259,6 +450,10 @@ bool pipe_init() {
         cudaEventCreateWithFlags(&G.ev_done, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&pc.ev_fork, cudaEventDisableTiming);
+    cudaFuncSetAttribute(pipe_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHeadCtx);
+    cudaFuncSetAttribute(pipe_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHeadCtx);
+    cudaFuncSetAttribute(pipe_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSpec);
+    cudaFuncSetAttribute(pipe_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemExact);
     pc.init = cudaGetLastError() == cudaSuccess;
     return pc.init;
 }
@@ -291,7 +486,7 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         const int nfr = nframes - k * Fc < Fc ? nframes - k * Fc : Fc;
         // ---- front end of chunk k on the side stream (buffers b are free once the frame steps of chunk k-2 are done) ----
         if (k >= 2) cudaStreamWaitEvent(G.side, G.ev_steps[b], 0);
-        pipe_prepass_kernel<<<cdiv(n, tpb), tpb, 0, G.side>>>(c.pool, slots, sidx, g, c.d_pcm, fbase, nfr, (int16_t *)G.D.p, (EncPlan *)G.plans[b].p,
+        pipe_prepass_kernel<<<cdiv(n, 32), 128, 0, G.side>>>(c.pool, slots, sidx, g, c.d_pcm, fbase, nfr, (int16_t *)G.D.p, (EncPlan *)G.plans[b].p,
                                                               (int *)G.m0.p);
         pipe_fe1_kernel<<<cdiv(n * nfr, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.side>>>(c.pool, slots, g, nfr, (const int16_t *)G.D.p,
                                                                                     (const EncPlan *)G.plans[b].p, (const int *)G.m0.p, (int *)G.P[b].p,
@@ -305,12 +500,12 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         cudaStreamWaitEvent(G.main, G.ev_fe[b], 0);
         for (int fi = 0; fi < nfr; fi++) {
             const int f = fbase + fi;
-            pipe_head_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (const FeFrame *)G.fe[b].p,
+            pipe_head_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemHeadCtx, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (const FeFrame *)G.fe[b].p,
                                                                (EncPipeCtx *)G.ctx.p, c.d_data);
             pipe_comb_kernel<<<cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, fi, (const int *)G.P[b].p, (EncPipeCtx *)G.ctx.p,
                                                                                           (EncPipeBuf *)G.buf.p);
             pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
-            pipe_decide_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p);
+            pipe_decide_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemHeadCtx, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p);
             if (!pc.split_bands) {
                 pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
                                                                                         (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets,
@@ -319,13 +514,13 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
             } else {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
                                                                                        (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
-                pipe_spec_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p,
-                                                                   (LeafList *)G.leaves.p);
+                pipe_spec_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemSpec, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (BandPrep *)G.prep.p,
+                                                                                           (LeafList *)G.leaves.p);
                 pipe_leaves_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p, (LeafList *)G.leaves.p,
                                                                                          (const int16_t *)G.xall.p);
-                pipe_exact_kernel<<<cdiv(n, tpb), tpb, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p,
-                                                                    (const BandPrep *)G.prep.p, (const LeafList *)G.leaves.p, (int16_t *)G.xall.p, c.d_data,
-                                                                    c.d_rets, c.d_ranges, pc.d_stats);
+                pipe_exact_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemExact, G.main>>>(
+                    c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (BandPrep *)G.prep.p, (LeafList *)G.leaves.p,
+                    (int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges, pc.d_stats);
                 launches += 8;
             }
         }
