@@ -35,10 +35,12 @@ struct PipeBufs {              // device views of one group's buffers
 // ---- staging for the thread-per-stream kernels ------------------------------------------------------------------------------------
 // A scalar stage walks a few KB of per-stream data with dependent accesses; from global memory every one of them costs an L2 round
 // trip (the first version of K4 ran 21 cycles per instruction).  So a block takes 32 streams: all its 128 threads copy the streams'
-// structs into shared memory (coalesced, several loads in flight), warp 0 runs the stage — one lane per stream — on the copies, and
-// the block writes back what the stage changed.  Struct strides are chosen against bank conflicts: an odd number of words, or
+// structs into shared memory (coalesced, several loads in flight), the stage runs on the copies and the block writes back what the
+// stage changed.  The stages are divergent (every stream is somewhere else in its own partition tree), and a warp serialises its
+// divergent lanes, so a stage's latency grows with the streams per warp: only L (1, 2 or 4, CB200_ENC_SCALAR_L) lanes of a warp
+// take a stream each.  The machine is nowhere near issue bound in these stages; the idle lanes cost nothing that matters.  Struct strides are chosen against bank conflicts: an odd number of words, or
 // 2 * odd where the struct holds an 8-byte pointer.
-enum { kScalarT = 32, kScalarThreads = 128 };
+enum { kScalarThreads = 256 };   // 8 warps; a block takes T = 8 * L streams, L streams per warp (lanes 0..L-1 work)
 constexpr int odd_stride(int words) { return words | 1; }
 constexpr int even_odd_stride(int words) { return ((words + 1) / 2 % 2 == 1) ? (words + 1) / 2 * 2 : (words + 1) / 2 * 2 + 2; }
 constexpr int kHeadWords = CB_ENC_HEAD_BYTES / 4, kHeadStride = odd_stride(kHeadWords);
@@ -56,6 +58,20 @@ __device__ __forceinline__ void stage_copy_in(int *sm, int stride, int words, in
         int *dst = sm + k * stride;
 #pragma unroll 4
         for (int w = lane; w < words; w += 32) dst[w] = src[w];
+    }
+}
+// Of the state head a frame step owns [rangeFinal, preemph_memE) and [vbr_reservoir, end of head): the Opus-layer fields, hp_mem and
+// preemph_memE belong to the prepass, which is working on the NEXT chunk on another stream at the same time — a frame step that
+// wrote its whole copy of the head back would undo the prepass's updates.
+constexpr int kHeadOwn0 = (int)(offsetof(CbEncState, rangeFinal) / 4), kHeadOwn1 = (int)(offsetof(CbEncState, preemph_memE) / 4);
+constexpr int kHeadOwn2 = (int)(offsetof(CbEncState, vbr_reservoir) / 4);
+__device__ __forceinline__ void stage_copy_out_head(const int *sm, int *const *ptrs, int nvalid) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < nvalid; k += kScalarThreads / 32) {
+        int *dst = ptrs[k];
+        const int *src = sm + k * kHeadStride;
+        for (int w = kHeadOwn0 + lane; w < kHeadWords; w += 32)
+            if (w < kHeadOwn1 || w >= kHeadOwn2) dst[w] = src[w];
     }
 }
 __device__ __forceinline__ void stage_copy_out(const int *sm, int stride, int words, int *const *ptrs, int nvalid) {
@@ -228,13 +244,16 @@ pipe_fe2_kernel(PipeGeom g, int nfr, const EncPlan *plans, const int *P, FeFrame
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------------------------------
+template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
 pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, const FeFrame *fe,
                  EncPipeCtx *ctx, uint8_t *data) {
     extern __shared__ __align__(16) int sm[];
+    constexpr int kScalarT = 8 * L;
     __shared__ int *p_head[kScalarT], *p_ctx[kScalarT];
     int *sm_head = sm, *sm_ctx = sm + kScalarT * kHeadStride + (kScalarT * kHeadStride & 1);
-    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int t0 = blockIdx.x * kScalarT;
+    const int tid = (threadIdx.x & 31) < L ? (int)(threadIdx.x >> 5) * L + (int)(threadIdx.x & 31) : kScalarT;   // the stream this thread works on, if any
     const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
     if (tid < nvalid) { p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]); p_ctx[tid] = reinterpret_cast<int *>(ctx + t0 + tid); }
     __syncthreads();
@@ -247,7 +266,7 @@ pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
                   *reinterpret_cast<EncPipeCtx *>(sm_ctx + tid * kCtxStride), out);
     }
     __syncthreads();
-    stage_copy_out(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_out_head(sm_head, p_head, nvalid);
     stage_copy_out(sm_ctx, kCtxStride, kHeadCtxWords, p_ctx, nvalid);   // K1 writes the leading scalars of the context only
 }
 
@@ -277,12 +296,15 @@ pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------------------------------------
+template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
 pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx) {
     extern __shared__ __align__(16) int sm[];
+    constexpr int kScalarT = 8 * L;
     __shared__ int *p_head[kScalarT], *p_ctx[kScalarT];
     int *sm_head = sm, *sm_ctx = sm + kScalarT * kHeadStride + (kScalarT * kHeadStride & 1);
-    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int t0 = blockIdx.x * kScalarT;
+    const int tid = (threadIdx.x & 31) < L ? (int)(threadIdx.x >> 5) * L + (int)(threadIdx.x & 31) : kScalarT;   // the stream this thread works on, if any
     const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
     if (tid < nvalid) { p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]); p_ctx[tid] = reinterpret_cast<int *>(ctx + t0 + tid); }
     __syncthreads();
@@ -292,7 +314,7 @@ pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *c
     if (tid < nvalid)
         pipe_decide(reinterpret_cast<CbEncState *>(sm_head + tid * kHeadStride), g, *reinterpret_cast<EncPipeCtx *>(sm_ctx + tid * kCtxStride));
     __syncthreads();
-    stage_copy_out(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_out_head(sm_head, p_head, nvalid);
     stage_copy_out(sm_ctx, kCtxStride, kCtxWords, p_ctx, nvalid);
 }
 
@@ -324,12 +346,15 @@ pipe_prep_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const Enc
     FreeWarpTeam tm{{lane}};
     pipe_band_prep(tm, pool + slots[s], g, ctx[s], buf[s], prep[s], xall + (size_t)s * kXallStride, sm[wib]);
 }
+template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
 pipe_spec_kernel(const CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, BandPrep *prep, LeafList *leaves) {
     extern __shared__ __align__(16) int sm[];
+    constexpr int kScalarT = 8 * L;
     __shared__ int *p_prep[kScalarT], *p_leaf[kScalarT];
     int *sm_prep = sm, *sm_leaf = sm + kScalarT * kPrepStride;
-    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int t0 = blockIdx.x * kScalarT;
+    const int tid = (threadIdx.x & 31) < L ? (int)(threadIdx.x >> 5) * L + (int)(threadIdx.x & 31) : kScalarT;   // the stream this thread works on, if any
     const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
     if (tid < nvalid) { p_prep[tid] = reinterpret_cast<int *>(prep + t0 + tid); p_leaf[tid] = reinterpret_cast<int *>(leaves + t0 + tid); }
     __syncthreads();
@@ -350,13 +375,16 @@ pipe_leaves_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const E
     FreeWarpTeam tm{{lane}};
     pipe_leaves(tm, pool + slots[s], ctx[s], leaves[s], xall + (size_t)s * kXallStride, sm[wib]);
 }
+template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
 pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
                   BandPrep *prep, LeafList *leaves, int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, int *misses) {
     extern __shared__ __align__(16) int sm[];
+    constexpr int kScalarT = 8 * L;
     __shared__ int *p_head[kScalarT], *p_prep[kScalarT], *p_leaf[kScalarT];
     int *sm_head = sm, *sm_prep = sm_head + kScalarT * kHeadStride, *sm_leaf = sm_prep + kScalarT * kPrepStride;
-    const int t0 = blockIdx.x * kScalarT, tid = threadIdx.x;
+    const int t0 = blockIdx.x * kScalarT;
+    const int tid = (threadIdx.x & 31) < L ? (int)(threadIdx.x >> 5) * L + (int)(threadIdx.x & 31) : kScalarT;   // the stream this thread works on, if any
     const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
     if (tid < nvalid) {
         p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]);
@@ -382,7 +410,7 @@ pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
         atomicAdd(misses + 1, L.count);
     }
     __syncthreads();
-    stage_copy_out(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
+    stage_copy_out_head(sm_head, p_head, nvalid);
 }
 
 // ---- end of the span: the last 1024 pre-emphasised samples go back into the state -------------------------------------------------
@@ -396,9 +424,9 @@ __global__ void pipe_epilogue_kernel(CbEncState *pool, const int *slots, PipeGeo
     }
 }
 
-constexpr int kSmemHeadCtx = (kScalarT * kHeadStride + 1 + kScalarT * kCtxStride) * 4;
-constexpr int kSmemSpec = (kScalarT * kPrepStride + kScalarT * kLeafStride) * 4;
-constexpr int kSmemExact = (kScalarT * kHeadStride + kScalarT * kPrepStride + kScalarT * kLeafStride) * 4;
+constexpr int smem_head_ctx(int T) { return (T * kHeadStride + 1 + T * kCtxStride) * 4; }
+constexpr int smem_spec(int T) { return (T * kPrepStride + T * kLeafStride) * 4; }
+constexpr int smem_exact(int T) { return (T * kHeadStride + T * kPrepStride + T * kLeafStride) * 4; }
 
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
@@ -423,11 +451,20 @@ struct PipeCtx {
     bool init = false;
     int groups = 2;
     int chunk = 16;
+    int scalar_l = 1;           // streams per warp in the thread-per-stream stages
     int split_bands = 1;        // 1: the band loop as prep / chain-S / leaves / chain-X; 0: one warp-per-stream stage (A/B)
     Group g[kMaxGroups];
     cudaEvent_t ev_fork = nullptr;
     int *d_stats = nullptr;     // [0] leaves chain-X had to search itself, [1] leaves listed by chain-S
 } pc;
+
+template <int L>
+void set_scalar_smem() {
+    cudaFuncSetAttribute(pipe_head_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_head_ctx(8 * L));
+    cudaFuncSetAttribute(pipe_decide_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_head_ctx(8 * L));
+    cudaFuncSetAttribute(pipe_spec_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_spec(8 * L));
+    cudaFuncSetAttribute(pipe_exact_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_exact(8 * L));
+}
 
 bool pipe_init() {
     if (pc.init) return true;
@@ -450,15 +487,22 @@ bool pipe_init() {
         cudaEventCreateWithFlags(&G.ev_done, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&pc.ev_fork, cudaEventDisableTiming);
-    cudaFuncSetAttribute(pipe_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHeadCtx);
-    cudaFuncSetAttribute(pipe_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemHeadCtx);
-    cudaFuncSetAttribute(pipe_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemSpec);
-    cudaFuncSetAttribute(pipe_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemExact);
+    if (const char *e = getenv("CB200_ENC_SCALAR_L")) pc.scalar_l = atoi(e);
+    if (pc.scalar_l != 1 && pc.scalar_l != 2 && pc.scalar_l != 4) pc.scalar_l = 1;
+    set_scalar_smem<1>(); set_scalar_smem<2>(); set_scalar_smem<4>();
     pc.init = cudaGetLastError() == cudaSuccess;
     return pc.init;
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// launch a thread-per-stream stage with the configured number of streams per warp
+#define CB_SCALAR_LAUNCH(KERNEL, SMEMFN, STREAM, ...)                                                                         \
+    switch (pc.scalar_l) {                                                                                                    \
+    case 4: KERNEL<4><<<cdiv(n, 32), kScalarThreads, SMEMFN(32), STREAM>>>(__VA_ARGS__); break;                               \
+    case 2: KERNEL<2><<<cdiv(n, 16), kScalarThreads, SMEMFN(16), STREAM>>>(__VA_ARGS__); break;                               \
+    default: KERNEL<1><<<cdiv(n, 8), kScalarThreads, SMEMFN(8), STREAM>>>(__VA_ARGS__); break;                                \
+    }
 
 // one group: streams [k0, k0+n) of the pipeline's list
 int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
@@ -500,12 +544,12 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         cudaStreamWaitEvent(G.main, G.ev_fe[b], 0);
         for (int fi = 0; fi < nfr; fi++) {
             const int f = fbase + fi;
-            pipe_head_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemHeadCtx, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (const FeFrame *)G.fe[b].p,
-                                                               (EncPipeCtx *)G.ctx.p, c.d_data);
+            CB_SCALAR_LAUNCH(pipe_head_kernel, smem_head_ctx, G.main, c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
+                             (const FeFrame *)G.fe[b].p, (EncPipeCtx *)G.ctx.p, c.d_data)
             pipe_comb_kernel<<<cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, fi, (const int *)G.P[b].p, (EncPipeCtx *)G.ctx.p,
                                                                                           (EncPipeBuf *)G.buf.p);
             pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
-            pipe_decide_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemHeadCtx, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p);
+            CB_SCALAR_LAUNCH(pipe_decide_kernel, smem_head_ctx, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p)
             if (!pc.split_bands) {
                 pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
                                                                                         (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets,
@@ -514,13 +558,11 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
             } else {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
                                                                                        (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
-                pipe_spec_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemSpec, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (BandPrep *)G.prep.p,
-                                                                                           (LeafList *)G.leaves.p);
+                CB_SCALAR_LAUNCH(pipe_spec_kernel, smem_spec, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (BandPrep *)G.prep.p, (LeafList *)G.leaves.p)
                 pipe_leaves_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p, (LeafList *)G.leaves.p,
                                                                                          (const int16_t *)G.xall.p);
-                pipe_exact_kernel<<<cdiv(n, kScalarT), kScalarThreads, kSmemExact, G.main>>>(
-                    c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (BandPrep *)G.prep.p, (LeafList *)G.leaves.p,
-                    (int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges, pc.d_stats);
+                CB_SCALAR_LAUNCH(pipe_exact_kernel, smem_exact, G.main, c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p,
+                                 (BandPrep *)G.prep.p, (LeafList *)G.leaves.p, (int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges, pc.d_stats)
                 launches += 8;
             }
         }
