@@ -321,6 +321,29 @@ struct ExactPolicy {
     CB_MEM void finish() {}
 };
 
+// Inline policy: the real coder, and every leaf searched by the whole team the moment the walk reaches it.  ALL lanes of the team
+// run the walk with identical scalars (range coder included), so nothing is broadcast; only the leaf's vector work is split.
+template <class TM>
+struct InlinePolicy {
+    TM tm;
+    EcEnc ec;
+    int16_t *Xall;             // the stream's prepared vectors (team-shared memory)
+    const BandPrep *prep;
+    PvqScratch *ps;
+    CB_MEM unsigned tell_frac() const { return ec.tell_frac(); }
+    CB_MEM void encode(unsigned fl, unsigned fh, unsigned ft) { ec.encode(fl, fh, ft); }
+    CB_MEM void uint_(unsigned fl, unsigned ft) { ec.uint_(fl, ft); }
+    CB_MEM void bit_logp(int v, unsigned logp) { ec.bit_logp(v, logp); }
+    CB_MEM void sign_bit(int off) { ec.bits((unsigned)(Xall[off] < 0), 1); }
+    CB_MEM void n2_sign(int band, int c) {
+        const int d = prep->n2_d[band];
+        ec.bits((unsigned)(c ? wneg(d) < 0 : d < 0), 1);
+    }
+    CB_MEM void begin_band(int) {}
+    CB_MEM void leaf(int, int off, int N, int K, int B, int spread) { alg_quant(tm, Xall + off, N, K, spread, B, ec, *ps); }
+    CB_MEM void finish() {}
+};
+
 struct WalkCtx {
     const BandPrep *prep;
     int i, intensity, spread, remaining_bits;

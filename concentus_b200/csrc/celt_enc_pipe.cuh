@@ -1181,4 +1181,37 @@ CB_DEV_NOINLINE int pipe_band_exact_finish(CbEncState *st, const PipeGeom &g, co
     return V.ret;
 }
 
+// ---- the band loop as prep + ONE walk with the real coder, leaves searched inline by the team (no speculation) -----------------------
+struct WalkScratch {
+    int16_t Xall[kXallStride];
+    PvqScratch pvq;
+};
+template <class TM>
+CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, const EncPlan &pl, EncPipeCtx &X, const BandPrep &P, const int16_t *XallG,
+                                   WalkScratch &S, uint8_t *out) {
+    if (!X.code) return X.v.ret;
+    EncVars &V = X.v;
+    const int C = X.cfg.C, N = g.N;
+    CB_NOUNROLL for (int v = 0; v < 3; v++) {
+        if (v > 0 && C == 1) break;
+        CB_TEAM_FOR(i, N, tm) S.Xall[v * kMaxFrame + i] = XallG[v * kMaxFrame + i];
+    }
+    tm.sync();
+    InlinePolicy<TM> p;
+    p.tm = tm;
+    p.ec = V.ec;
+    p.Xall = S.Xall;
+    p.prep = &P;
+    p.ps = &S.pvq;
+    band_walk(p, P, X.cfg.end, C, X.pulses, V.shortBlocks, st->spread_decision, V.dual_stereo, st->intensity, X.tf_res,
+              V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, g.LM, V.codedBands);
+    tm.sync();
+    if (tm.lane() == 0) {
+        V.ec = p.ec;
+        V.ret = pipe_finish(st, g, pl, X, out);
+    }
+    tm.sync();
+    return V.ret;
+}
+
 }  // namespace cb

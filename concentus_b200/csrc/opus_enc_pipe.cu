@@ -285,7 +285,7 @@ pipe_comb_kernel(CbEncState *pool, const int *slots, PipeGeom g, int fi, const i
 }
 
 // ---- K3: one warp per stream ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
 pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, EncPipeBuf *buf) {
     __shared__ __align__(16) TransformScratch sm[CB_PIPE_WPB];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,7 +337,7 @@ pipe_bands_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
 }
 
 // ---- K5a..K5d: the band loop as prep / chain-S / leaves / chain-X (celt_enc_bandpipe.cuh) ----------------------------------------
-__global__ void __launch_bounds__(CB_PIPE_WPB * 32)
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
 pipe_prep_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, const EncPipeBuf *buf, BandPrep *prep, int16_t *xall) {
     __shared__ __align__(16) PrepScratch sm[CB_PIPE_WPB];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,6 +413,25 @@ pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
     stage_copy_out_head(sm_head, p_head, nvalid);
 }
 
+// ---- K5 as prep + one inline walk: one warp per stream, all of a launch's streams resident at once (<= 72 registers) ----------------
+__global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
+pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
+                 const BandPrep *prep, const int16_t *xall, uint8_t *data, int *rets, unsigned *ranges) {
+    __shared__ __align__(16) WalkScratch sm[CB_PIPE_WPB];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    if (s >= g.n) return;
+    FreeWarpTeam tm{{lane}};
+    CbEncState *st = pool + slots[s];
+    const size_t k = (size_t)sidx[s] * g.F + f;
+    const int r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib],
+                                          data + k * g.stride);
+    if (lane == 0) {
+        rets[k] = r;
+        if (ranges) ranges[k] = st->rangeFinal;
+    }
+}
+
 // ---- end of the span: the last 1024 pre-emphasised samples go back into the state -------------------------------------------------
 __global__ void pipe_epilogue_kernel(CbEncState *pool, const int *slots, PipeGeom g, const int *P, int last_nfr) {
     const int s = blockIdx.x;
@@ -452,7 +471,7 @@ struct PipeCtx {
     int groups = 2;
     int chunk = 16;
     int scalar_l = 1;           // streams per warp in the thread-per-stream stages
-    int split_bands = 1;        // 1: the band loop as prep / chain-S / leaves / chain-X; 0: one warp-per-stream stage (A/B)
+    int split_bands = 2;        // the band loop as 2: prep + one inline walk; 1: prep / chain-S / leaves / chain-X; 0: one stage (A/B)
     Group g[kMaxGroups];
     cudaEvent_t ev_fork = nullptr;
     int *d_stats = nullptr;     // [0] leaves chain-X had to search itself, [1] leaves listed by chain-S
@@ -555,6 +574,13 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                                                                                         (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets,
                                                                                         c.d_ranges);
                 launches += 5;
+            } else if (pc.split_bands == 2) {
+                pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
+                                                                                       (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
+                pipe_walk_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
+                                                                                       (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p,
+                                                                                       (const int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges);
+                launches += 6;
             } else {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
                                                                                        (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);

@@ -140,7 +140,7 @@ int hostsim_encode_stream_script(const int16_t *pcm, int F, int frame_size, int 
 // ---- encoder, frame-synchronous pipeline (celt_enc_pipe.cuh): the same slices the pipeline kernels run, 1-lane teams ----------
 #include "../../concentus_b200/csrc/celt_enc_pipe.cuh"
 
-static int g_band_mode = 1;          // 0: the band loop as one stage (pipe_bands); 1: prep / chain-S / leaves / chain-X
+static int g_band_mode = 1;          // 0: the band loop as one stage (pipe_bands); 1: prep / chain-S / leaves / chain-X; 2: prep + one inline walk
 static long long g_leaves = 0, g_misses = 0, g_frames = 0;
 
 extern "C" {
@@ -187,6 +187,7 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
     cb::LeafScratch *lfs = (cb::LeafScratch *)calloc(1, sizeof(cb::LeafScratch));
     cb::BandPrep *bp = (cb::BandPrep *)calloc(1, sizeof(cb::BandPrep));
     cb::LeafList *ll = (cb::LeafList *)calloc(1, sizeof(cb::LeafList));
+    cb::WalkScratch *ws = (cb::WalkScratch *)calloc(1, sizeof(cb::WalkScratch));
     std::vector<int16_t> xall(cb::kXallStride);
     std::vector<int> tin(960 + 120);
     int sc[4];
@@ -223,6 +224,9 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
             int r;
             if (g_band_mode == 0) {
                 r = cb::pipe_bands(tm, st, g, plans[fi], *X, *B, *bs, o);
+            } else if (g_band_mode == 2) {
+                cb::pipe_band_prep(tm, st, g, *X, *B, *bp, xall.data(), *prs);
+                r = cb::pipe_band_inline_finish(tm, st, g, plans[fi], *X, *bp, xall.data(), *ws, o);
             } else {
                 cb::pipe_band_prep(tm, st, g, *X, *B, *bp, xall.data(), *prs);
                 cb::pipe_band_spec(st, g, *X, *bp, *ll);
@@ -240,7 +244,7 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
             for (int i = 0; i < cb::kPipeHist; i++) P[(size_t)c * g.pstride + i] = P[(size_t)c * g.pstride + nfr * g.N + i];
         if (rc < 0) break;
     }
-    free(ll); free(bp); free(lfs); free(prs);
+    free(ws); free(ll); free(bp); free(lfs); free(prs);
     free(bs); free(ts); free(ps); free(B); free(X); free(st);
     return rc;
 }

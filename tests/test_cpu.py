@@ -191,25 +191,30 @@ def _hostsim_encode_pipe(hs, pcm, fs, br, ch, vbr, cvbr, cx, Fs=48000, max_bytes
 
 
 @needs_ref
-def test_hostsim_encoder_pipeline_vs_oracle_mini_sweep():
+@pytest.mark.parametrize("band_mode", [2, 1, 0], ids=["inline_walk", "split_chains", "one_stage"])
+def test_hostsim_encoder_pipeline_vs_oracle_mini_sweep(band_mode):
     """The pipeline's slicing of the frame (prepass / front end / head / comb / transform / decide / bands) against the oracle:
-    frame size x channels x bitrate x CBR/VBR/CVBR x complexity x signal kind, chunk lengths that do and do not divide the span."""
+    frame size x channels x bitrate x CBR/VBR/CVBR x complexity x signal kind, chunk lengths that do and do not divide the span.
+    band_mode: the three forms of the band stage (celt_enc_pipe.cuh K5)."""
     hs = _hostsim()
-    rs = np.random.RandomState(12)
+    hs.hostsim_set_band_mode(band_mode)
+    rs = np.random.RandomState(12 + band_mode)
     cases = [(k, ch, fs, br, m, cx) for k in ("music", "tone", "clicks", "noise") for ch in (1, 2) for fs in (120, 240, 480, 960)
              for br in (32000, 48000, 64000, 96000, 128000, 192000, 256000, 510000) for m in ((0, 0), (1, 0), (1, 1)) for cx in (0, 5, 10)]
-    for n, i in enumerate(rs.permutation(len(cases))[:150]):
+    for n, i in enumerate(rs.permutation(len(cases))[:(150, 100, 50)[2 - band_mode]]):
         kind, ch, fs, br, (vbr, cvbr), cx = cases[i]
         x = O.test_signal(24000, ch, 500 + int(i), kind)
         d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx, max_bytes=1276)
         rc, out, lens, rng = _hostsim_encode_pipe(hs, x, fs, br, ch, vbr, cvbr, cx, Fc=(1, 3, 4, 7, 16)[n % 5])
         assert rc == 0, (cases[i], rc)
         assert _same_packets(d, o, l, out, lens) and np.array_equal(r, rng), cases[i]
+    hs.hostsim_set_band_mode(2)
 
 
 @needs_ref
 def test_hostsim_encoder_pipeline_long_and_api_rates():
     hs = _hostsim()
+    hs.hostsim_set_band_mode(2)
     x = O.test_signal(48000 * 21, 2, 5, "music")
     d, o, l, r = O.encode_stream(x, 960, 96000, 2, vbr=1, cvbr=1, complexity=10, max_bytes=1276)
     rc, out, lens, rng = _hostsim_encode_pipe(hs, x, 960, 96000, 2, 1, 1, 10, Fc=16)

@@ -33,8 +33,8 @@ def cubin_symbols(path, kern):
         for ln in txt.splitlines():
             f = ln.split()
             if len(f) >= 7 and f[0].startswith("0x") and kern in f[-1]:
-                if f[3] == "0x12" and not f[-1].startswith("."):
-                    ksize = int(f[2], 16)
+                if f[3] in ("0x12", "0x2") and not f[-1].startswith(".") and not f[-1].startswith("$"):
+                    ksize = int(f[2], 16)   # kernels in an anonymous namespace are local FUNC symbols
                 elif f[3] in ("0x2", "0x22") and f[-1].startswith("$") and "$" in f[-1][1:]:
                     name = f[-1].split("$")[-1]
                     out.append((int(f[1], 16), int(f[2], 16), name))
@@ -75,7 +75,8 @@ def main():
             cur[1] = r
         elif r and r[0].startswith("0x") and cur is not None:
             cur[2].append(r)
-    sec = [s for s in sections if kern in s[0]][-1]
+    short = kern.split("ILi")[0]   # the report names kernels demangled, the cubin mangled
+    sec = [s for s in sections if kern in s[0] or short in s[0]][-1]
     hdr, body = sec[1], sec[2]
     col = {h: i for i, h in enumerate(hdr)}
     base = int(body[0][0], 16)
