@@ -43,6 +43,8 @@ EXPORTS = [
     "opus_encoder_get_size", "opus_encoder_create", "opus_encoder_init", "opus_encode", "opus_encoder_ctl", "opus_encoder_destroy",
     "opus_packet_pad", "opus_packet_unpad", "opus_encode_batch", "opus_encode_span", "opus_encode_span_device", "opus_encode_span_ranges", "opus_encoder_sync",
     "opus_b200_enc_synchronize", "opus_b200_enc_stream", "opus_b200_enc_kernel_launches", "opus_b200_enc_last_kernel_ms",
+    "opus_repacketizer_get_size", "opus_repacketizer_init", "opus_repacketizer_create", "opus_repacketizer_destroy", "opus_repacketizer_cat",
+    "opus_repacketizer_get_nb_frames", "opus_repacketizer_out_range", "opus_repacketizer_out",
     "opus_b200_enc_set_pipeline", "opus_b200_enc_path_counts", "opus_b200_enc_band_stats",
 ]
 

@@ -7,7 +7,8 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRCS = [os.path.join(HERE, "csrc", "opus_capi.cu"), os.path.join(HERE, "csrc", "opus_enc_capi.cu"), os.path.join(HERE, "csrc", "opus_enc_pipe.cu")]
+SRCS = [os.path.join(HERE, "csrc", "opus_capi.cu"), os.path.join(HERE, "csrc", "opus_enc_capi.cu"), os.path.join(HERE, "csrc", "opus_enc_pipe.cu"),
+        os.path.join(HERE, "csrc", "opus_repacketizer.cu")]
 OBJDIR = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libconcentus_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -632,6 +632,7 @@ CB_DEV_NOINLINE void pipe_head(CbEncState *st, const PipeGeom &g, const EncPlan 
 // K2 — one channel: comb pre-filter (celt_encoder.c:1164-1185) and transient_analysis (:227-378).  tin: N + overlap ints of team
 // scratch, sc: 4 ints.  pre: the channel's window of P (history first).  inc: the channel's row of `in` (overlap + N).
 // ---------------------------------------------------------------------------------------------------------------------------
+// (tin == nullptr: the comb filter only — the pipeline runs transient_analysis in its own kernel, one thread per channel)
 template <class TM>
 CB_DEV void pipe_comb_channel(TM tm, CbEncState *st, const PipeGeom &g, EncPipeCtx &X, const int *pre, int *inc, int c, int *tin, int *sc) {
     if (!X.code) return;
@@ -641,11 +642,64 @@ CB_DEV void pipe_comb_channel(TM tm, CbEncState *st, const PipeGeom &g, EncPipeC
     comb_filter_fir_team(tm, inc + ov, pre + kCombMaxPeriod, X.pf_T0, V.pitch_index, N, -X.pf_g0, -V.gain1, X.pf_tap0, V.prefilter_tapset, ov);
     tm.sync();
     CB_TEAM_FOR(i, ov, tm) st->in_mem[c * ov + i] = inc[N + i];
-    if (X.cfg.complexity >= 1) {
+    if (X.cfg.complexity >= 1 && tin != nullptr) {
         CB_TEAM_FOR(i, N + ov, tm) tin[i] = inc[i] >> 12;
         tm.sync();
         transient_analysis_team(tm, tin, N + ov, 1, sc, &X.v.mask_metric[c]);
     }
+}
+
+// transient_analysis (celt_encoder.c:227-378) of ONE channel by ONE thread, in two parts: the high-pass recurrence is fed sample by
+// sample (the caller streams the channel through tiles), the rest works on the channel's row of high-passed int16 samples.
+struct TransientHp {
+    int mem0, mem1, mx, mn;
+    CB_MEM void reset() { mem0 = mem1 = mx = mn = 0; }
+    // x: the input sample >> SIG_SHIFT, i: its index.  Returns the high-passed sample (opus_val16).
+    CB_MEM int step(int x, int i) {
+        const int y = wadd(mem0, x);
+        mem0 = wsub(wadd(mem1, y), shl32(x, 1));
+        mem1 = wsub(x, y >> 1);
+        const int t = i < 12 ? 0 : s16(y >> 2);
+        mx = imax(mx, t);
+        mn = imin(mn, t);
+        return t;
+    }
+};
+// row: len high-passed samples; clobbered (pairwise energies and the two followers are built in place).  Returns mask_metric.
+CB_DEV_NOINLINE int transient_finish_row(int16_t *row, int len, int mx, int mn) {
+    const int len2 = len / 2;
+    const int shift = 14 - celt_ilog2(1 + imax(mx, -mn));
+    int mean = 0;
+    CB_NOUNROLL for (int i = 0; i < len2; i++) {
+        int a = row[2 * i], b = row[2 * i + 1];
+        if (shift != 0) {   // SHL16 with a NEGATIVE count (maxabs == 32768): what the reference's C expression does on x86
+            a = (int16_t)((unsigned)(uint16_t)a << (shift & 31));
+            b = (int16_t)((unsigned)(uint16_t)b << (shift & 31));
+        }
+        const int x2 = s16(pshr32(wadd(mul16_16(a, a), mul16_16(b, b)), 16));
+        row[i] = (int16_t)x2;
+        mean = wadd(mean, x2);
+    }
+    int mem0 = 0;
+    CB_NOUNROLL for (int i = 0; i < len2; i++) {
+        mem0 = s16(mem0 + pshr32(row[i] - mem0, 4));
+        row[i] = (int16_t)mem0;
+    }
+    mem0 = 0;
+    int maxE = 0;
+    CB_NOUNROLL for (int i = len2 - 1; i >= 0; i--) {
+        mem0 = s16(mem0 + pshr32(row[i] - mem0, 3));
+        row[i] = (int16_t)mem0;
+        maxE = imax(maxE, mem0);
+    }
+    const int m = mul16_16(celt_sqrt(mean), celt_sqrt(mul16_16(maxE, len2 >> 1)));
+    const int norm = shl32(len2, 6 + 14) / wadd(1, m >> 1);
+    int unmask = 0;
+    CB_NOUNROLL for (int i = 12; i < len2 - 5; i += 4) {
+        const int id = imax(0, imin(127, mul16_32_q15(row[i] + 1, norm)));
+        unmask += kInvTable[id];
+    }
+    return 64 * unmask * 4 / (6 * (len2 - 17));
 }
 
 // spreading_decision (bands.c:428-519), the statistics of X (everything before the recursive averages)

@@ -733,33 +733,4 @@ opus_int32 opus_encode(OpusEncoder *st, const opus_int16 *pcm, int analysis_fram
     return r;
 }
 
-// opus_packet_pad / opus_packet_unpad (repacketizer.c:239-273) for single-frame (code 0 / padded code 3) packets — what
-// this engine's encoder emits.  Multi-frame packets: OPUS_UNIMPLEMENTED (the repacketizer is SURVEY.md §8f rank 2).
-int opus_packet_pad(unsigned char *data, opus_int32 len, opus_int32 new_len) {
-    if (len < 1) return OPUS_BAD_ARG;
-    if (len == new_len) return OPUS_OK;
-    if (len > new_len) return OPUS_BAD_ARG;
-    if ((data[0] & 3) != 0) return OPUS_UNIMPLEMENTED;
-    return packet_pad_single(data, len, new_len);
-}
-opus_int32 opus_packet_unpad(unsigned char *data, opus_int32 len) {
-    if (len < 1) return OPUS_BAD_ARG;
-    if ((data[0] & 3) == 0) return len;
-    if ((data[0] & 3) != 3 || len < 2 || (data[1] & 0x3F) != 1 || (data[1] & 0x80)) return OPUS_UNIMPLEMENTED;
-    int pos = 2, pad = 0;
-    if (data[1] & 0x40) {
-        int p;
-        do {
-            if (pos >= len) return OPUS_INVALID_PACKET;
-            p = data[pos++];
-            pad += p == 255 ? 254 : p;
-        } while (p == 255);
-    }
-    const int payload = len - pos - pad;
-    if (payload < 0) return OPUS_INVALID_PACKET;
-    data[0] &= 0xFC;
-    memmove(data + 1, data + pos, (size_t)payload);
-    return payload + 1;
-}
-
 }  // extern "C"

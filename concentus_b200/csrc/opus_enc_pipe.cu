@@ -270,18 +270,60 @@ pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
     stage_copy_out(sm_ctx, kCtxStride, kHeadCtxWords, p_ctx, nvalid);   // K1 writes the leading scalars of the context only
 }
 
-// ---- K2: one warp per (stream, channel) ---------------------------------------------------------------------------------------
-struct CombScratch { int tin[kMaxFrame + kOverlap]; int sc[4]; };
+// ---- K2a: comb pre-filter, one warp per (stream, channel) -----------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32)
 pipe_comb_kernel(CbEncState *pool, const int *slots, PipeGeom g, int fi, const int *P, EncPipeCtx *ctx, EncPipeBuf *buf) {
-    __shared__ CombScratch sm[CB_PIPE_WPB];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * CB_PIPE_WPB + wib;
     if (w >= g.n * g.CC) return;
     const int s = w / g.CC, c = w - s * g.CC;
     FreeWarpTeam tm{{lane}};
     const int *pre = P + ((size_t)s * g.CC + c) * g.pstride + fi * g.N;
-    pipe_comb_channel(tm, pool + slots[s], g, ctx[s], pre, buf[s].in + c * (g.N + kOverlap), c, sm[wib].tin, sm[wib].sc);
+    pipe_comb_channel(tm, pool + slots[s], g, ctx[s], pre, buf[s].in + c * (g.N + kOverlap), c, nullptr, nullptr);
+}
+
+// ---- K2b: transient_analysis, one THREAD per (stream, channel) ----------------------------------------------------------------
+// The analysis is three recurrences along time (a second-order high-pass with a floor in its feedback, two one-pole followers):
+// order dependent within a channel, independent across channels.  With a warp per channel a single lane did all of it (64 K warp
+// instructions per stream and frame, the most expensive stage of the pipeline); here a block takes 32 channels, streams them
+// through shared-memory tiles (coalesced loads by the whole block) and lane r of warp 0 runs channel r.
+enum { kTrTile = 64, kTrTileRow = kTrTile + 1, kTrRowWords = (kMaxFrame + kOverlap) / 2 + 1 };
+__global__ void __launch_bounds__(128)
+pipe_transient_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf) {
+    extern __shared__ __align__(16) int smt[];
+    int *tile = smt;                                                      // [32][kTrTileRow]
+    int16_t *rows = reinterpret_cast<int16_t *>(smt + 32 * kTrTileRow);   // [32][2 * kTrRowWords]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p0 = blockIdx.x * 32;
+    const int npairs = g.n * g.CC;
+    const int nvalid = npairs - p0 < 32 ? npairs - p0 : 32;
+    const int len = g.N + kOverlap;
+    const bool worker = warp == 0 && lane < nvalid;
+    int ws = 0, wc = 0;
+    bool act = false;
+    if (worker) {
+        ws = (p0 + lane) / g.CC;
+        wc = (p0 + lane) - ws * g.CC;
+        act = ctx[ws].code && ctx[ws].cfg.complexity >= 1;
+    }
+    TransientHp hp;
+    hp.reset();
+    int16_t *row = rows + lane * (2 * kTrRowWords);
+    for (int pos = 0; pos < len; pos += kTrTile) {
+        const int nt = len - pos < kTrTile ? len - pos : kTrTile;
+        for (int k = warp; k < nvalid; k += 4) {
+            const int s = (p0 + k) / g.CC, c = (p0 + k) - s * g.CC;
+            const int *src = buf[s].in + c * (g.N + kOverlap) + pos;
+            for (int i = lane; i < nt; i += 32) tile[k * kTrTileRow + i] = src[i];
+        }
+        __syncthreads();
+        if (worker && act) {
+            const int *t = tile + lane * kTrTileRow;
+            for (int i = 0; i < nt; i++) row[pos + i] = (int16_t)hp.step(t[i] >> 12, pos + i);
+        }
+        __syncthreads();
+    }
+    if (worker && act) ctx[ws].v.mask_metric[wc] = transient_finish_row(row, len, hp.mx, hp.mn);
 }
 
 // ---- K3: one warp per stream ------------------------------------------------------------------------------------------------
@@ -443,6 +485,7 @@ __global__ void pipe_epilogue_kernel(CbEncState *pool, const int *slots, PipeGeo
     }
 }
 
+constexpr int kSmemTransient = (32 * kTrTileRow + 32 * kTrRowWords) * 4;
 constexpr int smem_head_ctx(int T) { return (T * kHeadStride + 1 + T * kCtxStride) * 4; }
 constexpr int smem_spec(int T) { return (T * kPrepStride + T * kLeafStride) * 4; }
 constexpr int smem_exact(int T) { return (T * kHeadStride + T * kPrepStride + T * kLeafStride) * 4; }
@@ -506,6 +549,7 @@ bool pipe_init() {
         cudaEventCreateWithFlags(&G.ev_done, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&pc.ev_fork, cudaEventDisableTiming);
+    cudaFuncSetAttribute(pipe_transient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient);
     if (const char *e = getenv("CB200_ENC_SCALAR_L")) pc.scalar_l = atoi(e);
     if (pc.scalar_l != 1 && pc.scalar_l != 2 && pc.scalar_l != 4) pc.scalar_l = 1;
     set_scalar_smem<1>(); set_scalar_smem<2>(); set_scalar_smem<4>();
@@ -567,20 +611,21 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                              (const FeFrame *)G.fe[b].p, (EncPipeCtx *)G.ctx.p, c.d_data)
             pipe_comb_kernel<<<cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, fi, (const int *)G.P[b].p, (EncPipeCtx *)G.ctx.p,
                                                                                           (EncPipeBuf *)G.buf.p);
+            pipe_transient_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p);
             pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
             CB_SCALAR_LAUNCH(pipe_decide_kernel, smem_head_ctx, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p)
             if (!pc.split_bands) {
                 pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
                                                                                         (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets,
                                                                                         c.d_ranges);
-                launches += 5;
+                launches += 6;
             } else if (pc.split_bands == 2) {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
                                                                                        (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
                 pipe_walk_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
                                                                                        (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p,
                                                                                        (const int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges);
-                launches += 6;
+                launches += 7;
             } else {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
                                                                                        (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
@@ -589,7 +634,7 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                                                                                          (const int16_t *)G.xall.p);
                 CB_SCALAR_LAUNCH(pipe_exact_kernel, smem_exact, G.main, c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p,
                                  (BandPrep *)G.prep.p, (LeafList *)G.leaves.p, (int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges, pc.d_stats)
-                launches += 8;
+                launches += 9;
             }
         }
         cudaEventRecord(G.ev_steps[b], G.main);

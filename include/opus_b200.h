@@ -109,8 +109,21 @@ opus_int32 opus_encode(OpusEncoder *st, const opus_int16 *pcm, int frame_size, u
                        opus_int32 max_data_bytes);                                              /* opus_encoder.c:2007 */
 int opus_encoder_ctl(OpusEncoder *st, int request, ...);                                        /* opus_encoder.c:2031 */
 void opus_encoder_destroy(OpusEncoder *st);                                                     /* opus_encoder.c:2509 */
-int opus_packet_pad(unsigned char *data, opus_int32 len, opus_int32 new_len);                   /* repacketizer.c:239 (single-frame packets) */
-opus_int32 opus_packet_unpad(unsigned char *data, opus_int32 len);                              /* repacketizer.c:260 (single-frame packets) */
+int opus_packet_pad(unsigned char *data, opus_int32 len, opus_int32 new_len);                   /* repacketizer.c:239 */
+opus_int32 opus_packet_unpad(unsigned char *data, opus_int32 len);                              /* repacketizer.c:260 */
+
+/* ---- repacketizer: opus-fix/include/opus.h:628-750, src/repacketizer.c:37-236 (host code: merges / splits packets of one
+ * configuration without touching the compressed frames) ---- */
+typedef struct OpusRepacketizer OpusRepacketizer;
+int opus_repacketizer_get_size(void);                                                           /* repacketizer.c:37  */
+OpusRepacketizer *opus_repacketizer_init(OpusRepacketizer *rp);                                 /* repacketizer.c:42  */
+OpusRepacketizer *opus_repacketizer_create(void);                                               /* repacketizer.c:48  */
+void opus_repacketizer_destroy(OpusRepacketizer *rp);                                           /* repacketizer.c:57  */
+int opus_repacketizer_cat(OpusRepacketizer *rp, const unsigned char *data, opus_int32 len);     /* repacketizer.c:93  */
+int opus_repacketizer_get_nb_frames(OpusRepacketizer *rp);                                      /* repacketizer.c:98  */
+opus_int32 opus_repacketizer_out_range(OpusRepacketizer *rp, int begin, int end, unsigned char *data,
+                                       opus_int32 maxlen);                                      /* repacketizer.c:229 */
+opus_int32 opus_repacketizer_out(OpusRepacketizer *rp, unsigned char *data, opus_int32 maxlen); /* repacketizer.c:234 */
 
 /* ---- packet helpers: opus-fix/include/opus.h:527-594, src/opus.c:169-352, src/opus_decoder.c:921-981 ---- */
 int opus_packet_parse(const unsigned char *data, opus_int32 len, unsigned char *out_toc, const unsigned char *frames[48],

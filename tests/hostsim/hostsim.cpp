@@ -217,8 +217,21 @@ int hostsim_encode_stream_pipe(const int16_t *pcm, int F, int frame_size, int ch
         for (int fi = 0; fi < nfr; fi++) {
             uint8_t *o = out + (size_t)(f0 + fi) * stride;
             cb::pipe_head(st, g, plans[fi], fe[fi], *X, o);
-            for (int c = 0; c < channels; c++)
-                cb::pipe_comb_channel(tm, st, g, *X, P.data() + (size_t)c * g.pstride + fi * g.N, B->in + c * (g.N + cb::kOverlap), c, tin.data(), sc);
+            for (int c = 0; c < channels; c++) {
+                int *inc = B->in + c * (g.N + cb::kOverlap);
+                if ((f0 + fi) & 1) {
+                    cb::pipe_comb_channel(tm, st, g, *X, P.data() + (size_t)c * g.pstride + fi * g.N, inc, c, tin.data(), sc);
+                } else {   // the pipeline's form: comb only, then transient_analysis of the channel by one thread (odd / even frames alternate)
+                    cb::pipe_comb_channel(tm, st, g, *X, P.data() + (size_t)c * g.pstride + fi * g.N, inc, c, nullptr, sc);
+                    if (X->code && X->cfg.complexity >= 1) {
+                        std::vector<int16_t> row(g.N + cb::kOverlap);
+                        cb::TransientHp hp;
+                        hp.reset();
+                        for (int i = 0; i < g.N + cb::kOverlap; i++) row[i] = (int16_t)hp.step(inc[i] >> 12, i);
+                        X->v.mask_metric[c] = cb::transient_finish_row(row.data(), g.N + cb::kOverlap, hp.mx, hp.mn);
+                    }
+                }
+            }
             cb::pipe_transform(tm, st, g, *X, *B, *ts);
             cb::pipe_decide(st, g, *X);
             int r;
