@@ -47,6 +47,17 @@ struct LeafList {
     uint32_t index[kMaxLeafTasks];             // icwrs of the searched pulse vector
 };
 
+// bits2pulses (rate.h:53-78) as a table: the binary search over the pulse cache only compares bits - 1 with cache entries <= 255,
+// so every bits >= 257 gives what 257 gives (checked exhaustively on the host for all bands and LM).  Filled at start-up by the
+// function itself (opus_enc_pipe.cu).
+enum { kB2pBits = 258 };
+#if defined(__CUDACC__)
+static __device__ uint8_t g_b2p_lut[(kMaxLM + 2) * kNbEBands * kB2pBits];
+CB_DEV int bits2pulses_fast(int band, int LM, int bits) { return g_b2p_lut[((LM + 1) * kNbEBands + band) * kB2pBits + imin(bits, kB2pBits - 1)]; }
+#else
+CB_DEV int bits2pulses_fast(int band, int LM, int bits) { return bits2pulses(band, LM, bits); }
+#endif
+
 // ---- prep ---------------------------------------------------------------------------------------------------------------------
 
 // quant_band's reordering of one vector (bands.c:1062-1100): recombine / time-divide haar steps, then the hadamard de-interleave.
@@ -269,6 +280,7 @@ struct SpecPolicy {
     CB_MEM void finish() {
         while (cur_band < kNbEBands) list->band_first[++cur_band] = (uint8_t)list->count;
     }
+    CB_MEM void skip_bands(int) {}
 };
 
 // chain-X policy: the real coder, the real indices; a leaf chain-S did not list as such is searched here
@@ -293,6 +305,7 @@ struct ExactPolicy {
         ec.bits((unsigned)(c ? wneg(d) < 0 : d < 0), 1);
     }
     CB_MEM void begin_band(int) {}
+    CB_MEM void skip_bands(int) {}
     CB_MEM void leaf(int band, int off, int N, int K, int B, int spread) {
         int hit = -1;
         const int cnt = list->count;
@@ -339,9 +352,10 @@ struct InlinePolicy {
         const int d = prep->n2_d[band];
         ec.bits((unsigned)(c ? wneg(d) < 0 : d < 0), 1);
     }
-    CB_MEM void begin_band(int) {}
+    CB_MEM void begin_band(int) { tm.phase(); }
     CB_MEM void leaf(int, int off, int N, int K, int B, int spread) { alg_quant(tm, Xall + off, N, K, spread, B, ec, *ps); }
     CB_MEM void finish() {}
+    CB_MEM void skip_bands(int n) { CB_NOUNROLL for (int i = 0; i < n; i++) tm.phase(); }   // every warp passes kNbEBands phase()s per frame
 };
 
 struct WalkCtx {
@@ -444,7 +458,7 @@ CB_DEV_NOINLINE void walk_band_vector(P &p, WalkCtx &w, int v, int off, int N, i
                 else { c.off = f.off + n; c.b = sbits; c.h = 2 * f.h + 2; }
                 sp++;
             } else {
-                int q = bits2pulses(w.i, f.LM, f.b);
+                int q = bits2pulses_fast(w.i, f.LM, f.b);
                 int curr_bits = pulses2bits(w.i, f.LM, q);
                 w.remaining_bits -= curr_bits;
                 while (w.remaining_bits < 0 && q > 0) {
@@ -554,6 +568,7 @@ CB_DEV void band_walk(P &p, const BandPrep &prep, int end, int C, const int *pul
         }
         balance += pulses[i] + tell;
     }
+    p.skip_bands(kNbEBands - end);
     p.finish();
 }
 

@@ -311,6 +311,7 @@ CB_DEV int pvq_pick(WarpTeam tm, PvqBest best, int levels) {
     return tm.bcast(best.id, 0);
 }
 CB_DEV int pvq_pick(FreeWarpTeam tm, PvqBest best, int levels) { return pvq_pick(static_cast<WarpTeam>(tm), best, levels); }
+CB_DEV int pvq_pick(SyncWarpTeam tm, PvqBest best, int levels) { return pvq_pick(static_cast<WarpTeam>(tm), best, levels); }
 #endif
 
 // alg_quant (vq.c:161-325), no resynthesis.  The greedy search is the encoder's hottest loop (profiles/): every lane scans its

@@ -1243,7 +1243,10 @@ struct WalkScratch {
 template <class TM>
 CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, const EncPlan &pl, EncPipeCtx &X, const BandPrep &P, const int16_t *XallG,
                                    WalkScratch &S, uint8_t *out) {
-    if (!X.code) return X.v.ret;
+    if (!X.code) {
+        CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) tm.phase();
+        return X.v.ret;
+    }
     EncVars &V = X.v;
     const int C = X.cfg.C, N = g.N;
     CB_NOUNROLL for (int v = 0; v < 3; v++) {

@@ -125,6 +125,11 @@ struct WarpTeam {
 struct FreeWarpTeam : WarpTeam {
     CB_MEM void phase() const {}
 };
+// A warp team whose phase() is a block barrier whatever the build flags say (the pipeline's band-walk kernel: the warps of a block
+// step through the bands together so that they share the instruction cache lines of the band they are in).
+struct SyncWarpTeam : WarpTeam {
+    CB_MEM void phase() const { __syncthreads(); }
+};
 #endif
 
 }  // namespace cb

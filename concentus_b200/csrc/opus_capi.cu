@@ -909,7 +909,7 @@ int opus_decode_batch(OpusDecoder **st, const unsigned char *const *data, const 
             int i = idx[k];
             sts[k] = st[i];
             int l = (data && data[i]) ? len[i] : 0;
-            if (len[i] < 0) l = -1;
+            if (len[i] < 0 && data && data[i]) l = -1;
             lens[k] = l;
             offs[k] = total;
             if (l > 0) total += l;
@@ -961,7 +961,8 @@ int opus_decoder_sync(OpusDecoder **st, int n) {
 int opus_decode(OpusDecoder *st, const unsigned char *data, opus_int32 len, opus_int16 *pcm, int frame_size, int decode_fec) {
     if (frame_size <= 0) return OPUS_BAD_ARG;
     if (!st || st->magic != kDecMagic || !pcm) return OPUS_BAD_ARG;
-    if (len < 0) return OPUS_BAD_ARG;
+    if (decode_fec < 0 || decode_fec > 1) return OPUS_BAD_ARG;
+    if (len < 0 && data != nullptr) return OPUS_BAD_ARG;   // a NULL packet is a lost packet whatever its length says (opus_decoder.c:611-629)
     std::lock_guard<std::mutex> lk(g.mu);
     if (!ctx_init_locked()) return OPUS_INTERNAL_ERROR;
     const int channels = st->st.channels;

@@ -4,7 +4,9 @@
 // A launch's streams are cut into G groups; each group advances frame by frame through K1..K5 on its own CUDA stream, with the
 // front end (P0 / FE1 / FE2) of the NEXT chunk of frames running on a side stream.  Kernels of different groups overlap, so the
 // thread-per-stream stages (a few hundred warps, latency bound) of one group hide behind the warp-per-stream stages of another.
-#define CB_SMALL_CODE 1
+#if !defined(CB_PIPE_BIG_CODE)
+#define CB_SMALL_CODE 1   // celt_simt.cuh: medium helpers as real calls, loops not unrolled (A/B: -DCB_PIPE_BIG_CODE)
+#endif
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -456,22 +458,42 @@ pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
 }
 
 // ---- K5 as prep + one inline walk: one warp per stream, all of a launch's streams resident at once (<= 72 registers) ----------------
-__global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
+// SYNC: the warps of a block meet at every band (SyncWarpTeam), so a block's warps run the same region of the walk's code.
+template <int WPB, bool SYNC>
+__global__ void __launch_bounds__(WPB * 32, 28 / WPB)
 pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
                  const BandPrep *prep, const int16_t *xall, uint8_t *data, int *rets, unsigned *ranges) {
-    __shared__ __align__(16) WalkScratch sm[CB_PIPE_WPB];
+    extern __shared__ __align__(16) unsigned char smw[];
+    WalkScratch *sm = reinterpret_cast<WalkScratch *>(smw);
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * CB_PIPE_WPB + wib;
-    if (s >= g.n) return;
-    FreeWarpTeam tm{{lane}};
+    const int s = blockIdx.x * WPB + wib;
+    if (s >= g.n) {
+        if (SYNC)
+            for (int i = 0; i < kNbEBands; i++) __syncthreads();
+        return;
+    }
     CbEncState *st = pool + slots[s];
     const size_t k = (size_t)sidx[s] * g.F + f;
-    const int r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib],
-                                          data + k * g.stride);
+    int r;
+    if (SYNC) {
+        SyncWarpTeam tm{{lane}};
+        r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib], data + k * g.stride);
+    } else {
+        FreeWarpTeam tm{{lane}};
+        r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib], data + k * g.stride);
+    }
     if (lane == 0) {
         rets[k] = r;
         if (ranges) ranges[k] = st->rangeFinal;
     }
+}
+
+__global__ void b2p_lut_kernel() {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (kMaxLM + 2) * kNbEBands * kB2pBits) return;
+    const int bits = t % kB2pBits, row = t / kB2pBits;
+    const int band = row % kNbEBands, LM = row / kNbEBands - 1;
+    g_b2p_lut[t] = (uint8_t)bits2pulses(band, LM, bits);
 }
 
 // ---- end of the span: the last 1024 pre-emphasised samples go back into the state -------------------------------------------------
@@ -513,6 +535,7 @@ struct PipeCtx {
     bool init = false;
     int groups = 2;
     int chunk = 16;
+    int walk_mode = 0;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band
     int scalar_l = 1;           // streams per warp in the thread-per-stream stages
     int split_bands = 2;        // the band loop as 2: prep + one inline walk; 1: prep / chain-S / leaves / chain-X; 0: one stage (A/B)
     Group g[kMaxGroups];
@@ -549,6 +572,11 @@ bool pipe_init() {
         cudaEventCreateWithFlags(&G.ev_done, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&pc.ev_fork, cudaEventDisableTiming);
+    if (const char *e = getenv("CB200_ENC_WALK")) pc.walk_mode = atoi(e);
+    cudaFuncSetAttribute(pipe_walk_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(14 * sizeof(WalkScratch)));
+    cudaFuncSetAttribute(pipe_walk_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(28 * sizeof(WalkScratch)));
+    b2p_lut_kernel<<<((kMaxLM + 2) * kNbEBands * kB2pBits + 255) / 256, 256>>>();
+    cudaDeviceSynchronize();
     cudaFuncSetAttribute(pipe_transient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient);
     if (const char *e = getenv("CB200_ENC_SCALAR_L")) pc.scalar_l = atoi(e);
     if (pc.scalar_l != 1 && pc.scalar_l != 2 && pc.scalar_l != 4) pc.scalar_l = 1;
@@ -622,9 +650,17 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
             } else if (pc.split_bands == 2) {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
                                                                                        (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
-                pipe_walk_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
-                                                                                       (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p,
-                                                                                       (const int16_t *)G.xall.p, c.d_data, c.d_rets, c.d_ranges);
+#define CB_WALK_LAUNCH(WPB, SYNC)                                                                                                         \
+    pipe_walk_kernel<WPB, SYNC><<<cdiv(n, WPB), WPB * 32, WPB * sizeof(WalkScratch), G.main>>>(                                            \
+        c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p, (const int16_t *)G.xall.p, \
+        c.d_data, c.d_rets, c.d_ranges)
+                switch (pc.walk_mode) {
+                case 1: CB_WALK_LAUNCH(4, true); break;
+                case 2: CB_WALK_LAUNCH(7, true); break;
+                case 3: CB_WALK_LAUNCH(14, true); break;
+                case 4: CB_WALK_LAUNCH(28, true); break;
+                default: CB_WALK_LAUNCH(4, false); break;
+                }
                 launches += 7;
             } else {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
