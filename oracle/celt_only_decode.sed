@@ -8,3 +8,5 @@ s/for(i=0;i<64;i++)/for(i=32;i<64;i++)/
 /mode=fast_rand()%3;/,/lmodes\[mode\]);/d
 # 3. de Bruijn sequence over all mode pairs -> over all CELT mode pairs
 s/packet\[0\]=modes\[i\]<<2;/packet[0]=(32|(modes[i]\&31))<<2;/
+# 4. the pre-selected packet (tmodes = 25 << 2 = TOC 0x64) is a HYBRID packet: removed
+/int tmodes\[1\]={25<<2};/,/pre-selected random packets OK/d

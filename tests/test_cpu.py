@@ -616,3 +616,76 @@ def test_hostsim_random_wide_sweep():
             if not (r[2] and r[3]):
                 bad.append(r)
     assert not bad, bad[:3]
+
+
+@needs_ref
+def test_repacketizer_and_pad_unpad_match_the_reference():
+    """opus_repacketizer_* and opus_packet_pad / opus_packet_unpad for packets of every frame-count code (host code of the library,
+    opus-fix/src/repacketizer.c:37-273): same return codes and bytes as the reference on random merges, splits and paddings."""
+    import concentus_b200 as cb
+    L, R = cb.lib(), O.ref()
+    for lib in (L, R):
+        lib.opus_repacketizer_create.restype = C.c_void_p
+        lib.opus_repacketizer_init.restype = C.c_void_p
+        lib.opus_repacketizer_init.argtypes = [C.c_void_p]
+        lib.opus_repacketizer_destroy.argtypes = [C.c_void_p]
+        lib.opus_repacketizer_cat.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        lib.opus_repacketizer_get_nb_frames.argtypes = [C.c_void_p]
+        lib.opus_repacketizer_out.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        lib.opus_repacketizer_out_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int32]
+        lib.opus_packet_pad.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        lib.opus_packet_unpad.argtypes = [C.c_void_p, C.c_int32]
+    assert L.opus_repacketizer_get_size() > 0
+    rs = np.random.RandomState(5)
+    rp_l, rp_r = L.opus_repacketizer_create(), R.opus_repacketizer_create()
+    n_multi = 0
+    for trial in range(60):
+        fs = (120, 240, 480, 960)[trial % 4]
+        ch = 1 + (trial // 4) % 2
+        vbr = (trial // 8) % 2
+        x = O.test_signal(fs * 12, ch, 900 + trial, ("music", "tone", "clicks", "noise")[trial % 4])
+        d, o, l, _ = O.encode_stream(x, fs, (24000, 64000, 128000)[trial % 3], ch, vbr=vbr, cvbr=0)
+        pk = [np.ascontiguousarray(d[o[f]:o[f] + l[f]]) for f in range(len(l))]
+        if trial % 5 == 4:
+            pk[3] = np.ascontiguousarray(pk[3][:1])            # a TOC-only packet among them
+        if trial % 7 == 6:
+            pk[2] = pk[2].copy(); pk[2][0] ^= 0x08             # a packet of another configuration: must be refused
+        L.opus_repacketizer_init(rp_l); R.opus_repacketizer_init(rp_r)
+        ncat = int(rs.randint(1, 9))
+        for k in range(ncat):
+            a = L.opus_repacketizer_cat(rp_l, O.ptr(pk[k]), len(pk[k]))
+            b = R.opus_repacketizer_cat(rp_r, O.ptr(pk[k]), len(pk[k]))
+            assert a == b, (trial, k, a, b)
+        nf = L.opus_repacketizer_get_nb_frames(rp_l)
+        assert nf == R.opus_repacketizer_get_nb_frames(rp_r)
+        for maxlen in (3000, int(rs.randint(1, 600)), 1):
+            ol, orr = np.zeros(3000, dtype=np.uint8), np.zeros(3000, dtype=np.uint8)
+            a = L.opus_repacketizer_out(rp_l, O.ptr(ol), maxlen)
+            b = R.opus_repacketizer_out(rp_r, O.ptr(orr), maxlen)
+            assert a == b and (a < 0 or np.array_equal(ol[:a], orr[:a])), (trial, maxlen, a, b)
+            if nf >= 1:
+                lo = int(rs.randint(0, nf)); hi = int(rs.randint(lo, nf + 2))
+                a = L.opus_repacketizer_out_range(rp_l, lo, hi, O.ptr(ol), maxlen)
+                b = R.opus_repacketizer_out_range(rp_r, lo, hi, O.ptr(orr), maxlen)
+                assert a == b and (a < 0 or np.array_equal(ol[:a], orr[:a])), (trial, lo, hi, maxlen, a, b)
+        # pad / unpad of the merged (multi-frame) packet, in place
+        ol = np.zeros(4000, dtype=np.uint8)
+        n = L.opus_repacketizer_out(rp_l, O.ptr(ol), 3000)
+        if n > 0:
+            n_multi += nf > 1
+            for new_len in (n, n + 1, n + 2, n + int(rs.randint(3, 700)), n - 1):
+                bl, br = ol.copy(), ol.copy()
+                a = L.opus_packet_pad(O.ptr(bl), n, new_len)
+                b = R.opus_packet_pad(O.ptr(br), n, new_len)
+                assert a == b, (trial, n, new_len, a, b)
+                if a == 0:
+                    assert np.array_equal(bl[:new_len], br[:new_len]), (trial, n, new_len)
+                    a = L.opus_packet_unpad(O.ptr(bl), new_len)
+                    b = R.opus_packet_unpad(O.ptr(br), new_len)
+                    assert a == b and np.array_equal(bl[:a], br[:a]), (trial, new_len, a, b)
+    assert n_multi >= 30
+    for bad in (0, -3):
+        buf = np.zeros(16, dtype=np.uint8)
+        assert L.opus_packet_pad(O.ptr(buf), bad, 8) == R.opus_packet_pad(O.ptr(buf), bad, 8)
+        assert L.opus_packet_unpad(O.ptr(buf), bad) == R.opus_packet_unpad(O.ptr(buf), bad)
+    L.opus_repacketizer_destroy(rp_l); R.opus_repacketizer_destroy(rp_r)
