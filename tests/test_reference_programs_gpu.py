@@ -68,7 +68,7 @@ def test_reference_api_test_on_our_library():
     """tests/test_opus_api.c minus multistream: every ctl / argument-validation / return code of the decoder, encoder, packet
     parser and repacketizer sections (6.7 M API invocations)."""
     r = _run([_need("test_opus_api_b200")], 900)
-    assert r.returncode == 0 and "All repacketizer tests passed" in r.stdout and "All encoder interface tests passed" in r.stdout \\
+    assert r.returncode == 0 and "All repacketizer tests passed" in r.stdout and "All encoder interface tests passed" in r.stdout \
         and "All decoder interface tests passed" in r.stdout, (r.stdout[-600:], r.stderr[-300:])
 
 
