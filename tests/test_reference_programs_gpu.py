@@ -50,7 +50,7 @@ def test_opus_demo_on_our_library_matches_the_oracle_byte_for_byte(tmp_path):
     r = _run([ours, "-d", "48000", "2", str(tmp_path / "ref.bit"), str(tmp_path / "ours.pcm")], 600)
     assert r.returncode == 0, (r.stdout[-400:], r.stderr[-400:])
     a, b = (tmp_path / "ref.pcm").read_bytes(), (tmp_path / "ours.pcm").read_bytes()
-    assert len(a) == 480000 * 4 and a == b, "opus_demo -d on libconcentus_b200.so differs from the reference's PCM"
+    assert len(a) >= 480000 * 4 and a == b, "opus_demo -d on libconcentus_b200.so differs from the reference's PCM"
     # and the reference's default mode (encode + decode in one run, with its per-packet final-range check between the two)
     r = _run([ours, "restricted-lowdelay", "48000", "2", "96000", "-cvbr", "-framesize", "10", str(raw), str(tmp_path / "both.pcm")], 900)
     assert r.returncode == 0 and "Error: Range coder state mismatch" not in r.stderr, r.stderr[-400:]
