@@ -533,10 +533,10 @@ struct Group {
 };
 struct PipeCtx {
     bool init = false;
-    int groups = 2;
+    int groups = 1;             // stream groups on separate CUDA streams (measured: no gain, the stages are issue bound with all streams resident)
     int chunk = 16;
     int walk_mode = 0;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band
-    int scalar_l = 1;           // streams per warp in the thread-per-stream stages
+    int scalar_l = 2;           // streams per warp in the thread-per-stream stages
     int split_bands = 2;        // the band loop as 2: prep + one inline walk; 1: prep / chain-S / leaves / chain-X; 0: one stage (A/B)
     Group g[kMaxGroups];
     cudaEvent_t ev_fork = nullptr;
@@ -579,7 +579,7 @@ bool pipe_init() {
     cudaDeviceSynchronize();
     cudaFuncSetAttribute(pipe_transient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient);
     if (const char *e = getenv("CB200_ENC_SCALAR_L")) pc.scalar_l = atoi(e);
-    if (pc.scalar_l != 1 && pc.scalar_l != 2 && pc.scalar_l != 4) pc.scalar_l = 1;
+    if (pc.scalar_l != 1 && pc.scalar_l != 2 && pc.scalar_l != 4) pc.scalar_l = 2;
     set_scalar_smem<1>(); set_scalar_smem<2>(); set_scalar_smem<4>();
     pc.init = cudaGetLastError() == cudaSuccess;
     return pc.init;

@@ -61,15 +61,16 @@ def test_opus_demo_on_our_library_matches_the_oracle_byte_for_byte(tmp_path):
 
 def test_reference_padding_test_on_our_library():
     r = _run([_need("test_opus_padding_b200")], 300)
-    assert r.returncode == 0 and "All padding tests passed" in r.stdout, (r.stdout[-300:], r.stderr[-300:])
+    assert r.returncode == 0 and "All padding tests passed" in r.stdout + r.stderr, (r.stdout[-300:], r.stderr[-300:])
 
 
 def test_reference_api_test_on_our_library():
     """tests/test_opus_api.c minus multistream: every ctl / argument-validation / return code of the decoder, encoder, packet
     parser and repacketizer sections (6.7 M API invocations)."""
     r = _run([_need("test_opus_api_b200")], 900)
-    assert r.returncode == 0 and "All repacketizer tests passed" in r.stdout and "All encoder interface tests passed" in r.stdout \
-        and "All decoder interface tests passed" in r.stdout, (r.stdout[-600:], r.stderr[-300:])
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "All repacketizer tests passed" in out and "All encoder interface tests passed" in out \
+        and "All decoder interface tests passed" in out, (r.stdout[-600:], r.stderr[-300:])
 
 
 def test_reference_decode_test_on_our_library():
@@ -79,4 +80,5 @@ def test_reference_decode_test_on_our_library():
     channel counts) must agree on the final range.  The same filtered source passes on the reference library (checked at build)."""
     r = _run([_need("test_opus_decode_b200")], 1500)
     assert r.returncode == 0, (r.stdout[-600:], r.stderr[-300:])
-    assert "all 3-byte prefix for length 4, mode" in r.stdout and "all mode pairs (4096)*10" in r.stdout and "Decoders stopped" in r.stdout
+    out = r.stdout + r.stderr
+    assert "all 3-byte prefix for length 4, mode" in out and "all mode pairs (4096)*10" in out and "Decoders stopped" in out
