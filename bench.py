@@ -247,8 +247,8 @@ def mixed_config(args, world):
 
 
 def shard_range(n, rank, world):
-    from concentus_b200.shard import shard
-    return shard(n, rank, world)
+    from concentus_b200.shard import shard_range as sr
+    return sr(n, world, rank)
 
 
 # ------------------------------------------------------------------------------------------------------------------------------

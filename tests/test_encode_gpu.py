@@ -412,3 +412,92 @@ def test_pipeline_groups_chunks_and_mixed_paths():
             assert v.value == int(rr[-1]), s
     for h in hs:
         L.opus_encoder_destroy(C.c_void_p(h))
+
+
+def _encode_mixed_batch(cb, pcms, ch, fs, Fs, settings, application=None):
+    """One span launch over streams with per-stream (bitrate, vbr, cvbr, complexity); returns (data [n, F, 1276], lens [n, F], final ranges)."""
+    L = cb.lib()
+    n = len(pcms)
+    F = pcms[0].shape[0] // fs
+    enc = cb.EncoderBatch(n, Fs, ch, application=application or cb.OPUS_APPLICATION_RESTRICTED_LOWDELAY)
+    for i, (br, vbr, cvbr, cx) in enumerate(settings):
+        hp = C.c_void_p(enc.handles[i])
+        for req, v in ((cb.OPUS_SET_BITRATE_REQUEST, br), (cb.OPUS_SET_VBR_REQUEST, vbr), (cb.OPUS_SET_VBR_CONSTRAINT_REQUEST, cvbr),
+                       (cb.OPUS_SET_COMPLEXITY_REQUEST, cx)):
+            assert L.opus_encoder_ctl(hp, req, C.c_int32(v)) == 0
+    d, l = enc.encode_span(np.concatenate([p[:F * fs] for p in pcms]), F, fs)
+    fr = enc.final_ranges()
+    enc.close()
+    return d.reshape(n, F, 1276), l.reshape(n, F), fr
+
+
+@pytest.mark.parametrize("fs", [120, 240, 480, 960])
+@pytest.mark.parametrize("ch", [1, 2])
+def test_encode_sweep_matrix(fs, ch, enc_path):
+    """BASELINE configs[3], encoder side: frame size x {mono, stereo} x {32, 64, 128, 256, 510 kbps} x {CBR, VBR, CVBR}: the 15
+    rate / mode combinations of a (frame size, channels) cell are one span launch (per-stream settings), every stream a different
+    signal, packets byte-for-byte against the oracle."""
+    cb = _cb()
+    settings = [(br, vbr, cvbr, 10) for br in (32000, 64000, 128000, 256000, 510000) for (vbr, cvbr) in ((0, 0), (1, 0), (1, 1))]
+    kinds = ("music", "tone", "clicks", "noise")
+    pcms = [O.test_signal(48000, ch, 5000 + 17 * fs + i, kinds[i % 4]) for i in range(len(settings))]
+    d, l, fr = _encode_mixed_batch(cb, pcms, ch, fs, 48000, settings)
+    F = l.shape[1]
+    for i, (br, vbr, cvbr, cx) in enumerate(settings):
+        rd, rl, rr = _ref_encode(pcms[i], fs, br, ch, vbr, cvbr, cx)
+        assert np.array_equal(rl, l[i]), ("len", fs, ch, settings[i], int(np.nonzero(rl != l[i])[0][0]))
+        for f in range(F):
+            assert np.array_equal(rd[f, :rl[f]], d[i, f, :rl[f]]), ("bytes", fs, ch, settings[i], f)
+        assert int(rr[-1]) == int(fr[i]), ("final range", fs, ch, settings[i])
+
+
+def _raw_fixture(Fs, ch, seconds):
+    import os
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    name = "%dKhz_%s.raw" % (Fs // 1000, "Stereo" if ch == 2 else "Mono")
+    p = os.path.join(root, name) if (Fs == 48000 and ch == 2) else os.path.join(root, "raw", name)
+    x = np.fromfile(p, dtype="<i2").reshape(-1, ch)
+    n = Fs * seconds
+    return np.ascontiguousarray(np.resize(x, (n, ch)) if len(x) < n else x[:n])
+
+
+@pytest.mark.parametrize("fs", [120, 240, 480, 960])
+def test_encode_long_streams_from_the_reference_fixture(fs, enc_path):
+    """>= 20 s per stream for every frame size (the VBR controller's vbr_count saturates at 970 frames, the energy histories and
+    the CVBR reservoir settle well after one second), on the reference's own parity input 48Khz Stereo.raw (CSharp/ParityTest)."""
+    cb = _cb()
+    x = _raw_fixture(48000, 2, 20)
+    pcms = [x, np.ascontiguousarray(np.roll(x, 48000 * 3, axis=0))]
+    settings = [(96000, 1, 0, 10), (64000, 1, 1, 10)]
+    d, l, fr = _encode_mixed_batch(cb, pcms, 2, fs, 48000, settings)
+    for i, (br, vbr, cvbr, cx) in enumerate(settings):
+        rd, rl, rr = _ref_encode(pcms[i], fs, br, 2, vbr, cvbr, cx)
+        assert np.array_equal(rl, l[i]), ("len", fs, settings[i], int(np.nonzero(rl != l[i])[0][0]))
+        bad = [f for f in range(len(rl)) if not np.array_equal(rd[f, :rl[f]], d[i, f, :rl[f]])]
+        assert not bad, ("bytes", fs, settings[i], bad[0])
+        assert int(rr[-1]) == int(fr[i])
+
+
+@pytest.mark.parametrize("Fs", [8000, 12000, 16000, 24000, 48000])
+@pytest.mark.parametrize("ch", [1, 2])
+def test_raw_fixtures_every_api_rate(Fs, ch):
+    """The reference's parity inputs at every API rate (Java/ConcentusTestConsole/.../AudioData/<rate>Khz {Mono,Stereo}.raw, the files
+    CSharp/ParityTest feeds both codecs): encode 5 s (20 ms frames, VBR and CBR), packets against the oracle, then decode the
+    packets at the same rate, PCM against the oracle."""
+    cb = _cb()
+    x = _raw_fixture(Fs, ch, 5)
+    fs = Fs // 50
+    for br, vbr in ((64000, 1), (32000, 0)):
+        d, l, fr = _encode_mixed_batch(cb, [x], ch, fs, Fs, [(br, vbr, 0, 10)])
+        rd, ro, rl, rr = O.encode_stream(x, fs, br, ch, Fs=Fs, vbr=vbr, cvbr=0, complexity=10, max_bytes=1276)
+        rd = rd.reshape(-1, 1276)
+        assert np.array_equal(rl, l[0]), ("len", Fs, ch, br)
+        for f in range(len(rl)):
+            assert np.array_equal(rd[f, :rl[f]], d[0, f, :rl[f]]), ("bytes", Fs, ch, br, f)
+        F = len(rl)
+        offs = np.arange(F, dtype=np.int64) * 1276
+        dec = cb.DecoderBatch(1, Fs, ch)
+        pcm, rets = dec.decode_span(rd.reshape(-1), offs, rl, F, fs)
+        dec.close()
+        rp, _, rret = O.decode_stream(rd.reshape(-1), offs, rl, fs, ch, Fs=Fs)
+        assert np.array_equal(rets, rret) and np.array_equal(pcm, rp), ("decode", Fs, ch, br)
