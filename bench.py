@@ -723,15 +723,7 @@ def bench_mixed(E, args):
     dec_step()
     barrier(E)
     assert bool((d_ret == FRAME).all().item())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        dec_step()
-    e1.record(stream)
-    barrier(E)
-    dms = all_max(E, e0.elapsed_time(e1))
-    dec_value = NT * seconds * args.steps / (dms / 1e3)
-    # parity: the first copy of a few programmes (rotation 0 on the rank that holds it) against the oracle
+    # parity (the first launch decoded from fresh states): the first copy of a few programmes (rotation 0) against the oracle
     parity = None
     if E.rank == 0 and not args.no_parity:
         pick = [s for s in np.linspace(0, min(S, U) - 1, min(16, S)).astype(int).tolist() if rot[s] == 0]
@@ -745,6 +737,14 @@ def bench_mixed(E, args):
                 bad.append(int(lo + s))
         parity = {"decode_streams_checked": len(pick), "decode_mismatching": bad}
         assert not bad, "mixed decode parity failed: %s" % bad
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        dec_step()
+    e1.record(stream)
+    barrier(E)
+    dms = all_max(E, e0.elapsed_time(e1))
+    dec_value = NT * seconds * args.steps / (dms / 1e3)
     dec.close()
     del d_blob, d_pcm
     torch.cuda.empty_cache()

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/opus_b200.h"
+#include "host_runtime.h"
 #include "opus_decoder_dev.cuh"
 
 using namespace cb;
@@ -32,7 +33,7 @@ struct OpusDecoder {
     int32_t slot;          // device pool slot or -1
     uint64_t gen;          // generation of the slot contents this block refers to
     int32_t host_current;  // 1: `st` below is up to date
-    int32_t reserved;
+    int32_t device;        // the device whose pool `slot` refers to
     CbDecState st;
 };
 static const uint32_t kDecMagic = 0x0B200DECu;
@@ -206,39 +207,9 @@ __global__ void gather_states_kernel(const CbDecState *pool, const int *slots, C
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-struct SlotInfo {
-    const void *owner;
-    uint64_t gen;
-};
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool reserve(size_t n) {
-        if (n <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = n + n / 4 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) return false;
-        cap = want;
-        return true;
-    }
-};
-struct PinBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool reserve(size_t n) {
-        if (n <= cap) return true;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = n + n / 4 + 256;
-        if (cudaMallocHost(&p, want) != cudaSuccess) return false;
-        cap = want;
-        return true;
-    }
-};
+typedef CbSlotInfo SlotInfo;
+typedef CbDevBuf DevBuf;
+typedef CbPinBuf PinBuf;
 
 struct Ctx {
     std::mutex mu;
@@ -268,20 +239,48 @@ struct Ctx {
     double stage_ms[3] = {0, 0, 0};
     long long stage_launches[3] = {0, 0, 0};
     int smem_per_block = 0;
+    // slots of this device's pool whose owners moved to another device: released by the next call here (see release_elsewhere)
+    std::mutex deferred_mu;
+    std::vector<std::pair<int, const void *>> deferred;
 };
-Ctx g;
+// One context per device; a thread works on the device it selected with opus_b200_init (host_runtime.h).
+Ctx g_ctxs[kCbMaxDevices];
+thread_local int tl_device = -1;
+int g_default_device = -1;
+inline int cur_device() {
+    const int d = tl_device >= 0 ? tl_device : g_default_device;
+    return d < 0 || d >= kCbMaxDevices ? 0 : d;
+}
+#define g (g_ctxs[cur_device()])
 
-enum { kStageStates = 256 };
+enum { kStageStates = 4096 };   // states per upload / download slice: one copy, one kernel, one synchronisation for a whole batch
 
+void release_slot_locked(OpusDecoder *d);
 bool ctx_init_locked() {
-    if (g.tried) return g.ok;
+    if (g.tried) {
+        if (g.ok) {
+            cudaSetDevice(g.device);
+            if (!g.deferred.empty()) {
+                std::lock_guard<std::mutex> lk(g.deferred_mu);
+                for (auto &pr : g.deferred)
+                    if (pr.first >= 0 && pr.first < g.pool_cap && g.reg[pr.first].owner == pr.second) {
+                        g.reg[pr.first].owner = nullptr;
+                        g.reg[pr.first].gen++;
+                        g.free_slots.push_back(pr.first);
+                    }
+                g.deferred.clear();
+            }
+        }
+        return g.ok;
+    }
     g.tried = true;
+    g.device = cur_device();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         fprintf(stderr, "concentus_b200: no CUDA device available — this library has no CPU path\n");
         return false;
     }
-    if (g.device >= ndev) g.device = 0;
+    if (g.device >= ndev) return false;
     if (cudaSetDevice(g.device) != cudaSuccess) return false;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -312,8 +311,8 @@ bool ctx_init_locked() {
     g.smem_per_block = (int)(CB_WPB * sizeof(SynthScratch));
     cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem_per_block);
     cudaFuncSetAttribute(parse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);   // stage A wants L1, not shared
-    if (!g.h_stage.reserve(sizeof(CbDecState) * kStageStates)) return false;
-    if (!g.d_stage.reserve(sizeof(CbDecState) * kStageStates)) return false;
+    if (!g.h_stage.reserve(sizeof(CbDecState) * 64)) return false;
+    if (!g.d_stage.reserve(sizeof(CbDecState) * 64)) return false;
     g.ok = (cudaGetLastError() == cudaSuccess);
     return g.ok;
 }
@@ -337,15 +336,25 @@ bool pool_reserve_locked(int need_total) {
 }
 
 inline bool resident(const OpusDecoder *d) {
-    return d->slot >= 0 && d->slot < g.pool_cap && g.reg[d->slot].owner == d && g.reg[d->slot].gen == d->gen;
+    return d->device == g.device && d->slot >= 0 && d->slot < g.pool_cap && g.reg[d->slot].owner == d && g.reg[d->slot].gen == d->gen;
+}
+// the block's slot lives in another device's pool: that device's next call gives it back
+void release_elsewhere(OpusDecoder *d) {
+    if (d->slot >= 0 && d->device >= 0 && d->device < kCbMaxDevices && d->device != g.device) {
+        Ctx &o = g_ctxs[d->device];
+        std::lock_guard<std::mutex> lk(o.deferred_mu);
+        o.deferred.emplace_back(d->slot, (const void *)d);
+        d->slot = -1;
+    }
 }
 
 // Bring the host copy of `d` up to date (download from its slot when the slot holds the newer state).
 int make_host_current_locked(OpusDecoder *d) {
     if (d->host_current) return OPUS_OK;
     // stale host block: the state it refers to must still be in its slot with the same generation
-    // (this also covers a block that was memcpy'd while its original was device-resident)
-    if (d->slot < 0 || d->slot >= g.pool_cap || g.reg[d->slot].gen != d->gen) return OPUS_INVALID_STATE;
+    // (this also covers a block that was memcpy'd while its original was device-resident).  A state resident on ANOTHER device
+    // has to be synchronised by a thread of that device first (opus_decoder_sync): OPUS_INVALID_STATE here.
+    if (d->device != g.device || d->slot < 0 || d->slot >= g.pool_cap || g.reg[d->slot].gen != d->gen) return OPUS_INVALID_STATE;
     if (cudaMemcpyAsync(&d->st, g.pool + d->slot, sizeof(CbDecState), cudaMemcpyDeviceToHost, g.stream) != cudaSuccess)
         return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
@@ -354,6 +363,7 @@ int make_host_current_locked(OpusDecoder *d) {
 }
 
 void release_slot_locked(OpusDecoder *d) {
+    release_elsewhere(d);
     if (d->slot >= 0 && d->slot < g.pool_cap && g.reg[d->slot].owner == d) {
         g.reg[d->slot].owner = nullptr;
         g.reg[d->slot].gen++;
@@ -389,17 +399,21 @@ int make_resident_locked(OpusDecoder **st, int n, int *h_slots) {
                 int rc = make_host_current_locked(d);
                 if (rc != OPUS_OK) return rc;
             }
+            release_elsewhere(d);
             d->slot = g.free_slots.back();
             g.free_slots.pop_back();
+            d->device = g.device;
             g.reg[d->slot].owner = d;
             d->gen = ++g.reg[d->slot].gen;
             up_idx.push_back(i);
         }
         h_slots[i] = d->slot;
     }
+    {
+        const size_t slice = up_idx.size() < (size_t)kStageStates ? up_idx.size() : (size_t)kStageStates;
+        if (slice > 0 && (!g.h_stage.reserve(sizeof(CbDecState) * slice) || !g.d_stage.reserve(sizeof(CbDecState) * slice))) return OPUS_ALLOC_FAIL;
+    }
     CbDecState *hs = (CbDecState *)g.h_stage.p;
-    int *hsl = (int *)g.h_slots.p;   // caller reserved >= n ints... use a separate region at the tail
-    (void)hsl;
     for (size_t base = 0; base < up_idx.size(); base += kStageStates) {
         int cnt = (int)((up_idx.size() - base) < (size_t)kStageStates ? (up_idx.size() - base) : kStageStates);
         std::vector<int> sl(cnt);
@@ -411,7 +425,7 @@ int make_resident_locked(OpusDecoder **st, int n, int *h_slots) {
         if (!g.d_slots.reserve(sizeof(int) * (size_t)(n > kStageStates ? n : kStageStates))) return OPUS_ALLOC_FAIL;
         cudaMemcpyAsync(g.d_stage.p, hs, sizeof(CbDecState) * (size_t)cnt, cudaMemcpyHostToDevice, g.stream);
         cudaMemcpyAsync(g.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, g.stream);
-        scatter_states_kernel<<<cnt, 256, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (const CbDecState *)g.d_stage.p, cnt);
+        scatter_states_kernel<<<cnt < 2048 ? cnt : 2048, 256, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (const CbDecState *)g.d_stage.p, cnt);
         if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     }
     return OPUS_OK;
@@ -440,14 +454,18 @@ int sync_states_locked(OpusDecoder **st, int n, bool release) {
             }
         }
     }
+    {
+        const size_t slice = idx.size() < (size_t)kStageStates ? idx.size() : (size_t)kStageStates;
+        if (slice > 0 && (!g.h_stage.reserve(sizeof(CbDecState) * slice) || !g.d_stage.reserve(sizeof(CbDecState) * slice))) return OPUS_ALLOC_FAIL;
+    }
     CbDecState *hs = (CbDecState *)g.h_stage.p;
     for (size_t base = 0; base < idx.size(); base += kStageStates) {
         int cnt = (int)((idx.size() - base) < (size_t)kStageStates ? (idx.size() - base) : kStageStates);
         std::vector<int> sl(cnt);
         for (int k = 0; k < cnt; k++) sl[k] = st[idx[base + k]]->slot;
-        if (!g.d_slots.reserve(sizeof(int) * (size_t)kStageStates)) return OPUS_ALLOC_FAIL;
+        if (!g.d_slots.reserve(sizeof(int) * (size_t)cnt)) return OPUS_ALLOC_FAIL;
         cudaMemcpyAsync(g.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, g.stream);
-        gather_states_kernel<<<cnt, 256, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (CbDecState *)g.d_stage.p, cnt);
+        gather_states_kernel<<<cnt < 2048 ? cnt : 2048, 256, 0, g.stream>>>(g.pool, (const int *)g.d_slots.p, (CbDecState *)g.d_stage.p, cnt);
         cudaMemcpyAsync(hs, g.d_stage.p, sizeof(CbDecState) * (size_t)cnt, cudaMemcpyDeviceToHost, g.stream);
         if (cudaStreamSynchronize(g.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
         for (int k = 0; k < cnt; k++) {
@@ -574,11 +592,16 @@ void enqueue_chunk(const Plan &pl, int c, const int *d_slots, const uint8_t *d_d
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
+// Select the device the CALLING THREAD codes on (and initialise its context).  The first call of the process also sets the device
+// of threads that never call this.
 int opus_b200_init(int device) {
+    if (device < 0 || device >= kCbMaxDevices) return OPUS_BAD_ARG;
+    tl_device = device;
+    if (g_default_device < 0) g_default_device = device;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.tried) g.device = device;
     return ctx_init_locked() ? OPUS_OK : OPUS_INTERNAL_ERROR;
 }
+int opus_b200_current_device(void) { return cur_device(); }
 // The device this process codes on (initialises the runtime); -1 when CUDA is unusable.  Used by the encoder half
 // (opus_enc_capi.cu) so both halves share one device selection.
 int opus_b200_device_index(void) {
@@ -674,13 +697,14 @@ int opus_decoder_init(OpusDecoder *st, opus_int32 Fs, int channels) {
         return OPUS_BAD_ARG;
     {   // re-initialising a live block in place (the reference's tests do): give its pool slot back first
         std::lock_guard<std::mutex> lk(g.mu);
-        if (g.ok && st->magic == kDecMagic && st->slot >= 0 && st->slot < g.pool_cap && g.reg[st->slot].owner == st) release_slot_locked(st);
+        if (g.ok && st->magic == kDecMagic && st->slot >= 0) release_slot_locked(st);
     }
     memset(st, 0, sizeof(OpusDecoder));
     st->magic = kDecMagic;
     st->slot = -1;
     st->gen = 0;
     st->host_current = 1;
+    st->device = -1;
     if (dec_state_init(&st->st, Fs, channels) != 0) return OPUS_BAD_ARG;
     return OPUS_OK;
 }

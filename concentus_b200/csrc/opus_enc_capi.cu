@@ -21,6 +21,7 @@
 
 #include "../../include/opus_b200.h"
 #include "enc_pipe_host.h"
+#include "host_runtime.h"
 #include "opus_encoder_dev.cuh"
 
 using namespace cb;
@@ -34,7 +35,7 @@ struct OpusEncoder {
     int32_t slot;
     uint64_t gen;
     int32_t host_current;
-    int32_t reserved;
+    int32_t device;        // the device whose pool `slot` refers to
     CbEncState st;
 };
 static const uint32_t kEncMagic = 0x0B200E4Cu;
@@ -121,31 +122,9 @@ namespace {
 
 inline int hmin(int a, int b) { return a < b ? a : b; }
 
-struct SlotInfo { const void *owner; uint64_t gen; };
-struct DevBuf {
-    void *p = nullptr; size_t cap = 0;
-    bool reserve(size_t n) {
-        if (n <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) return false;
-        cap = want;
-        return true;
-    }
-};
-struct PinBuf {
-    void *p = nullptr; size_t cap = 0;
-    bool reserve(size_t n) {
-        if (n <= cap) return true;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 256;
-        if (cudaMallocHost(&p, want) != cudaSuccess) return false;
-        cap = want;
-        return true;
-    }
-};
+typedef CbSlotInfo SlotInfo;
+typedef CbDevBuf DevBuf;
+typedef CbPinBuf PinBuf;
 
 struct EncCtx {
     std::mutex mu;
@@ -168,15 +147,36 @@ struct EncCtx {
     long long launches = 0;
     float last_ms = 0.f;
     double total_ms = 0;
+    int device = 0;
+    std::mutex deferred_mu;
+    std::vector<std::pair<int, const void *>> deferred;   // slots of this pool whose owners moved to another device
 };
-EncCtx e;
-enum { kStageStates = 128 };
+// one context per device; the calling thread's device is the one it selected with opus_b200_init (host_runtime.h)
+EncCtx e_ctxs[kCbMaxDevices];
+#define e (e_ctxs[opus_b200_current_device()])
+enum { kStageStates = 4096 };   // states per upload / download slice
 
 bool ctx_init_locked() {
-    if (e.tried) return e.ok;
+    if (e.tried) {
+        if (e.ok) {
+            cudaSetDevice(e.device);
+            if (!e.deferred.empty()) {
+                std::lock_guard<std::mutex> lk(e.deferred_mu);
+                for (auto &pr : e.deferred)
+                    if (pr.first >= 0 && pr.first < e.pool_cap && e.reg[pr.first].owner == pr.second) {
+                        e.reg[pr.first].owner = nullptr;
+                        e.reg[pr.first].gen++;
+                        e.free_slots.push_back(pr.first);
+                    }
+                e.deferred.clear();
+            }
+        }
+        return e.ok;
+    }
     e.tried = true;
     const int dev = opus_b200_device_index();
     if (dev < 0) return false;
+    e.device = dev;
     if (cudaSetDevice(dev) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
@@ -191,7 +191,7 @@ bool ctx_init_locked() {
     cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e.ev_legacy, cudaEventDisableTiming);
     if (const char *v = getenv("CB200_ENC_PIPE")) e.use_pipe = atoi(v);
-    if (!e.h_stage.reserve(sizeof(CbEncState) * kStageStates) || !e.d_stage.reserve(sizeof(CbEncState) * kStageStates)) return false;
+    if (!e.h_stage.reserve(sizeof(CbEncState) * 64) || !e.d_stage.reserve(sizeof(CbEncState) * 64)) return false;
     cudaFuncSetAttribute(encode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(CB_ENC_WPB * sizeof(EncWarpSmem)));
 #ifndef CB_ENC_CARVEOUT
 #define CB_ENC_CARVEOUT 70   // % of the 228 KB: the block needs 157 KB of shared memory; the rest stays L1 for stacks and tables
@@ -220,12 +220,22 @@ bool pool_reserve_locked(int need_total) {
 }
 
 inline bool resident(const OpusEncoder *d) {
-    return d->slot >= 0 && d->slot < e.pool_cap && e.reg[d->slot].owner == d && e.reg[d->slot].gen == d->gen;
+    return d->device == e.device && d->slot >= 0 && d->slot < e.pool_cap && e.reg[d->slot].owner == d && e.reg[d->slot].gen == d->gen;
+}
+// the block's slot lives in another device's pool: that device's next call gives it back
+void release_elsewhere(OpusEncoder *d) {
+    if (d->slot >= 0 && d->device >= 0 && d->device < kCbMaxDevices && d->device != e.device) {
+        EncCtx &o = e_ctxs[d->device];
+        std::lock_guard<std::mutex> lk(o.deferred_mu);
+        o.deferred.emplace_back(d->slot, (const void *)d);
+        d->slot = -1;
+    }
 }
 
 int make_host_current_locked(OpusEncoder *d) {
     if (d->host_current) return OPUS_OK;
-    if (d->slot < 0 || d->slot >= e.pool_cap || e.reg[d->slot].gen != d->gen) return OPUS_INVALID_STATE;
+    // (a state resident on another device has to be synchronised by a thread of that device: OPUS_INVALID_STATE here)
+    if (d->device != e.device || d->slot < 0 || d->slot >= e.pool_cap || e.reg[d->slot].gen != d->gen) return OPUS_INVALID_STATE;
     if (cudaMemcpyAsync(&d->st, e.pool + d->slot, sizeof(CbEncState), cudaMemcpyDeviceToHost, e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     d->host_current = 1;
@@ -233,6 +243,7 @@ int make_host_current_locked(OpusEncoder *d) {
 }
 
 void release_slot_locked(OpusEncoder *d) {
+    release_elsewhere(d);
     if (d->slot >= 0 && d->slot < e.pool_cap && e.reg[d->slot].owner == d) {
         e.reg[d->slot].owner = nullptr;
         e.reg[d->slot].gen++;
@@ -266,13 +277,19 @@ int make_resident_locked(OpusEncoder **st, int n, int *h_slots) {
                 int rc = make_host_current_locked(d);
                 if (rc != OPUS_OK) return rc;
             }
+            release_elsewhere(d);
             d->slot = e.free_slots.back();
             e.free_slots.pop_back();
+            d->device = e.device;
             e.reg[d->slot].owner = d;
             d->gen = ++e.reg[d->slot].gen;
             up_idx.push_back(i);
         }
         h_slots[i] = d->slot;
+    }
+    {
+        const size_t slice = up_idx.size() < (size_t)kStageStates ? up_idx.size() : (size_t)kStageStates;
+        if (slice > 0 && (!e.h_stage.reserve(sizeof(CbEncState) * slice) || !e.d_stage.reserve(sizeof(CbEncState) * slice))) return OPUS_ALLOC_FAIL;
     }
     CbEncState *hs = (CbEncState *)e.h_stage.p;
     if (!e.d_slots.reserve(sizeof(int) * (size_t)(n > kStageStates ? n : kStageStates))) return OPUS_ALLOC_FAIL;
@@ -286,7 +303,7 @@ int make_resident_locked(OpusEncoder **st, int n, int *h_slots) {
         }
         cudaMemcpyAsync(e.d_stage.p, hs, sizeof(CbEncState) * (size_t)cnt, cudaMemcpyHostToDevice, e.stream);
         cudaMemcpyAsync(e.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, e.stream);
-        enc_scatter_states_kernel<<<cnt, 256, 0, e.stream>>>(e.pool, (const int *)e.d_slots.p, (const CbEncState *)e.d_stage.p, cnt);
+        enc_scatter_states_kernel<<<cnt < 2048 ? cnt : 2048, 256, 0, e.stream>>>(e.pool, (const int *)e.d_slots.p, (const CbEncState *)e.d_stage.p, cnt);
         if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
     }
     return OPUS_OK;
@@ -314,6 +331,10 @@ int sync_states_locked(OpusEncoder **st, int n, bool release) {
             }
         }
     }
+    {
+        const size_t slice = idx.size() < (size_t)kStageStates ? idx.size() : (size_t)kStageStates;
+        if (slice > 0 && (!e.h_stage.reserve(sizeof(CbEncState) * slice) || !e.d_stage.reserve(sizeof(CbEncState) * slice))) return OPUS_ALLOC_FAIL;
+    }
     CbEncState *hs = (CbEncState *)e.h_stage.p;
     if (!e.d_slots.reserve(sizeof(int) * (size_t)kStageStates)) return OPUS_ALLOC_FAIL;
     for (size_t base = 0; base < idx.size(); base += kStageStates) {
@@ -321,7 +342,7 @@ int sync_states_locked(OpusEncoder **st, int n, bool release) {
         std::vector<int> sl(cnt);
         for (int k = 0; k < cnt; k++) sl[k] = st[idx[base + k]]->slot;
         cudaMemcpyAsync(e.d_slots.p, sl.data(), sizeof(int) * (size_t)cnt, cudaMemcpyHostToDevice, e.stream);
-        enc_gather_states_kernel<<<cnt, 256, 0, e.stream>>>(e.pool, (const int *)e.d_slots.p, (CbEncState *)e.d_stage.p, cnt);
+        enc_gather_states_kernel<<<cnt < 2048 ? cnt : 2048, 256, 0, e.stream>>>(e.pool, (const int *)e.d_slots.p, (CbEncState *)e.d_stage.p, cnt);
         cudaMemcpyAsync(hs, e.d_stage.p, sizeof(CbEncState) * (size_t)cnt, cudaMemcpyDeviceToHost, e.stream);
         if (cudaStreamSynchronize(e.stream) != cudaSuccess) return OPUS_INTERNAL_ERROR;
         for (int k = 0; k < cnt; k++) {
@@ -544,13 +565,14 @@ int opus_encoder_init(OpusEncoder *st, opus_int32 Fs, int channels, int applicat
         return OPUS_BAD_ARG;
     {   // re-initialising a live block in place: give its pool slot back first
         std::lock_guard<std::mutex> lk(e.mu);
-        if (e.ok && st->magic == kEncMagic && st->slot >= 0 && st->slot < e.pool_cap && e.reg[st->slot].owner == st) release_slot_locked(st);
+        if (e.ok && st->magic == kEncMagic && st->slot >= 0) release_slot_locked(st);
     }
     memset(st, 0, sizeof(OpusEncoder));
     st->magic = kEncMagic;
     st->slot = -1;
     st->gen = 0;
     st->host_current = 1;
+    st->device = -1;
     if (enc_state_init(&st->st, Fs, channels, application) != 0) return OPUS_BAD_ARG;
     return OPUS_OK;
 }

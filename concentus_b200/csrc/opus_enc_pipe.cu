@@ -15,6 +15,7 @@
 
 #include "celt_enc_pipe.cuh"
 #include "enc_pipe_host.h"
+#include "host_runtime.h"
 
 using namespace cb;
 
@@ -512,18 +513,7 @@ constexpr int smem_head_ctx(int T) { return (T * kHeadStride + 1 + T * kCtxStrid
 constexpr int smem_spec(int T) { return (T * kPrepStride + T * kLeafStride) * 4; }
 constexpr int smem_exact(int T) { return (T * kHeadStride + T * kPrepStride + T * kLeafStride) * 4; }
 
-struct DevBuf {
-    void *p = nullptr; size_t cap = 0;
-    bool reserve(size_t n) {
-        if (n <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 8 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) return false;
-        cap = want;
-        return true;
-    }
-};
+typedef CbDevBuf DevBuf;
 
 enum { kMaxGroups = 8 };
 struct Group {
@@ -541,7 +531,9 @@ struct PipeCtx {
     Group g[kMaxGroups];
     cudaEvent_t ev_fork = nullptr;
     int *d_stats = nullptr;     // [0] leaves chain-X had to search itself, [1] leaves listed by chain-S
-} pc;
+};
+PipeCtx pcs[kCbMaxDevices];     // one per device (host_runtime.h)
+#define pc (pcs[opus_b200_current_device()])
 
 template <int L>
 void set_scalar_smem() {
