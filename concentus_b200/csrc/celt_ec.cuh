@@ -214,7 +214,7 @@ struct EcEnc {
             if (rem >= 0) error |= write_byte((unsigned)(rem + carry));
             if (ext > 0) {
                 unsigned sym = (unsigned)(kEcSymMax + carry) & kEcSymMax;
-                do error |= write_byte(sym);
+                CB_NOUNROLL do error |= write_byte(sym);
                 while (--ext > 0);
             }
             rem = c & kEcSymMax;
@@ -223,8 +223,8 @@ struct EcEnc {
         }
     }
     // entenc.c:145-152
-    CB_MEM void normalize() {
-        while (rng <= CB_EC_CODE_BOT) {
+    CB_MEM_TINY void normalize() {
+        CB_NOUNROLL while (rng <= CB_EC_CODE_BOT) {
             carry_out((int)(val >> kEcCodeShift));
             val = (val << kEcSymBits) & (CB_EC_CODE_TOP - 1);
             rng <<= kEcSymBits;
@@ -238,7 +238,7 @@ struct EcEnc {
         offs = 0; rng = CB_EC_CODE_TOP; rem = -1; val = 0; ext = 0; storage = size; error = 0;
     }
     CB_MEM int tell() const { return nbits_total - ec_ilog(rng); }
-    CB_MEM unsigned tell_frac() const {
+    CB_MEM_TINY unsigned tell_frac() const {
         unsigned nbits = (unsigned)nbits_total << 3;
         int l = ec_ilog(rng);
         unsigned r = rng >> (l - 16);
@@ -294,7 +294,7 @@ struct EcEnc {
         unsigned window = end_window;
         int used = nend_bits;
         if (used + (int)nb > kEcWindow) {
-            do {
+            CB_NOUNROLL do {
                 error |= write_byte_at_end(window & kEcSymMax);
                 window >>= kEcSymBits;
                 used -= kEcSymBits;

@@ -82,7 +82,7 @@ CB_DEV int band_reorder_team(TM tm, int16_t *X, int N, int B, int tf_change, int
 }
 // the same bookkeeping without the vector work (the chains need B)
 CB_DEV int band_reorder_B(int N, int B, int tf_change) {
-    int N_B = (int)udiv((unsigned)N, (unsigned)B);
+    int N_B = N >> celt_ilog2(B);                 // B is 1, 2, 4 or 8
     int recombine = 0;
     if (tf_change > 0) recombine = tf_change;
     B >>= recombine;
@@ -189,6 +189,26 @@ CB_DEV void band_prep_team(TM tm, int16_t *Xall, const int *bandE, const int *tf
     }
 }
 
+// ---- the walk's scalar state --------------------------------------------------------------------------------------------------
+struct WalkCtx {
+    const BandPrep *prep;
+    int i, intensity, spread, remaining_bits;
+};
+struct WalkFrame {
+    int off, N, b, B, LM, h;
+    int mbits, sbits, itheta, rebalance0, mid_first, stage;
+};
+// The scalar state of a team's walk.  In the warp-per-stream walk every lane runs the scalar code with identical values; kept in
+// registers / on the stack that is 32 private copies of the coder, the partition stack and the band context per warp — half a KB
+// of local memory per LANE, 28 warps per SM: far beyond L1 (profiles/r2b_pipe_walk: 29 % of the stalls were local loads that
+// missed).  So the team keeps ONE copy in shared memory: every lane loads the same word (a broadcast) and stores the same value.
+struct WalkShared {
+    EcEnc ec;
+    WalkCtx w;
+    SplitCtx split;
+    WalkFrame st[5];
+};
+
 // ---- the scalar chain ---------------------------------------------------------------------------------------------------------
 
 // A range coder that only knows how many bits have been spent: (rng, nbits_total) of entenc.c, no bytes.
@@ -256,6 +276,12 @@ struct SpecPolicy {
     TellCoder ec;
     LeafList *list;
     int cur_band;
+    WalkCtx wc;
+    SplitCtx sc;
+    WalkFrame fr[5];
+    CB_MEM WalkCtx &wctx() { return wc; }
+    CB_MEM SplitCtx &split() { return sc; }
+    CB_MEM WalkFrame *frames() { return fr; }
     CB_MEM unsigned tell_frac() const { return ec.tell_frac(); }
     CB_MEM void encode(unsigned fl, unsigned fh, unsigned ft) { ec.encode(fl, fh, ft); }
     CB_MEM void uint_(unsigned fl, unsigned ft) { ec.uint_(fl, ft); }
@@ -292,6 +318,12 @@ struct ExactPolicy {
     PvqScratch *ps;            // thread scratch of the in-thread search
     int cursor;
     int misses;
+    WalkCtx wc;
+    SplitCtx sc;
+    WalkFrame fr[5];
+    CB_MEM WalkCtx &wctx() { return wc; }
+    CB_MEM SplitCtx &split() { return sc; }
+    CB_MEM WalkFrame *frames() { return fr; }
     CB_MEM unsigned tell_frac() const { return ec.tell_frac(); }
     CB_MEM void encode(unsigned fl, unsigned fh, unsigned ft) { ec.encode(fl, fh, ft); }
     CB_MEM void uint_(unsigned fl, unsigned ft) { ec.uint_(fl, ft); }
@@ -339,10 +371,14 @@ struct ExactPolicy {
 template <class TM>
 struct InlinePolicy {
     TM tm;
-    EcEnc ec;
+    WalkShared *sh;            // the team's one copy of the scalar state (team-shared memory)
+    EcEnc &ec;                 // = sh->ec
     int16_t *Xall;             // the stream's prepared vectors (team-shared memory)
     const BandPrep *prep;
     PvqScratch *ps;
+    CB_MEM WalkCtx &wctx() { return sh->w; }
+    CB_MEM SplitCtx &split() { return sh->split; }
+    CB_MEM WalkFrame *frames() { return sh->st; }
     CB_MEM unsigned tell_frac() const { return ec.tell_frac(); }
     CB_MEM void encode(unsigned fl, unsigned fh, unsigned ft) { ec.encode(fl, fh, ft); }
     CB_MEM void uint_(unsigned fl, unsigned ft) { ec.uint_(fl, ft); }
@@ -353,14 +389,12 @@ struct InlinePolicy {
         ec.bits((unsigned)(c ? wneg(d) < 0 : d < 0), 1);
     }
     CB_MEM void begin_band(int) { tm.phase(); }
-    CB_MEM void leaf(int, int off, int N, int K, int B, int spread) { alg_quant(tm, Xall + off, N, K, spread, B, ec, *ps); }
+    CB_MEM void leaf(int, int off, int N, int K, int B, int spread) {
+        alg_quant(tm, Xall + off, N, K, spread, B, ec, *ps);
+        tm.sync();             // the lanes go on through the scalar state together
+    }
     CB_MEM void finish() {}
     CB_MEM void skip_bands(int n) { CB_NOUNROLL for (int i = 0; i < n; i++) tm.phase(); }   // every warp passes kNbEBands phase()s per frame
-};
-
-struct WalkCtx {
-    const BandPrep *prep;
-    int i, intensity, spread, remaining_bits;
 };
 
 // compute_theta, encoder half (bands.c:645-817), given the raw angle
@@ -408,11 +442,6 @@ CB_DEV_NOINLINE void theta_code(P &p, WalkCtx &w, SplitCtx &sctx, int itheta, in
     sctx.inv = inv; sctx.imid = imid; sctx.iside = iside; sctx.delta = delta; sctx.itheta = itheta; sctx.qalloc = qalloc;
 }
 
-struct WalkFrame {
-    int off, N, b, B, LM, h;
-    int mbits, sbits, itheta, rebalance0, mid_first, stage;
-};
-
 // quant_band (bands.c:1044-1170) on vector v of the band, positioned at `off`: the reordering was done by prep, the partition
 // (bands.c:864-1040) is walked with prep's angle tree
 template <class P>
@@ -426,7 +455,7 @@ CB_DEV_NOINLINE void walk_band_vector(P &p, WalkCtx &w, int v, int off, int N, i
     }
     B = band_reorder_B(N, B, tf_change);
     const int16_t *tree = w.prep->tree[w.i][v];
-    WalkFrame st[5];
+    WalkFrame *st = p.frames();
     int sp = 0;
     st[0].off = off; st[0].N = N; st[0].b = b; st[0].B = B; st[0].LM = LM; st[0].h = 0; st[0].stage = 0;
     while (sp >= 0) {
@@ -434,7 +463,7 @@ CB_DEV_NOINLINE void walk_band_vector(P &p, WalkCtx &w, int v, int off, int N, i
         if (f.stage == 0) {
             const uint8_t *cache = pulse_cache(w.i, f.LM);
             if (f.LM != -1 && f.b > cache[cache[0]] + 12 && f.N > 2) {
-                SplitCtx s;
+                SplitCtx &s = p.split();
                 const int n = f.N >> 1, lm = f.LM - 1, B0 = f.B;
                 const int Bn = (B0 + 1) >> 1;
                 int bb = f.b;
@@ -496,7 +525,7 @@ CB_DEV void band_walk(P &p, const BandPrep &prep, int end, int C, const int *pul
                       const int *tf_res, int total_bits, int balance, int LM, int codedBands) {
     const int M = 1 << LM;
     const int B = shortBlocks ? M : 1;
-    WalkCtx w;
+    WalkCtx &w = p.wctx();
     w.prep = &prep; w.intensity = intensity; w.spread = spread;
     CB_NOUNROLL for (int i = 0; i < end; i++) {
         w.i = i;
@@ -532,7 +561,11 @@ CB_DEV void band_walk(P &p, const BandPrep &prep, int end, int C, const int *pul
             } else {
                 SplitCtx s;
                 int bs = b;
-                theta_code(p, w, s, prep.theta_st[i], N, &bs, B, LM, 1);
+                {
+                    SplitCtx &sr = p.split();   // the nested walks reuse the policy's split context: keep this band's own copy
+                    theta_code(p, w, sr, prep.theta_st[i], N, &bs, B, LM, 1);
+                    s = sr;
+                }
                 // itheta == 0: the band was turned into its intensity mid (XB), the side is empty
                 const int vm = s.itheta == 0 ? 2 : 0;
                 const int offM = s.itheta == 0 ? offB : offX;

@@ -196,7 +196,7 @@ static int g_dbg_tell[3][32]; static unsigned g_dbg_rng[3][32]; static int g_dbg
 #endif
 // One residue class of exp_rotation1 (vq.c:43-67): the pairs (i, i+stride) with i = r (mod stride) form an independent chain.
 // Each sweep carries the element it shares with the next pair in a register: one load and one store per step.
-CB_DEV void exp_rotation1_chain(int16_t *X, int len, int stride, int c, int s, int r) {
+CB_DEV_TINY void exp_rotation1_chain(int16_t *X, int len, int stride, int c, int s, int r) {
     const int ms = s16(-s);
     if (r < len - stride) {
         int i = r;
@@ -272,6 +272,22 @@ CB_DEV_NOINLINE unsigned pvq_encode_index(TM tm, int n, int K, const int16_t *y)
     return (unsigned)tm.sum((int)acc);
 }
 
+// The same sum when position j lives in lane j (n <= team width): iy = the lane's signed pulse count (0 on lanes >= n)
+template <class TM>
+CB_DEV unsigned pvq_index_lane(TM tm, int n, int K, int iy) {
+    const int j = tm.lane();
+    const int a = iabs(iy);
+    const int S = K - tm.exscan(a);   // S_j
+    unsigned acc = 0;
+    if (j < n - 1) {
+        acc = pvq_u(n - j, S - a);
+        if (iy < 0) acc += pvq_u(n - j, S + 1);
+    } else if (j == n - 1) {
+        acc = iy < 0;
+    }
+    return (unsigned)tm.sum((int)acc);
+}
+
 // Scratch of the PVQ search: y (doubled pulses), iy (pulses), sign, per band (N <= 176)
 struct PvqScratch {
     int16_t y[176], iy[176];
@@ -292,6 +308,17 @@ CB_DEV int pvq_pick(SoloTeam, const PvqBest &best, int) { return best.id; }
 // WarpTeam: a float estimate of num/den picks a provisional winner with one redux.max; its (num, den) are then compared
 // EXACTLY (the reference's cross-multiplication) on every lane.  No lane strictly better: the winner is the lowest id among the
 // exact ties (one redux.min).  Otherwise (the estimate mis-ordered two near-equal ratios) the exact shuffle tree decides.
+// the exact shuffle tree (rare: the float estimate mis-ordered two near-equal ratios); a real call, out of the hot loop's code
+static __device__ __noinline__ int pvq_pick_tree(WarpTeam tm, PvqBest best, int levels) {
+    CB_NOUNROLL for (int lv = 0; lv < levels; lv++) {
+        PvqBest o;
+        o.num = tm.shfl_xor(best.num, 1 << lv);
+        o.den = tm.shfl_xor(best.den, 1 << lv);
+        o.id = tm.shfl_xor(best.id, 1 << lv);
+        if (pvq_better(o, best)) best = o;
+    }
+    return tm.bcast(best.id, 0);
+}
 CB_DEV int pvq_pick(WarpTeam tm, PvqBest best, int levels) {
     const unsigned full = 0xffffffffu;
     const unsigned key = best.den > 0 ? __float_as_uint(__fdividef((float)best.num, (float)best.den)) + 1u : 0u;
@@ -301,14 +328,7 @@ CB_DEV int pvq_pick(WarpTeam tm, PvqBest best, int levels) {
     const int l = mul16_16(den_m, best.num), r = mul16_16(best.den, num_m);
     if (__ballot_sync(full, l > r) == 0u)
         return (int)__reduce_min_sync(full, l == r && best.den > 0 ? (unsigned)best.id : 0x7fffffffu);
-    CB_NOUNROLL for (int lv = 0; lv < levels; lv++) {
-        PvqBest o;
-        o.num = tm.shfl_xor(best.num, 1 << lv);
-        o.den = tm.shfl_xor(best.den, 1 << lv);
-        o.id = tm.shfl_xor(best.id, 1 << lv);
-        if (pvq_better(o, best)) best = o;
-    }
-    return tm.bcast(best.id, 0);
+    return pvq_pick_tree(tm, best, levels);
 }
 CB_DEV int pvq_pick(FreeWarpTeam tm, PvqBest best, int levels) { return pvq_pick(static_cast<WarpTeam>(tm), best, levels); }
 CB_DEV int pvq_pick(SyncWarpTeam tm, PvqBest best, int levels) { return pvq_pick(static_cast<WarpTeam>(tm), best, levels); }
@@ -321,8 +341,9 @@ CB_DEV int pvq_pick(SyncWarpTeam tm, PvqBest best, int levels) { return pvq_pick
 // alg_quant for N <= team width: position j lives in lane j's registers (|X|, y, iy, sign), nothing touches shared memory
 // until the pulse vector is handed to the indexer.  Same arithmetic and tie-breaking as the general version below.
 // (the search only: the pulse vector is left in ps.iy)
+// Returns the lane's signed pulse count.
 template <class TM>
-CB_DEV_NOINLINE void alg_quant_small_core(TM tm, int16_t *X, int N, int K, PvqScratch &ps) {
+CB_DEV_NOINLINE int alg_quant_small_core(TM tm, int16_t *X, int N, int K, PvqScratch &ps) {
     const int j = tm.lane();
     const bool active = j < N;
     int xj = active ? (int)X[j] : 0;
@@ -373,11 +394,13 @@ CB_DEV_NOINLINE void alg_quant_small_core(TM tm, int16_t *X, int N, int K, PvqSc
             iyj++;
         }
     }
+    const int iys = active ? (sgn < 0 ? -iyj : iyj) : 0;
     if (active) {
         X[j] = (int16_t)mul16_16(sgn, xj);
-        ps.iy[j] = (int16_t)(sgn < 0 ? -iyj : iyj);
+        ps.iy[j] = (int16_t)iys;
     }
     tm.sync();
+    return iys;
 }
 
 // the general search (any N), pulse vector left in ps.iy
@@ -469,8 +492,12 @@ CB_DEV_NOINLINE void alg_quant_core(TM tm, int16_t *X, int N, int K, PvqScratch 
 template <class TM>
 CB_DEV_NOINLINE void alg_quant(TM tm, int16_t *X, int N, int K, int spread, int B, EcEnc &enc, PvqScratch &ps) {
     exp_rotation_enc(tm, X, N, B, K, spread);
-    if (TM::W > 1 && N <= TM::W) alg_quant_small_core(tm, X, N, K, ps);
-    else alg_quant_core(tm, X, N, K, ps);
+    if (TM::W > 1 && N <= TM::W) {
+        const int iy = alg_quant_small_core(tm, X, N, K, ps);
+        enc.uint_(pvq_index_lane(tm, N, K, iy), pvq_v(N, K));
+        return;
+    }
+    alg_quant_core(tm, X, N, K, ps);
 #if defined(CB_WALK_DEBUG)
     { unsigned idx = pvq_encode_index(tm, N, K, ps.iy); if (g_dbg_log) printf("   [%s] leaf N=%d K=%d B=%d idx=%u\n", g_dbg_which == 0 ? "ref" : "slow", N, K, B, idx); }
 #endif

@@ -1239,6 +1239,7 @@ CB_DEV_NOINLINE int pipe_band_exact_finish(CbEncState *st, const PipeGeom &g, co
 struct WalkScratch {
     int16_t Xall[kXallStride];
     PvqScratch pvq;
+    WalkShared sh;
 };
 template <class TM>
 CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, const EncPlan &pl, EncPipeCtx &X, const BandPrep &P, const int16_t *XallG,
@@ -1254,17 +1255,20 @@ CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, con
         CB_TEAM_FOR(i, N, tm) S.Xall[v * kMaxFrame + i] = XallG[v * kMaxFrame + i];
     }
     tm.sync();
-    InlinePolicy<TM> p;
-    p.tm = tm;
-    p.ec = V.ec;
-    p.Xall = S.Xall;
-    p.prep = &P;
-    p.ps = &S.pvq;
+#if defined(CB_WALK_LOCAL)
+    WalkShared lsh;            // A/B: the scalar state as 32 private copies on the stack
+    WalkShared &SH = lsh;
+#else
+    WalkShared &SH = S.sh;
+#endif
+    SH.ec = V.ec;              // every lane stores the same values
+    tm.sync();
+    InlinePolicy<TM> p{tm, &SH, SH.ec, S.Xall, &P, &S.pvq};
     band_walk(p, P, X.cfg.end, C, X.pulses, V.shortBlocks, st->spread_decision, V.dual_stereo, st->intensity, X.tf_res,
               V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, g.LM, V.codedBands);
     tm.sync();
     if (tm.lane() == 0) {
-        V.ec = p.ec;
+        V.ec = SH.ec;
         V.ret = pipe_finish(st, g, pl, X, out);
     }
     tm.sync();

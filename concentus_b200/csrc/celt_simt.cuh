@@ -27,6 +27,16 @@
 #define CB_MATH __device__ __forceinline__
 #define CB_NOUNROLL
 #endif
+// CB_TINY_CODE (the encoder pipeline's kernels, on top of CB_SMALL_CODE): the band-walk kernel's hot set was 46 KB of SASS against a
+// 32 KB instruction cache per SM (33 % of its warp samples "no instruction"), so the range coder's renormalisation, ec_tell_frac
+// and the rotation chain become real calls shared by their callers.
+#if defined(CB_TINY_CODE)
+#define CB_MEM_TINY __device__ __noinline__
+#define CB_DEV_TINY static __device__ __noinline__
+#else
+#define CB_MEM_TINY __device__ __forceinline__
+#define CB_DEV_TINY __device__ __forceinline__
+#endif
 #else
 #define CB_DEV static inline
 #define CB_MEM inline
@@ -36,6 +46,8 @@
 #define CB_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
 #define CB_MATH static inline
 #define CB_NOUNROLL
+#define CB_MEM_TINY inline
+#define CB_DEV_TINY static inline
 struct int4 { int x, y, z, w; };   // host simulation stand-ins for the CUDA vector types
 struct int2 { int x, y; };
 #endif
@@ -65,6 +77,12 @@ struct WarpTeam {
     int lane_;
     CB_MEM int lane() const { return lane_; }
     CB_MEM void sync() const { __syncwarp(); }
+    // warp-wide reductions: one redux.sync each (wrapping 32-bit add, signed max, or) instead of a five-step shuffle tree
+#if !defined(CB_NO_REDUX)
+    CB_MEM int sum(int v) const { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
+    CB_MEM int max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+    CB_MEM unsigned bor(unsigned v) const { return __reduce_or_sync(0xffffffffu, v); }
+#else
     CB_MEM int sum(int v) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -80,6 +98,7 @@ struct WarpTeam {
         for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
         return v;
     }
+#endif
     CB_MEM int bcast(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
     CB_MEM int shfl_xor(int v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
     // Phase boundary of a frame: with CB_PHASE_SYNC the warps of a block (each on its own stream) wait for each other here,

@@ -6,6 +6,9 @@
 // thread-per-stream stages (a few hundred warps, latency bound) of one group hide behind the warp-per-stream stages of another.
 #if !defined(CB_PIPE_BIG_CODE)
 #define CB_SMALL_CODE 1   // celt_simt.cuh: medium helpers as real calls, loops not unrolled (A/B: -DCB_PIPE_BIG_CODE)
+#if !defined(CB_PIPE_NO_TINY)
+#define CB_TINY_CODE 1    // ... and the range coder's renormalisation / tell / the rotation chain as shared calls
+#endif
 #endif
 #include <cuda_runtime.h>
 
@@ -329,6 +332,138 @@ pipe_transient_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf) {
     if (worker && act) ctx[ws].v.mask_metric[wc] = transient_finish_row(row, len, hp.mx, hp.mn);
 }
 
+// ---- K2b, second version: the same analysis with the chains kept short ------------------------------------------------------------
+// The first version spent 190 us per frame step on 8,192 threads: every step of its recurrences waited for a shared-memory load and
+// a tile hand-over.  Here a block still takes 32 channels, but
+//   A  lane r of warp 0 runs channel r's high-pass straight from global memory with 16-byte loads one step ahead of the chain
+//      (a 128-byte line serves 32 steps out of L1) and stores pairs of int16 results;
+//   B  all 128 threads square and add the pairs (four threads per channel) — position-parallel, the mean is a wrapping sum;
+//   C  lane r of warp 0 runs the forward and the backward follower on 32-bit words (two values per load), unrolled so that the
+//      loads are issued ahead of the chain;
+//   D  all threads: the unmasking sum, four threads per channel.
+enum { kTr2Row = kMaxFrame + kOverlap + 2, kTr2E = (kMaxFrame + kOverlap) / 2 + 2 };   // int16 strides: 2 * odd words
+static_assert((kTr2Row / 2) % 2 == 1 && (kTr2E / 2) % 2 == 1, "row strides must be an odd number of words");
+constexpr int kSmemTransient2 = 32 * (kTr2Row + kTr2E) * 2;
+__global__ void __launch_bounds__(128)
+pipe_transient2_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf) {
+    extern __shared__ __align__(16) int smt[];
+    int16_t *rows = reinterpret_cast<int16_t *>(smt);          // [32][kTr2Row]
+    int16_t *Es = rows + 32 * kTr2Row;                          // [32][kTr2E]
+    __shared__ int s_mx[32], s_mn[32], s_act[32], s_maxE[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p0 = blockIdx.x * 32;
+    const int npairs = g.n * g.CC;
+    const int nvalid = npairs - p0 < 32 ? npairs - p0 : 32;
+    const int len = g.N + kOverlap, len2 = len / 2;
+    // ---- A ----
+    if (warp == 0) {
+        bool act = false;
+        int mx = 0, mn = 0;
+        if (lane < nvalid) {
+            const int ws = (p0 + lane) / g.CC, wc = (p0 + lane) - ws * g.CC;
+            act = ctx[ws].code && ctx[ws].cfg.complexity >= 1;
+            if (act) {
+                const int4 *src = reinterpret_cast<const int4 *>(buf[ws].in + wc * len);
+                int *row = reinterpret_cast<int *>(rows + lane * kTr2Row);
+                int mem0 = 0, mem1 = 0;
+                const int nq = len >> 2;
+                int4 v = src[0];
+#pragma unroll 2
+                for (int k = 0; k < nq; k++) {
+                    const int4 nx = src[k + 1 < nq ? k + 1 : k];
+                    int t[4];
+                    const int xs[4] = {v.x >> 12, v.y >> 12, v.z >> 12, v.w >> 12};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int x = xs[j];
+                        const int y = wadd(mem0, x);
+                        mem0 = wsub(wadd(mem1, y), shl32(x, 1));
+                        mem1 = wsub(x, y >> 1);
+                        t[j] = 4 * k + j < 12 ? 0 : s16(y >> 2);
+                        mx = imax(mx, t[j]);
+                        mn = imin(mn, t[j]);
+                    }
+                    row[2 * k] = (t[0] & 0xffff) | (t[1] << 16);
+                    row[2 * k + 1] = (t[2] & 0xffff) | (t[3] << 16);
+                    v = nx;
+                }
+            }
+        }
+        s_act[lane] = act;
+        s_mx[lane] = mx;
+        s_mn[lane] = mn;
+    }
+    __syncthreads();
+    // ---- B ----
+    const int r = tid >> 2, q = tid & 3;
+    const bool act = s_act[r] != 0;
+    int mean = 0;
+    if (act) {
+        const int shift = 14 - celt_ilog2(1 + imax(s_mx[r], -s_mn[r]));
+        const int *row = reinterpret_cast<const int *>(rows + r * kTr2Row);
+        int16_t *E = Es + r * kTr2E;
+        for (int i = q; i < len2; i += 4) {
+            const int w = row[i];
+            int a = s16(w), b = w >> 16;
+            if (shift != 0) {   // SHL16 with a NEGATIVE count (maxabs == 32768): what the reference's C expression does on x86
+                a = (int16_t)((unsigned)(uint16_t)a << (shift & 31));
+                b = (int16_t)((unsigned)(uint16_t)b << (shift & 31));
+            }
+            const int x2 = s16(pshr32(wadd(mul16_16(a, a), mul16_16(b, b)), 16));
+            E[i] = (int16_t)x2;
+            mean = wadd(mean, x2);
+        }
+    }
+    mean = wadd(mean, __shfl_xor_sync(0xffffffffu, mean, 1));
+    mean = wadd(mean, __shfl_xor_sync(0xffffffffu, mean, 2));
+    __syncthreads();
+    // ---- C ----
+    if (warp == 0 && s_act[lane]) {
+        int *Ew = reinterpret_cast<int *>(Es + lane * kTr2E);
+        const int nw = len2 >> 1;
+        int mem0 = 0;
+#pragma unroll 4
+        for (int k = 0; k < nw; k++) {
+            const int w = Ew[k];
+            mem0 = s16(mem0 + pshr32(s16(w) - mem0, 4));
+            const int lo = mem0;
+            mem0 = s16(mem0 + pshr32((w >> 16) - mem0, 4));
+            Ew[k] = (lo & 0xffff) | (mem0 << 16);
+        }
+        mem0 = 0;
+        int maxE = 0;
+#pragma unroll 4
+        for (int k = nw - 1; k >= 0; k--) {
+            const int w = Ew[k];
+            mem0 = s16(mem0 + pshr32((w >> 16) - mem0, 3));
+            const int hi = mem0;
+            maxE = imax(maxE, mem0);
+            mem0 = s16(mem0 + pshr32(s16(w) - mem0, 3));
+            maxE = imax(maxE, mem0);
+            Ew[k] = (mem0 & 0xffff) | (hi << 16);
+        }
+        s_maxE[lane] = maxE;
+    }
+    __syncthreads();
+    // ---- D ----
+    int unmask = 0;
+    if (act) {
+        const int m = mul16_16(celt_sqrt(mean), celt_sqrt(mul16_16(s_maxE[r], len2 >> 1)));
+        const int norm = shl32(len2, 6 + 14) / wadd(1, m >> 1);
+        const int16_t *E = Es + r * kTr2E;
+        for (int i = 12 + 4 * q; i < len2 - 5; i += 16) {
+            const int id = imax(0, imin(127, mul16_32_q15(E[i] + 1, norm)));
+            unmask += kInvTable[id];
+        }
+    }
+    unmask += __shfl_xor_sync(0xffffffffu, unmask, 1);
+    unmask += __shfl_xor_sync(0xffffffffu, unmask, 2);
+    if (act && q == 0) {
+        const int ws = (p0 + r) / g.CC, wc = (p0 + r) - ws * g.CC;
+        ctx[ws].v.mask_metric[wc] = 64 * unmask * 4 / (6 * (len2 - 17));
+    }
+}
+
 // ---- K3: one warp per stream ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
 pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, EncPipeBuf *buf) {
@@ -527,6 +662,7 @@ struct PipeCtx {
     int chunk = 16;
     int walk_mode = 0;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band
     int scalar_l = 2;           // streams per warp in the thread-per-stream stages
+    int transient_v = 2;        // transient analysis kernel: 2 = short chains (pipe_transient2_kernel), 1 = the tiled first version (A/B)
     int split_bands = 2;        // the band loop as 2: prep + one inline walk; 1: prep / chain-S / leaves / chain-X; 0: one stage (A/B)
     Group g[kMaxGroups];
     cudaEvent_t ev_fork = nullptr;
@@ -570,6 +706,8 @@ bool pipe_init() {
     b2p_lut_kernel<<<((kMaxLM + 2) * kNbEBands * kB2pBits + 255) / 256, 256>>>();
     cudaDeviceSynchronize();
     cudaFuncSetAttribute(pipe_transient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient);
+    cudaFuncSetAttribute(pipe_transient2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient2);
+    if (const char *e = getenv("CB200_ENC_TRANSIENT")) pc.transient_v = atoi(e);
     if (const char *e = getenv("CB200_ENC_SCALAR_L")) pc.scalar_l = atoi(e);
     if (pc.scalar_l != 1 && pc.scalar_l != 2 && pc.scalar_l != 4) pc.scalar_l = 2;
     set_scalar_smem<1>(); set_scalar_smem<2>(); set_scalar_smem<4>();
@@ -631,7 +769,10 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                              (const FeFrame *)G.fe[b].p, (EncPipeCtx *)G.ctx.p, c.d_data)
             pipe_comb_kernel<<<cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, fi, (const int *)G.P[b].p, (EncPipeCtx *)G.ctx.p,
                                                                                           (EncPipeBuf *)G.buf.p);
-            pipe_transient_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p);
+            if (pc.transient_v == 2)
+                pipe_transient2_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient2, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p);
+            else
+                pipe_transient_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p);
             pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
             CB_SCALAR_LAUNCH(pipe_decide_kernel, smem_head_ctx, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p)
             if (!pc.split_bands) {

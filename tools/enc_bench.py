@@ -23,7 +23,8 @@ uniq = min(n, 64)
 base = [O.test_signal(fs * F, ch, 500 + i, ("music", "tone", "clicks", "music")[i % 4]) for i in range(uniq)]
 pcm = np.concatenate([base[i % uniq] for i in range(n)])
 enc = cb.EncoderBatch(n, 48000, ch, bitrate=br, vbr=1, cvbr=0, complexity=10)
-for rep in range(3):
+best = 1e30
+for rep in range(int(os.environ.get("REPS", "3"))):
     t0 = time.time()
     d, l = enc.encode_span(pcm, F, fs)
     t1 = time.time()
@@ -31,6 +32,8 @@ for rep in range(3):
     audio_s = n * F * fs / 48000.0
     print("rep %d: kernel %.1f ms -> %.0fx realtime (e2e %.0fx), mean packet %.1f B, errors %d" % (
         rep, ms, audio_s / (ms * 1e-3), audio_s / (t1 - t0), l[l > 0].mean(), int((l < 0).sum())))
+    if rep > 0: best = min(best, ms)
+print("best kernel %.1f ms -> %.0fx realtime" % (best, audio_s / (best * 1e-3)))
 # spot-check parity on a few streams (first span only is comparable: the state carried on)
 enc.close()
 enc = cb.EncoderBatch(n, 48000, ch, bitrate=br, vbr=1, cvbr=0, complexity=10)
