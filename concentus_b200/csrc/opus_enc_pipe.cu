@@ -38,6 +38,62 @@ struct PipeBufs {              // device views of one group's buffers
     EncPipeBuf *buf;           // [n]
 };
 
+// ---- per-stream dataflow between the kernels of a frame step ---------------------------------------------------------------------
+// Stream-ordered launches make every kernel wait for the SLOWEST stream of its predecessor (a stream's cost varies with its content:
+// the average warp of the band walk is done at 78 % of the kernel's time), and the thread-per-stream stages leave the machine idle.
+// With Flow the kernels of a chunk are launched with programmatic stream serialisation: a kernel's blocks may start as soon as every
+// block of the previous kernel has STARTED, and what a stream's stage really needs — the previous stage of the SAME stream — is
+// tracked in a per-stream progress counter: a stage waits until the counter shows its predecessor done (acquire) and adds its own
+// unit when its results are written (fence + atomic).  Every earlier kernel is fully resident by the time a block can spin, so the
+// spin always ends; it is bounded anyway, and a time-out only raises a flag the host turns into OPUS_INTERNAL_ERROR.
+struct Flow {
+    int *prog;       // [n] units completed per stream since the call began; nullptr: plain stream-ordered launches
+    int need;        // units that must be complete before this stage may touch the stream
+    int *err;        // raised when a wait timed out (never in a correct run)
+    int open;        // let the next kernel of the stream start early (griddepcontrol.launch_dependents)
+};
+__device__ __forceinline__ void flow_open(const Flow &fl) {
+#if defined(__CUDA_ARCH__)
+    if (fl.open) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void flow_wait_one(const Flow &fl, int s) {
+    const int *p = fl.prog + s;
+    int v, spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if (v >= fl.need) break;
+        __nanosleep(200);
+        if (++spins > (1 << 21) || *(volatile int *)fl.err) { atomicExch(fl.err, 1); break; }
+    }
+}
+// warp-per-item kernels: lane 0 waits for the warp's stream
+__device__ __forceinline__ void flow_wait_warp(const Flow &fl, int s) {
+    if (!fl.prog) return;
+    if ((threadIdx.x & 31) == 0) flow_wait_one(fl, s);
+    __syncwarp();
+    __threadfence();
+}
+__device__ __forceinline__ void flow_done_warp(const Flow &fl, int s) {
+    if (!fl.prog) return;
+    __threadfence();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) atomicAdd(fl.prog + s, 1);
+}
+// block-per-group-of-streams kernels: thread k waits for / signals stream s0 + k
+__device__ __forceinline__ void flow_wait_block(const Flow &fl, int s0, int nvalid) {
+    if (!fl.prog) return;
+    if ((int)threadIdx.x < nvalid) flow_wait_one(fl, s0 + threadIdx.x);
+    __syncthreads();
+    __threadfence();
+}
+__device__ __forceinline__ void flow_done_block(const Flow &fl, int s0, int nvalid) {
+    if (!fl.prog) return;
+    __threadfence();
+    __syncthreads();
+    if ((int)threadIdx.x < nvalid) atomicAdd(fl.prog + s0 + threadIdx.x, 1);
+}
+
 // ---- staging for the thread-per-stream kernels ------------------------------------------------------------------------------------
 // A scalar stage walks a few KB of per-stream data with dependent accesses; from global memory every one of them costs an L2 round
 // trip (the first version of K4 ran 21 cycles per instruction).  So a block takes 32 streams: all its 128 threads copy the streams'
@@ -253,7 +309,7 @@ pipe_fe2_kernel(PipeGeom g, int nfr, const EncPlan *plans, const int *P, FeFrame
 template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
 pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, const FeFrame *fe,
-                 EncPipeCtx *ctx, uint8_t *data) {
+                 EncPipeCtx *ctx, uint8_t *data, Flow fl) {
     extern __shared__ __align__(16) int sm[];
     constexpr int kScalarT = 8 * L;
     __shared__ int *p_head[kScalarT], *p_ctx[kScalarT];
@@ -261,6 +317,8 @@ pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
     const int t0 = blockIdx.x * kScalarT;
     const int tid = (threadIdx.x & 31) < L ? (int)(threadIdx.x >> 5) * L + (int)(threadIdx.x & 31) : kScalarT;   // the stream this thread works on, if any
     const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
+    flow_open(fl);
+    flow_wait_block(fl, t0, nvalid);
     if (tid < nvalid) { p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]); p_ctx[tid] = reinterpret_cast<int *>(ctx + t0 + tid); }
     __syncthreads();
     stage_copy_in(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
@@ -274,18 +332,22 @@ pipe_head_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
     __syncthreads();
     stage_copy_out_head(sm_head, p_head, nvalid);
     stage_copy_out(sm_ctx, kCtxStride, kHeadCtxWords, p_ctx, nvalid);   // K1 writes the leading scalars of the context only
+    flow_done_block(fl, t0, nvalid);
 }
 
 // ---- K2a: comb pre-filter, one warp per (stream, channel) -----------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32)
-pipe_comb_kernel(CbEncState *pool, const int *slots, PipeGeom g, int fi, const int *P, EncPipeCtx *ctx, EncPipeBuf *buf) {
+pipe_comb_kernel(CbEncState *pool, const int *slots, PipeGeom g, int fi, const int *P, EncPipeCtx *ctx, EncPipeBuf *buf, Flow fl) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * CB_PIPE_WPB + wib;
+    flow_open(fl);
     if (w >= g.n * g.CC) return;
     const int s = w / g.CC, c = w - s * g.CC;
+    flow_wait_warp(fl, s);
     FreeWarpTeam tm{{lane}};
     const int *pre = P + ((size_t)s * g.CC + c) * g.pstride + fi * g.N;
     pipe_comb_channel(tm, pool + slots[s], g, ctx[s], pre, buf[s].in + c * (g.N + kOverlap), c, nullptr, nullptr);
+    flow_done_warp(fl, s);
 }
 
 // ---- K2b: transient_analysis, one THREAD per (stream, channel) ----------------------------------------------------------------
@@ -345,7 +407,7 @@ enum { kTr2Row = kMaxFrame + kOverlap + 2, kTr2E = (kMaxFrame + kOverlap) / 2 + 
 static_assert((kTr2Row / 2) % 2 == 1 && (kTr2E / 2) % 2 == 1, "row strides must be an odd number of words");
 constexpr int kSmemTransient2 = 32 * (kTr2Row + kTr2E) * 2;
 __global__ void __launch_bounds__(128)
-pipe_transient2_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf) {
+pipe_transient2_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf, Flow fl) {
     extern __shared__ __align__(16) int smt[];
     int16_t *rows = reinterpret_cast<int16_t *>(smt);          // [32][kTr2Row]
     int16_t *Es = rows + 32 * kTr2Row;                          // [32][kTr2E]
@@ -355,6 +417,12 @@ pipe_transient2_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf) {
     const int npairs = g.n * g.CC;
     const int nvalid = npairs - p0 < 32 ? npairs - p0 : 32;
     const int len = g.N + kOverlap, len2 = len / 2;
+    flow_open(fl);
+    if (fl.prog) {   // thread k waits for the stream of channel p0 + k
+        if (tid < nvalid) flow_wait_one(fl, (p0 + tid) / g.CC);
+        __syncthreads();
+        __threadfence();
+    }
     // ---- A ----
     if (warp == 0) {
         bool act = false;
@@ -458,27 +526,34 @@ pipe_transient2_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf) {
     }
     unmask += __shfl_xor_sync(0xffffffffu, unmask, 1);
     unmask += __shfl_xor_sync(0xffffffffu, unmask, 2);
-    if (act && q == 0) {
+    if (q == 0 && r < nvalid) {
         const int ws = (p0 + r) / g.CC, wc = (p0 + r) - ws * g.CC;
-        ctx[ws].v.mask_metric[wc] = 64 * unmask * 4 / (6 * (len2 - 17));
+        if (act) ctx[ws].v.mask_metric[wc] = 64 * unmask * 4 / (6 * (len2 - 17));
+        if (fl.prog) {
+            __threadfence();
+            atomicAdd(fl.prog + ws, 1);
+        }
     }
 }
 
 // ---- K3: one warp per stream ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
-pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, EncPipeBuf *buf) {
+pipe_transform_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, EncPipeBuf *buf, Flow fl) {
     __shared__ __align__(16) TransformScratch sm[CB_PIPE_WPB];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    flow_open(fl);
     if (s >= g.n) return;
+    flow_wait_warp(fl, s);
     FreeWarpTeam tm{{lane}};
     pipe_transform(tm, pool + slots[s], g, ctx[s], buf[s], sm[wib]);
+    flow_done_warp(fl, s);
 }
 
 // ---- K4 ---------------------------------------------------------------------------------------------------------------------
 template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
-pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx) {
+pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *ctx, Flow fl) {
     extern __shared__ __align__(16) int sm[];
     constexpr int kScalarT = 8 * L;
     __shared__ int *p_head[kScalarT], *p_ctx[kScalarT];
@@ -486,6 +561,8 @@ pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *c
     const int t0 = blockIdx.x * kScalarT;
     const int tid = (threadIdx.x & 31) < L ? (int)(threadIdx.x >> 5) * L + (int)(threadIdx.x & 31) : kScalarT;   // the stream this thread works on, if any
     const int nvalid = g.n - t0 < kScalarT ? g.n - t0 : kScalarT;
+    flow_open(fl);
+    flow_wait_block(fl, t0, nvalid);
     if (tid < nvalid) { p_head[tid] = reinterpret_cast<int *>(pool + slots[t0 + tid]); p_ctx[tid] = reinterpret_cast<int *>(ctx + t0 + tid); }
     __syncthreads();
     stage_copy_in(sm_head, kHeadStride, kHeadWords, p_head, nvalid);
@@ -496,6 +573,7 @@ pipe_decide_kernel(CbEncState *pool, const int *slots, PipeGeom g, EncPipeCtx *c
     __syncthreads();
     stage_copy_out_head(sm_head, p_head, nvalid);
     stage_copy_out(sm_ctx, kCtxStride, kCtxWords, p_ctx, nvalid);
+    flow_done_block(fl, t0, nvalid);
 }
 
 // ---- K5: one warp per stream ------------------------------------------------------------------------------------------------
@@ -518,13 +596,17 @@ pipe_bands_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
 
 // ---- K5a..K5d: the band loop as prep / chain-S / leaves / chain-X (celt_enc_bandpipe.cuh) ----------------------------------------
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32, 7)
-pipe_prep_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, const EncPipeBuf *buf, BandPrep *prep, int16_t *xall) {
+pipe_prep_kernel(const CbEncState *pool, const int *slots, PipeGeom g, const EncPipeCtx *ctx, const EncPipeBuf *buf, BandPrep *prep, int16_t *xall,
+                 Flow fl) {
     __shared__ __align__(16) PrepScratch sm[CB_PIPE_WPB];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * CB_PIPE_WPB + wib;
+    flow_open(fl);
     if (s >= g.n) return;
+    flow_wait_warp(fl, s);
     FreeWarpTeam tm{{lane}};
     pipe_band_prep(tm, pool + slots[s], g, ctx[s], buf[s], prep[s], xall + (size_t)s * kXallStride, sm[wib]);
+    flow_done_warp(fl, s);
 }
 template <int L>
 __global__ void __launch_bounds__(kScalarThreads)
@@ -598,15 +680,23 @@ pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
 template <int WPB, bool SYNC>
 __global__ void __launch_bounds__(WPB * 32, 28 / WPB)
 pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
-                 const BandPrep *prep, const int16_t *xall, uint8_t *data, int *rets, unsigned *ranges) {
+                 const BandPrep *prep, const int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, Flow fl) {
     extern __shared__ __align__(16) unsigned char smw[];
     WalkScratch *sm = reinterpret_cast<WalkScratch *>(smw);
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * WPB + wib;
+    flow_open(fl);
     if (s >= g.n) {
         if (SYNC)
             for (int i = 0; i < kNbEBands; i++) __syncthreads();
         return;
+    }
+    flow_wait_warp(fl, s);
+    // prep's results are produced while this kernel is already running (dataflow launches): they must not be read through the
+    // non-coherent path the compiler picks for memory a kernel provably never writes — so the kernel "may" write them.
+    if (g.n < 0) {
+        const_cast<BandPrep *>(prep)[s].hasB[0] = 0;
+        const_cast<int16_t *>(xall)[0] = 0;
     }
     CbEncState *st = pool + slots[s];
     const size_t k = (size_t)sidx[s] * g.F + f;
@@ -619,9 +709,11 @@ pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
         r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib], data + k * g.stride);
     }
     if (lane == 0) {
+        if (fl.prog && *(volatile int *)fl.err) r = -3;   // OPUS_INTERNAL_ERROR: a dataflow wait timed out somewhere in this launch
         rets[k] = r;
         if (ranges) ranges[k] = st->rangeFinal;
     }
+    flow_done_warp(fl, s);
 }
 
 __global__ void b2p_lut_kernel() {
@@ -654,14 +746,20 @@ enum { kMaxGroups = 8 };
 struct Group {
     cudaStream_t main = nullptr, side = nullptr;
     cudaEvent_t ev_fe[2] = {nullptr, nullptr}, ev_steps[2] = {nullptr, nullptr}, ev_done = nullptr;
-    DevBuf D, P[2], plans[2], fe[2], m0, ctx, buf, prep, leaves, xall;
+    DevBuf D, P[2], plans[2], fe[2], m0, ctx, buf, prep, leaves, xall, prog;
 };
 struct PipeCtx {
     bool init = false;
     int groups = 1;             // stream groups on separate CUDA streams (measured: no gain, the stages are issue bound with all streams resident)
-    int chunk = 16;
-    int walk_mode = 0;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band
+    int chunk = 8;              // frames per front-end chunk (measured 4..50: 8 is best, profiles/r2_encoder_ab.md)
+    int walk_mode = 3;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band (measured: 3)
     int scalar_l = 2;           // streams per warp in the thread-per-stream stages
+    int flow = 0;               // per-stream dataflow between the kernels of a frame step (struct Flow); 0: stream-ordered launches.
+                                // Measured (profiles/r2_encoder_ab.md): 8 % SLOWER than stream order — spinning blocks hold the slots ready
+                                // blocks need — and the band walk faults when it overlaps its predecessor; kept as an A/B knob only.
+    int flow_noopen = 0;                // debugging: kernels of a frame step that do not let their successor start early
+    int flow_mask = -1, flow_seq = 0;   // debugging: which of a frame step's seven kernels get the early launch
+    int *d_flow_err = nullptr;  // raised by a timed-out dataflow wait
     int transient_v = 2;        // transient analysis kernel: 2 = short chains (pipe_transient2_kernel), 1 = the tiled first version (A/B)
     int split_bands = 2;        // the band loop as 2: prep + one inline walk; 1: prep / chain-S / leaves / chain-X; 0: one stage (A/B)
     Group g[kMaxGroups];
@@ -689,10 +787,21 @@ bool pipe_init() {
     if (const char *e = getenv("CB200_ENC_SPLIT_BANDS")) pc.split_bands = atoi(e);
     if (cudaMalloc(&pc.d_stats, 2 * sizeof(int)) != cudaSuccess) return false;
     cudaMemset(pc.d_stats, 0, 2 * sizeof(int));
+    if (cudaMalloc(&pc.d_flow_err, sizeof(int)) != cudaSuccess) return false;
+    cudaMemset(pc.d_flow_err, 0, sizeof(int));
+    if (const char *e = getenv("CB200_ENC_FLOW")) pc.flow = atoi(e);
+    if (const char *e = getenv("CB200_ENC_FLOW_MASK")) pc.flow_mask = atoi(e);
+    if (const char *e = getenv("CB200_ENC_FLOW_NOOPEN")) pc.flow_noopen = atoi(e);
+    if (const char *e = getenv("CB200_ENC_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(e));
+    int prio_lo = 0, prio_hi = 0, prio = 1;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char *e = getenv("CB200_ENC_PRIO")) prio = atoi(e);
     for (int i = 0; i < kMaxGroups; i++) {
         Group &G = pc.g[i];
-        if (cudaStreamCreateWithFlags(&G.main, cudaStreamNonBlocking) != cudaSuccess) return false;
-        if (cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking) != cudaSuccess) return false;
+        // The frame steps are one-wave kernels that want every SM: their blocks go first; the front end of the next chunk (many
+        // short blocks) fills what is left instead of pushing a frame step's last blocks into a second wave.
+        if (cudaStreamCreateWithPriority(&G.main, cudaStreamNonBlocking, prio ? prio_hi : 0) != cudaSuccess) return false;
+        if (cudaStreamCreateWithPriority(&G.side, cudaStreamNonBlocking, prio ? prio_lo : 0) != cudaSuccess) return false;
         for (int b = 0; b < 2; b++) {
             cudaEventCreateWithFlags(&G.ev_fe[b], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&G.ev_steps[b], cudaEventDisableTiming);
@@ -717,12 +826,36 @@ bool pipe_init() {
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// A launch that may begin before the previous kernel of the stream has finished (programmatic stream serialisation) when `early`.
+template <typename... KArgs, typename... Args>
+void launch_flow(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool early, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = early && pc.flow == 1 ? 1 : 0;   // CB200_ENC_FLOW=2: the counters without the early launches (debugging)
+    if (early && pc.flow == 1 && pc.flow_mask >= 0) cfg.numAttrs = (pc.flow_mask >> (pc.flow_seq % 7)) & 1;
+    pc.flow_seq++;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // launch a thread-per-stream stage with the configured number of streams per warp
 #define CB_SCALAR_LAUNCH(KERNEL, SMEMFN, STREAM, ...)                                                                         \
     switch (pc.scalar_l) {                                                                                                    \
     case 4: KERNEL<4><<<cdiv(n, 32), kScalarThreads, SMEMFN(32), STREAM>>>(__VA_ARGS__); break;                               \
     case 2: KERNEL<2><<<cdiv(n, 16), kScalarThreads, SMEMFN(16), STREAM>>>(__VA_ARGS__); break;                               \
     default: KERNEL<1><<<cdiv(n, 8), kScalarThreads, SMEMFN(8), STREAM>>>(__VA_ARGS__); break;                                \
+    }
+#define CB_SCALAR_LAUNCH_FLOW(KERNEL, SMEMFN, STREAM, EARLY, ...)                                                             \
+    switch (pc.scalar_l) {                                                                                                    \
+    case 4: launch_flow(KERNEL<4>, cdiv(n, 32), kScalarThreads, SMEMFN(32), STREAM, EARLY, __VA_ARGS__); break;               \
+    case 2: launch_flow(KERNEL<2>, cdiv(n, 16), kScalarThreads, SMEMFN(16), STREAM, EARLY, __VA_ARGS__); break;               \
+    default: launch_flow(KERNEL<1>, cdiv(n, 8), kScalarThreads, SMEMFN(8), STREAM, EARLY, __VA_ARGS__); break;                \
     }
 
 // one group: streams [k0, k0+n) of the pipeline's list
@@ -742,6 +875,12 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
             return -7;
     const int *slots = c.d_slots + k0, *sidx = c.d_sidx + k0;
     int launches = 0;
+    const bool flow = pc.flow && pc.split_bands == 2 && pc.walk_mode == 0 && pc.transient_v == 2;
+
+    if (flow) {
+        if (!G.prog.reserve((size_t)n * sizeof(int))) return -7;
+        cudaMemsetAsync(G.prog.p, 0, (size_t)n * sizeof(int), G.main);
+    }
     const int nchunks = cdiv(nframes, Fc);
     const int tpb = 64;
     int prev_nfr = 0;
@@ -765,16 +904,46 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         cudaStreamWaitEvent(G.main, G.ev_fe[b], 0);
         for (int fi = 0; fi < nfr; fi++) {
             const int f = fbase + fi;
+            if (flow) {
+                // units a stream completes per frame: head 1, comb CC, transient CC, transform 1, decide 1, prep 1, walk 1
+                const int U = 5 + 2 * g.CC, base = (k * Fc + fi) * U;
+                int *prog = (int *)G.prog.p;
+                int kidx = 0;
+                auto FL = [&](int need) {
+                    Flow fl;
+                    fl.prog = prog; fl.need = base + need; fl.err = pc.d_flow_err;
+                    fl.open = pc.flow == 1 && !((pc.flow_noopen >> kidx++) & 1);
+                    return fl;
+                };
+                const bool chained = fi > 0;   // the chunk's first kernel waits for the front end's event: launched in stream order
+                CB_SCALAR_LAUNCH_FLOW(pipe_head_kernel, smem_head_ctx, G.main, chained, c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
+                                      (const FeFrame *)G.fe[b].p, (EncPipeCtx *)G.ctx.p, c.d_data, FL(0))
+                launch_flow(pipe_comb_kernel, cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main, true, c.pool, slots, g, fi, (const int *)G.P[b].p,
+                            (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, FL(1));
+                launch_flow(pipe_transient2_kernel, cdiv(n * g.CC, 32), 128, (size_t)kSmemTransient2, G.main, true, g, (EncPipeCtx *)G.ctx.p,
+                            (const EncPipeBuf *)G.buf.p, FL(1 + g.CC));
+                launch_flow(pipe_transform_kernel, cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main, true, c.pool, slots, g, (EncPipeCtx *)G.ctx.p,
+                            (EncPipeBuf *)G.buf.p, FL(1 + 2 * g.CC));
+                CB_SCALAR_LAUNCH_FLOW(pipe_decide_kernel, smem_head_ctx, G.main, true, c.pool, slots, g, (EncPipeCtx *)G.ctx.p, FL(2 + 2 * g.CC))
+                launch_flow(pipe_prep_kernel, cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main, true, (const CbEncState *)c.pool, slots, g,
+                            (const EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p, FL(3 + 2 * g.CC));
+                launch_flow(pipe_walk_kernel<4, false>, cdiv(n, 4), 4 * 32, 4 * sizeof(WalkScratch), G.main, true, c.pool, slots, sidx, g, f, fi,
+                            (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p, (const int16_t *)G.xall.p, c.d_data,
+                            c.d_rets, c.d_ranges, FL(4 + 2 * g.CC));
+                launches += 7;
+                continue;
+            }
+            const Flow nofl{nullptr, 0, nullptr, 0};
             CB_SCALAR_LAUNCH(pipe_head_kernel, smem_head_ctx, G.main, c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
-                             (const FeFrame *)G.fe[b].p, (EncPipeCtx *)G.ctx.p, c.d_data)
+                             (const FeFrame *)G.fe[b].p, (EncPipeCtx *)G.ctx.p, c.d_data, nofl)
             pipe_comb_kernel<<<cdiv(n * g.CC, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, fi, (const int *)G.P[b].p, (EncPipeCtx *)G.ctx.p,
-                                                                                          (EncPipeBuf *)G.buf.p);
+                                                                                          (EncPipeBuf *)G.buf.p, nofl);
             if (pc.transient_v == 2)
-                pipe_transient2_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient2, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p);
+                pipe_transient2_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient2, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p, nofl);
             else
                 pipe_transient_kernel<<<cdiv(n * g.CC, 32), 128, kSmemTransient, G.main>>>(g, (EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p);
-            pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p);
-            CB_SCALAR_LAUNCH(pipe_decide_kernel, smem_head_ctx, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p)
+            pipe_transform_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, nofl);
+            CB_SCALAR_LAUNCH(pipe_decide_kernel, smem_head_ctx, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p, nofl)
             if (!pc.split_bands) {
                 pipe_bands_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p,
                                                                                         (EncPipeCtx *)G.ctx.p, (EncPipeBuf *)G.buf.p, c.d_data, c.d_rets,
@@ -782,11 +951,11 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                 launches += 6;
             } else if (pc.split_bands == 2) {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
-                                                                                       (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
+                                                                                       (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p, nofl);
 #define CB_WALK_LAUNCH(WPB, SYNC)                                                                                                         \
     pipe_walk_kernel<WPB, SYNC><<<cdiv(n, WPB), WPB * 32, WPB * sizeof(WalkScratch), G.main>>>(                                            \
         c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p, (const int16_t *)G.xall.p, \
-        c.d_data, c.d_rets, c.d_ranges)
+        c.d_data, c.d_rets, c.d_ranges, nofl)
                 switch (pc.walk_mode) {
                 case 1: CB_WALK_LAUNCH(4, true); break;
                 case 2: CB_WALK_LAUNCH(7, true); break;
@@ -797,7 +966,7 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                 launches += 7;
             } else {
                 pipe_prep_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p,
-                                                                                       (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p);
+                                                                                       (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p, nofl);
                 CB_SCALAR_LAUNCH(pipe_spec_kernel, smem_spec, G.main, c.pool, slots, g, (EncPipeCtx *)G.ctx.p, (BandPrep *)G.prep.p, (LeafList *)G.leaves.p)
                 pipe_leaves_kernel<<<cdiv(n, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.main>>>(c.pool, slots, g, (const EncPipeCtx *)G.ctx.p, (LeafList *)G.leaves.p,
                                                                                          (const int16_t *)G.xall.p);
@@ -857,6 +1026,12 @@ int enc_pipe_enqueue(const EncPipeCall &c, cudaStream_t stream) {
         cudaEventRecord(Gr.ev_done, Gr.main);
         cudaStreamWaitEvent(stream, Gr.ev_done, 0);
     }
-    if (cudaGetLastError() != cudaSuccess) return -3;
+    {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            fprintf(stderr, "concentus_b200: encoder pipeline launch failed: %s\n", cudaGetErrorString(e));
+            return -3;
+        }
+    }
     return launches;
 }

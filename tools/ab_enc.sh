@@ -3,5 +3,5 @@
 # usage: tools/ab_enc.sh variant...     ("cur" = the in-tree library)
 for v in "$@"; do
   if [ "$v" = cur ]; then lib=/root/repo/concentus_b200/libconcentus_b200.so; else lib=/root/repo/build_variants/$v.so; fi
-  echo "$v: $(CB200_LIB=$lib REPS=5 python tools/enc_bench.py 4096 50 2>&1 | grep -E 'best|parity' | tr '\n' ' ')"
+  echo "$v: $(CB200_LIB=$lib python tools/enc_bench_dev.py 4096 ${FRAMES:-50} 2>&1 | grep -E "best" | tr '\n' ' ')"
 done
