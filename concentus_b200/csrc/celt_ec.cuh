@@ -223,7 +223,7 @@ struct EcEnc {
         }
     }
     // entenc.c:145-152
-    CB_MEM_TINY void normalize() {
+    CB_MEM void normalize_inl() {
         CB_NOUNROLL while (rng <= CB_EC_CODE_BOT) {
             carry_out((int)(val >> kEcCodeShift));
             val = (val << kEcSymBits) & (CB_EC_CODE_TOP - 1);
@@ -231,6 +231,9 @@ struct EcEnc {
             nbits_total += kEcSymBits;
         }
     }
+    // the band walk's symbols (encode / bit_logp / uint) share one copy of the loop under CB_TINY_CODE; the header symbols of the
+    // thread-per-stream stages (encode_bin / icdf / laplace) keep it inline: there a call is latency, not instruction-cache space
+    CB_MEM_TINY void normalize() { normalize_inl(); }
     // entenc.c:170-184
     CB_MEM void init(uint8_t *b, unsigned size) {
         buf = b; end_offs = 0; end_window = 0; nend_bits = 0;
@@ -268,7 +271,7 @@ struct EcEnc {
         } else {
             rng -= r * ((1u << bits) - fh);
         }
-        normalize();
+        normalize_inl();
     }
     // entenc.c:249-277
     CB_MEM_NOINLINE void bit_logp(int v, unsigned logp) {
@@ -287,7 +290,7 @@ struct EcEnc {
         } else {
             rng -= r * tab[s];
         }
-        normalize();
+        normalize_inl();
     }
     // entenc.c:346-384
     CB_MEM_NOINLINE void bits(unsigned fl, unsigned nb) {

@@ -758,6 +758,71 @@ struct TransformScratch {
     int16_t X[2 * kMaxFrame];
 };
 
+// tf_analysis metrics (celt_encoder.c:580-640) of every band at once.  tf_band_metric (celt_encoder.cuh) walks one band per lane:
+// the bands are 8 to 176 values wide, so a few lanes did nearly all of it (4.5 active lanes, 30 % of K3's instructions).  Here the
+// Haar steps run over the whole spectrum as one position-parallel pass (a band starts at a multiple of 2^LM, so the butterflies of
+// levels < LM never straddle bands; the extra level of the long-block case pairs blocks of 2^(LM+1) values, which only the
+// width-1 bands — excluded from that level — could break), and a band's L1 norm is a team sum.  Band b's running best lives in
+// lane b % W.  tmp / tmp1: team scratch for the analysed channel.  Returns the lane's share of tf_sum.
+template <class TM>
+CB_DEV void haar_pass_team(TM tm, int16_t *X, int p0, int p1, int stride) {
+    const int npairs = (p1 - p0) >> 1;
+    CB_TEAM_FOR(w, npairs, tm) {
+        const int blk = w / stride, i = w - blk * stride;
+        const int a = p0 + blk * 2 * stride + i, b = a + stride;
+        const int t1 = mul16_16(23170, X[a]);
+        const int t2 = mul16_16(23170, X[b]);
+        X[a] = (int16_t)pshr32(wadd(t1, t2), 15);
+        X[b] = (int16_t)pshr32(wsub(t1, t2), 15);
+    }
+    tm.sync();
+}
+template <class TM>
+CB_DEV int tf_metrics_team(TM tm, const int16_t *Xc, int effEnd, int LM, int isTransient, int bias, int16_t *tmp, int16_t *tmp1, int *metric) {
+    constexpr int BPL = (kNbEBands + TM::W - 1) / TM::W;   // bands per lane
+    int bestL1[BPL], bestLvl[BPL];
+    const int total = kEBands[effEnd] << LM;
+    int nnarrow = 0;                                       // the leading width-1 bands
+    while (nnarrow < effEnd && band_width(nnarrow) == 1) nnarrow++;
+    const int pw = kEBands[nnarrow] << LM;                 // first position of the wider bands
+    CB_TEAM_FOR(j, total, tm) tmp[j] = Xc[j];
+    tm.sync();
+    // L1 of every band of t at weight LMw; what(b, L1) is applied by the band's lane
+    auto all_bands = [&](const int16_t *t, int first, int LMw, auto what) {
+        CB_NOUNROLL for (int b = first; b < effEnd; b++) {
+            const int lo = kEBands[b] << LM, n = band_width(b) << LM;
+            int part = 0;
+            CB_TEAM_FOR(j, n, tm) part += iabs((int)t[lo + j]);
+            const int L1 = tm.sum(part);
+            if (tm.lane() == b % TM::W) what(BPL == 1 ? 0 : b / TM::W, mac16_32_q15(L1, LMw * bias, L1));
+        }
+    };
+    all_bands(tmp, 0, isTransient ? LM : 0, [&](int k, int L1) { bestL1[k] = L1; bestLvl[k] = 0; });
+    if (isTransient && nnarrow < effEnd) {
+        CB_TEAM_FOR(j, total - pw, tm) tmp1[pw + j] = tmp[pw + j];
+        tm.sync();
+        haar_pass_team(tm, tmp1, pw, total, 1 << LM);
+        all_bands(tmp1, nnarrow, LM + 1, [&](int k, int L1) { if (L1 < bestL1[k]) { bestL1[k] = L1; bestLvl[k] = -1; } });
+    }
+    CB_NOUNROLL for (int k = 0; k < LM + !isTransient; k++) {
+        const int Bw = isTransient ? LM - k - 1 : k + 1;
+        const int first = k < LM ? 0 : nnarrow;            // level LM: the long-block extra, not for the width-1 bands
+        if (first >= effEnd) break;
+        haar_pass_team(tm, tmp, k < LM ? 0 : pw, total, 1 << k);
+        all_bands(tmp, first, Bw, [&](int q, int L1) { if (L1 < bestL1[q]) { bestL1[q] = L1; bestLvl[q] = k + 1; } });
+    }
+    int tf_sum = 0;
+    CB_TEAM_FOR(i, effEnd, tm) {
+        const int q = BPL == 1 ? 0 : i / TM::W;
+        const int narrow = band_width(i) == 1;
+        int m = isTransient ? 2 * bestLvl[q] : -2 * bestLvl[q];
+        tf_sum += (isTransient ? LM : 0) - m / 2;
+        if (narrow && (m == 0 || m == -2 * LM)) m -= 1;
+        metric[i] = m;
+    }
+    return tf_sum;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // K3 — transform and analysis of one stream's frame (celt_encoder.c:1642-1880 plus the X-only halves of :1900-1990).
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -854,14 +919,7 @@ CB_DEV void pipe_transform(TM tm, CbEncState *st, const PipeGeom &g, EncPipeCtx 
     if (V.do_tf) {
         const int bias = mul16_16_q14(1311, imax(-4096, 8192 - V.tf_estimate));
         const int16_t *Xc = S.X + V.tf_chan * N;
-        int tf_sum = 0;
-        CB_TEAM_FOR(i, effEnd, tm) {
-            const int lo = kEBands[i] << LM;
-            const int Nb = band_width(i) << LM;
-            int term;
-            X.metric[i] = tf_band_metric(Xc + lo, Nb, band_width(i) == 1, isTransient, LM, bias, S.u.tf.tf_tmp + lo, S.u.tf.tf_tmp1 + lo, &term);
-            tf_sum += term;
-        }
+        int tf_sum = tf_metrics_team(tm, Xc, effEnd, LM, isTransient, bias, S.u.tf.tf_tmp, S.u.tf.tf_tmp1, X.metric);
         tf_sum = tm.sum(tf_sum);
         if (L0) X.tf_sum_team = tf_sum;
     }

@@ -262,6 +262,114 @@ pipe_prepass_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeo
     }
 }
 
+// ---- P0, second version: one THREAD per stream, no tiles ------------------------------------------------------------------------
+// The first version staged every 64 samples through shared memory with three block barriers (147 us per frame, and since the front
+// end's kernels are NOT hidden behind the frame steps — the machine is full, profiles/r2_encoder_ab.md — all of it was span time).
+// A thread now walks its own PCM row with 16-byte loads (a 128-byte line serves eight of them out of L1, the next lines are
+// prefetched), runs both channels' dc_reject chains side by side (independent, so they interleave in the pipeline), and stores
+// 16-byte vectors.  Needs whole vectors per frame row (every 48 / 24 / 16 / 8 kHz frame size; not 12 kHz 2.5 ms).
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__global__ void __launch_bounds__(32)
+pipe_prepass2_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, const int16_t *pcm, int fbase, int nfr, int16_t *D,
+                     EncPlan *plans, int *m0out) {
+    const int t = blockIdx.x * 32 + threadIdx.x;
+    if (t >= g.n) return;
+    CbEncState *st = pool + slots[t];
+    const int CC = g.CC, fsz = g.fsz;
+    const size_t row = (size_t)fsz * CC;
+    int hm0 = st->hp_mem[0], hm1 = st->hp_mem[1], hm2 = 0, hm3 = 0;
+    m0out[2 * t] = st->preemph_memE[0];
+    if (CC == 2) {
+        hm2 = st->hp_mem[2];
+        hm3 = st->hp_mem[3];
+        m0out[2 * t + 1] = st->preemph_memE[1];
+    } else {
+        m0out[2 * t + 1] = 0;
+    }
+    int last_l = 0, last_r = 0, any_coded = 0;
+    for (int fi = 0; fi < nfr; fi++) {
+        PlanPre pp;
+        pp.code = 0; pp.ret = 0; pp.want_width = 0; pp.fade = 0; pp.g1 = 0; pp.g2 = 0; pp.dc_shift = 0;
+        pipe_plan_pre(st, fsz, g.max_bytes, pp);
+        int xx = 0, xy = 0, yy = 0;
+        if (pp.code) {
+            const int4 *src = reinterpret_cast<const int4 *>(pcm + ((size_t)sidx[t] * g.F + fbase + fi) * row);
+            int4 *dst = reinterpret_cast<int4 *>(D + ((size_t)t * g.Fc + fi) * row);
+            const int nv = (int)(row >> 3);          // 16-byte vectors in the row
+            const int shift = pp.dc_shift;
+            int4 v = src[0];
+            if (CC == 2) {
+                for (int k = 0; k < nv; k++) {
+                    if ((k & 7) == 0) prefetch_l1(src + (k + 16 < nv ? k + 16 : nv - 1));
+                    const int4 nx = src[k + 1 < nv ? k + 1 : k];
+                    const int w[4] = {v.x, v.y, v.z, v.w};
+                    int o[4];
+                    int pxx = 0, pxy = 0, pyy = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int xl = s16(w[j]), xr = w[j] >> 16;
+                        if (pp.want_width) {
+                            pxx += mul16_16(xl, xl) >> 2;
+                            pxy += mul16_16(xl, xr) >> 2;
+                            pyy += mul16_16(xr, xr) >> 2;
+                        }
+                        int vl = dc_reject_step(xl, hm0, hm1, shift);
+                        int vr = dc_reject_step(xr, hm2, hm3, shift);
+                        if (pp.fade) {
+                            const int gq = stereo_fade_gain(4 * k + j, pp.g1, pp.g2, g.Fs);
+                            int diff = s16((vl - vr) >> 1);
+                            diff = mul16_16_q15(gq, diff);
+                            const int l = vl, r = vr;
+                            vl = (int)(int16_t)(l - diff);
+                            vr = (int)(int16_t)(r + diff);
+                        }
+                        o[j] = (vl & 0xffff) | (vr << 16);
+                        last_l = vl;
+                        last_r = vr;
+                    }
+                    if (pp.want_width) {
+                        xx = wadd(xx, pxx >> 10);
+                        xy = wadd(xy, pxy >> 10);
+                        yy = wadd(yy, pyy >> 10);
+                    }
+                    dst[k] = make_int4(o[0], o[1], o[2], o[3]);
+                    v = nx;
+                }
+            } else {
+                for (int k = 0; k < nv; k++) {
+                    if ((k & 7) == 0) prefetch_l1(src + (k + 16 < nv ? k + 16 : nv - 1));
+                    const int4 nx = src[k + 1 < nv ? k + 1 : k];
+                    const int w[4] = {v.x, v.y, v.z, v.w};
+                    int o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int a = dc_reject_step(s16(w[j]), hm0, hm1, shift);
+                        const int b = dc_reject_step(w[j] >> 16, hm0, hm1, shift);
+                        o[j] = (a & 0xffff) | (b << 16);
+                        last_l = b;
+                    }
+                    dst[k] = make_int4(o[0], o[1], o[2], o[3]);
+                    v = nx;
+                }
+            }
+            any_coded = 1;
+        }
+        EncPlan pl;
+        pipe_plan_post(st, pp, fsz, xx, xy, yy, pl);
+        plans[(size_t)t * g.Fc + fi] = pl;
+    }
+    if (any_coded) {
+        st->hp_mem[0] = hm0;
+        st->hp_mem[1] = hm1;
+        st->preemph_memE[0] = g.upsample == 1 ? mul16_16(kPreemphCoef0, last_l) >> 3 : 0;
+        if (CC == 2) {
+            st->hp_mem[2] = hm2;
+            st->hp_mem[3] = hm3;
+            st->preemph_memE[1] = g.upsample == 1 ? mul16_16(kPreemphCoef0, last_r) >> 3 : 0;
+        }
+    }
+}
+
 // ---- FE1: pre-emphasis + maxima, one warp per (stream, frame); the warp of frame 0 also installs the 1024-sample history ----
 __global__ void __launch_bounds__(CB_PIPE_WPB * 32)
 pipe_fe1_kernel(const CbEncState *pool, const int *slots, PipeGeom g, int nfr, const int16_t *D, const EncPlan *plans, const int *m0, int *P,
@@ -757,6 +865,8 @@ struct PipeCtx {
     int flow = 0;               // per-stream dataflow between the kernels of a frame step (struct Flow); 0: stream-ordered launches.
                                 // Measured (profiles/r2_encoder_ab.md): 8 % SLOWER than stream order — spinning blocks hold the slots ready
                                 // blocks need — and the band walk faults when it overlaps its predecessor; kept as an A/B knob only.
+    int prepass_v = 2;                  // Opus-layer prepass: 2 = thread per stream with vector loads, 1 = the tiled first version (A/B)
+    int probe_fe2 = 1;                  // dev probe: run the pitch stage this many times
     int flow_noopen = 0;                // debugging: kernels of a frame step that do not let their successor start early
     int flow_mask = -1, flow_seq = 0;   // debugging: which of a frame step's seven kernels get the early launch
     int *d_flow_err = nullptr;  // raised by a timed-out dataflow wait
@@ -792,6 +902,8 @@ bool pipe_init() {
     if (const char *e = getenv("CB200_ENC_FLOW")) pc.flow = atoi(e);
     if (const char *e = getenv("CB200_ENC_FLOW_MASK")) pc.flow_mask = atoi(e);
     if (const char *e = getenv("CB200_ENC_FLOW_NOOPEN")) pc.flow_noopen = atoi(e);
+    if (const char *e = getenv("CB200_ENC_PROBE_FE2")) pc.probe_fe2 = atoi(e);
+    if (const char *e = getenv("CB200_ENC_PREPASS")) pc.prepass_v = atoi(e);
     if (const char *e = getenv("CB200_ENC_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(e));
     int prio_lo = 0, prio_hi = 0, prio = 1;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -890,14 +1002,22 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         const int nfr = nframes - k * Fc < Fc ? nframes - k * Fc : Fc;
         // ---- front end of chunk k on the side stream (buffers b are free once the frame steps of chunk k-2 are done) ----
         if (k >= 2) cudaStreamWaitEvent(G.side, G.ev_steps[b], 0);
-        pipe_prepass_kernel<<<cdiv(n, 32), 128, 0, G.side>>>(c.pool, slots, sidx, g, c.d_pcm, fbase, nfr, (int16_t *)G.D.p, (EncPlan *)G.plans[b].p,
-                                                              (int *)G.m0.p);
+        if (pc.prepass_v == 2 && (row * sizeof(int16_t)) % 16 == 0 && (g.CC == 2 || g.CC == 1))
+            pipe_prepass2_kernel<<<cdiv(n, 32), 32, 0, G.side>>>(c.pool, slots, sidx, g, c.d_pcm, fbase, nfr, (int16_t *)G.D.p, (EncPlan *)G.plans[b].p,
+                                                                (int *)G.m0.p);
+        else
+            pipe_prepass_kernel<<<cdiv(n, 32), 128, 0, G.side>>>(c.pool, slots, sidx, g, c.d_pcm, fbase, nfr, (int16_t *)G.D.p, (EncPlan *)G.plans[b].p,
+                                                                  (int *)G.m0.p);
         pipe_fe1_kernel<<<cdiv(n * nfr, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.side>>>(c.pool, slots, g, nfr, (const int16_t *)G.D.p,
                                                                                     (const EncPlan *)G.plans[b].p, (const int *)G.m0.p, (int *)G.P[b].p,
                                                                                     k > 0 ? (const int *)G.P[b ^ 1].p : nullptr, prev_nfr,
                                                                                     (FeFrame *)G.fe[b].p);
         pipe_fe2_kernel<<<cdiv(n * nfr, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.side>>>(g, nfr, (const EncPlan *)G.plans[b].p, (const int *)G.P[b].p,
                                                                                     (FeFrame *)G.fe[b].p);
+        if (pc.probe_fe2 > 1)   // dev probe: how much of the front end's cost reaches the span's time (fe2 is idempotent)
+            for (int r = 1; r < pc.probe_fe2; r++)
+                pipe_fe2_kernel<<<cdiv(n * nfr, CB_PIPE_WPB), CB_PIPE_WPB * 32, 0, G.side>>>(g, nfr, (const EncPlan *)G.plans[b].p, (const int *)G.P[b].p,
+                                                                                            (FeFrame *)G.fe[b].p);
         cudaEventRecord(G.ev_fe[b], G.side);
         launches += 3;
         // ---- frame steps of chunk k on the main stream ----
