@@ -94,6 +94,8 @@ __device__ __forceinline__ void flow_done_block(const Flow &fl, int s0, int nval
     if ((int)threadIdx.x < nvalid) atomicAdd(fl.prog + s0 + threadIdx.x, 1);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---- staging for the thread-per-stream kernels ------------------------------------------------------------------------------------
 // A scalar stage walks a few KB of per-stream data with dependent accesses; from global memory every one of them costs an L2 round
 // trip (the first version of K4 ran 21 cycles per instruction).  So a block takes 32 streams: all its 128 threads copy the streams'
@@ -268,7 +270,6 @@ pipe_prepass_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeo
 // A thread now walks its own PCM row with 16-byte loads (a 128-byte line serves eight of them out of L1, the next lines are
 // prefetched), runs both channels' dc_reject chains side by side (independent, so they interleave in the pipeline), and stores
 // 16-byte vectors.  Needs whole vectors per frame row (every 48 / 24 / 16 / 8 kHz frame size; not 12 kHz 2.5 ms).
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __global__ void __launch_bounds__(32)
 pipe_prepass2_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, const int16_t *pcm, int fbase, int nfr, int16_t *D,
                      EncPlan *plans, int *m0out) {
@@ -546,6 +547,7 @@ pipe_transient2_kernel(PipeGeom g, EncPipeCtx *ctx, const EncPipeBuf *buf, Flow 
                 int4 v = src[0];
 #pragma unroll 2
                 for (int k = 0; k < nq; k++) {
+                    if ((k & 7) == 0) prefetch_l1(src + (k + 16 < nq ? k + 16 : nq - 1));   // two 128-byte lines ahead of the chain
                     const int4 nx = src[k + 1 < nq ? k + 1 : k];
                     int t[4];
                     const int xs[4] = {v.x >> 12, v.y >> 12, v.z >> 12, v.w >> 12};
