@@ -617,7 +617,14 @@ int opus_encoder_ctl(OpusEncoder *st, int request, ...) {
         }
     }
     int ret;
-    if (request == OPUS_RESET_STATE) {
+    if (request == 10024) {
+        // OPUS_SET_LFE (celt.h:113, opus_encoder.c:2455): the multistream encoder's switch for a low-frequency-effects channel.  The
+        // default (0) is accepted; the LFE analysis path itself is part of the multistream scope that is not built.
+        ret = va_arg(ap, opus_int32) == 0 ? OPUS_OK : OPUS_UNIMPLEMENTED;
+    } else if (request == 10026) {
+        // OPUS_SET_ENERGY_MASK (celt.h:116, opus_encoder.c:2462): a surround masking curve; only "none" (NULL) is accepted
+        ret = va_arg(ap, void *) == nullptr ? OPUS_OK : OPUS_UNIMPLEMENTED;
+    } else if (request == OPUS_RESET_STATE) {
         ret = enc_ctl(&st->st, request, 0, nullptr);
     } else if (enc_ctl_is_get(request)) {
         opus_int32 *p = va_arg(ap, opus_int32 *);

@@ -689,3 +689,27 @@ def test_repacketizer_and_pad_unpad_match_the_reference():
         assert L.opus_packet_pad(O.ptr(buf), bad, 8) == R.opus_packet_pad(O.ptr(buf), bad, 8)
         assert L.opus_packet_unpad(O.ptr(buf), bad) == R.opus_packet_unpad(O.ptr(buf), bad)
     L.opus_repacketizer_destroy(rp_l); R.opus_repacketizer_destroy(rp_r)
+
+
+def test_public_header_compiles_reference_style_ctl_calls(tmp_path):
+    """include/opus_b200.h carries the reference's OPUS_SET_* / OPUS_GET_* convenience macros (opus_defines.h:107-122), so a source
+    written against opus.h compiles against it unchanged (the macros were missing)."""
+    src = tmp_path / "ctl.c"
+    src.write_text('''
+#include "opus_b200.h"
+int f(OpusEncoder *e, OpusDecoder *d) {
+    opus_int32 v; opus_uint32 r; int rc = 0;
+    rc |= opus_encoder_ctl(e, OPUS_SET_BITRATE(64000));
+    rc |= opus_encoder_ctl(e, OPUS_SET_VBR(1));
+    rc |= opus_encoder_ctl(e, OPUS_SET_COMPLEXITY(10));
+    rc |= opus_encoder_ctl(e, OPUS_GET_LOOKAHEAD(&v));
+    rc |= opus_encoder_ctl(e, OPUS_GET_FINAL_RANGE(&r));
+    rc |= opus_encoder_ctl(e, OPUS_SET_LFE(0));
+    rc |= opus_decoder_ctl(d, OPUS_SET_GAIN(0));
+    rc |= opus_decoder_ctl(d, OPUS_GET_LAST_PACKET_DURATION(&v));
+    return rc;
+}
+''')
+    r = subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "ctl.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

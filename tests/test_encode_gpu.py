@@ -159,6 +159,10 @@ def test_scalar_api_and_state_copy():
     assert L.opus_encoder_ctl(hp, cb.OPUS_SET_COMPLEXITY_REQUEST, C.c_int32(10)) == 0
     assert L.opus_encoder_ctl(hp, cb.OPUS_SET_COMPLEXITY_REQUEST, C.c_int32(11)) == cb.OPUS_BAD_ARG
     assert L.opus_encoder_ctl(hp, 999999, C.c_int32(0)) == cb.OPUS_UNIMPLEMENTED
+    # the multistream-only switches of the CELT layer (opus_encoder.c:2455-2469): their defaults are accepted, nothing else
+    assert L.opus_encoder_ctl(hp, 10024, C.c_int32(0)) == 0                       # OPUS_SET_LFE(0)
+    assert L.opus_encoder_ctl(hp, 10024, C.c_int32(1)) == cb.OPUS_UNIMPLEMENTED
+    assert L.opus_encoder_ctl(hp, 10026, C.c_void_p(None)) == 0                   # OPUS_SET_ENERGY_MASK(NULL)
     out = np.zeros(1276, dtype=np.uint8)
     half = F // 2
     for f in range(half):

@@ -3,7 +3,7 @@
 # usage: tools/ab_env.sh VAR value...        (E2E=1 tools/ab_env.sh ... also times the host-buffer path, 60 s streams)
 var=$1; shift
 for v in "$@"; do
-  if [ -n "$E2E" ]; then args="--steps 1 --warmup 1 --no-cpu --no-encode"; else args="--seconds 12 --steps 2 --warmup 2 --no-e2e --no-cpu --no-encode"; fi
+  if [ -n "$E2E" ]; then args="--steps 1 --warmup 1 --no-cpu --no-encode --no-mixed --no-parity"; else args="--seconds 12 --steps 2 --warmup 2 --no-e2e --no-cpu --no-encode --no-mixed --no-parity"; fi
   env $var=$v python bench.py $args > gpurun_out/ab_env.log 2>&1
   python - <<PY
 import json
