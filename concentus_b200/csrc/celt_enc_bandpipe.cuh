@@ -388,13 +388,17 @@ struct InlinePolicy {
         const int d = prep->n2_d[band];
         ec.bits((unsigned)(c ? wneg(d) < 0 : d < 0), 1);
     }
-    CB_MEM void begin_band(int) { tm.phase(); }
+    unsigned sync_mask;        // bands at whose start the block's warps meet (SyncWarpTeam); every warp passes the same barriers
+    CB_MEM void begin_band(int i) { if ((sync_mask >> i) & 1u) tm.phase(); }
     CB_MEM void leaf(int, int off, int N, int K, int B, int spread) {
         alg_quant(tm, Xall + off, N, K, spread, B, ec, *ps);
         tm.sync();             // the lanes go on through the scalar state together
     }
     CB_MEM void finish() {}
-    CB_MEM void skip_bands(int n) { CB_NOUNROLL for (int i = 0; i < n; i++) tm.phase(); }   // every warp passes kNbEBands phase()s per frame
+    CB_MEM void skip_bands(int n) {   // the bands this frame does not code: the barriers of the mask are still passed
+        CB_NOUNROLL for (int i = kNbEBands - n; i < kNbEBands; i++)
+            if ((sync_mask >> i) & 1u) tm.phase();
+    }
 };
 
 // compute_theta, encoder half (bands.c:645-817), given the raw angle

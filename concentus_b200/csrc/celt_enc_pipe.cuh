@@ -1301,9 +1301,10 @@ struct WalkScratch {
 };
 template <class TM>
 CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, const EncPlan &pl, EncPipeCtx &X, const BandPrep &P, const int16_t *XallG,
-                                   WalkScratch &S, uint8_t *out) {
+                                   WalkScratch &S, uint8_t *out, unsigned sync_mask = 0x1fffffu) {
     if (!X.code) {
-        CB_NOUNROLL for (int i = 0; i < kNbEBands; i++) tm.phase();
+        CB_NOUNROLL for (int i = 0; i < kNbEBands; i++)
+            if ((sync_mask >> i) & 1u) tm.phase();
         return X.v.ret;
     }
     EncVars &V = X.v;
@@ -1321,7 +1322,7 @@ CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, con
 #endif
     SH.ec = V.ec;              // every lane stores the same values
     tm.sync();
-    InlinePolicy<TM> p{tm, &SH, SH.ec, S.Xall, &P, &S.pvq};
+    InlinePolicy<TM> p{tm, &SH, SH.ec, S.Xall, &P, &S.pvq, sync_mask};
     band_walk(p, P, X.cfg.end, C, X.pulses, V.shortBlocks, st->spread_decision, V.dual_stereo, st->intensity, X.tf_res,
               V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, g.LM, V.codedBands);
     tm.sync();

@@ -790,7 +790,7 @@ pipe_exact_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom 
 template <int WPB, bool SYNC>
 __global__ void __launch_bounds__(WPB * 32, 28 / WPB)
 pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g, int f, int fi, const EncPlan *plans, EncPipeCtx *ctx,
-                 const BandPrep *prep, const int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, Flow fl) {
+                 const BandPrep *prep, const int16_t *xall, uint8_t *data, int *rets, unsigned *ranges, Flow fl, unsigned sync_mask) {
     extern __shared__ __align__(16) unsigned char smw[];
     WalkScratch *sm = reinterpret_cast<WalkScratch *>(smw);
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -798,7 +798,8 @@ pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
     flow_open(fl);
     if (s >= g.n) {
         if (SYNC)
-            for (int i = 0; i < kNbEBands; i++) __syncthreads();
+            for (int i = 0; i < kNbEBands; i++)
+                if ((sync_mask >> i) & 1u) __syncthreads();
         return;
     }
     flow_wait_warp(fl, s);
@@ -813,7 +814,8 @@ pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
     int r;
     if (SYNC) {
         SyncWarpTeam tm{{lane}};
-        r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib], data + k * g.stride);
+        r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib], data + k * g.stride,
+                                    sync_mask);
     } else {
         FreeWarpTeam tm{{lane}};
         r = pipe_band_inline_finish(tm, st, g, plans[(size_t)s * g.Fc + fi], ctx[s], prep[s], xall + (size_t)s * kXallStride, sm[wib], data + k * g.stride);
@@ -863,6 +865,7 @@ struct PipeCtx {
     int groups = 1;             // stream groups on separate CUDA streams (measured: no gain, the stages are issue bound with all streams resident)
     int chunk = 8;              // frames per front-end chunk (measured 4..50: 8 is best, profiles/r2_encoder_ab.md)
     int walk_mode = 3;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band (measured: 3)
+    unsigned walk_sync_mask = 0x1fffffu;   // bands at whose start the walk's block meets (CB200_ENC_WALK_SYNC, hex)
     int scalar_l = 2;           // streams per warp in the thread-per-stream stages
     int flow = 0;               // per-stream dataflow between the kernels of a frame step (struct Flow); 0: stream-ordered launches.
                                 // Measured (profiles/r2_encoder_ab.md): 8 % SLOWER than stream order — spinning blocks hold the slots ready
@@ -924,6 +927,7 @@ bool pipe_init() {
     }
     cudaEventCreateWithFlags(&pc.ev_fork, cudaEventDisableTiming);
     if (const char *e = getenv("CB200_ENC_WALK")) pc.walk_mode = atoi(e);
+    if (const char *e = getenv("CB200_ENC_WALK_SYNC")) pc.walk_sync_mask = (unsigned)strtoul(e, nullptr, 16);
     cudaFuncSetAttribute(pipe_walk_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(14 * sizeof(WalkScratch)));
     cudaFuncSetAttribute(pipe_walk_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(28 * sizeof(WalkScratch)));
     b2p_lut_kernel<<<((kMaxLM + 2) * kNbEBands * kB2pBits + 255) / 256, 256>>>();
@@ -1051,7 +1055,7 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
                             (const EncPipeCtx *)G.ctx.p, (const EncPipeBuf *)G.buf.p, (BandPrep *)G.prep.p, (int16_t *)G.xall.p, FL(3 + 2 * g.CC));
                 launch_flow(pipe_walk_kernel<4, false>, cdiv(n, 4), 4 * 32, 4 * sizeof(WalkScratch), G.main, true, c.pool, slots, sidx, g, f, fi,
                             (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p, (const int16_t *)G.xall.p, c.d_data,
-                            c.d_rets, c.d_ranges, FL(4 + 2 * g.CC));
+                            c.d_rets, c.d_ranges, FL(4 + 2 * g.CC), 0u);
                 launches += 7;
                 continue;
             }
@@ -1077,7 +1081,7 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
 #define CB_WALK_LAUNCH(WPB, SYNC)                                                                                                         \
     pipe_walk_kernel<WPB, SYNC><<<cdiv(n, WPB), WPB * 32, WPB * sizeof(WalkScratch), G.main>>>(                                            \
         c.pool, slots, sidx, g, f, fi, (const EncPlan *)G.plans[b].p, (EncPipeCtx *)G.ctx.p, (const BandPrep *)G.prep.p, (const int16_t *)G.xall.p, \
-        c.d_data, c.d_rets, c.d_ranges, nofl)
+        c.d_data, c.d_rets, c.d_ranges, nofl, pc.walk_sync_mask)
                 switch (pc.walk_mode) {
                 case 1: CB_WALK_LAUNCH(4, true); break;
                 case 2: CB_WALK_LAUNCH(7, true); break;
