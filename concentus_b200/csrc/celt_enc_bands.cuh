@@ -221,27 +221,62 @@ CB_DEV_TINY void exp_rotation1_chain(int16_t *X, int len, int stride, int c, int
     }
 }
 
-// exp_rotation, encoder direction (vq.c:70-113 with dir = +1): per block the stride-1 sweep (one chain), then the stride2 sweep
-// (stride2 chains); blocks are independent, so the team runs `stride` resp. `stride*stride2` chains at a time.
-template <class TM>
-CB_DEV_NOINLINE void exp_rotation_enc(TM tm, int16_t *X, int len, int stride, int K, int spread) {
-    if (2 * K >= len || spread == kSpreadNone) return;
-    int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
-    int gain = s16(celt_div(mul16_16(32767, len), len + factor * K));
-    int theta = mul16_16_q15(gain, gain) >> 1;
-    int c = celt_cos_norm(theta);
-    int s = celt_cos_norm(s16(32767 - theta));
+// The rotation's parameters (vq.c:80-93): c, s from (len, K, spread) through celt_div and two celt_cos_norm, stride2 from (len, stride).
+CB_DEV void rotation_params(int len, int K, int spread, int &c, int &s) {
+    const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
+    const int gain = s16(celt_div(mul16_16(32767, len), len + factor * K));
+    const int theta = mul16_16_q15(gain, gain) >> 1;
+    c = celt_cos_norm(theta);
+    s = celt_cos_norm(s16(32767 - theta));
+}
+CB_DEV int rotation_stride2(int len, int stride) {
     int stride2 = 0;
     if (len >= 8 * stride) {
         stride2 = 1;
         while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
     }
-    len = (int)udiv((unsigned)len, (unsigned)stride);
+    return stride2;
+}
+// CB_ROT_LUT (the encoder pipeline): ~170 uniform scalar instructions per leaf for those parameters — a ninth of the band walk —
+// become two loads from tables the pipeline fills at start-up WITH the functions above (opus_enc_pipe.cu, rot_lut_kernel).
+enum { kRotLen = 177, kRotK = 88 };   // leaves are <= 176 values wide; the rotation runs only when 2 K < len
+#if defined(CB_ROT_LUT) && defined(__CUDACC__)
+static __device__ uint32_t g_rot_cs[3 * kRotLen * kRotK];   // (c & 0xffff) | s << 16, by (spread - 1, len, K)
+static __device__ uint8_t g_rot_s2[kRotLen * 4];            // stride2 by (len, log2 stride)
+static __device__ uint32_t g_inv16[32];                     // ceil(65536 / d): x / d == x * inv >> 16 for x < 256, d < 32
+#endif
+
+// exp_rotation, encoder direction (vq.c:70-113 with dir = +1): per block the stride-1 sweep (one chain), then the stride2 sweep
+// (stride2 chains); blocks are independent, so the team runs `stride` resp. `stride*stride2` chains at a time.
+template <class TM>
+CB_DEV_NOINLINE void exp_rotation_enc(TM tm, int16_t *X, int len, int stride, int K, int spread) {
+    if (2 * K >= len || spread == kSpreadNone) return;
+    int c, s, stride2;
+    const int lstride = celt_ilog2(stride);                  // stride (= B) is 1, 2, 4 or 8
+#if defined(CB_ROT_LUT) && defined(__CUDACC__)
+    {
+        const uint32_t w = g_rot_cs[((spread - 1) * kRotLen + len) * kRotK + K];
+        c = (int)(w & 0xffffu);
+        s = (int)(w >> 16);
+        stride2 = g_rot_s2[len * 4 + lstride];
+    }
+#else
+    rotation_params(len, K, spread, c, s);
+    stride2 = rotation_stride2(len, stride);
+#endif
+    len >>= lstride;
     CB_TEAM_FOR(b, stride, tm) exp_rotation1_chain(X + b * len, len, 1, c, s16(-s), 0);
     tm.sync();
     if (stride2) {
+#if defined(CB_ROT_LUT) && defined(__CUDACC__)
+        const uint32_t inv = g_inv16[stride2];
+#endif
         CB_TEAM_FOR(w, stride * stride2, tm) {
+#if defined(CB_ROT_LUT) && defined(__CUDACC__)
+            const int b = (int)(((uint32_t)w * inv) >> 16), r = w - b * stride2;
+#else
             const int b = w / stride2, r = w - b * stride2;
+#endif
             exp_rotation1_chain(X + b * len, len, stride2, s, s16(-c), r);
         }
         tm.sync();

@@ -9,6 +9,9 @@
 #if !defined(CB_PIPE_NO_TINY)
 #define CB_TINY_CODE 1    // ... and the range coder's renormalisation / tell / the rotation chain as shared calls
 #endif
+#if !defined(CB_PIPE_NO_ROT_LUT)
+#define CB_ROT_LUT 1      // celt_enc_bands.cuh: the spreading rotation's parameters from tables filled at start-up
+#endif
 #endif
 #include <cuda_runtime.h>
 
@@ -828,6 +831,24 @@ pipe_walk_kernel(CbEncState *pool, const int *slots, const int *sidx, PipeGeom g
     flow_done_warp(fl, s);
 }
 
+#if defined(CB_ROT_LUT)
+__global__ void rot_lut_kernel() {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 3 * kRotLen * kRotK) {
+        const int K = t % kRotK, len = (t / kRotK) % kRotLen, spread = t / (kRotK * kRotLen) + 1;
+        uint32_t w = 0;
+        if (len >= 2 && 2 * K < len) {
+            int c, s;
+            rotation_params(len, K, spread, c, s);
+            w = ((uint32_t)c & 0xffffu) | ((uint32_t)s << 16);
+        }
+        g_rot_cs[t] = w;
+    }
+    if (t < kRotLen * 4) g_rot_s2[t] = (uint8_t)rotation_stride2(t >> 2, 1 << (t & 3));
+    if (t < 32) g_inv16[t] = t < 2 ? 65536u : (65536u + (uint32_t)t - 1u) / (uint32_t)t;
+}
+#endif
+
 __global__ void b2p_lut_kernel() {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (kMaxLM + 2) * kNbEBands * kB2pBits) return;
@@ -931,6 +952,9 @@ bool pipe_init() {
     cudaFuncSetAttribute(pipe_walk_kernel<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(14 * sizeof(WalkScratch)));
     cudaFuncSetAttribute(pipe_walk_kernel<28, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(28 * sizeof(WalkScratch)));
     b2p_lut_kernel<<<((kMaxLM + 2) * kNbEBands * kB2pBits + 255) / 256, 256>>>();
+#if defined(CB_ROT_LUT)
+    rot_lut_kernel<<<(3 * kRotLen * kRotK + 255) / 256, 256>>>();
+#endif
     cudaDeviceSynchronize();
     cudaFuncSetAttribute(pipe_transient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient);
     cudaFuncSetAttribute(pipe_transient2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTransient2);
