@@ -373,7 +373,8 @@ struct InlinePolicy {
     TM tm;
     WalkShared *sh;            // the team's one copy of the scalar state (team-shared memory)
     EcEnc &ec;                 // = sh->ec
-    int16_t *Xall;             // the stream's prepared vectors (team-shared memory)
+    const int16_t *Xall;       // the stream's prepared vectors [X | Y | intensity mid] where prep left them (global memory, L2)
+    int16_t *leafbuf;          // team-shared copy of the leaf being quantised (176 values)
     const BandPrep *prep;
     PvqScratch *ps;
     CB_MEM WalkCtx &wctx() { return sh->w; }
@@ -391,7 +392,11 @@ struct InlinePolicy {
     unsigned sync_mask;        // bands at whose start the block's warps meet (SyncWarpTeam); every warp passes the same barriers
     CB_MEM void begin_band(int i) { if ((sync_mask >> i) & 1u) tm.phase(); }
     CB_MEM void leaf(int, int off, int N, int K, int B, int spread) {
-        alg_quant(tm, Xall + off, N, K, spread, B, ec, *ps);
+        // Only the leaf being searched is staged: a whole-frame copy of the vectors (5.6 KB per warp, 160 KB per SM) left the
+        // kernel ~50 KB of L1 for its tables, the angle trees and the spills.
+        CB_TEAM_FOR(j, N, tm) leafbuf[j] = Xall[off + j];
+        tm.sync();
+        alg_quant(tm, leafbuf, N, K, spread, B, ec, *ps);
         tm.sync();             // the lanes go on through the scalar state together
     }
     CB_MEM void finish() {}

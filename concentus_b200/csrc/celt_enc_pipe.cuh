@@ -1295,7 +1295,7 @@ CB_DEV_NOINLINE int pipe_band_exact_finish(CbEncState *st, const PipeGeom &g, co
 
 // ---- the band loop as prep + ONE walk with the real coder, leaves searched inline by the team (no speculation) -----------------------
 struct WalkScratch {
-    int16_t Xall[kXallStride];
+    int16_t leaf[176];
     PvqScratch pvq;
     WalkShared sh;
 };
@@ -1308,12 +1308,7 @@ CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, con
         return X.v.ret;
     }
     EncVars &V = X.v;
-    const int C = X.cfg.C, N = g.N;
-    CB_NOUNROLL for (int v = 0; v < 3; v++) {
-        if (v > 0 && C == 1) break;
-        CB_TEAM_FOR(i, N, tm) S.Xall[v * kMaxFrame + i] = XallG[v * kMaxFrame + i];
-    }
-    tm.sync();
+    const int C = X.cfg.C;
 #if defined(CB_WALK_LOCAL)
     WalkShared lsh;            // A/B: the scalar state as 32 private copies on the stack
     WalkShared &SH = lsh;
@@ -1322,7 +1317,7 @@ CB_DEV int pipe_band_inline_finish(TM tm, CbEncState *st, const PipeGeom &g, con
 #endif
     SH.ec = V.ec;              // every lane stores the same values
     tm.sync();
-    InlinePolicy<TM> p{tm, &SH, SH.ec, S.Xall, &P, &S.pvq, sync_mask};
+    InlinePolicy<TM> p{tm, &SH, SH.ec, XallG, S.leaf, &P, &S.pvq, sync_mask};
     band_walk(p, P, X.cfg.end, C, X.pulses, V.shortBlocks, st->spread_decision, V.dual_stereo, st->intensity, X.tf_res,
               V.nbCompressedBytes * (8 << kBitRes) - V.anti_collapse_rsv, V.balance, g.LM, V.codedBands);
     tm.sync();
