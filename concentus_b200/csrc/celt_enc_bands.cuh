@@ -242,7 +242,7 @@ CB_DEV int rotation_stride2(int len, int stride) {
 enum { kRotLen = 177, kRotK = 88 };   // leaves are <= 176 values wide; the rotation runs only when 2 K < len
 #if defined(CB_ROT_LUT) && defined(__CUDACC__)
 static __device__ uint32_t g_rot_cs[3 * kRotLen * kRotK];   // (c & 0xffff) | s << 16, by (spread - 1, len, K)
-static __device__ uint8_t g_rot_s2[kRotLen * 4];            // stride2 by (len, log2 stride)
+static __device__ uint8_t g_rot_s2[kRotLen * 8];            // stride2 by (len, log2 stride): the time-divided short blocks reach stride 16+
 static __device__ uint32_t g_inv16[32];                     // ceil(65536 / d): x / d == x * inv >> 16 for x < 256, d < 32
 #endif
 
@@ -258,7 +258,7 @@ CB_DEV_NOINLINE void exp_rotation_enc(TM tm, int16_t *X, int len, int stride, in
         const uint32_t w = g_rot_cs[((spread - 1) * kRotLen + len) * kRotK + K];
         c = (int)(w & 0xffffu);
         s = (int)(w >> 16);
-        stride2 = g_rot_s2[len * 4 + lstride];
+        stride2 = g_rot_s2[len * 8 + lstride];
     }
 #else
     rotation_params(len, K, spread, c, s);

@@ -844,7 +844,7 @@ __global__ void rot_lut_kernel() {
         }
         g_rot_cs[t] = w;
     }
-    if (t < kRotLen * 4) g_rot_s2[t] = (uint8_t)rotation_stride2(t >> 2, 1 << (t & 3));
+    if (t < kRotLen * 8) g_rot_s2[t] = (uint8_t)rotation_stride2(t >> 3, 1 << (t & 7));
     if (t < 32) g_inv16[t] = t < 2 ? 65536u : (65536u + (uint32_t)t - 1u) / (uint32_t)t;
 }
 #endif
