@@ -229,6 +229,8 @@ struct Ctx {
     // they run on smaller chunks (measured: e2e 108 K -> 126 K x realtime; the device-resident path keeps the large ones)
     size_t ir_budget_host = (size_t)6 << 30;   // env CB200_IR_HOST_MB (4 / 6 / 8 GB measured: 119 K / 126 K / 116 K)
     int run_len = 3;                      // packets per stage-A thread (env CB200_RUN)
+    int parse_wave_blocks = 0;            // blocks of parse_kernel resident at once on this device (occupancy x SMs)
+    int max_waves = 1;                    // stage-A waves per chunk (env CB200_WAVES; 0: what the IR budget allows).  Measured at 4,096 streams x 60 s: 1 wave (108-frame chunks) 157.7 K x, 2 waves 147.4 K x, 3 (the 16 GB budget) 145.4 K x: more, shorter chunks pipeline the three stages better
     PinBuf h_stage, h_slots, h_misc;
     long long launches = 0;
     float last_ms = 0.f;
@@ -304,6 +306,15 @@ bool ctx_init_locked() {
     if (const char *e = getenv("CB200_IR_MB")) g.ir_budget = (size_t)atol(e) << 20;
     if (const char *e = getenv("CB200_IR_HOST_MB")) g.ir_budget_host = (size_t)atol(e) << 20;
     if (const char *e = getenv("CB200_RUN")) g.run_len = atoi(e) > 0 ? atoi(e) : 5;
+    if (const char *e = getenv("CB200_WAVES")) g.max_waves = atoi(e);
+    {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, parse_kernel, CB_PARSE_THREADS, 0) == cudaSuccess)
+            g.parse_wave_blocks = per_sm * sms;
+        if (getenv("CB200_NO_WAVE_SIZING")) g.parse_wave_blocks = 0;
+    }
     {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && g.ir_budget > free_b / 10) g.ir_budget = free_b / 10;
@@ -520,6 +531,23 @@ bool plan_call(Plan &pl, int n, int F, int cap, int fec, int Fs, bool host_io) {
     if (fc < 1) fc = 1;
     if (fc > (size_t)F) fc = (size_t)F;
     if (fc > (size_t)pl.R) fc -= fc % pl.R;
+    // Stage A is a latency-bound kernel of equal-cost threads: its blocks run in waves of `parse_wave_blocks`, and a chunk a few
+    // blocks over a whole number of waves pays for another wave (measured: 114-frame chunks of 4,096 streams = 1,216 blocks on
+    // 1,184 slots decode at 140 K x, 90-frame chunks at 149 K x).  So a chunk holds whole waves: k * floor(W * threads / n) runs.
+    if (g.parse_wave_blocks > 0) {
+        const size_t runs_per_wave = (size_t)g.parse_wave_blocks * CB_PARSE_THREADS / (size_t)n;
+        if (runs_per_wave >= 1) {
+            size_t k = fc / (runs_per_wave * pl.R);                       // whole waves the IR budget allows
+            if (g.max_waves > 0) {
+                // ... of which `max_waves` are used, but never chunks shorter than ~96 packets (very large batches: a wave of
+                // 65,536 streams is 6 packets, and stages B / C pay per launch)
+                size_t want = (size_t)g.max_waves, floor_k = (96 + runs_per_wave * pl.R - 1) / (runs_per_wave * pl.R);
+                if (want < floor_k) want = floor_k;
+                if (k > want) k = want;
+            }
+            if (k >= 1) fc = k * runs_per_wave * pl.R;
+        }
+    }
     // equal chunks (a multiple of the run length) instead of full ones plus a remnant
     const size_t nch = ((size_t)F + fc - 1) / fc;
     size_t eq = ((size_t)F + nch - 1) / nch;
