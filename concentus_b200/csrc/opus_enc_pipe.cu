@@ -1,9 +1,12 @@
 // opus_enc_pipe.cu — kernels and host orchestration of the frame-synchronous encoder pipeline (celt_enc_pipe.cuh has the design
 // and the per-stage device functions; enc_pipe_host.h is the interface opus_enc_capi.cu calls).
 //
-// A launch's streams are cut into G groups; each group advances frame by frame through K1..K5 on its own CUDA stream, with the
-// front end (P0 / FE1 / FE2) of the NEXT chunk of frames running on a side stream.  Kernels of different groups overlap, so the
-// thread-per-stream stages (a few hundred warps, latency bound) of one group hide behind the warp-per-stream stages of another.
+// A launch's streams advance frame by frame through K1..K5 on the main CUDA stream, with the front end (P0 / FE1 / FE2) of the
+// NEXT chunk of frames on a side stream.  Every frame-step kernel is ONE wave holding all streams of the launch (4,096 streams =
+// 27.7 warps per SM at 72 registers = the whole register file), so a kernel's duration is a stream's dependent-instruction chain
+// and the span's time is the sum of its kernels — measured: work on the side stream costs its full stand-alone time, stream groups
+// on separate CUDA streams (CB200_ENC_GROUPS) and per-stream dataflow launches (CB200_ENC_FLOW) are slower
+// (profiles/r2_encoder_ab.md).  What pays is a shorter chain per kernel: the knobs below default to what measured best.
 #if !defined(CB_PIPE_BIG_CODE)
 #define CB_SMALL_CODE 1   // celt_simt.cuh: medium helpers as real calls, loops not unrolled (A/B: -DCB_PIPE_BIG_CODE)
 #if !defined(CB_PIPE_NO_TINY)
