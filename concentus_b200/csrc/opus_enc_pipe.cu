@@ -887,6 +887,7 @@ struct Group {
 struct PipeCtx {
     bool init = false;
     int groups = 1;             // stream groups on separate CUDA streams (measured: no gain, the stages are issue bound with all streams resident)
+    int first_chunk = 2;        // frames in the first chunk of a span (its front end is exposed); 0: same as the others
     int chunk = 8;              // frames per front-end chunk (measured 4..50: 8 is best, profiles/r2_encoder_ab.md)
     int walk_mode = 3;          // band-walk kernel: 0 = 4 free-running warps per block; 1..4 = 4 / 7 / 14 / 28 warps meeting at every band (measured: 3)
     unsigned walk_sync_mask = 0x1fffffu;   // bands at whose start the walk's block meets (CB200_ENC_WALK_SYNC, hex)
@@ -923,6 +924,7 @@ bool pipe_init() {
     if (pc.groups > kMaxGroups) pc.groups = kMaxGroups;
     if (const char *e = getenv("CB200_ENC_CHUNK")) pc.chunk = atoi(e);
     if (pc.chunk < 1) pc.chunk = 1;
+    if (const char *e = getenv("CB200_ENC_FIRST_CHUNK")) pc.first_chunk = atoi(e);
     if (const char *e = getenv("CB200_ENC_SPLIT_BANDS")) pc.split_bands = atoi(e);
     if (cudaMalloc(&pc.d_stats, 2 * sizeof(int)) != cudaSuccess) return false;
     cudaMemset(pc.d_stats, 0, 2 * sizeof(int));
@@ -1026,13 +1028,15 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         if (!G.prog.reserve((size_t)n * sizeof(int))) return -7;
         cudaMemsetAsync(G.prog.p, 0, (size_t)n * sizeof(int), G.main);
     }
-    const int nchunks = cdiv(nframes, Fc);
-    const int tpb = 64;
+    // The front end of the FIRST chunk overlaps nothing (the frame steps wait for it), and its prepass is a chain over the chunk's
+    // frames: the first chunk is short (CB200_ENC_FIRST_CHUNK frames), the rest have Fc.
+    int nchunks = 0, done = 0;
     int prev_nfr = 0;
-    for (int k = 0; k < nchunks; k++) {
+    for (int k = 0; done < nframes; k++) {
         const int b = k & 1;
-        const int fbase = c.f0 + k * Fc;
-        const int nfr = nframes - k * Fc < Fc ? nframes - k * Fc : Fc;
+        const int fbase = c.f0 + done;
+        const int want = k == 0 && pc.first_chunk > 0 && pc.first_chunk < Fc ? pc.first_chunk : Fc;
+        const int nfr = nframes - done < want ? nframes - done : want;
         // ---- front end of chunk k on the side stream (buffers b are free once the frame steps of chunk k-2 are done) ----
         if (k >= 2) cudaStreamWaitEvent(G.side, G.ev_steps[b], 0);
         if (pc.prepass_v == 2 && (row * sizeof(int16_t)) % 16 == 0 && (g.CC == 2 || g.CC == 1))
@@ -1059,7 +1063,7 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
             const int f = fbase + fi;
             if (flow) {
                 // units a stream completes per frame: head 1, comb CC, transient CC, transform 1, decide 1, prep 1, walk 1
-                const int U = 5 + 2 * g.CC, base = (k * Fc + fi) * U;
+                const int U = 5 + 2 * g.CC, base = (done + fi) * U;
                 int *prog = (int *)G.prog.p;
                 int kidx = 0;
                 auto FL = [&](int need) {
@@ -1130,6 +1134,8 @@ int enqueue_group(Group &G, const EncPipeCall &c, int k0, int n, PipeGeom g) {
         }
         cudaEventRecord(G.ev_steps[b], G.main);
         prev_nfr = nfr;
+        done += nfr;
+        nchunks = k + 1;
     }
     pipe_epilogue_kernel<<<n, 128, 0, G.main>>>(c.pool, slots, g, (const int *)G.P[(nchunks - 1) & 1].p, prev_nfr);
     launches++;
