@@ -201,7 +201,7 @@ def test_hostsim_encoder_pipeline_vs_oracle_mini_sweep(band_mode):
     rs = np.random.RandomState(12 + band_mode)
     cases = [(k, ch, fs, br, m, cx) for k in ("music", "tone", "clicks", "noise") for ch in (1, 2) for fs in (120, 240, 480, 960)
              for br in (32000, 48000, 64000, 96000, 128000, 192000, 256000, 510000) for m in ((0, 0), (1, 0), (1, 1)) for cx in (0, 5, 10)]
-    for n, i in enumerate(rs.permutation(len(cases))[:(150, 100, 50)[2 - band_mode]]):
+    for n, i in enumerate(rs.permutation(len(cases))[:(500, 100, 50)[2 - band_mode]]):   # the inline walk is what the GPU runs
         kind, ch, fs, br, (vbr, cvbr), cx = cases[i]
         x = O.test_signal(24000, ch, 500 + int(i), kind)
         d, o, l, r = O.encode_stream(x, fs, br, ch, vbr=vbr, cvbr=cvbr, complexity=cx, max_bytes=1276)
